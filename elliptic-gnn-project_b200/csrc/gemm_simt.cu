@@ -1,0 +1,255 @@
+// K6 (SIMT path) -- dense projections with exact-fp32 FFMA accumulation.
+//
+// This is the fp32-parity path (plain TF32 cannot meet rel 1e-5) and the
+// reference the tcgen05 bf16 path (gemm_tcgen05.cu) is checked against.  It covers the
+// three products of a Linear layer through one strided interface:
+//   forward  C = X W^T      (A k-contiguous, B k-contiguous)
+//   dgrad    D = G W        (A k-contiguous, B n-contiguous)
+//   wgrad    dW = G^T X     (A m-contiguous, B n-contiguous, reduction over the node axis,
+//                            split-K with a fixed-order second stage => deterministic)
+// plus two skinny specialisations for the 2-class output layer (N<=8 forward, M<=8 wgrad),
+// which are pure streaming reductions.
+#include "common.cuh"
+
+namespace egnn {
+namespace {
+
+constexpr int BM = 128, BN = 64, BK = 16, kThreads = 256;
+
+struct GemmParams {
+  const void* A;
+  const void* B;
+  void* C;
+  const float* bias;
+  float* ws;
+  int64_t a_sm, a_sk, b_sk, b_sn, ld_c;
+  int64_t M, N, K;
+  int64_t k_per_split;  // multiple of BK
+  int c_dtype, accumulate, split_k;
+};
+
+__device__ __forceinline__ void store_c(const GemmParams& P, int64_t m, int64_t n, float v) {
+  if (P.bias) v += P.bias[n];
+  if (P.c_dtype == EGNN_F32) {
+    float* c = reinterpret_cast<float*>(P.C) + m * P.ld_c + n;
+    if (P.accumulate) v += *c;
+    *c = v;
+  } else {
+    __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(P.C) + m * P.ld_c + n;
+    if (P.accumulate) v += __bfloat162float(*c);
+    *c = __float2bfloat16_rn(v);
+  }
+}
+
+template <typename TA, typename TB>
+__global__ void __launch_bounds__(kThreads) gemm_simt(GemmParams P) {
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+  const TA* __restrict__ A = reinterpret_cast<const TA*>(P.A);
+  const TB* __restrict__ B = reinterpret_cast<const TB*>(P.B);
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int64_t m0 = (int64_t)blockIdx.x * BM, n0 = (int64_t)blockIdx.y * BN;
+  const int64_t kb = (int64_t)blockIdx.z * P.k_per_split;
+  const int64_t ke = min(P.K, kb + P.k_per_split);
+  const bool a_mfast = P.a_sm <= P.a_sk, b_nfast = P.b_sn <= P.b_sk;
+
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int64_t k0 = kb; k0 < ke; k0 += BK) {
+#pragma unroll
+    for (int i = 0; i < (BM * BK) / kThreads; ++i) {
+      int idx = tid + i * kThreads;
+      int mm = a_mfast ? (idx % BM) : (idx / BK);
+      int kk = a_mfast ? (idx / BM) : (idx % BK);
+      int64_t m = m0 + mm, k = k0 + kk;
+      As[kk][mm] = (m < P.M && k < ke) ? to_f32(A[m * P.a_sm + k * P.a_sk]) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < (BN * BK) / kThreads; ++i) {
+      int idx = tid + i * kThreads;
+      int nn = b_nfast ? (idx % BN) : (idx / BK);
+      int kk = b_nfast ? (idx / BN) : (idx % BK);
+      int64_t n = n0 + nn, k = k0 + kk;
+      Bs[kk][nn] = (n < P.N && k < ke) ? to_f32(B[k * P.b_sk + n * P.b_sn]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 8]);
+      float4 a1 = *reinterpret_cast<const float4*>(&As[kk][ty * 8 + 4]);
+      float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int64_t m = m0 + ty * 8 + i;
+    if (m >= P.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int64_t n = n0 + tx * 4 + j;
+      if (n >= P.N) continue;
+      if (P.split_k > 1)
+        P.ws[((int64_t)blockIdx.z * P.M + m) * P.N + n] = acc[i][j];
+      else
+        store_c(P, m, n, acc[i][j]);
+    }
+  }
+}
+
+// fixed-order second stage of split-K
+__global__ void __launch_bounds__(kThreads) splitk_reduce(GemmParams P) {
+  int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= P.M * P.N) return;
+  float s = 0.f;
+  for (int z = 0; z < P.split_k; ++z) s += P.ws[(int64_t)z * P.M * P.N + i];
+  store_c(P, i / P.N, i % P.N, s);
+}
+
+// ---- skinny forward: C[M, N<=8] = A[M,K] . W[N,K]^T, one warp per row, lanes split K ----
+template <typename TA, typename TB, int NOUT>
+__global__ void __launch_bounds__(kThreads) gemm_skinny_fwd(GemmParams P) {
+  const TA* __restrict__ A = reinterpret_cast<const TA*>(P.A);
+  const TB* __restrict__ W = reinterpret_cast<const TB*>(P.B);
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * kThreads + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * kThreads) >> 5;
+  for (int64_t m = warp; m < P.M; m += n_warps) {
+    float s[NOUT];
+#pragma unroll
+    for (int j = 0; j < NOUT; ++j) s[j] = 0.f;
+    for (int64_t k = lane; k < P.K; k += 32) {
+      float a = to_f32(A[m * P.a_sm + k]);
+#pragma unroll
+      for (int j = 0; j < NOUT; ++j)
+        if (j < P.N) s[j] = fmaf(a, to_f32(W[j * P.b_sn + k]), s[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < NOUT; ++j)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+    if (lane == 0)
+      for (int j = 0; j < NOUT && j < P.N; ++j) store_c(P, m, j, s[j]);
+  }
+}
+
+// ---- skinny wgrad: dW[Mo<=8, N] = G^T . X ; G [R, Mo] (a_sk = ldg, a_sm = 1), X [R, N] ----
+// CTA = row chunk, thread = output column; partials -> ws[chunk][Mo][N], then splitk_reduce.
+template <typename TA, typename TB, int MOUT>
+__global__ void __launch_bounds__(kThreads) gemm_skinny_wgrad(GemmParams P) {
+  const TA* __restrict__ G = reinterpret_cast<const TA*>(P.A);
+  const TB* __restrict__ X = reinterpret_cast<const TB*>(P.B);
+  const int64_t r0 = (int64_t)blockIdx.x * P.k_per_split;
+  const int64_t r1 = min(P.K, r0 + P.k_per_split);
+  for (int64_t n = threadIdx.x; n < P.N; n += kThreads) {
+    float s[MOUT];
+#pragma unroll
+    for (int j = 0; j < MOUT; ++j) s[j] = 0.f;
+    for (int64_t r = r0; r < r1; ++r) {
+      float x = to_f32(X[r * P.b_sk + n]);
+#pragma unroll
+      for (int j = 0; j < MOUT; ++j)
+        if (j < P.M) s[j] = fmaf(to_f32(G[r * P.a_sk + j]), x, s[j]);
+    }
+    for (int j = 0; j < MOUT && j < P.M; ++j)
+      P.ws[((int64_t)blockIdx.x * P.M + j) * P.N + n] = s[j];
+  }
+}
+
+template <typename TA, typename TB>
+int run(GemmParams& P, cudaStream_t st) {
+  const char* fn = "egnn_gemm";
+  // skinny forward (2-class logits): N <= 8, both operands k-contiguous
+  if (P.N <= 8 && P.a_sk == 1 && P.b_sk == 1 && P.split_k <= 1 && P.K <= 4096) {
+    int64_t blocks = ceil_div(P.M, kThreads / 32);
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    if (P.N <= 2) gemm_skinny_fwd<TA, TB, 2><<<(unsigned)blocks, kThreads, 0, st>>>(P);
+    else gemm_skinny_fwd<TA, TB, 8><<<(unsigned)blocks, kThreads, 0, st>>>(P);
+    EGNN_LAUNCH_CHECK(fn);
+    return 0;
+  }
+  // skinny wgrad: M <= 8, A m-contiguous, B n-contiguous, long reduction
+  if (P.M <= 8 && P.a_sm == 1 && P.b_sn == 1 && P.K >= 4096 && P.ws) {
+    int64_t chunks = kNumSMs * 4;
+    int64_t per = ceil_div(P.K, chunks);
+    chunks = ceil_div(P.K, per);
+    P.k_per_split = per;
+    P.split_k = (int)chunks;
+    if (P.M <= 2) gemm_skinny_wgrad<TA, TB, 2><<<(unsigned)chunks, kThreads, 0, st>>>(P);
+    else gemm_skinny_wgrad<TA, TB, 8><<<(unsigned)chunks, kThreads, 0, st>>>(P);
+    EGNN_LAUNCH_CHECK(fn);
+    splitk_reduce<<<(unsigned)ceil_div(P.M * P.N, kThreads), kThreads, 0, st>>>(P);
+    EGNN_LAUNCH_CHECK(fn);
+    return 0;
+  }
+  int split = P.split_k < 1 ? 1 : P.split_k;
+  int64_t per = ceil_div(ceil_div(P.K, split), BK) * BK;
+  split = (int)ceil_div(P.K, per);
+  P.k_per_split = per;
+  P.split_k = split;
+  dim3 grid((unsigned)ceil_div(P.M, BM), (unsigned)ceil_div(P.N, BN), (unsigned)split);
+  gemm_simt<TA, TB><<<grid, kThreads, 0, st>>>(P);
+  EGNN_LAUNCH_CHECK(fn);
+  if (split > 1) {
+    splitk_reduce<<<(unsigned)ceil_div(P.M * P.N, kThreads), kThreads, 0, st>>>(P);
+    EGNN_LAUNCH_CHECK(fn);
+  }
+  return 0;
+}
+
+}  // namespace
+
+int gemm_tcgen05_dispatch(const void* A, int64_t lda, const void* B, int64_t ldb, void* C,
+                          int c_dtype, int64_t ld_c, int64_t M, int64_t N, int64_t K,
+                          const float* bias, int accumulate, cudaStream_t st);  // gemm_tcgen05.cu
+bool gemm_tcgen05_supported(int64_t lda, int64_t ldb, int64_t ld_c, int64_t M, int64_t N, int64_t K,
+                            const void* A, const void* B, const void* C);
+}  // namespace egnn
+
+using namespace egnn;
+
+extern "C" size_t egnn_gemm_workspace_floats(int64_t M, int64_t N, int64_t K, int split_k) {
+  (void)K;
+  if (M <= 8) return (size_t)(kNumSMs * 4 + 1) * (size_t)M * (size_t)N;  // skinny wgrad chunks
+  return split_k > 1 ? (size_t)split_k * (size_t)M * (size_t)N : 0;
+}
+
+extern "C" int egnn_gemm(const void* A, int a_dtype, int64_t a_sm, int64_t a_sk, const void* B,
+                         int b_dtype, int64_t b_sk, int64_t b_sn, void* C, int c_dtype, int64_t ld_c,
+                         int64_t M, int64_t N, int64_t K, const float* bias, int accumulate,
+                         int split_k, float* workspace, int impl, void* stream) {
+  const char* fn = "egnn_gemm";
+  EGNN_REQUIRE(A && B && C, fn, "null pointer");
+  EGNN_REQUIRE(M >= 0 && N > 0 && K > 0, fn, "bad shape");
+  EGNN_REQUIRE(ld_c >= N, fn, "ld_c < N");
+  EGNN_REQUIRE(split_k <= 1 || workspace, fn, "split_k > 1 needs a workspace");
+  EGNN_REQUIRE(impl >= 0 && impl <= 2, fn, "bad impl");
+  if (M == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool tc_shape = a_dtype == EGNN_BF16 && b_dtype == EGNN_BF16 && a_sk == 1 && b_sk == 1 &&
+                        split_k <= 1 &&
+                        gemm_tcgen05_supported(a_sm, b_sn, ld_c, M, N, K, A, B, C);
+  if (impl == 2 && !tc_shape) return fail(fn, "shape/dtype/layout not supported by the tcgen05 path");
+  if (impl == 2 || (impl == 0 && tc_shape))
+    return gemm_tcgen05_dispatch(A, a_sm, B, b_sn, C, c_dtype, ld_c, M, N, K, bias, accumulate, st);
+  GemmParams P;
+  P.A = A; P.B = B; P.C = C; P.bias = bias; P.ws = workspace;
+  P.a_sm = a_sm; P.a_sk = a_sk; P.b_sk = b_sk; P.b_sn = b_sn; P.ld_c = ld_c;
+  P.M = M; P.N = N; P.K = K; P.k_per_split = K;
+  P.c_dtype = c_dtype; P.accumulate = accumulate; P.split_k = split_k;
+  if (a_dtype == EGNN_F32 && b_dtype == EGNN_F32) return run<float, float>(P, st);
+  if (a_dtype == EGNN_BF16 && b_dtype == EGNN_BF16) return run<__nv_bfloat16, __nv_bfloat16>(P, st);
+  if (a_dtype == EGNN_BF16 && b_dtype == EGNN_F32) return run<__nv_bfloat16, float>(P, st);
+  if (a_dtype == EGNN_F32 && b_dtype == EGNN_BF16) return run<float, __nv_bfloat16>(P, st);
+  return fail(fn, "unsupported dtype");
+}

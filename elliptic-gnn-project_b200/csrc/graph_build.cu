@@ -1,0 +1,526 @@
+// K1 -- graph build on device: symmetrise, self-loop rewrite, stable destination/source
+// sorted views (CSR / CSC), degree and gcn_norm.  Integer outputs are bit-exact with the
+// reference's edge lists; float weights are bit-exact with torch CPU `deg.pow_(-0.5)`
+// (SURVEY.md F10).  Replaces src/train_gnn.py:319-326 and PyG add_remaining_self_loops /
+// gcn_norm, which the reference re-runs inside every GCNConv/GATConv forward.
+//
+// Algorithm: expand to an int32 edge list -> LSD radix sort (8-bit digits, stable
+// in-tile ranking with __match_any_sync) of (key = dst | src, value = edge id) ->
+// histogram + exclusive scan for the row pointers.  All kernels are HBM-bound integer
+// streaming passes; grids are sized from the host-known capacity, the true edge count
+// lives in info[0] on the device so no host synchronisation is needed.
+#include "common.cuh"
+
+namespace egnn {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kScanItems = 8;                       // per thread
+constexpr int kScanTile = kThreads * kScanItems;    // 2048
+constexpr int kSortItems = 8;
+constexpr int kSortTile = kThreads * kSortItems;    // 2048
+
+// ---- block-wide exclusive scan of one int per thread (256 threads) --------------------
+__device__ __forceinline__ int block_excl_scan(int v, int* total, int* smem /*>=9 ints*/) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) smem[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int s = (lane < kThreads / 32) ? smem[lane] : 0;
+    int si = s;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, si, o);
+      if (lane >= o) si += t;
+    }
+    if (lane < kThreads / 32) smem[lane] = si - s;  // exclusive warp offsets
+    if (lane == kThreads / 32 - 1) smem[8] = si;    // block total
+  }
+  __syncthreads();
+  int res = smem[warp] + inc - v;
+  *total = smem[8];
+  __syncthreads();  // smem reusable afterwards
+  return res;
+}
+
+// ---- generic exclusive scan, 3 kernels -------------------------------------------------
+__global__ void __launch_bounds__(kThreads) scan_tile_sums(const int* __restrict__ in, int64_t n,
+                                                           int* __restrict__ tile_sums) {
+  __shared__ int sm[9];
+  int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+  int s = 0;
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i)
+    if (base + i < n) s += in[base + i];
+  int total;
+  block_excl_scan(s, &total, sm);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+// single block: in-place exclusive scan of tile_sums[0..m), total -> *total_out (may be null)
+__global__ void __launch_bounds__(kThreads) scan_sums_inplace(int* __restrict__ sums, int64_t m,
+                                                              int* __restrict__ total_out) {
+  __shared__ int sm[9];
+  int carry = 0;
+  for (int64_t base = 0; base < m; base += kThreads) {
+    int64_t i = base + threadIdx.x;
+    int v = (i < m) ? sums[i] : 0;
+    int total;
+    int ex = block_excl_scan(v, &total, sm);
+    if (i < m) sums[i] = carry + ex;
+    carry += total;
+  }
+  if (threadIdx.x == 0 && total_out) *total_out = carry;
+}
+
+__global__ void __launch_bounds__(kThreads) scan_apply(const int* __restrict__ in, int64_t n,
+                                                       const int* __restrict__ tile_offs,
+                                                       int* __restrict__ out) {
+  __shared__ int sm[9];
+  int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+  int v[kScanItems];
+  int s = 0;
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) {
+    v[i] = (base + i < n) ? in[base + i] : 0;
+    s += v[i];
+  }
+  int total;
+  int ex = block_excl_scan(s, &total, sm) + tile_offs[blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) {
+    if (base + i < n) out[base + i] = ex;
+    ex += v[i];
+  }
+}
+
+// exclusive scan of in[0..n) -> out[0..n) (in may alias out); total -> total_out (nullable)
+int exclusive_scan(const int* in, int* out, int64_t n, int* tile_sums, int* total_out,
+                   cudaStream_t st) {
+  if (n <= 0) return 0;
+  int64_t tiles = ceil_div(n, kScanTile);
+  scan_tile_sums<<<(unsigned)tiles, kThreads, 0, st>>>(in, n, tile_sums);
+  EGNN_LAUNCH_CHECK("scan_tile_sums");
+  scan_sums_inplace<<<1, kThreads, 0, st>>>(tile_sums, tiles, total_out);
+  EGNN_LAUNCH_CHECK("scan_sums_inplace");
+  scan_apply<<<(unsigned)tiles, kThreads, 0, st>>>(in, n, tile_sums, out);
+  EGNN_LAUNCH_CHECK("scan_apply");
+  return 0;
+}
+
+// ---- edge-list expansion ---------------------------------------------------------------
+// logical edge i of cat([ei, ei.flip(0)]) : i <  E -> (ei[0,i],   ei[1,i])
+//                                           i >= E -> (ei[1,i-E], ei[0,i-E])
+__device__ __forceinline__ void logical_edge(const int64_t* __restrict__ ei, int64_t E, int64_t i,
+                                             int64_t& s, int64_t& d) {
+  if (i < E) {
+    s = ei[i];
+    d = ei[E + i];
+  } else {
+    s = ei[E + (i - E)];
+    d = ei[i - E];
+  }
+}
+
+// no self-loop rewrite: straight int64 -> int32 conversion (+ range validation)
+__global__ void __launch_bounds__(kThreads) expand_plain(const int64_t* __restrict__ ei, int64_t E,
+                                                         int64_t E_log, int64_t n_nodes,
+                                                         int* __restrict__ src32,
+                                                         int* __restrict__ dst32,
+                                                         int* __restrict__ info) {
+  int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i == 0) info[0] = (int)E_log;
+  if (i >= E_log) return;
+  int64_t s, d;
+  logical_edge(ei, E, i, s, d);
+  bool bad = (s < 0) | (s >= n_nodes) | (d < 0) | (d >= n_nodes);
+  if (bad) {
+    atomicAdd(&info[1], 1);
+    s = 0;
+    d = 0;
+  }
+  src32[i] = (int)s;
+  dst32[i] = (int)d;
+}
+
+// self-loop rewrite, pass 1: keep flags (src != dst)
+__global__ void __launch_bounds__(kThreads) loop_flags(const int64_t* __restrict__ ei, int64_t E,
+                                                       int64_t E_log, int64_t n_nodes,
+                                                       int* __restrict__ keep,
+                                                       int* __restrict__ info) {
+  int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= E_log) return;
+  int64_t s, d;
+  logical_edge(ei, E, i, s, d);
+  bool bad = (s < 0) | (s >= n_nodes) | (d < 0) | (d >= n_nodes);
+  if (bad) atomicAdd(&info[1], 1);
+  keep[i] = (!bad && s != d) ? 1 : 0;
+}
+
+// pass 2: stable compaction of the kept edges, then N self loops; info[0] = E_nl + N
+__global__ void __launch_bounds__(kThreads) loop_compact(const int64_t* __restrict__ ei, int64_t E,
+                                                         int64_t E_log, int64_t n_nodes,
+                                                         const int* __restrict__ pos,
+                                                         const int* __restrict__ n_kept,
+                                                         int* __restrict__ src32,
+                                                         int* __restrict__ dst32,
+                                                         int* __restrict__ info) {
+  int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const int e_nl = *n_kept;
+  if (i == 0) info[0] = e_nl + (int)n_nodes;
+  if (i < E_log) {
+    int64_t s, d;
+    logical_edge(ei, E, i, s, d);
+    bool ok = (s >= 0) & (s < n_nodes) & (d >= 0) & (d < n_nodes) & (s != d);
+    if (ok) {
+      int p = pos[i];
+      src32[p] = (int)s;
+      dst32[p] = (int)d;
+    }
+  }
+  if (i < n_nodes) {
+    src32[e_nl + i] = (int)i;
+    dst32[e_nl + i] = (int)i;
+  }
+}
+
+// ---- LSD radix sort (stable) ------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) radix_hist(const int* __restrict__ keys,
+                                                       const int* __restrict__ n_ptr, int shift,
+                                                       int* __restrict__ table, int nblk) {
+  __shared__ int h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const int n = *n_ptr;
+  int64_t base = (int64_t)blockIdx.x * kSortTile;
+#pragma unroll
+  for (int it = 0; it < kSortItems; ++it) {
+    int64_t i = base + it * kThreads + threadIdx.x;
+    if (i < n) atomicAdd(&h[(keys[i] >> shift) & 255], 1);
+  }
+  __syncthreads();
+  table[threadIdx.x * nblk + blockIdx.x] = h[threadIdx.x];
+}
+
+// vals_in == nullptr -> value = element index (first pass)
+__global__ void __launch_bounds__(kThreads) radix_scatter(const int* __restrict__ keys_in,
+                                                          const int* __restrict__ vals_in,
+                                                          int* __restrict__ keys_out,
+                                                          int* __restrict__ vals_out,
+                                                          const int* __restrict__ n_ptr, int shift,
+                                                          const int* __restrict__ table, int nblk) {
+  __shared__ int warp_cnt[kThreads / 32][256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < (kThreads / 32) * 256; i += kThreads) (&warp_cnt[0][0])[i] = 0;
+  __syncthreads();
+  const int n = *n_ptr;
+  const int64_t wbase = (int64_t)blockIdx.x * kSortTile + (int64_t)warp * (32 * kSortItems);
+  int key[kSortItems], val[kSortItems], rank[kSortItems];
+  const unsigned lt_mask = (1u << lane) - 1u;
+#pragma unroll
+  for (int it = 0; it < kSortItems; ++it) {
+    int64_t i = wbase + it * 32 + lane;
+    bool valid = i < n;
+    key[it] = valid ? keys_in[i] : 0;
+    val[it] = valid ? (vals_in ? vals_in[i] : (int)i) : 0;
+    int digit = valid ? ((key[it] >> shift) & 255) : 256;
+    unsigned peers = __match_any_sync(0xffffffffu, digit);
+    int r = __popc(peers & lt_mask);
+    int basecnt = 0;
+    if (valid) basecnt = warp_cnt[warp][digit];
+    __syncwarp();
+    if (valid && r == 0) warp_cnt[warp][digit] = basecnt + __popc(peers);
+    __syncwarp();
+    rank[it] = basecnt + r;
+  }
+  __syncthreads();
+  {  // thread d owns digit d: global base for (digit, this block) + prefix over warps
+    int d = threadIdx.x;
+    int run = table[d * nblk + blockIdx.x];
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) {
+      int c = warp_cnt[w][d];
+      warp_cnt[w][d] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < kSortItems; ++it) {
+    int64_t i = wbase + it * 32 + lane;
+    if (i < n) {
+      int pos = warp_cnt[warp][(key[it] >> shift) & 255] + rank[it];
+      keys_out[pos] = key[it];
+      vals_out[pos] = val[it];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) count_keys(const int* __restrict__ keys,
+                                                       const int* __restrict__ n_ptr,
+                                                       int* __restrict__ counts, int64_t cap) {
+  int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i < cap && i < *n_ptr) atomicAdd(&counts[keys[i]], 1);
+}
+
+__global__ void __launch_bounds__(kThreads) gather_csr(const int* __restrict__ perm,
+                                                       const int* __restrict__ src32,
+                                                       const int* __restrict__ n_ptr, int64_t cap,
+                                                       int* __restrict__ csr_src,
+                                                       int* __restrict__ csr_eid,
+                                                       int* __restrict__ inv) {
+  int64_t p = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (p >= cap) return;
+  if (p < *n_ptr) {
+    int e = perm[p];
+    csr_eid[p] = e;
+    csr_src[p] = src32[e];
+    inv[e] = (int)p;
+  } else {  // defined contents in the unused tail
+    csr_eid[p] = -1;
+    csr_src[p] = 0;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) gather_csc(const int* __restrict__ perm,
+                                                       const int* __restrict__ dst32,
+                                                       const int* __restrict__ inv,
+                                                       const int* __restrict__ n_ptr, int64_t cap,
+                                                       int* __restrict__ csc_dst,
+                                                       int* __restrict__ csc_pos) {
+  int64_t q = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (q >= cap) return;
+  if (q < *n_ptr) {
+    int e = perm[q];
+    csc_dst[q] = dst32[e];
+    csc_pos[q] = inv[e];
+  } else {
+    csc_dst[q] = 0;
+    csc_pos[q] = 0;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) write_ei2(const int* __restrict__ src32,
+                                                      const int* __restrict__ dst32,
+                                                      const int* __restrict__ n_ptr, int64_t cap,
+                                                      int64_t* __restrict__ ei2) {
+  int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= cap) return;
+  bool v = i < *n_ptr;
+  ei2[i] = v ? src32[i] : -1;
+  ei2[cap + i] = v ? dst32[i] : -1;
+}
+
+// deg^-1/2 exactly as torch CPU pow_(-0.5): rn(1 / rn(sqrt(deg))), inf -> 0
+__global__ void __launch_bounds__(kThreads) deg_inv_sqrt(const int* __restrict__ csr_ptr,
+                                                         int64_t n_nodes, float* __restrict__ dis) {
+  int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n_nodes) return;
+  int d = csr_ptr[i + 1] - csr_ptr[i];
+  dis[i] = d > 0 ? __fdiv_rn(1.0f, __fsqrt_rn((float)d)) : 0.0f;
+}
+
+__global__ void __launch_bounds__(kThreads) norm_weights(const int* __restrict__ src32,
+                                                         const int* __restrict__ dst32,
+                                                         const int* __restrict__ inv,
+                                                         const int* __restrict__ n_ptr, int64_t cap,
+                                                         const float* __restrict__ dis,
+                                                         float* __restrict__ w_edge,
+                                                         float* __restrict__ w_csr) {
+  int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (e >= cap) return;
+  if (e < *n_ptr) {
+    float w = __fmul_rn(dis[src32[e]], dis[dst32[e]]);  // dis[row]*1*dis[col]
+    if (w_edge) w_edge[e] = w;
+    if (w_csr) w_csr[inv[e]] = w;
+  } else if (w_edge) {
+    w_edge[e] = 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) permute_weights(const float* __restrict__ w_csr,
+                                                            const int* __restrict__ csc_pos,
+                                                            const int* __restrict__ n_ptr,
+                                                            int64_t cap, float* __restrict__ w_csc) {
+  int64_t q = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (q >= cap) return;
+  w_csc[q] = (q < *n_ptr) ? w_csr[csc_pos[q]] : 0.f;
+}
+
+// rows with more than kLongRow entries: appended (order irrelevant) to a list the SpMM serves
+// with whole CTAs; count -> *n_long
+__global__ void __launch_bounds__(kThreads) collect_long_rows(const int* __restrict__ ptr, int64_t n_nodes,
+                                                              int threshold, int* __restrict__ list,
+                                                              int* __restrict__ n_long) {
+  int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n_nodes) return;
+  if (ptr[i + 1] - ptr[i] > threshold) list[atomicAdd(n_long, 1)] = (int)i;
+}
+
+inline size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
+
+struct Workspace {
+  int *src32, *dst32, *keysA, *keysB, *valsA, *valsB, *inv, *keep, *counts, *table, *tile_sums;
+  size_t bytes;
+};
+
+Workspace carve(char* base, int64_t n_nodes, int64_t E_log, int64_t cap) {
+  Workspace w;
+  size_t off = 0;
+  auto take = [&](int64_t n_int) {
+    int* p = reinterpret_cast<int*>(base + off);
+    off += align_up((size_t)n_int * sizeof(int));
+    return p;
+  };
+  int64_t nblk = ceil_div(cap, kSortTile);
+  int64_t table_n = 256 * nblk;
+  int64_t longest = cap;
+  if (n_nodes + 1 > longest) longest = n_nodes + 1;
+  if (table_n > longest) longest = table_n;
+  w.src32 = take(cap);
+  w.dst32 = take(cap);
+  w.keysA = take(cap);
+  w.keysB = take(cap);
+  w.valsA = take(cap);
+  w.valsB = take(cap);
+  w.inv = take(cap);
+  w.keep = take(E_log + 1);
+  w.counts = take(n_nodes + 2);
+  w.table = take(table_n);
+  w.tile_sums = take(ceil_div(longest, kScanTile) + 1);
+  w.bytes = off;
+  return w;
+}
+
+// stable sort of (keys, iota) by key over `bits` bits; result permutation in *perm_out
+int radix_sort_perm(const int* keys, const int* n_ptr, int64_t cap, int bits, Workspace& w,
+                    int** perm_out, cudaStream_t st) {
+  int nblk = (int)ceil_div(cap, kSortTile);
+  const int* kin = keys;
+  const int* vin = nullptr;
+  int* kout = w.keysA;
+  int* vout = w.valsA;
+  for (int shift = 0; shift < bits; shift += 8) {
+    radix_hist<<<nblk, kThreads, 0, st>>>(kin, n_ptr, shift, w.table, nblk);
+    EGNN_LAUNCH_CHECK("radix_hist");
+    int rc = exclusive_scan(w.table, w.table, (int64_t)256 * nblk, w.tile_sums, nullptr, st);
+    if (rc) return rc;
+    radix_scatter<<<nblk, kThreads, 0, st>>>(kin, vin, kout, vout, n_ptr, shift, w.table, nblk);
+    EGNN_LAUNCH_CHECK("radix_scatter");
+    kin = kout;
+    vin = vout;
+    kout = (kout == w.keysA) ? w.keysB : w.keysA;
+    vout = (vout == w.valsA) ? w.valsB : w.valsA;
+  }
+  *perm_out = const_cast<int*>(vin);
+  return 0;
+}
+
+}  // namespace
+}  // namespace egnn
+
+using namespace egnn;
+
+extern "C" size_t egnn_graph_workspace_bytes(int64_t n_nodes, int64_t n_edges_in, int flags) {
+  int64_t E_log = (flags & EGNN_G_SYMMETRIZE) ? 2 * n_edges_in : n_edges_in;
+  int64_t cap = E_log + ((flags & EGNN_G_SELF_LOOPS) ? n_nodes : 0);
+  if (cap < 1) cap = 1;
+  Workspace w = carve(nullptr, n_nodes, E_log, cap);
+  return w.bytes + 256;
+}
+
+extern "C" int egnn_graph_build(const int64_t* ei, int64_t E, int64_t n_nodes, int flags,
+                                int want_norm, int32_t* info, int32_t* csr_ptr, int32_t* csr_src,
+                                int32_t* csr_eid, int32_t* csc_ptr, int32_t* csc_dst,
+                                int32_t* csc_pos, int32_t* csr_long, int32_t* csc_long,
+                                int64_t* ei2, float* dis, float* w_edge,
+                                float* w_csr, float* w_csc, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  const char* fn = "egnn_graph_build";
+  cudaStream_t st = (cudaStream_t)stream;
+  EGNN_REQUIRE(n_nodes > 0 && E >= 0, fn, "n_nodes must be > 0 and n_edges >= 0");
+  EGNN_REQUIRE(E == 0 || ei != nullptr, fn, "edge_index is null");
+  EGNN_REQUIRE(info && csr_ptr && csr_src && csr_eid && csc_ptr && csc_dst && csc_pos, fn,
+               "null output pointer");
+  const bool sym = flags & EGNN_G_SYMMETRIZE, loops = flags & EGNN_G_SELF_LOOPS;
+  const int64_t E_log = sym ? 2 * E : E;
+  int64_t cap = E_log + (loops ? n_nodes : 0);
+  EGNN_REQUIRE(cap < (int64_t)2147483647 && n_nodes < (int64_t)2147483647, fn,
+               "graph too large for int32 indices");
+  EGNN_REQUIRE(workspace_bytes >= egnn_graph_workspace_bytes(n_nodes, E, flags), fn,
+               "workspace too small");
+  const bool norm = want_norm || loops;
+  if (norm) EGNN_REQUIRE(dis && w_csr && w_csc, fn, "norm outputs are null");
+  const int64_t cap1 = cap < 1 ? 1 : cap;
+  char* wbase = reinterpret_cast<char*>(((uintptr_t)workspace + 255) & ~uintptr_t(255));
+  Workspace w = carve(wbase, n_nodes, E_log, cap1);
+  int* n_ptr = info;  // info[0] = E2
+
+  cudaMemsetAsync(info, 0, 4 * sizeof(int), st);
+  const unsigned gE = (unsigned)ceil_div(E_log > 0 ? E_log : 1, kThreads);
+  const unsigned gC = (unsigned)ceil_div(cap1, kThreads);
+  if (!loops) {
+    expand_plain<<<gE, kThreads, 0, st>>>(ei, E, E_log, n_nodes, w.src32, w.dst32, info);
+    EGNN_LAUNCH_CHECK("expand_plain");
+  } else {
+    if (E_log > 0) {
+      loop_flags<<<gE, kThreads, 0, st>>>(ei, E, E_log, n_nodes, w.keep, info);
+      EGNN_LAUNCH_CHECK("loop_flags");
+    }
+    // exclusive scan over E_log+1 entries: entry E_log receives the kept count
+    cudaMemsetAsync(w.keep + E_log, 0, sizeof(int), st);
+    int rc = exclusive_scan(w.keep, w.keep, E_log + 1, w.tile_sums, nullptr, st);
+    if (rc) return rc;
+    int64_t m = E_log > n_nodes ? E_log : n_nodes;
+    loop_compact<<<(unsigned)ceil_div(m, kThreads), kThreads, 0, st>>>(
+        ei, E, E_log, n_nodes, w.keep, w.keep + E_log, w.src32, w.dst32, info);
+    EGNN_LAUNCH_CHECK("loop_compact");
+  }
+  int bits = 1;
+  while (((int64_t)1 << bits) < n_nodes) ++bits;
+
+  for (int view = 0; view < 2; ++view) {  // 0: CSR by dst, 1: CSC by src
+    const int* keys = view == 0 ? w.dst32 : w.src32;
+    int* ptr = view == 0 ? csr_ptr : csc_ptr;
+    cudaMemsetAsync(w.counts, 0, (size_t)(n_nodes + 2) * sizeof(int), st);
+    count_keys<<<gC, kThreads, 0, st>>>(keys, n_ptr, w.counts, cap1);
+    EGNN_LAUNCH_CHECK("count_keys");
+    int rc = exclusive_scan(w.counts, ptr, n_nodes + 1, w.tile_sums, nullptr, st);
+    if (rc) return rc;
+    int* perm = nullptr;
+    rc = radix_sort_perm(keys, n_ptr, cap1, bits, w, &perm, st);
+    if (rc) return rc;
+    int* long_list = view == 0 ? csr_long : csc_long;
+    if (long_list) {
+      collect_long_rows<<<(unsigned)ceil_div(n_nodes, kThreads), kThreads, 0, st>>>(ptr, n_nodes, 64, long_list,
+                                                                                  info + 2 + view);
+      EGNN_LAUNCH_CHECK("collect_long_rows");
+    }
+    if (view == 0) {
+      gather_csr<<<gC, kThreads, 0, st>>>(perm, w.src32, n_ptr, cap1, csr_src, csr_eid, w.inv);
+      EGNN_LAUNCH_CHECK("gather_csr");
+    } else {
+      gather_csc<<<gC, kThreads, 0, st>>>(perm, w.dst32, w.inv, n_ptr, cap1, csc_dst, csc_pos);
+      EGNN_LAUNCH_CHECK("gather_csc");
+    }
+  }
+  if (ei2) {
+    write_ei2<<<gC, kThreads, 0, st>>>(w.src32, w.dst32, n_ptr, cap1, ei2);
+    EGNN_LAUNCH_CHECK("write_ei2");
+  }
+  if (norm) {
+    deg_inv_sqrt<<<(unsigned)ceil_div(n_nodes, kThreads), kThreads, 0, st>>>(csr_ptr, n_nodes, dis);
+    EGNN_LAUNCH_CHECK("deg_inv_sqrt");
+    norm_weights<<<gC, kThreads, 0, st>>>(w.src32, w.dst32, w.inv, n_ptr, cap1, dis, w_edge, w_csr);
+    EGNN_LAUNCH_CHECK("norm_weights");
+    permute_weights<<<gC, kThreads, 0, st>>>(w_csr, csc_pos, n_ptr, cap1, w_csc);
+    EGNN_LAUNCH_CHECK("permute_weights");
+  }
+  return 0;
+}

@@ -1,0 +1,243 @@
+/* egnn_b200.h -- C-ABI of the B200-native GNN message-passing hot path.
+ *
+ * The reference (Adredes-weslee/elliptic-gnn-project) has no FFI: its seam is the
+ * torch_geometric class surface used by src/models/gnn.py.  Each entry point below
+ * names the reference call it replaces (path:line relative to the reference root, or
+ * the PyG 2.5.3 routine restated in SURVEY.md Appendix A).  The Python host layer
+ * (elliptic-gnn-project_b200/*.py) binds these with ctypes and wraps them in
+ * torch.autograd.Function; INTEGRATION.md shows the stub a maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void*; calls only enqueue work (no host
+ *     synchronisation, CUDA-graph capturable) unless documented otherwise;
+ *   - memory is owned by the caller (torch's caching allocator); nothing is freed here;
+ *   - return value 0 = ok; nonzero = error, text via egnn_last_error();
+ *   - there is NO CPU fallback: a build without a visible sm_100 device fails at launch.
+ *   - dtype codes: EGNN_F32 = 0, EGNN_BF16 = 1.  Index arrays inside the library are
+ *     int32 (N, E < 2^31); the boundary edge_index is int64 like the reference's
+ *     (src/data/dataset_elliptic.py:245).
+ */
+#ifndef EGNN_B200_H
+#define EGNN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EGNN_ABI_VERSION 1
+
+enum { EGNN_F32 = 0, EGNN_BF16 = 1 };
+
+/* graph-build flags */
+enum {
+  EGNN_G_SYMMETRIZE = 1, /* edge list := cat([ei, ei.flip(0)])   src/train_gnn.py:319-326 */
+  EGNN_G_SELF_LOOPS = 2  /* PyG add_remaining_self_loops: drop loops, append (i,i) i<N   */
+};
+
+/* SpMM modes */
+enum {
+  EGNN_SPMM_SUM = 0,      /* out[i] = sum_p in[col[p]]                                    */
+  EGNN_SPMM_MEAN = 1,     /* out[i] = (sum_p in[col[p]]) / max(rowlen(i),1)   (SAGE fwd)   */
+  EGNN_SPMM_DIV_NBR = 2,  /* out[i] = sum_p in[col[p]] / nbr_cnt[col[p]]      (SAGE bwd)   */
+  EGNN_SPMM_WEIGHTED = 3  /* out[i] = sum_p rn(w[p]*in[col[p]])               (GCN)        */
+};
+
+/* activation codes for the fused elementwise kernels */
+enum { EGNN_ACT_NONE = 0, EGNN_ACT_RELU = 1, EGNN_ACT_ELU = 2 };
+
+int egnn_abi_version(void);
+const char* egnn_last_error(void);
+/* number of kernel launches this library has enqueued since load (for bench.py's
+ * `gpu_launches`); host counter, thread-safe. */
+uint64_t egnn_launch_count(void);
+
+/* ---------------------------------------------------------------- K1: graph build ---- */
+/* Replaces: edge symmetrisation src/train_gnn.py:319-326; PyG add_remaining_self_loops,
+ * gcn_norm (GCNConv.forward, GATConv.forward: every call); the COO
+ * gather/scatter order that PyG's scatter_add_ implies.
+ *
+ * Input  ei      int64 [2,E] row-major (row 0 = src, row 1 = dst), contiguous.
+ * The expanded edge list ei2 has E2 <= cap = (SYMMETRIZE ? 2E : E) + (SELF_LOOPS ? N : 0).
+ * Outputs (caller-allocated, capacities in elements):
+ *   info      int32 [4]   : {E2, number of out-of-range node ids, len(csr_long), len(csc_long)}
+ *   csr_ptr   int32 [N+1] : rows = destinations
+ *   csr_src   int32 [cap] : source of each in-edge; within a row in ORIGINAL edge order
+ *   csr_eid   int32 [cap] : index into ei2 of that edge
+ *   csc_ptr   int32 [N+1] : rows = sources
+ *   csc_dst   int32 [cap] : destination of each out-edge, original order within a row
+ *   csc_pos   int32 [cap] : position of that edge in CSR order (addresses per-edge arrays)
+ *   csr_long  int32 [cap/64+1] or NULL : destination rows with more than 64 in-edges (any order)
+ *   csc_long  int32 [cap/64+1] or NULL : source rows with more than 64 out-edges (any order)
+ *   ei2       int64 [2,cap] or NULL : the expanded edge list itself (parity checks)
+ *   dis       float [N]   or NULL : deg^-1/2 = rn(1/rn(sqrt(deg))), 0 where deg == 0
+ *   w_edge    float [cap] or NULL : gcn_norm weights in ei2 order
+ *   w_csr     float [cap] or NULL : same weights in CSR order
+ *   w_csc     float [cap] or NULL : same weights in CSC order
+ * The four float outputs are only written when EGNN_G_SELF_LOOPS is set or want_norm!=0.
+ */
+size_t egnn_graph_workspace_bytes(int64_t n_nodes, int64_t n_edges_in, int flags);
+int egnn_graph_build(const int64_t* ei, int64_t n_edges_in, int64_t n_nodes, int flags,
+                     int want_norm, int32_t* info, int32_t* csr_ptr, int32_t* csr_src,
+                     int32_t* csr_eid, int32_t* csc_ptr, int32_t* csc_dst, int32_t* csc_pos,
+                     int32_t* csr_long, int32_t* csc_long, int64_t* ei2, float* dis, float* w_edge, float* w_csr, float* w_csc,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------- K2/K3: SpMM --------- */
+/* Deterministic segmented gather-reduce over a sorted view (CSR for forward, CSC for the
+ * transposed backward).  One sub-warp per row; lanes split the FEATURE axis only; a row's
+ * edges are accumulated sequentially in stored order in fp32, so fp32 results are bitwise
+ * those of the CPU scatter_add_ path.  Replaces PyG MessagePassing.propagate for SAGEConv
+ * (index_select + scatter mean, A.2), GCNConv (A.1) and their autograd backward.
+ *   ptr [n_rows+1], col [nnz]; in [n_in_rows, ld_in]; out [n_rows, ld_out]
+ *   w        float [nnz]   (WEIGHTED) else NULL
+ *   nbr_cnt  int32 ptr array [n_in_rows+1] of the OTHER view (DIV_NBR: divides a gathered
+ *            row c by max(nbr_ptr[c+1]-nbr_ptr[c],1)) else NULL
+ *   long_rows/n_long  (both NULL or both set) list of rows with more than 64 entries and its
+ *            device-side length, from egnn_graph_build; those rows take the whole-CTA path
+ *   bias     float [F] or NULL, added after the reduction; act = EGNN_ACT_*
+ *   accumulate != 0: out += result (one rounding in out dtype after an fp32 add)
+ */
+int egnn_spmm(int mode, const int32_t* ptr, const int32_t* col, const float* w,
+              const int32_t* nbr_ptr, const int32_t* long_rows, const int32_t* n_long,
+              const void* in, int in_dtype, int64_t ld_in, void* out,
+              int out_dtype, int64_t ld_out, int64_t n_rows, int64_t n_feat, const float* bias,
+              int act, int accumulate, void* stream);
+
+/* ---------------------------------------------------------------- K6: dense ----------- */
+/* C[M,N] (+)= op(A)[M,K] . op(B)[K,N] (+ bias[N]).  Element (m,k) of op(A) is at
+ * A[m*a_sm + k*a_sk], element (k,n) of op(B) at B[k*b_sk + n*b_sn]; C row-major with ld_c.
+ * Covers Linear forward (x W^T), dgrad (g W) and wgrad (g^T x) of torch_geometric's
+ * nn.dense.Linear / torch.nn.Linear (src/models/gnn.py:141-144 and the convs' lin*).
+ * fp32 accumulate always.  impl: 0 = auto, 1 = SIMT FFMA, 2 = tcgen05 (bf16 inputs,
+ * K-major A and B only; error if the shape is not supported).
+ * split_k > 1 (and every M <= 8 reduction) needs egnn_gemm_workspace_floats(...) floats of
+ * workspace; partials are reduced in a fixed order (deterministic).
+ */
+size_t egnn_gemm_workspace_floats(int64_t M, int64_t N, int64_t K, int split_k);
+int egnn_gemm(const void* A, int a_dtype, int64_t a_sm, int64_t a_sk, const void* B, int b_dtype,
+              int64_t b_sk, int64_t b_sn, void* C, int c_dtype, int64_t ld_c, int64_t M,
+              int64_t N, int64_t K, const float* bias, int accumulate, int split_k,
+              float* workspace, int impl, void* stream);
+
+/* cast / copy with optional column padding: out[r, 0:F] = in[r, 0:F], out[r, F:ld_out] = 0 */
+int egnn_cast(const void* in, int in_dtype, int64_t ld_in, void* out, int out_dtype,
+              int64_t ld_out, int64_t n_rows, int64_t n_feat, void* stream);
+
+/* SAGEResBNNet._inject_time (src/models/gnn.py:168-179) / scalar-time append
+ * (src/train_gnn.py:314-317): out[r] = [x[r, 0:F] | table[clamp(t[r]-1, 0, T-1), 0:D] | 0-pad].
+ * table is float [T, D] (sin/cos LUT computed by the host with the reference's own torch
+ * ops, or the learned nn.Embedding weight).  out_f32 / out_bf16 may each be NULL. */
+int egnn_inject_time(const float* x, int64_t ld_x, const int64_t* t, const float* table,
+                     int64_t T, int64_t D, float* out_f32, void* out_bf16, int64_t ld_out,
+                     int64_t n_rows, int64_t n_feat, void* stream);
+
+/* column reductions over rows: sums[c] = sum_r a[r,c] (and sumsq[c] = sum_r a[r,c]^2 when
+ * sumsq != NULL), deterministic two-level tree, fp64 combine.  Used for bias gradients and
+ * BatchNorm batch statistics (nn.BatchNorm1d, src/models/gnn.py:134,189).
+ * workspace: egnn_colreduce_workspace_bytes(n_feat). */
+size_t egnn_colreduce_workspace_bytes(int64_t n_feat);
+int egnn_colreduce(const void* a, int dtype, int64_t ld, int64_t n_rows, int64_t n_feat,
+                   double* sums, double* sumsq, void* workspace, void* stream);
+
+/* ---------------------------------------------------------------- K7: BN / act / dropout */
+/* bn_finalize: from (sum, sumsq, count) -> mean, rstd = 1/sqrt(var_biased+eps); updates
+ * running_mean/var (momentum, unbiased var) when they are non-NULL. count_total allows the
+ * multi-GPU caller to pass globally reduced sums. */
+int egnn_bn_finalize(const double* sums, const double* sumsq, double count, int64_t n_feat,
+                     float eps, float momentum, float* mean, float* rstd, float* running_mean,
+                     float* running_var, void* stream);
+
+/* y = dropout(act(bn(z))) + res      -- src/models/gnn.py:186-192 (SAGE-ResBN hidden layer)
+ *   bn(z) = (z-mean)*rstd*gamma+beta when mean != NULL, else z (+ nothing)
+ *   dropout keep-mask = Philox4x32-10(seed; row0+r, col, layer) >= p  (see egnn_dropout_mask),
+ *   kept values scaled by 1/(1-p); p == 0 disables it.  seed_off (device int64, may be NULL)
+ *   is added to seed at run time so a captured CUDA graph draws a new mask on every replay
+ *   (advance it with egnn_counter_add inside the graph).
+ *   res may be NULL.  z/res/y share dtype `dtype`. */
+int egnn_bn_act_dropout_res_fwd(const void* z, const void* res, void* y, int dtype, int64_t ld,
+                                int64_t n_rows, int64_t n_feat, const float* mean,
+                                const float* rstd, const float* gamma, const float* beta, int act,
+                                float p, uint64_t seed, const int64_t* seed_off, uint32_t layer,
+                                int64_t row0, void* stream);
+
+/* backward stage 1: g = dy * keep/(1-p) * act'(.) ; sums[c] = sum g, sums_xhat[c] = sum g*xhat
+ * (BatchNorm dbeta, dgamma).  stage 2: dz = gamma*rstd*(g - sum_g/n - xhat*sum_gx/n) (or g
+ * when mean == NULL).  n_total = global row count (multi-GPU passes the global N). */
+int egnn_bn_act_dropout_bwd_reduce(const void* dy, const void* z, int dtype, int64_t ld,
+                                   int64_t n_rows, int64_t n_feat, const float* mean,
+                                   const float* rstd, const float* gamma, const float* beta,
+                                   int act, float p, uint64_t seed, const int64_t* seed_off,
+                                   uint32_t layer, int64_t row0, double* sum_g, double* sum_gx, void* workspace, void* stream);
+int egnn_bn_act_dropout_bwd_apply(const void* dy, const void* z, void* dz, int dtype, int64_t ld,
+                                  int64_t n_rows, int64_t n_feat, const float* mean,
+                                  const float* rstd, const float* gamma, const float* beta,
+                                  int act, float p, uint64_t seed, const int64_t* seed_off,
+                                  uint32_t layer, int64_t row0, const double* sum_g, const double* sum_gx, double n_total,
+                                  void* stream);
+
+/* *counter += inc on the device (one thread) */
+int egnn_counter_add(int64_t* counter, int64_t inc, void* stream);
+
+/* the keep-mask itself, uint8 [n_rows, n_feat] (for feeding the CPU oracle the same mask) */
+int egnn_dropout_mask(uint8_t* mask, int64_t n_rows, int64_t n_feat, float p, uint64_t seed,
+                      const int64_t* seed_off, uint32_t layer, int64_t row0, void* stream);
+
+/* ---------------------------------------------------------------- K4/K5: GAT ---------- */
+/* Fused PyG GATConv attention over the self-loop CSR:
+ *   fwd: a_s[n,h] = <xs[n,h,:], att_src[h,:]>, a_d likewise (egnn_gat_scores), then per
+ *        destination row: e = leaky_relu(a_s[src]+a_d[dst]), softmax over the row
+ *        (max-subtracted, +1e-16), out[dst,h,:] = sum alpha*xs[src,h,:]; alpha [cap,H] is
+ *        stored in CSR order for the backward.  concat=0 -> mean over heads. +bias.
+ *   bwd: see SURVEY.md A.3 backward formulas.
+ */
+int egnn_gat_scores(const float* xs, int64_t n_rows, int H, int C, const float* att_src,
+                    const float* att_dst, float* a_s, float* a_d, void* stream);
+int egnn_gat_fwd(const int32_t* csr_ptr, const int32_t* csr_src, const float* xs, const float* a_s,
+                 const float* a_d, float negative_slope, int H, int C, int concat,
+                 const float* bias, float* alpha, float* out, int64_t n_rows, void* stream);
+/* bwd pass A (CSR rows = destinations): dpre[p,h] and da_d[n,h];
+ * bwd pass B (CSC rows = sources): dxs[n,h,:] = sum alpha*do[dst] + da_s*att_src + da_d*att_dst,
+ *            da_s[n,h]. */
+int egnn_gat_bwd_dst(const int32_t* csr_ptr, const int32_t* csr_src, const float* xs,
+                     const float* a_s, const float* a_d, const float* alpha, const float* dout,
+                     float negative_slope, int H, int C, int concat, float* dpre, float* da_d,
+                     int64_t n_rows, void* stream);
+int egnn_gat_bwd_src(const int32_t* csc_ptr, const int32_t* csc_dst, const int32_t* csc_pos,
+                     const float* alpha, const float* dpre, const float* dout, const float* da_d,
+                     const float* att_src, const float* att_dst, int H, int C, int concat,
+                     float* dxs, float* da_s, int64_t n_rows, void* stream);
+
+/* datt_src[h,c] = sum_n da_s[n,h]*xs[n,h,c]; datt_dst likewise (double [H*C] each).
+ * workspace: egnn_colreduce_workspace_bytes(H*C). */
+int egnn_gat_att_grad(const float* xs, const float* da_s, const float* da_d, int64_t n_rows, int H,
+                      int C, double* datt_src, double* datt_dst, void* workspace, void* stream);
+
+/* ---------------------------------------------------------------- step tail ----------- */
+/* Masked weighted cross-entropy over precomputed train-row indices:
+ *   loss = (1/n_total) * sum_i cw[y_i] * (logsumexp(l_i) - l_i[y_i])      (2 classes)
+ * i.e. F.cross_entropy(weight=cw, reduction='none').mean()  (src/train_gnn.py:159-176).
+ * Writes dlogits [n_rows, 2] (zero outside the train rows) in `dtype`, and loss (float[1]).
+ * workspace: float[ egnn_ce_workspace_floats(n_idx) ]. */
+size_t egnn_ce_workspace_floats(int64_t n_idx);
+int egnn_masked_ce(const void* logits, int dtype, int64_t n_rows, const int64_t* y,
+                   const int64_t* idx, int64_t n_idx, const float* cw, double n_total,
+                   float* loss, void* dlogits, float* workspace, void* stream);
+
+/* Global-norm clip + Adam (coupled L2) over one flat fp32 parameter/grad buffer:
+ * torch.nn.utils.clip_grad_norm_(params, max_norm) then torch.optim.Adam.step()
+ * (src/train_gnn.py:203-207,357-359).  sqnorm_partial: float[egnn_adam_workspace_floats(n)].
+ * step_count: device int64 scalar incremented by the kernel (graph-replay safe). */
+size_t egnn_adam_workspace_floats(int64_t n);
+int egnn_clip_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                        int64_t n, float lr, float beta1, float beta2, float eps,
+                        float weight_decay, float max_norm, int64_t* step_count, float* grad_norm_out,
+                        float* workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EGNN_B200_H */
