@@ -1,1 +1,12 @@
-"""B200-native GNN message-passing hot path (GCN / SAGE / SAGE-ResBN / GAT)."""
+"""B200-native GNN message-passing hot path (GCN / SAGE / SAGE-ResBN / GAT).
+
+Drop-in for the conv layers and nets that `/root/reference/src/models/gnn.py` builds over the
+Elliptic transaction graph: same constructors, `forward(x, edge_index, t_idx)` signature and
+state-dict names, computed by hand-written sm_100a kernels behind a C-ABI shared library
+(`include/egnn_b200.h`, `libegnn_b200.so`).  CUDA only; no CPU or PyTorch fallback.
+"""
+from . import _lib  # noqa: F401
+from .graph import Graph, GraphCache, build_graph, cached_graph, symmetrize  # noqa: F401
+from .nn import GATConv, GCNConv, SAGEConv  # noqa: F401
+from .models import GATNet, GCNNet, SAGENet, SAGEResBNNet, build_model  # noqa: F401
+from . import ops, synthetic  # noqa: F401

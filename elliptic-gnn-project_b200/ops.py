@@ -1,0 +1,452 @@
+"""torch.autograd.Function wrappers over the C-ABI kernels.
+
+Each Function is the B200 replacement of one PyG / torch op sequence on the reference's
+hot path (`/root/reference/src/models/gnn.py`); forward and backward both run hand-written
+sm_100a kernels from libegnn_b200.so.  Nothing here falls back to CPU or to PyTorch ops
+for the heavy work; torch is used for allocation (stream-ordered caching allocator),
+autograd bookkeeping and a few O(F)-sized conversions.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import ACT_ELU, ACT_NONE, ACT_RELU, BF16, F32, check, dt, lib, ptr, stream
+from .graph import Graph
+
+_TD = {F32: torch.float32, BF16: torch.bfloat16}
+
+
+def amp_bf16() -> bool:
+    """True when the caller runs us under torch.autocast(device_type='cuda', dtype=bfloat16)."""
+    if not torch.is_autocast_enabled("cuda"):
+        return False
+    d = torch.get_autocast_dtype("cuda")
+    if d != torch.bfloat16:
+        raise RuntimeError(
+            "egnn_b200 implements bf16 autocast only; the reference's `amp: true` defaults to fp16 + "
+            "GradScaler (src/train_gnn.py:36-47).  Use torch.autocast('cuda', dtype=torch.bfloat16).")
+    return True
+
+
+def _rows(t: torch.Tensor) -> torch.Tensor:
+    """2-D, unit stride along features (row stride may exceed the width)."""
+    if t.dim() != 2:
+        raise ValueError("expected a 2-D [rows, features] tensor")
+    if t.size(1) > 1 and t.stride(1) != 1 or (t.size(0) > 1 and t.stride(0) < t.size(1)):
+        t = t.contiguous()
+    return t
+
+
+def _ld(t: torch.Tensor) -> int:
+    return t.stride(0) if t.size(0) > 1 else max(t.size(1), t.stride(0))
+
+
+# ------------------------------------------------------------------------------ raw ops --
+def cast(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    x = _rows(x)
+    out = torch.empty(x.shape, dtype=dtype, device=x.device)
+    check(lib().egnn_cast(ptr(x), dt(x), _ld(x), ptr(out), dt(out), out.size(1), x.size(0), x.size(1),
+                          stream()))
+    return out
+
+
+def spmm(g: Graph, view: str, mode: int, x: torch.Tensor, out_dtype: torch.dtype, *, bias=None,
+         act: int = ACT_NONE, out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    x = _rows(x)
+    n = g.n_nodes
+    if x.size(0) != n:
+        raise ValueError(f"feature matrix has {x.size(0)} rows, graph has {n} nodes")
+    if out is None:
+        out = torch.empty((n, x.size(1)), dtype=out_dtype, device=x.device)
+    if view == "csr":
+        p, c, w, long_rows, vi, nbr = g.csr_ptr, g.csr_src, g.w_csr, g.csr_long, 0, g.csc_ptr
+    else:
+        p, c, w, long_rows, vi, nbr = g.csc_ptr, g.csc_dst, g.w_csc, g.csc_long, 1, g.csr_ptr
+    n_long = g.info.data_ptr() + 4 * (2 + vi)
+    check(lib().egnn_spmm(mode, ptr(p), ptr(c), ptr(w) if mode == _lib.SPMM_WEIGHTED else None,
+                          ptr(nbr) if mode == _lib.SPMM_DIV_NBR else None, ptr(long_rows), n_long, ptr(x),
+                          dt(x), _ld(x), ptr(out), dt(out), _ld(out), n, x.size(1), ptr(bias), act,
+                          int(accumulate), stream()))
+    return out
+
+
+def _gemm(A, a_sm, a_sk, B, b_sk, b_sn, C, M, N, K, bias, accumulate, split_k=1, impl=0):
+    L = lib()
+    nws = L.egnn_gemm_workspace_floats(M, N, K, split_k)
+    ws = torch.empty(nws, dtype=torch.float32, device=C.device) if nws else None
+    check(L.egnn_gemm(ptr(A), dt(A), a_sm, a_sk, ptr(B), dt(B), b_sk, b_sn, ptr(C), dt(C), _ld(C), M, N, K,
+                      ptr(bias), int(accumulate), split_k, ptr(ws), impl, stream()))
+
+
+def linear_fwd(x, W, bias=None, out=None, accumulate=False, out_dtype=None, impl=0):
+    """out[M,N] (+)= x[M,K] @ W[N,K]^T (+ bias)."""
+    x, W = _rows(x), _rows(W)
+    M, K = x.shape
+    N = W.size(0)
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype or x.dtype, device=x.device)
+    _gemm(x, _ld(x), 1, W, 1, _ld(W), out, M, N, K, bias, accumulate, impl=impl)
+    return out
+
+
+def linear_dgrad(g, W, out=None, accumulate=False, out_dtype=None):
+    """out[M,K] (+)= g[M,N] @ W[N,K]."""
+    g, W = _rows(g), _rows(W)
+    M, N = g.shape
+    K = W.size(1)
+    if out is None:
+        out = torch.empty((M, K), dtype=out_dtype or g.dtype, device=g.device)
+    _gemm(g, _ld(g), 1, W, _ld(W), 1, out, M, K, N, None, accumulate)
+    return out
+
+
+def linear_wgrad(g, x):
+    """dW[N,K] = g[M,N]^T @ x[M,K], fp32, deterministic split over the node axis."""
+    g, x = _rows(g), _rows(x)
+    M, N = g.shape
+    K = x.size(1)
+    out = torch.empty((N, K), dtype=torch.float32, device=g.device)
+    tiles = -(-N // 128) * -(-K // 64)
+    split = max(1, min(-(-M // 512), -(-2 * 148 // tiles)))
+    _gemm(g, 1, _ld(g), x, _ld(x), 1, out, N, K, M, None, False, split_k=split)
+    return out
+
+
+def colsum(a: torch.Tensor, want_sq: bool = False) -> torch.Tensor:
+    """double [F] (or [2,F] with sum of squares): deterministic column sums over rows."""
+    a = _rows(a)
+    F = a.size(1)
+    L = lib()
+    out = torch.empty((2 if want_sq else 1, F), dtype=torch.float64, device=a.device)
+    ws = torch.empty(L.egnn_colreduce_workspace_bytes(F), dtype=torch.uint8, device=a.device)
+    check(L.egnn_colreduce(ptr(a), dt(a), _ld(a), a.size(0), F, out[0].data_ptr(),
+                           out[1].data_ptr() if want_sq else None, ptr(ws), stream()))
+    return out if want_sq else out[0]
+
+
+def dropout_mask(n_rows: int, n_feat: int, p: float, seed: int, layer: int, row0: int = 0,
+                 device="cuda", seed_off: Optional[torch.Tensor] = None) -> torch.Tensor:
+    m = torch.empty((n_rows, n_feat), dtype=torch.uint8, device=device)
+    check(lib().egnn_dropout_mask(ptr(m), n_rows, n_feat, float(p), int(seed), ptr(seed_off), int(layer),
+                                  int(row0), stream()))
+    return m
+
+
+# --------------------------------------------------------------------------- SAGEConv ----
+class SageConvFn(torch.autograd.Function):
+    """PyG SAGEConv(mean, root_weight, bias): lin_l(mean_j x_j) + lin_r(x)  (SURVEY.md A.2)."""
+
+    @staticmethod
+    def forward(ctx, x, w_l, b_l, w_r, g: Graph, bf16: bool):
+        cd = torch.bfloat16 if bf16 else torch.float32
+        x = _rows(x)
+        m = spmm(g, "csr", _lib.SPMM_MEAN, x, cd)
+        xg = x if x.dtype == cd else cast(x, cd)
+        wl = w_l if w_l.dtype == cd else cast(w_l, cd)
+        wr = w_r if w_r.dtype == cd else cast(w_r, cd)
+        z = linear_fwd(m, wl, bias=b_l, out_dtype=cd)
+        linear_fwd(xg, wr, out=z, accumulate=True)
+        ctx.g, ctx.x_dtype = g, x.dtype
+        ctx.save_for_backward(m, xg, wl, wr)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        m, xg, wl, wr = ctx.saved_tensors
+        g = ctx.g
+        dz = _rows(dz)
+        if dz.dtype != m.dtype:
+            dz = cast(dz, m.dtype)
+        dwl = linear_wgrad(dz, m)
+        dwr = linear_wgrad(dz, xg)
+        db = colsum(dz).float()
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dm = linear_dgrad(dz, wl)
+            dx = linear_dgrad(dz, wr)
+            spmm(g, "csc", _lib.SPMM_DIV_NBR, dm, dx.dtype, out=dx, accumulate=True)
+            if dx.dtype != ctx.x_dtype:
+                dx = cast(dx, ctx.x_dtype)
+        return dx, dwl, db, dwr, None, None
+
+
+# ---------------------------------------------------------------------------- GCNConv ----
+class GcnConvFn(torch.autograd.Function):
+    """PyG GCNConv: D^-1/2 (A+I) D^-1/2 (x W^T) + b on the self-loop graph."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, g: Graph, bf16: bool):
+        cd = torch.bfloat16 if bf16 else torch.float32
+        x = _rows(x)
+        xg = x if x.dtype == cd else cast(x, cd)
+        wc = w if w.dtype == cd else cast(w, cd)
+        h = linear_fwd(xg, wc, out_dtype=cd)
+        out = spmm(g, "csr", _lib.SPMM_WEIGHTED, h, torch.float32, bias=b)
+        ctx.g, ctx.x_dtype = g, x.dtype
+        ctx.save_for_backward(xg, wc)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        xg, wc = ctx.saved_tensors
+        g = ctx.g
+        dout = _rows(dout)
+        if dout.dtype != torch.float32:
+            dout = cast(dout, torch.float32)
+        dh = spmm(g, "csc", _lib.SPMM_WEIGHTED, dout, xg.dtype)
+        dw = linear_wgrad(dh, xg)
+        db = colsum(dout).float()
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = linear_dgrad(dh, wc)
+            if dx.dtype != ctx.x_dtype:
+                dx = cast(dx, ctx.x_dtype)
+        return dx, dw, db, None, None
+
+
+# ---------------------------------------------------------------------------- GATConv ----
+class GatConvFn(torch.autograd.Function):
+    """PyG GATConv (heads, concat | head-mean) on the self-loop graph."""
+
+    @staticmethod
+    def forward(ctx, x, w, att_src, att_dst, bias, g: Graph, H: int, C: int, concat: bool, slope: float,
+                bf16: bool):
+        cd = torch.bfloat16 if bf16 else torch.float32
+        x = _rows(x)
+        N = x.size(0)
+        xg = x if x.dtype == cd else cast(x, cd)
+        wc = w if w.dtype == cd else cast(w, cd)
+        xs = linear_fwd(xg, wc, out_dtype=torch.float32)  # [N, H*C]; attention path stays fp32
+        dev = x.device
+        a_s = torch.empty((N, H), dtype=torch.float32, device=dev)
+        a_d = torch.empty((N, H), dtype=torch.float32, device=dev)
+        asrc, adst = att_src.reshape(H * C).contiguous(), att_dst.reshape(H * C).contiguous()
+        L = lib()
+        check(L.egnn_gat_scores(ptr(xs), N, H, C, ptr(asrc), ptr(adst), ptr(a_s), ptr(a_d), stream()))
+        alpha = torch.empty((g.cap, H), dtype=torch.float32, device=dev)
+        out = torch.empty((N, H * C if concat else C), dtype=torch.float32, device=dev)
+        check(L.egnn_gat_fwd(ptr(g.csr_ptr), ptr(g.csr_src), ptr(xs), ptr(a_s), ptr(a_d), float(slope), H, C,
+                             int(concat), ptr(bias), ptr(alpha), ptr(out), N, stream()))
+        ctx.g, ctx.cfg, ctx.x_dtype = g, (H, C, concat, slope), x.dtype
+        ctx.save_for_backward(xg, wc, xs, a_s, a_d, alpha, asrc, adst)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        xg, wc, xs, a_s, a_d, alpha, asrc, adst = ctx.saved_tensors
+        g = ctx.g
+        H, C, concat, slope = ctx.cfg
+        N, dev = xs.size(0), xs.device
+        dout = _rows(dout)
+        if dout.dtype != torch.float32:
+            dout = cast(dout, torch.float32)
+        dout = dout.contiguous()
+        L = lib()
+        f32 = dict(dtype=torch.float32, device=dev)
+        dpre = torch.empty((g.cap, H), **f32)
+        da_d = torch.empty((N, H), **f32)
+        check(L.egnn_gat_bwd_dst(ptr(g.csr_ptr), ptr(g.csr_src), ptr(xs), ptr(a_s), ptr(a_d), ptr(alpha),
+                                 ptr(dout), float(slope), H, C, int(concat), ptr(dpre), ptr(da_d), N, stream()))
+        dxs = torch.empty((N, H * C), **f32)
+        da_s = torch.empty((N, H), **f32)
+        check(L.egnn_gat_bwd_src(ptr(g.csc_ptr), ptr(g.csc_dst), ptr(g.csc_pos), ptr(alpha), ptr(dpre),
+                                 ptr(dout), ptr(da_d), ptr(asrc), ptr(adst), H, C, int(concat), ptr(dxs),
+                                 ptr(da_s), N, stream()))
+        datt = torch.empty((2, H * C), dtype=torch.float64, device=dev)
+        ws = torch.empty(L.egnn_colreduce_workspace_bytes(H * C), dtype=torch.uint8, device=dev)
+        check(L.egnn_gat_att_grad(ptr(xs), ptr(da_s), ptr(da_d), N, H, C, datt[0].data_ptr(),
+                                  datt[1].data_ptr(), ptr(ws), stream()))
+        datt = datt.float()
+        dw = linear_wgrad(dxs, xg)
+        dbias = colsum(dout).float()
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = linear_dgrad(dxs, wc, out_dtype=xg.dtype)
+            if dx.dtype != ctx.x_dtype:
+                dx = cast(dx, ctx.x_dtype)
+        return (dx, dw, datt[0].view(1, H, C), datt[1].view(1, H, C), dbias, None, None, None, None, None,
+                None)
+
+
+# ------------------------------------------------- BN + activation + dropout + residual ---
+class DropoutState:
+    """Per-model dropout stream: `seed` is fixed, `offset` (device int64) advances once per
+    training forward so every step -- including CUDA-graph replays -- draws a fresh mask."""
+
+    def __init__(self, seed: int, device):
+        self.seed = int(seed) & 0x7FFFFFFFFFFFFFFF
+        self.offset = torch.zeros(1, dtype=torch.int64, device=device)
+
+    def advance(self, inc: int = 1):
+        check(lib().egnn_counter_add(ptr(self.offset), int(inc), stream()))
+
+
+class StatsReducer:
+    """Hook for timestep-sharded runs: sums BatchNorm partial statistics over ranks.
+    `n_total` is the global row count.  The default is the single-GPU identity."""
+
+    def __init__(self, n_total: Optional[int] = None, group=None):
+        self.n_total, self.group = n_total, group
+
+    def reduce_(self, buf: torch.Tensor) -> torch.Tensor:
+        if self.group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
+                                      and self.n_total is not None):
+            torch.distributed.all_reduce(buf, group=self.group)
+        return buf
+
+
+class BnActDropResFn(torch.autograd.Function):
+    """y = dropout(act(batchnorm(z))) + res -- `src/models/gnn.py:186-192`.  bn is optional
+    (gamma None), res is optional.  Training-mode BN uses batch statistics over all rows
+    (globally reduced through `reducer` when sharded) and updates the running buffers."""
+
+    @staticmethod
+    def forward(ctx, z, res, gamma, beta, running_mean, running_var, training: bool, act: int, p: float,
+                drop: Optional[DropoutState], layer: int, row0: int, eps: float, momentum: float,
+                reducer: Optional[StatsReducer]):
+        z = _rows(z).contiguous()
+        N, F = z.shape
+        L = lib()
+        dev = z.device
+        use_bn = gamma is not None
+        mean = rstd = None
+        n_total = float(reducer.n_total) if (reducer is not None and reducer.n_total) else float(N)
+        if use_bn:
+            if training:
+                st = colsum(z, want_sq=True)
+                if reducer is not None:
+                    reducer.reduce_(st)
+                mean = torch.empty(F, dtype=torch.float32, device=dev)
+                rstd = torch.empty(F, dtype=torch.float32, device=dev)
+                check(L.egnn_bn_finalize(st[0].data_ptr(), st[1].data_ptr(), n_total, F, float(eps),
+                                         float(momentum), ptr(mean), ptr(rstd), ptr(running_mean),
+                                         ptr(running_var), stream()))
+            else:
+                mean = running_mean
+                rstd = torch.rsqrt(running_var + eps)
+        p_eff = float(p) if (training and p > 0) else 0.0
+        if res is not None:
+            res = _rows(res)
+            if res.dtype != z.dtype:
+                res = cast(res, z.dtype)
+            res = res.contiguous()
+        y = torch.empty_like(z)
+        seed = drop.seed if drop is not None else 0
+        soff = drop.offset if drop is not None else None
+        check(L.egnn_bn_act_dropout_res_fwd(ptr(z), ptr(res), ptr(y), dt(z), F, N, F, ptr(mean), ptr(rstd),
+                                            ptr(gamma), ptr(beta), act, p_eff, seed, ptr(soff), layer, row0,
+                                            stream()))
+        ctx.cfg = (use_bn, act, p_eff, seed, layer, row0, n_total, reducer, res is not None)
+        ctx.soff = soff
+        ctx.save_for_backward(z, mean, rstd, gamma, beta)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        z, mean, rstd, gamma, beta = ctx.saved_tensors
+        use_bn, act, p_eff, seed, layer, row0, n_total, reducer, has_res = ctx.cfg
+        soff = ctx.soff
+        N, F = z.shape
+        L = lib()
+        dy = _rows(dy)
+        if dy.dtype != z.dtype:
+            dy = cast(dy, z.dtype)
+        dy = dy.contiguous()
+        dz = torch.empty_like(z)
+        dgamma = dbeta = None
+        if use_bn:
+            sg = torch.empty((2, F), dtype=torch.float64, device=z.device)
+            ws = torch.empty(L.egnn_colreduce_workspace_bytes(F), dtype=torch.uint8, device=z.device)
+            check(L.egnn_bn_act_dropout_bwd_reduce(ptr(dy), ptr(z), dt(z), F, N, F, ptr(mean), ptr(rstd),
+                                                   ptr(gamma), ptr(beta), act, p_eff, seed, ptr(soff), layer,
+                                                   row0, sg[0].data_ptr(), sg[1].data_ptr(), ptr(ws),
+                                                   stream()))
+            if reducer is not None:
+                reducer.reduce_(sg)
+            check(L.egnn_bn_act_dropout_bwd_apply(ptr(dy), ptr(z), ptr(dz), dt(z), F, N, F, ptr(mean),
+                                                  ptr(rstd), ptr(gamma), ptr(beta), act, p_eff, seed,
+                                                  ptr(soff), layer, row0, sg[0].data_ptr(), sg[1].data_ptr(),
+                                                  n_total, stream()))
+            sgf = sg.float()
+            dbeta, dgamma = sgf[0], sgf[1]
+        else:
+            check(L.egnn_bn_act_dropout_bwd_apply(ptr(dy), ptr(z), ptr(dz), dt(z), F, N, F, None, None, None,
+                                                  None, act, p_eff, seed, ptr(soff), layer, row0, None, None,
+                                                  1.0, stream()))
+        dres = dy if has_res else None
+        return (dz, dres, dgamma, dbeta) + (None,) * 11
+
+
+def act_dropout(z, act: int, p: float, training: bool, drop: Optional[DropoutState], layer: int,
+                row0: int = 0):
+    """dropout(act(z)) -- the ReLU/ELU + F.dropout pair of GCNNet/SAGENet/GATNet (gnn.py:29-30)."""
+    return BnActDropResFn.apply(z, None, None, None, None, None, training, act, p, drop, layer, row0, 0.0,
+                                0.0, None)
+
+
+# ------------------------------------------------------------------------ time features ---
+class InjectTimeFn(torch.autograd.Function):
+    """[x | table[clamp(t-1)]] zero-padded to a multiple of 4 columns (gnn.py:168-179)."""
+
+    @staticmethod
+    def forward(ctx, x, t, table, width: int):
+        x = _rows(x)
+        if x.dtype != torch.float32:
+            raise TypeError("node features must be float32")
+        N, F = x.shape
+        T, D = table.shape
+        tb = table.detach().contiguous().float()
+        out = torch.empty((N, width), dtype=torch.float32, device=x.device)
+        check(lib().egnn_inject_time(ptr(x), _ld(x), ptr(t.contiguous()), ptr(tb), T, D, ptr(out), None, width,
+                                     N, F, stream()))
+        ctx.dims = (F, D, T)
+        ctx.save_for_backward(t)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (t,) = ctx.saved_tensors
+        F, D, T = ctx.dims
+        dx = dout[:, :F] if ctx.needs_input_grad[0] else None
+        dtab = None
+        if ctx.needs_input_grad[2]:
+            # learned nn.Embedding (not used by the BASELINE configs): rows are few (T <= 49)
+            idx = torch.clamp(t.long() - 1, 0, T - 1)
+            dtab = torch.zeros((T, D), dtype=torch.float32, device=dout.device)
+            dtab.index_add_(0, idx, dout[:, F:F + D].float())
+        return dx, None, dtab, None
+
+
+# ------------------------------------------------------------------------------- loss ----
+class MaskedCEFn(torch.autograd.Function):
+    """`F.cross_entropy(logits[mask], y[mask], weight=cw, reduction='none').mean()`
+    (`src/train_gnn.py:159-176,201`) over precomputed train-row indices; forward also produces
+    d loss / d logits, so the backward is a scale."""
+
+    @staticmethod
+    def forward(ctx, logits, y, idx, cw, n_total: float):
+        logits = _rows(logits).contiguous()
+        if logits.size(1) != 2:
+            raise ValueError("masked_weighted_ce is specialised for the reference's 2 classes")
+        L = lib()
+        N = logits.size(0)
+        loss = torch.empty(1, dtype=torch.float32, device=logits.device)
+        dlog = torch.empty_like(logits)
+        ws = torch.empty(L.egnn_ce_workspace_floats(idx.numel()), dtype=torch.float32, device=logits.device)
+        check(L.egnn_masked_ce(ptr(logits), dt(logits), N, ptr(y), ptr(idx), idx.numel(), ptr(cw),
+                               float(n_total), ptr(loss), ptr(dlog), ptr(ws), stream()))
+        ctx.save_for_backward(dlog)
+        return loss.squeeze(0)
+
+    @staticmethod
+    def backward(ctx, gout):
+        (dlog,) = ctx.saved_tensors
+        return dlog * gout.to(dlog.dtype), None, None, None, None
+
+
+def masked_weighted_ce(logits, y, train_idx, cw, n_total: Optional[float] = None):
+    n_total = float(train_idx.numel()) if n_total is None else float(n_total)
+    return MaskedCEFn.apply(logits, y, train_idx, cw, n_total)

@@ -1,0 +1,110 @@
+"""K2/K3 parity: SpMM forward / transposed backward against the CPU scatter oracle.
+fp32 results must be BITWISE equal (sequential edge-order accumulation)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pyg_restated as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _graphs():
+    from egnn_b200 import synthetic
+    return {
+        "adv": synthetic.adversarial_tiny(),
+        "small": synthetic.make_elliptic_like(n_nodes=6000, n_edges=7000, n_timesteps=12, seed=3, hub_degree=200),
+    }
+
+
+def _feat(n, f, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, f, generator=g)
+    x[:, ::7] *= 50.0  # wide dynamic range so summation order shows up in the bits
+    return x
+
+
+@pytest.mark.parametrize("gname", ["adv", "small"])
+@pytest.mark.parametrize("F", [2, 4, 12, 32, 64, 128, 167, 168, 300])
+def test_mean_fwd_and_bwd_bitexact_fp32(egnn, gname, F):
+    from egnn_b200 import ops, _lib
+    gr = _graphs()[gname]
+    ei = torch.cat([gr.edge_index, gr.edge_index.flip(0)], dim=1)
+    n = gr.num_nodes
+    x = _feat(n, F).requires_grad_(True)
+    ref = O.scatter_mean(x.index_select(0, ei[0]), ei[1], n)
+    gout = _feat(n, F, seed=5)
+    ref.backward(gout)
+    g = egnn.build_graph(ei.cuda(), n)
+    got = ops.spmm(g, "csr", _lib.SPMM_MEAN, x.detach().cuda(), torch.float32)
+    assert torch.equal(got.cpu(), ref.detach()), "forward mean not bit-exact"
+    gx = ops.spmm(g, "csc", _lib.SPMM_DIV_NBR, gout.cuda(), torch.float32)
+    assert torch.equal(gx.cpu(), x.grad), "transposed backward not bit-exact"
+    # accumulate epilogue
+    base = _feat(n, F, seed=9).cuda()
+    acc = base.clone()
+    ops.spmm(g, "csc", _lib.SPMM_DIV_NBR, gout.cuda(), torch.float32, out=acc, accumulate=True)
+    assert torch.equal(acc.cpu(), base.cpu() + x.grad)
+
+
+@pytest.mark.parametrize("F", [2, 32, 128, 130])
+def test_gcn_weighted_bitexact_fp32(egnn, F):
+    from egnn_b200 import ops, _lib
+    gr = _graphs()["small"]
+    n = gr.num_nodes
+    ei = gr.edge_index
+    h = _feat(n, F).requires_grad_(True)
+    bias = torch.randn(F)
+    ei2, w = O.gcn_norm(ei, n)
+    ref = O.scatter_sum(w.view(-1, 1) * h.index_select(0, ei2[0]), ei2[1], n) + bias
+    gout = _feat(n, F, seed=2)
+    ref.backward(gout)
+    g = egnn.build_graph(ei.cuda(), n, self_loops=True)
+    got = ops.spmm(g, "csr", _lib.SPMM_WEIGHTED, h.detach().cuda(), torch.float32, bias=bias.cuda())
+    assert torch.equal(got.cpu(), ref.detach())
+    gh = ops.spmm(g, "csc", _lib.SPMM_WEIGHTED, gout.cuda(), torch.float32)
+    assert torch.equal(gh.cpu(), h.grad)
+
+
+@pytest.mark.parametrize("F", [64, 168])
+def test_bf16_paths(egnn, F):
+    """bf16 in/out with fp32 accumulation: compare against the fp32 oracle of the bf16-rounded input;
+    the only error left is the final rounding (half an ulp of bf16 = 2^-9 relative)."""
+    from egnn_b200 import ops, _lib
+    gr = _graphs()["small"]
+    ei = torch.cat([gr.edge_index, gr.edge_index.flip(0)], dim=1)
+    n = gr.num_nodes
+    xb = _feat(n, F).bfloat16()
+    ref = O.scatter_mean(xb.float().index_select(0, ei[0]), ei[1], n)
+    g = egnn.build_graph(ei.cuda(), n)
+    got = ops.spmm(g, "csr", _lib.SPMM_MEAN, xb.cuda(), torch.bfloat16)
+    assert torch.equal(got.cpu(), ref.bfloat16())
+    got32 = ops.spmm(g, "csr", _lib.SPMM_MEAN, xb.cuda(), torch.float32)
+    assert torch.equal(got32.cpu(), ref)
+    gotfb = ops.spmm(g, "csr", _lib.SPMM_MEAN, xb.float().cuda(), torch.bfloat16)
+    assert torch.equal(gotfb.cpu(), ref.bfloat16())
+
+
+def test_determinism_and_full_size(egnn):
+    from egnn_b200 import ops, _lib, synthetic
+    gr = synthetic.make_elliptic_like()
+    ei = torch.cat([gr.edge_index, gr.edge_index.flip(0)], dim=1).cuda()
+    g = egnn.build_graph(ei, gr.num_nodes)
+    x = torch.nn.functional.pad(gr.x, (0, 2)).cuda()
+    a = ops.spmm(g, "csr", _lib.SPMM_MEAN, x, torch.float32)
+    b = ops.spmm(g, "csr", _lib.SPMM_MEAN, x, torch.float32)
+    assert torch.equal(a, b)
+    # size-independent properties: linearity and the constant-vector fixed point
+    ones = torch.ones_like(x)
+    m1 = ops.spmm(g, "csr", _lib.SPMM_MEAN, ones, torch.float32)
+    deg = (g.csr_ptr[1:] - g.csr_ptr[:-1]).float()
+    assert torch.equal(m1[:, 0], (deg > 0).float())
+    s = ops.spmm(g, "csr", _lib.SPMM_SUM, ones, torch.float32)
+    assert torch.equal(s[:, 0], deg)
+    # transposed sum of ones = out-degree; total mass conserved
+    st = ops.spmm(g, "csc", _lib.SPMM_SUM, ones, torch.float32)
+    assert float(st[:, 0].sum()) == float(s[:, 0].sum()) == float(g.n_edges)
+    # spot-check 2000 random rows against the CPU oracle
+    idx = torch.randperm(gr.num_nodes)[:2000]
+    ref = O.scatter_mean(x.cpu().index_select(0, ei[0].cpu()), ei[1].cpu(), gr.num_nodes)
+    assert torch.equal(a.cpu()[idx], ref[idx])
