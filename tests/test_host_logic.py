@@ -1,0 +1,95 @@
+"""CPU tests of the host layer: the C-ABI library loads and exports every symbol the header
+declares, the drop-in modules carry PyG's state-dict layout, CPU tensors are rejected (no
+fallback), and the synthetic generator honours the loader's output contract."""
+import os
+import re
+
+import pytest
+import torch
+
+from oracle import pyg_restated as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(egnn):
+    from egnn_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "egnn_b200.h")).read()
+    declared = set(re.findall(r"\b(egnn_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.lib()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.egnn_abi_version() == 1
+    assert lib.egnn_launch_count() >= 0
+
+
+PARAMS = {"gcn": (dict(arch="gcn", hidden_dim=128, layers=3, dropout=0.5), 167, 38274),
+          "sage": (dict(arch="sage", hidden_dim=128, layers=2, dropout=0.5), 167, 43394),
+          "rec_k8": (dict(arch="sage_resbn", hidden_dim=64, layers=3, dropout=0.2, time_embed_dim=2,
+                          time_embed_type="sin", max_timestep=49), 166, 41090),
+          "gat": (dict(arch="gat", hidden_dim=32, layers=2, heads=4, dropout=0.5), 167, 5510),
+          "sage_l3": (dict(arch="sage", hidden_dim=128, layers=3, dropout=0.4), 167, 76290)}
+
+
+@pytest.mark.parametrize("name", list(PARAMS))
+def test_state_dict_layout_matches_pyg_names(egnn, name):
+    cfg, in_dim, n_params = PARAMS[name]
+    ours = egnn.build_model(cfg["arch"], in_dim, cfg)
+    ref = O.build_model(cfg["arch"], in_dim, cfg)
+    so, sr = ours.state_dict(), ref.state_dict()
+    assert list(so) == list(sr)
+    assert all(so[k].shape == sr[k].shape for k in so)
+    assert sum(p.numel() for p in ours.parameters()) == n_params
+    ref.load_state_dict(so, strict=True)
+    ours.load_state_dict(sr, strict=True)
+
+
+def test_state_dict_key_names():
+    import egnn_b200 as E
+    sd = E.build_model("gat", 10, dict(hidden_dim=8, layers=2, heads=2, dropout=0.1)).state_dict()
+    assert {"convs.0.lin.weight", "convs.0.att_src", "convs.0.att_dst", "convs.0.bias"} <= set(sd)
+    assert sd["convs.0.att_src"].shape == (1, 2, 4) and sd["convs.1.bias"].shape == (2,)
+    sd = E.build_model("gcn", 10, dict(hidden_dim=8, layers=2, dropout=0.1)).state_dict()
+    assert set(sd) == {"convs.0.lin.weight", "convs.0.bias", "convs.1.lin.weight", "convs.1.bias"}
+    with pytest.raises(ValueError):
+        E.build_model("nope", 3, {})
+
+
+def test_no_cpu_fallback(egnn):
+    conv = egnn.SAGEConv(4, 4)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        conv(torch.randn(3, 4), torch.tensor([[0, 1], [1, 2]]))
+    with pytest.raises(RuntimeError, match="GPU only"):
+        egnn.build_graph(torch.tensor([[0, 1], [1, 2]]), 3)
+    with pytest.raises(TypeError):
+        egnn.build_graph(torch.tensor([[0, 1], [1, 2]], dtype=torch.int32), 3)
+
+
+def test_sinusoid_table_matches_reference_formula():
+    from egnn_b200.models import sinusoid_table
+    for dim in (2, 3, 6):
+        assert torch.equal(sinusoid_table(49, dim), O.sinusoid_table(49, dim))
+    net = O.SAGEResBNNet(4, 8, 2, time_embed_dim=2, time_embed_type="sin", max_timestep=49)
+    t = torch.arange(1, 50)
+    assert torch.equal(net._inject_time(torch.zeros(49, 4), t)[:, 4:], sinusoid_table(49, 2))
+
+
+def test_synthetic_graph_contract():
+    from egnn_b200 import synthetic
+    gr = synthetic.make_elliptic_like(n_nodes=20000, n_edges=23000, n_timesteps=49, seed=42, hub_degree=300)
+    ei, t = gr.edge_index, gr.timestep
+    assert ei.dtype == torch.int64 and ei.shape == (2, 23000) and gr.x.shape == (20000, 166)
+    assert (t[ei[0]] == t[ei[1]]).all()                      # no cross-timestep edges (eda.py:124-150)
+    assert (ei[0] != ei[1]).all()
+    assert (ei[0] * 20000 + ei[1]).unique().numel() == 23000  # no duplicate directed pairs
+    assert (t[1:] >= t[:-1]).all() and t.min() == 1 and t.max() == 49
+    assert set(gr.y.unique().tolist()) == {-1, 0, 1}
+    deg = torch.bincount(ei[0], minlength=20000) + torch.bincount(ei[1], minlength=20000)
+    assert deg.max() >= 100  # hub (capped at half its timestep)
+    again = synthetic.make_elliptic_like(n_nodes=20000, n_edges=23000, n_timesteps=49, seed=42, hub_degree=300)
+    assert torch.equal(again.edge_index, ei) and torch.equal(again.x, gr.x)
+    rep = synthetic.replicate(gr, 3)
+    assert rep.num_nodes == 60000 and rep.edge_index.size(1) == 69000
+    assert torch.equal(rep.edge_index[:, 23000:46000], ei + 20000)
+    assert (rep.timestep[rep.edge_index[0]] == rep.timestep[rep.edge_index[1]]).all()
