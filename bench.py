@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py -- SAGE-ResBN (configs/rec_k8.yaml) full-batch train step on the synthetic
+Elliptic-shaped graph: epoch ms and GEdges/s fwd+bwd, with the SpMM roofline beside it.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One JSON line on stdout (rank 0).  A "step" is one reference `train_epoch` body
+(src/train_gnn.py:187-209): forward over all nodes, masked weighted CE, backward, global-norm
+clip, Adam.  N > 1 (launched by torch.distributed.run): weak scaling -- the graph is N
+block-diagonal replicas of the Elliptic-shaped graph, timestep-sharded over the ranks with zero
+halo; NCCL all-reduces only the flat weight-gradient buffer and the BatchNorm statistics.
+`--impl reference`: the reference's CPU path (restated PyG nets, oracle/) on the host cores.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+CFG = dict(arch="sage_resbn", hidden_dim=64, layers=3, dropout=0.20, weight_decay=5.0e-5, lr=5.0e-4,
+           grad_clip=1.0, symmetrize_edges=True, time_embed_dim=2, time_embed_type="sin", max_timestep=49,
+           train_window_k=8)  # /root/reference/configs/rec_k8.yaml
+METRIC = "SAGE-ResBN full-batch train step throughput (fwd+bwd+clip+Adam), GEdges/s"
+UNIT = "GEdges/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period: float = 0.02):
+        super().__init__(daemon=True)
+        self.index, self.period, self.samples, self.reasons, self.max_mhz = index, period, [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
+                 "sw_thermal_slowdown": 0x20, "hw_power_brake_slowdown": 0x80}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def host_graph(n_replicas: int):
+    from egnn_b200 import synthetic
+    gr = synthetic.make_elliptic_like(train_window_k=CFG["train_window_k"])
+    if n_replicas > 1:
+        gr = synthetic.replicate(gr, n_replicas)
+    return gr
+
+
+def spmm_bytes(n, f, e, in_es, out_es):
+    """Compulsory (algorithmic) bytes of one mean-SpMM: read every source row once, write every
+    output row once, plus col indices and row pointers."""
+    return n * f * in_es + n * f * out_es + 4 * e + 4 * (n + 1)
+
+
+# ------------------------------------------------------------------------------- ours -------
+def run_ours(args):
+    import torch.distributed as dist
+    import egnn_b200 as E
+    from egnn_b200 import _lib, ops
+    from egnn_b200.shard import ShardedContext, make_shard
+    from egnn_b200.train import TrainStep
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run for --gpus > 1")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    amp = True
+    gr = host_graph(world)
+    sh = make_shard(gr, rank, world)
+    lg = sh.graph
+    ei_host = torch.cat([lg.edge_index, lg.edge_index.flip(0)], dim=1).contiguous()  # symmetrize_edges
+    e_local, e_total = ei_host.size(1), 2 * gr.edge_index.size(1)
+    del gr
+    # pinned host buffers: the step's inputs as the reference holds them before data.to(device)
+    host = {"x": lg.x, "ei": ei_host, "t": lg.timestep, "y": lg.y, "m": lg.train_mask}
+    host = {k: v.contiguous().pin_memory() for k, v in host.items()}
+    devb = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+    torch.cuda.synchronize()
+    ctx = ShardedContext(sh, dev)
+    torch.manual_seed(42)
+    model = ctx.attach(E.build_model(CFG["arch"], lg.x.size(1), CFG).to(dev))
+    model.set_dropout_seed(42, dev)
+    if world > 1:  # identical initial weights on every rank
+        for p in model.parameters():
+            dist.broadcast(p.data, 0)
+    step = TrainStep(model, devb["x"], devb["ei"], devb["t"], devb["y"], devb["m"], lr=CFG["lr"],
+                     weight_decay=CFG["weight_decay"], grad_clip=CFG["grad_clip"], amp=amp,
+                     cw=ctx.class_weight, n_train_total=ctx.n_train_total,
+                     grad_reducer=ctx.reduce_grads if world > 1 else None)
+    n0 = _lib.launch_count()
+    step.run()
+    torch.cuda.synchronize()
+    launches_per_step = _lib.launch_count() - n0
+    graphed = True
+    try:
+        step.capture(warmup=max(1, args.warmup - 1))
+    except Exception as ex:  # e.g. a collective that cannot be captured: stay eager, say so
+        graphed = False
+        step.graph = None
+        if rank == 0:
+            print(f"[bench] CUDA-graph capture failed ({type(ex).__name__}: {ex}); timing eager", file=sys.stderr)
+        for _ in range(args.warmup):
+            step.run()
+    for _ in range(3):
+        step.run()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    # ---- device-resident timed region: exactly K steps -------------------------------------
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step.run()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    # ---- end-to-end: host buffers in, loss out, every step ------------------------------------
+    g_static = E.cached_graph(devb["ei"], lg.num_nodes)
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        for k in host:
+            devb[k].copy_(host[k], non_blocking=True)
+        E.build_graph(devb["ei"], lg.num_nodes, validate=False, out=g_static)  # new edge list -> new CSR/CSC
+        step.run()
+        loss_host.copy_(step.loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(loss_host)
+
+    for _ in range(2):
+        e2e_step()
+    e2e_steps = max(3, min(args.steps, 30))
+    barrier()
+    ev0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    ev1.record()
+    barrier()
+    ms_e2e = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = (float(v) for v in t.tolist())
+    ms_step, ms_e2e_step = ms / args.steps, ms_e2e / e2e_steps
+
+    # ---- roofline of the dominant sparse kernel (layer-0 mean SpMM, F=168, fp32 -> bf16), timed alone
+    peak, peak_src = peaks()
+    roof, kernels = None, []
+    if rank == 0:
+        g = g_static
+        N = lg.num_nodes
+
+        def time_kernel(fn, bufs, iters=20):
+            for b in bufs:
+                fn(b)
+            torch.cuda.synchronize()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for i in range(iters):
+                fn(bufs[i % len(bufs)])
+            b_.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b_) / iters
+
+        # rotate over 4 input copies (4 x 137 MB > 126 MB L2) so launches do not hit a warm L2
+        xs168 = [torch.randn(N, 168, device=dev) for _ in range(4)]
+        out168 = torch.empty(N, 168, dtype=torch.bfloat16, device=dev)
+        t168 = time_kernel(lambda b: ops.spmm(g, "csr", _lib.SPMM_MEAN, b, torch.bfloat16, out=out168), xs168)
+        b168 = spmm_bytes(N, 168, e_local, 4, 2)
+        del xs168
+        xs64 = [torch.randn(N, 64, device=dev).bfloat16() for _ in range(8)]
+        out64 = torch.empty(N, 64, dtype=torch.bfloat16, device=dev)
+        t64 = time_kernel(lambda b: ops.spmm(g, "csr", _lib.SPMM_MEAN, b, torch.bfloat16, out=out64), xs64)
+        t64b = time_kernel(lambda b: ops.spmm(g, "csc", _lib.SPMM_DIV_NBR, b, torch.bfloat16, out=out64), xs64)
+        b64 = spmm_bytes(N, 64, e_local, 2, 2)
+        roof = {"kernel": "spmm_vec<float,bf16,MEAN> F=168 (layer-0 aggregation)", "bound": "hbm",
+                "achieved": round(b168 / t168 / 1e6, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(b168 / t168 / 1e6 / peak, 4), "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes": b168, "us": round(t168 * 1e3, 2)}
+        kernels = [
+            {"kernel": "spmm mean fwd F=64 bf16", "us": round(t64 * 1e3, 2), "GBps": round(b64 / t64 / 1e6, 1)},
+            {"kernel": "spmm mean bwd (CSC) F=64 bf16", "us": round(t64b * 1e3, 2),
+             "GBps": round(b64 / t64b / 1e6, 1)},
+        ]
+
+    if rank == 0:
+        cpu = cpu_baseline_sample(budget_s=20.0) if world == 1 else None
+        line = {
+            "metric": METRIC, "value": round(e_total / (ms_step * 1e-3) / 1e9, 4), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4),
+            "epoch_ms": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "rec_k8: SAGE-ResBN 168->64->64->2, BN, residual, sin-2 time embed, "
+                                   "symmetrize_edges, dropout 0.2, bf16 autocast, full-batch",
+                       "nodes_per_gpu": lg.num_nodes, "edges_total": e_total, "replicas": world,
+                       "parallelism": f"timestep-sharded dp{world}", "cuda_graph": graphed,
+                       "l2": "inputs larger than L2 (x alone 135 MB; ~1 GB touched per step)"},
+            "clocks": clocks,
+            "e2e": {"value": round(e_total / (ms_e2e_step * 1e-3) / 1e9, 4), "unit": UNIT,
+                    "ms_per_step": round(ms_e2e_step, 4), "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "steps": e2e_steps,
+                    "includes": "pinned-host x/edge_index/timestep/y/mask -> device, CSR/CSC rebuild, step, loss -> host"},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "gpu_launches_per_step": int(launches_per_step),
+            "roofline": roof, "kernels": kernels, "cpu_baseline": cpu,
+            "loss": round(float(step.loss), 6),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------- reference ------
+def _cpu_setup(n_timesteps):
+    """The reference's CPU path on the first `n_timesteps` timesteps of the same graph."""
+    from oracle import pyg_restated as O
+    gr = host_graph(1)
+    if n_timesteps is not None and n_timesteps < 49:
+        keep_n = int((gr.timestep <= n_timesteps).sum())
+        ekeep = gr.edge_index[1] < keep_n
+        gr.x, gr.y, gr.timestep = gr.x[:keep_n], gr.y[:keep_n], gr.timestep[:keep_n]
+        gr.train_mask = gr.train_mask[:keep_n]
+        gr.edge_index = gr.edge_index[:, ekeep]
+        if gr.train_mask.sum() == 0:
+            gr.train_mask = gr.y >= 0
+    ei = torch.cat([gr.edge_index, gr.edge_index.flip(0)], dim=1)
+    torch.manual_seed(42)
+    model = O.build_model(CFG["arch"], gr.x.size(1), CFG)
+    opt = torch.optim.Adam(model.parameters(), lr=CFG["lr"], weight_decay=CFG["weight_decay"])
+    cw = O.class_weight(gr.y[gr.train_mask])
+
+    def step():
+        return O.train_step(model, gr.x, ei, gr.timestep, gr.y, gr.train_mask, cw, opt, CFG["grad_clip"])[0]
+
+    return step, ei.size(1)
+
+
+def cpu_baseline_sample(budget_s: float):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step, edges = _cpu_setup(4)          # calibration on 4 timesteps
+    step()
+    t0 = time.perf_counter()
+    step()
+    rate = edges / (time.perf_counter() - t0)
+    n_t = max(4, min(49, int(rate * budget_s / 3.0 / (468710 / 49.0))))
+    step, edges = _cpu_setup(n_t)
+    step()
+    ts = []
+    for _ in range(2):
+        t0 = time.perf_counter()
+        step()
+        ts.append(time.perf_counter() - t0)
+    best = min(ts)
+    return {"value": round(edges / best / 1e9, 6), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "ms_per_step": round(best * 1e3, 1),
+            "sample": f"restated-PyG SAGE-ResBN fp32 train step on the first {n_t}/49 timesteps "
+                      f"({edges} edges), 1 warm-up + best of 2",
+            "cpu": _cpu_name()}
+
+
+def _cpu_name():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def run_reference(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step, edges = _cpu_setup(4)
+    step()
+    t0 = time.perf_counter()
+    step()
+    rate = edges / (time.perf_counter() - t0)
+    total = args.steps + args.warmup
+    n_t = max(2, min(49, int(rate * 150.0 / total / (468710 / 49.0))))   # whole run <= ~150 s
+    step, edges = _cpu_setup(n_t)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    ms_step = dt / args.steps * 1e3
+    v = round(edges / (ms_step * 1e-3) / 1e9, 6)
+    sample = (f"restated-PyG (oracle/pyg_restated.py; torch_geometric is not installable here) SAGE-ResBN fp32 "
+              f"train step on the first {n_t}/49 timesteps ({edges} edges) per step")
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 2), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "rec_k8: SAGE-ResBN 168->64->64->2 (CPU, fp32; reference forces amp off on CPU)",
+                       "edges_per_step": edges},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": sample, "cpu": _cpu_name()},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -58,7 +58,9 @@ def symmetrize(edge_index: torch.Tensor) -> torch.Tensor:
 
 def build_graph(edge_index: torch.Tensor, num_nodes: int, symmetrize: bool = False,
                 self_loops: bool = False, want_norm: bool = False, keep_edge_list: bool = False,
-                validate: bool = True) -> Graph:
+                validate: bool = True, out: Optional[Graph] = None) -> Graph:
+    """Build the sorted views.  `out` re-uses the buffers of a previously built Graph of the same
+    shape (so a captured CUDA graph that reads them sees the new structure)."""
     if edge_index.dim() != 2 or edge_index.size(0) != 2:
         raise ValueError("edge_index must have shape [2, E]")
     if edge_index.dtype != torch.int64:
@@ -72,7 +74,10 @@ def build_graph(edge_index: torch.Tensor, num_nodes: int, symmetrize: bool = Fal
     cap = max(1, (2 * E if symmetrize else E) + (N if self_loops else 0))
     i32 = dict(dtype=torch.int32, device=dev)
     norm = want_norm or self_loops
-    g = Graph(
+    if out is not None:
+        if out.n_nodes != N or out.cap != cap or (norm and out.w_csr is None):
+            raise ValueError("`out` graph has a different shape")
+    g = out if out is not None else Graph(
         n_nodes=N, cap=cap, info=torch.empty(4, **i32),
         csr_ptr=torch.empty(N + 1, **i32), csr_src=torch.empty(cap, **i32), csr_eid=torch.empty(cap, **i32),
         csc_ptr=torch.empty(N + 1, **i32), csc_dst=torch.empty(cap, **i32), csc_pos=torch.empty(cap, **i32),

@@ -1,0 +1,145 @@
+"""Timestep-sharded data parallelism.
+
+The reference loader drops every cross-timestep edge (`/root/reference/src/data/
+dataset_elliptic.py:235-241`; invariant stated by `src/analysis/eda.py:124-150`), so the graph
+is a disjoint union of per-timestep blocks and node order is timestep-contiguous.  Whole
+(replica, timestep) blocks are assigned to ranks as CONTIGUOUS ranges (so a shard's global
+node ids are one interval and the Philox dropout mask keyed on `row0 + local_row` equals the
+single-GPU mask); every rank holds its rows of x / y / masks / timestep and a local edge list
+with re-based ids: zero halo, zero feature exchange.  Collectives (NCCL over NVLink):
+  * one all-reduce of the flat weight-gradient buffer per step;
+  * per BatchNorm layer one all-reduce of [sum, sumsq] (fwd) and [sum g, sum g*xhat] (bwd),
+    2 x hidden doubles each;
+  * once per run: global train-row count and class counts (loss normaliser, class weights).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+from .ops import StatsReducer
+from .synthetic import EllipticGraph
+
+
+def partition_contiguous(weights: Sequence[float], n_ranks: int) -> List[Tuple[int, int]]:
+    """Split `weights` into n_ranks contiguous ranges [lo, hi) minimising the maximum range sum
+    (binary search on the bottleneck + greedy fill).  Empty ranges are allowed only when there
+    are fewer units than ranks."""
+    w = [float(v) for v in weights]
+    n = len(w)
+    if n_ranks <= 0:
+        raise ValueError("n_ranks must be positive")
+
+    def fits(cap: float) -> Optional[List[Tuple[int, int]]]:
+        out, lo, acc = [], 0, 0.0
+        for i, v in enumerate(w):
+            if v > cap:
+                return None
+            if acc + v > cap:
+                out.append((lo, i))
+                lo, acc = i, 0.0
+            acc += v
+        out.append((lo, n))
+        return out if len(out) <= n_ranks else None
+
+    lo_c, hi_c = max(w, default=0.0), sum(w)
+    best = fits(hi_c)
+    for _ in range(60):
+        mid = 0.5 * (lo_c + hi_c)
+        r = fits(mid)
+        if r is None:
+            lo_c = mid
+        else:
+            best, hi_c = r, mid
+    # spread trailing empties: split the largest multi-unit ranges until we have n_ranks pieces
+    while len(best) < n_ranks:
+        cand = [(sum(w[a:b]), k) for k, (a, b) in enumerate(best) if b - a >= 2]
+        if not cand:
+            break
+        _, k = max(cand)
+        a, b = best[k]
+        run, cut, half = 0.0, a + 1, 0.5 * sum(w[a:b])
+        for i in range(a, b - 1):
+            run += w[i]
+            cut = i + 1
+            if run >= half:
+                break
+        best[k:k + 1] = [(a, cut), (cut, b)]
+    while len(best) < n_ranks:
+        best.append((n, n))
+    return best
+
+
+@dataclass
+class Shard:
+    rank: int
+    world: int
+    row0: int            # global id of this shard's first node
+    n_local: int
+    n_global: int
+    graph: EllipticGraph  # local rows, edge ids re-based to [0, n_local)
+
+
+def unit_bounds(timestep: torch.Tensor) -> torch.Tensor:
+    """Start offsets of the maximal runs of equal timestep value (= (replica, timestep) blocks);
+    last entry = N."""
+    n = timestep.numel()
+    change = torch.nonzero(timestep[1:] != timestep[:-1]).view(-1) + 1
+    return torch.cat([torch.zeros(1, dtype=torch.int64), change, torch.tensor([n])])
+
+
+def make_shard(gr: EllipticGraph, rank: int, world: int, feat_cost: float = 1.0) -> Shard:
+    """Cut the rank's contiguous block range out of a (CPU) graph.  Load model per block:
+    nodes*F (feature traffic) + edges (index traffic)."""
+    bounds = unit_bounds(gr.timestep)
+    n_units = bounds.numel() - 1
+    ei = gr.edge_index
+    unit_of_node = torch.bucketize(torch.arange(gr.num_nodes), bounds[1:], right=True)
+    e_unit = unit_of_node[ei[1]]
+    if not torch.equal(e_unit, unit_of_node[ei[0]]):
+        raise ValueError("edge crosses a timestep block: the graph does not shard without halo")
+    e_per_unit = torch.bincount(e_unit, minlength=n_units)
+    n_per_unit = bounds[1:] - bounds[:-1]
+    w = (n_per_unit.double() * feat_cost * gr.x.size(1) + e_per_unit.double()).tolist()
+    lo_u, hi_u = partition_contiguous(w, world)[rank]
+    lo = int(bounds[lo_u]) if lo_u < n_units else gr.num_nodes
+    hi = int(bounds[hi_u]) if hi_u <= n_units else gr.num_nodes
+    keep = (ei[1] >= lo) & (ei[1] < hi)
+    sl = lambda t: None if t is None else t[lo:hi].contiguous()
+    local = EllipticGraph(x=gr.x[lo:hi].contiguous(), edge_index=(ei[:, keep] - lo).contiguous(),
+                          y=sl(gr.y), timestep=sl(gr.timestep), train_mask=sl(gr.train_mask),
+                          val_mask=sl(gr.val_mask), test_mask=sl(gr.test_mask))
+    return Shard(rank=rank, world=world, row0=lo, n_local=hi - lo, n_global=gr.num_nodes, graph=local)
+
+
+class ShardedContext:
+    """What a rank needs to step its shard so that the result equals the single-GPU step on the
+    whole graph (up to the order of the cross-rank sums)."""
+
+    def __init__(self, shard: Shard, device, group=None):
+        self.shard, self.group = shard, group
+        y, tm = shard.graph.y, shard.graph.train_mask
+        counts = torch.tensor([float(tm.sum()), float(((y == 1) & tm).sum()), float(((y == 0) & tm).sum())],
+                              dtype=torch.float64, device=device)
+        if dist.is_initialized():
+            dist.all_reduce(counts, group=group)
+        self.n_train_total, pos, neg = (float(v) for v in counts.tolist())
+        if pos == 0 or neg == 0:      # class_weight(), src/train_gnn.py:116-123, on GLOBAL counts
+            self.class_weight = torch.tensor([1.0, 1.0], dtype=torch.float32)
+        else:
+            self.class_weight = torch.tensor([(pos + neg) / (2.0 * neg), (pos + neg) / (2.0 * pos)],
+                                             dtype=torch.float32)
+        self.stats_reducer = StatsReducer(n_total=shard.n_global, group=group)
+
+    def attach(self, model):
+        model.stats_reducer = self.stats_reducer
+        model.row0 = self.shard.row0
+        return model
+
+    def reduce_grads(self, flat_grad: torch.Tensor):
+        if dist.is_initialized():
+            dist.all_reduce(flat_grad, group=self.group)
+        return flat_grad
