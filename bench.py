@@ -145,9 +145,13 @@ def run_ours(args):
     step.run()
     torch.cuda.synchronize()
     launches_per_step = _lib.launch_count() - n0
-    graphed = True
+    graphed = not args.eager
     try:
-        step.capture(warmup=max(1, args.warmup - 1))
+        if graphed:
+            step.capture(warmup=max(1, args.warmup - 1))
+        else:
+            for _ in range(args.warmup):
+                step.run()
     except Exception as ex:  # e.g. a collective that cannot be captured: stay eager, say so
         graphed = False
         step.graph = None
@@ -246,7 +250,7 @@ def run_ours(args):
         ]
 
     if rank == 0:
-        cpu = cpu_baseline_sample(budget_s=20.0) if world == 1 else None
+        cpu = cpu_baseline_sample(budget_s=20.0) if (world == 1 and not args.no_cpu_baseline) else None
         line = {
             "metric": METRIC, "value": round(e_total / (ms_step * 1e-3) / 1e9, 4), "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4),
@@ -372,6 +376,8 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--eager", action="store_true", help="do not capture a CUDA graph (profiling runs)")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU baseline leg (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -9,6 +9,8 @@
 //                            split-K with a fixed-order second stage => deterministic)
 // plus two skinny specialisations for the 2-class output layer (N<=8 forward, M<=8 wgrad),
 // which are pure streaming reductions.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace egnn {
@@ -21,6 +23,7 @@ struct GemmParams {
   const void* B;
   void* C;
   const float* bias;
+  const int32_t* row_div_ptr;
   float* ws;
   int64_t a_sm, a_sk, b_sk, b_sn, ld_c;
   int64_t M, N, K;
@@ -30,6 +33,10 @@ struct GemmParams {
 
 __device__ __forceinline__ void store_c(const GemmParams& P, int64_t m, int64_t n, float v) {
   if (P.bias) v += P.bias[n];
+  if (P.row_div_ptr) {
+    int d = P.row_div_ptr[m + 1] - P.row_div_ptr[m];
+    v = __fdiv_rn(v, (float)(d > 1 ? d : 1));
+  }
   if (P.c_dtype == EGNN_F32) {
     float* c = reinterpret_cast<float*>(P.C) + m * P.ld_c + n;
     if (P.accumulate) v += *c;
@@ -209,25 +216,32 @@ int run(GemmParams& P, cudaStream_t st) {
 
 }  // namespace
 
-int gemm_tcgen05_dispatch(const void* A, int64_t lda, const void* B, int64_t ldb, void* C,
-                          int c_dtype, int64_t ld_c, int64_t M, int64_t N, int64_t K,
-                          const float* bias, int accumulate, cudaStream_t st);  // gemm_tcgen05.cu
+int gemm_tcgen05_dispatch(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int c_dtype,
+                          int64_t ld_c, int64_t M, int64_t N, int64_t K, const float* bias, int accumulate,
+                          const int32_t* row_div_ptr, cudaStream_t st);  // gemm_tcgen05.cu
 bool gemm_tcgen05_supported(int64_t lda, int64_t ldb, int64_t ld_c, int64_t M, int64_t N, int64_t K,
                             const void* A, const void* B, const void* C);
+size_t wgrad_tcgen05_workspace_floats(int64_t N_out, int64_t K_in);
+bool wgrad_tcgen05_supported(const void* G, int64_t ldg, const void* X, int64_t ldx, int64_t M_rows, int64_t N_out,
+                             int64_t K_in);
+int wgrad_tcgen05_dispatch(const void* G, int64_t ldg, const void* X, int64_t ldx, float* dW, int64_t M_rows,
+                           int64_t N_out, int64_t K_in, int accumulate, float* workspace, cudaStream_t st);
 }  // namespace egnn
 
 using namespace egnn;
 
 extern "C" size_t egnn_gemm_workspace_floats(int64_t M, int64_t N, int64_t K, int split_k) {
   (void)K;
-  if (M <= 8) return (size_t)(kNumSMs * 4 + 1) * (size_t)M * (size_t)N;  // skinny wgrad chunks
-  return split_k > 1 ? (size_t)split_k * (size_t)M * (size_t)N : 0;
+  size_t need = split_k > 1 ? (size_t)split_k * (size_t)M * (size_t)N : 0;
+  if (M <= 8) need = std::max(need, (size_t)(kNumSMs * 4 + 1) * (size_t)M * (size_t)N);  // skinny wgrad chunks
+  if (M <= 256 && N <= 256) need = std::max(need, wgrad_tcgen05_workspace_floats(M, N));     // tcgen05 wgrad
+  return need;
 }
 
 extern "C" int egnn_gemm(const void* A, int a_dtype, int64_t a_sm, int64_t a_sk, const void* B,
                          int b_dtype, int64_t b_sk, int64_t b_sn, void* C, int c_dtype, int64_t ld_c,
-                         int64_t M, int64_t N, int64_t K, const float* bias, int accumulate,
-                         int split_k, float* workspace, int impl, void* stream) {
+                         int64_t M, int64_t N, int64_t K, const float* bias, const int32_t* row_div_ptr,
+                         int accumulate, int split_k, float* workspace, int impl, void* stream) {
   const char* fn = "egnn_gemm";
   EGNN_REQUIRE(A && B && C, fn, "null pointer");
   EGNN_REQUIRE(M >= 0 && N > 0 && K > 0, fn, "bad shape");
@@ -236,14 +250,21 @@ extern "C" int egnn_gemm(const void* A, int a_dtype, int64_t a_sm, int64_t a_sk,
   EGNN_REQUIRE(impl >= 0 && impl <= 2, fn, "bad impl");
   if (M == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  const bool tc_shape = a_dtype == EGNN_BF16 && b_dtype == EGNN_BF16 && a_sk == 1 && b_sk == 1 &&
-                        split_k <= 1 &&
-                        gemm_tcgen05_supported(a_sm, b_sn, ld_c, M, N, K, A, B, C);
-  if (impl == 2 && !tc_shape) return fail(fn, "shape/dtype/layout not supported by the tcgen05 path");
-  if (impl == 2 || (impl == 0 && tc_shape))
-    return gemm_tcgen05_dispatch(A, a_sm, B, b_sn, C, c_dtype, ld_c, M, N, K, bias, accumulate, st);
+  const bool both_bf16 = a_dtype == EGNN_BF16 && b_dtype == EGNN_BF16;
+  // tensor-core forward / dgrad: both operands contiguous along the contraction
+  const bool tc_tn = both_bf16 && a_sk == 1 && b_sk == 1 && N >= 8 &&
+                     gemm_tcgen05_supported(a_sm, b_sn, ld_c, M, N, K, A, B, C);
+  // tensor-core wgrad: both operands contiguous along the non-contracted dimension, long reduction
+  const bool tc_wg = both_bf16 && a_sm == 1 && b_sn == 1 && c_dtype == EGNN_F32 && ld_c == N && !bias &&
+                     !row_div_ptr && workspace && M >= 8 && K >= 1024 &&
+                     wgrad_tcgen05_supported(A, a_sk, B, b_sk, K, M, N);
+  if (impl == 2 && !(tc_tn || tc_wg)) return fail(fn, "shape/dtype/layout not supported by the tcgen05 path");
+  if (impl != 1 && tc_tn)
+    return gemm_tcgen05_dispatch(A, a_sm, B, b_sn, C, c_dtype, ld_c, M, N, K, bias, accumulate, row_div_ptr, st);
+  if (impl != 1 && tc_wg)
+    return wgrad_tcgen05_dispatch(A, a_sk, B, b_sk, (float*)C, K, M, N, accumulate, workspace, st);
   GemmParams P;
-  P.A = A; P.B = B; P.C = C; P.bias = bias; P.ws = workspace;
+  P.A = A; P.B = B; P.C = C; P.bias = bias; P.row_div_ptr = row_div_ptr; P.ws = workspace;
   P.a_sm = a_sm; P.a_sk = a_sk; P.b_sk = b_sk; P.b_sn = b_sn; P.ld_c = ld_c;
   P.M = M; P.N = N; P.K = K; P.k_per_split = K;
   P.c_dtype = c_dtype; P.accumulate = accumulate; P.split_k = split_k;

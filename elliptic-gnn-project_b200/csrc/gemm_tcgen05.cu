@@ -1,13 +1,524 @@
-// K6 (tensor-core path) -- placeholder until the tcgen05/TMA kernel lands; reports
-// "unsupported" so egnn_gemm(impl=auto) uses the SIMT path and impl=2 fails loudly.
+// K6 (tensor-core path) -- bf16 dense projections on tcgen05 / TMEM / TMA (sm_100a).
+//
+// Two persistent, warp-specialised kernels (1 CTA per SM, 256 threads):
+//   gemm_tn_kernel    C[M,N] = A[M,K] . W[N,K]^T (+bias, /rowcount, +=C)   Linear forward, and
+//                     dgrad through a pre-transposed weight.  Both operands K-major.
+//                     W stays resident in shared memory for the whole kernel; 128-row A tiles
+//                     stream through a TMA ring; two TMEM accumulators overlap the epilogue of
+//                     tile i with the MMAs of tile i+1.
+//   gemm_wgrad_kernel dW[N,K] = G[M,N]^T . X[M,K]   reduction over the node axis M.  Both
+//                     operands are MN-major (contiguous along the non-contracted dimension);
+//                     every CTA accumulates its 64-node slabs into TMEM and writes one fp32
+//                     partial, a second kernel sums the partials in a fixed order
+//                     (deterministic, no float atomics).
+// warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warp 2 = TMEM allocator,
+// warps 4..7 = epilogue (tcgen05.ld -> registers -> global).
+//
+// Shared-memory operand layouts are the canonical UMMA SWIZZLE_128B layouts, written by TMA
+// with CU_TENSOR_MAP_SWIZZLE_128B boxes whose inner extent is 64 bf16 (128 bytes):
+//   K-major : row r of the operand = 128 B at r*128; 8-row groups are 1024 B apart (SBO);
+//             one MMA (K=16) advances the start address by 32 B inside the swizzled row.
+//   MN-major: row k (contraction index) = 128 B holding 64 consecutive MN elements; 8-row
+//             groups 1024 B apart (SBO); the next 64 MN elements are a separate TMA box LBO
+//             bytes further; one MMA (K=16) advances the start address by 2048 B.
+#include <cuda.h>
+
 #include "common.cuh"
+
 namespace egnn {
-bool gemm_tcgen05_supported(int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, const void*,
-                            const void*, const void*) {
-  return false;
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int BM = 128;          // UMMA M (cta_group::1)
+constexpr int BK = 64;           // bf16 elements per 128-byte swizzled row
+constexpr int kStageBytesA = BM * BK * 2;  // 16 KB
+
+// ------------------------------------------------------------------ PTX wrappers ---------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
 }
-int gemm_tcgen05_dispatch(const void*, int64_t, const void*, int64_t, void*, int, int64_t, int64_t,
-                          int64_t, int64_t, const float*, int, cudaStream_t) {
-  return fail("egnn_gemm", "tcgen05 path not built");
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// UMMA shared-memory descriptor, SWIZZLE_128B, version 1 (Blackwell)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // version
+  d |= (uint64_t)2 << 61;  // LayoutType::SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D=f32, A=B=bf16, M=128, N=n
+__host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+struct Epilogue {
+  void* C;
+  const float* bias;
+  const int32_t* row_div_ptr;  // optional: divide row m by max(ptr[m+1]-ptr[m], 1)
+  int64_t ld_c;
+  int c_dtype, accumulate;
+};
+
+// ------------------------------------------------------------------ forward / dgrad --------
+// smem map (dynamic, 1024-aligned): [W chunks: KC * Npad*128][A ring: S * 16 KB][barriers]
+template <int kStages>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, int M, int N,
+               int Npad, int K, Epilogue ep) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~uintptr_t(1023));
+  const int KC = (K + BK - 1) / BK;
+  const int w_chunk_bytes = Npad * 128;
+  uint8_t* sW = smem;
+  uint8_t* sA = smem + (size_t)KC * w_chunk_bytes;  // Npad*128 is a multiple of 1024 (Npad % 8 == 0)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + (size_t)kStages * kStageBytesA);
+  uint64_t* full = bars;                    // [kStages]
+  uint64_t* empty = bars + kStages;         // [kStages]
+  uint64_t* w_full = bars + 2 * kStages;    // [1]
+  uint64_t* t_full = w_full + 1;            // [2]
+  uint64_t* t_empty = t_full + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = (M + BM - 1) / BM;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < 2 * Npad) tmem_cols <<= 1;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(w_full, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&t_full[b], 1); mbar_init(&t_empty[b], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // weights: all K chunks, resident for the whole kernel
+      mbar_expect_tx(w_full, (uint32_t)(KC * w_chunk_bytes));
+      for (int kc = 0; kc < KC; ++kc) tma_load_2d(sW + (size_t)kc * w_chunk_bytes, &tmW, w_full, kc * BK, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        for (int kc = 0; kc < KC; ++kc) {
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], kStageBytesA);
+          tma_load_2d(sA + (size_t)s * kStageBytesA, &tmA, &full[s], kc * BK, t * BM);
+          if (++s == kStages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc(Npad, 0, 0);
+    mbar_wait(w_full, 0);
+    int s = 0;
+    uint32_t ph = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1);  // how many times this buffer was used before
+      mbar_wait(&t_empty[buf], (use & 1) ^ 1);
+      tcgen05_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * Npad);
+      for (int kc = 0; kc < KC; ++kc) {
+        mbar_wait(&full[s], ph);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const int k_left = K - kc * BK;
+          const int n_k = k_left >= BK ? BK / 16 : (k_left + 15) / 16;
+          const uint32_t a_addr = smem_u32(sA + (size_t)s * kStageBytesA);
+          const uint32_t b_addr = smem_u32(sW + (size_t)kc * w_chunk_bytes);
+          for (int k4 = 0; k4 < n_k; ++k4) {
+            uint64_t ad = make_desc(a_addr + k4 * 32, 16, 1024);
+            uint64_t bd = make_desc(b_addr + k4 * 32, 16, 1024);
+            tcgen05_mma_bf16(d_tmem, ad, bd, idesc, (kc | k4) != 0);
+          }
+          tcgen05_commit(&empty[s]);                       // frees the smem stage when the MMAs retire
+          if (kc == KC - 1) tcgen05_commit(&t_full[buf]);  // accumulator ready for the epilogue
+        }
+        __syncwarp();
+        if (++s == kStages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;  // TMEM sub-partition of this warp
+    int it = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1);
+      mbar_wait(&t_full[buf], use & 1);
+      tcgen05_fence_after();
+      const int64_t row = (int64_t)t * BM + q * 32 + lane;
+      const bool row_ok = row < M;
+      float rdiv = 1.f;
+      if (ep.row_div_ptr && row_ok) {
+        int d = ep.row_div_ptr[row + 1] - ep.row_div_ptr[row];
+        rdiv = (float)(d > 1 ? d : 1);
+      }
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * Npad);
+      for (int c0 = 0; c0 < N; c0 += 8) {
+        float v[8];
+        tmem_ld8(t_addr + c0, v);
+        if (row_ok) {
+          const int nv = min(8, N - c0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (ep.bias && j < nv) v[j] += ep.bias[c0 + j];
+            if (ep.row_div_ptr) v[j] = __fdiv_rn(v[j], rdiv);
+          }
+          if (ep.c_dtype == EGNN_F32) {
+            float* c = reinterpret_cast<float*>(ep.C) + row * ep.ld_c + c0;
+            if (nv == 8 && (((uintptr_t)c) & 15) == 0) {
+              if (ep.accumulate) {
+                float4 o0 = *reinterpret_cast<float4*>(c), o1 = *reinterpret_cast<float4*>(c + 4);
+                v[0] += o0.x; v[1] += o0.y; v[2] += o0.z; v[3] += o0.w;
+                v[4] += o1.x; v[5] += o1.y; v[6] += o1.z; v[7] += o1.w;
+              }
+              *reinterpret_cast<float4*>(c) = make_float4(v[0], v[1], v[2], v[3]);
+              *reinterpret_cast<float4*>(c + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            } else {
+              for (int j = 0; j < nv; ++j) c[j] = ep.accumulate ? c[j] + v[j] : v[j];
+            }
+          } else {
+            __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(ep.C) + row * ep.ld_c + c0;
+            if (nv == 8 && (((uintptr_t)c) & 15) == 0) {
+              if (ep.accumulate) {
+                F8 o = ld8(c);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] += o.v[j];
+              }
+              F8 r;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) r.v[j] = v[j];
+              st8(c, r);
+            } else {
+              for (int j = 0; j < nv; ++j)
+                c[j] = __float2bfloat16_rn(ep.accumulate ? __bfloat162float(c[j]) + v[j] : v[j]);
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_empty[buf]);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
+  }
+}
+
+// ------------------------------------------------------------------ wgrad ------------------
+// dW^T tile: UMMA M axis = K_in (two 128-wide M tiles when K_in > 128), N axis = N_out.
+// smem stage = [X blocks: MB * 8 KB][G blocks: NB * 8 KB], each block = 64 nodes x 64 columns.
+template <int kStages>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, int M_rows,
+                  int N_out, int Nopad, int K_in, float* __restrict__ partial) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~uintptr_t(1023));
+  const int MT = K_in > 128 ? 2 : 1;   // 128-wide M tiles over K_in
+  const int MB = MT * 2;               // 64-column X blocks per stage
+  const int NB = (Nopad + 63) / 64;    // 64-column G blocks per stage
+  const int stage_bytes = (MB + NB) * 8192;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kStages;
+  uint64_t* done = bars + 2 * kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_slabs = (M_rows + 63) / 64;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < MT * Nopad) tmem_cols <<= 1;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const bool has_work = (int)blockIdx.x < n_slabs;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int sl = blockIdx.x; sl < n_slabs; sl += gridDim.x) {
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
+        uint8_t* st = smem + (size_t)s * stage_bytes;
+        for (int b = 0; b < MB; ++b) tma_load_2d(st + b * 8192, &tmX, &full[s], b * 64, sl * 64);
+        for (int b = 0; b < NB; ++b) tma_load_2d(st + (MB + b) * 8192, &tmG, &full[s], b * 64, sl * 64);
+        if (++s == kStages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc(Nopad, 1, 1);
+    int s = 0;
+    uint32_t ph = 0;
+    bool first = true;
+    for (int sl = blockIdx.x; sl < n_slabs; sl += gridDim.x) {
+      mbar_wait(&full[s], ph);
+      tcgen05_fence_after();
+      if (elect_one()) {
+        const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
+        for (int mt = 0; mt < MT; ++mt) {
+          for (int k4 = 0; k4 < 4; ++k4) {
+            uint64_t ad = make_desc(st + mt * 16384 + k4 * 2048, 8192, 1024);
+            uint64_t bd = make_desc(st + MB * 8192 + k4 * 2048, 8192, 1024);
+            tcgen05_mma_bf16(tmem_base + (uint32_t)(mt * Nopad), ad, bd, idesc, (!first || k4 != 0) ? 1u : 0u);
+          }
+        }
+        tcgen05_commit(&empty[s]);
+      }
+      __syncwarp();
+      first = false;
+      if (++s == kStages) { s = 0; ph ^= 1; }
+    }
+    if (has_work && elect_one()) tcgen05_commit(done);
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    float* out = partial + (size_t)blockIdx.x * N_out * K_in;
+    if (has_work) {
+      mbar_wait(done, 0);
+      tcgen05_fence_after();
+    }
+    for (int mt = 0; mt < MT; ++mt) {
+      const int k = mt * 128 + q * 32 + lane;  // K_in index owned by this thread (TMEM lane)
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * Nopad);
+      for (int c0 = 0; c0 < N_out; c0 += 8) {
+        float v[8];
+        if (has_work) {
+          tmem_ld8(t_addr + c0, v);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = 0.f;
+        }
+        if (k < K_in) {
+          const int nv = min(8, N_out - c0);
+          for (int j = 0; j < nv; ++j) out[(size_t)(c0 + j) * K_in + k] = v[j];  // coalesced over lanes
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
+  }
+}
+
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int n_part,
+                                                           int64_t n_elem, float* __restrict__ out,
+                                                           int accumulate) {
+  int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n_elem) return;
+  float s = 0.f;
+  for (int p = 0; p < n_part; ++p) s += partial[(size_t)p * n_elem + i];
+  out[i] = accumulate ? out[i] + s : s;
+}
+
+// ------------------------------------------------------------------ host side ---------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// bf16 [rows, cols] row-major with leading dimension ld (elements); box = 64 cols x box_rows
+bool make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+constexpr int kStagesTN = 6;
+constexpr int kStagesWG = 4;
+
+}  // namespace
+
+bool gemm_tcgen05_supported(int64_t lda, int64_t ldb, int64_t ld_c, int64_t M, int64_t N, int64_t K,
+                            const void* A, const void* B, const void* C) {
+  (void)ld_c; (void)C;
+  if (M < 1 || N < 8 || N > 256 || K < 8 || K > 512) return false;
+  if (lda % 8 || ldb % 8) return false;                          // TMA: 16-byte global strides
+  if (((uintptr_t)A | (uintptr_t)B) & 15) return false;
+  if (M >= (int64_t)1 << 31) return false;
+  const int Npad = (int)((N + 15) / 16 * 16);
+  const int KC = (int)((K + BK - 1) / BK);
+  size_t smem = (size_t)KC * Npad * 128 + (size_t)kStagesTN * kStageBytesA + 256 + 1024;
+  return smem <= 227 * 1024 && 2 * Npad <= 512;
+}
+
+int gemm_tcgen05_dispatch(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int c_dtype,
+                          int64_t ld_c, int64_t M, int64_t N, int64_t K, const float* bias, int accumulate,
+                          const int32_t* row_div_ptr, cudaStream_t st) {
+  const char* fn = "egnn_gemm(tcgen05)";
+  const int Npad = (int)((N + 15) / 16 * 16);
+  const int KC = (int)((K + BK - 1) / BK);
+  CUtensorMap tmA, tmW;
+  if (!make_map(&tmA, A, M, K, lda, BM) || !make_map(&tmW, B, N, K, ldb, Npad))
+    return fail(fn, "cuTensorMapEncodeTiled failed");
+  size_t smem = (size_t)KC * Npad * 128 + (size_t)kStagesTN * kStageBytesA + 256 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(gemm_tn_kernel<kStagesTN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_set = true;
+  }
+  int n_tiles = (int)((M + BM - 1) / BM);
+  int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
+  Epilogue ep{C, bias, row_div_ptr, ld_c, c_dtype, accumulate};
+  gemm_tn_kernel<kStagesTN><<<grid, kThreads, smem, st>>>(tmA, tmW, (int)M, (int)N, Npad, (int)K, ep);
+  EGNN_LAUNCH_CHECK(fn);
+  return 0;
+}
+
+size_t wgrad_tcgen05_workspace_floats(int64_t N_out, int64_t K_in) { return (size_t)kNumSMs * N_out * K_in; }
+
+bool wgrad_tcgen05_supported(const void* G, int64_t ldg, const void* X, int64_t ldx, int64_t M_rows, int64_t N_out,
+                             int64_t K_in) {
+  if (N_out < 8 || N_out > 256 || K_in < 8 || K_in > 256 || M_rows < 1 || M_rows >= (int64_t)1 << 31) return false;
+  if (ldg % 8 || ldx % 8) return false;
+  if (((uintptr_t)G | (uintptr_t)X) & 15) return false;
+  const int Nopad = (int)((N_out + 15) / 16 * 16);
+  const int MT = K_in > 128 ? 2 : 1;
+  const int stage = (MT * 2 + (Nopad + 63) / 64) * 8192;
+  return (size_t)kStagesWG * stage + 256 + 1024 <= 227 * 1024 && MT * Nopad <= 512;
+}
+
+// dW[N_out, K_in] (fp32, ld = K_in) (+)= G[M,N_out]^T X[M,K_in]; workspace >= wgrad_tcgen05_workspace_floats
+int wgrad_tcgen05_dispatch(const void* G, int64_t ldg, const void* X, int64_t ldx, float* dW, int64_t M_rows,
+                           int64_t N_out, int64_t K_in, int accumulate, float* workspace, cudaStream_t st) {
+  const char* fn = "egnn_gemm(tcgen05 wgrad)";
+  const int Nopad = (int)((N_out + 15) / 16 * 16);
+  const int MT = K_in > 128 ? 2 : 1;
+  const int stage = (MT * 2 + (Nopad + 63) / 64) * 8192;
+  CUtensorMap tmX, tmG;
+  if (!make_map(&tmX, X, M_rows, K_in, ldx, 64) || !make_map(&tmG, G, M_rows, N_out, ldg, 64))
+    return fail(fn, "cuTensorMapEncodeTiled failed");
+  size_t smem = (size_t)kStagesWG * stage + 256 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(gemm_wgrad_kernel<kStagesWG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_set = true;
+  }
+  int n_slabs = (int)((M_rows + 63) / 64);
+  int grid = n_slabs < kNumSMs ? n_slabs : kNumSMs;
+  gemm_wgrad_kernel<kStagesWG><<<grid, kThreads, smem, st>>>(tmX, tmG, (int)M_rows, (int)N_out, Nopad, (int)K_in,
+                                                            workspace);
+  EGNN_LAUNCH_CHECK(fn);
+  int64_t n_elem = N_out * K_in;
+  wgrad_reduce_kernel<<<(unsigned)ceil_div(n_elem, 256), 256, 0, st>>>(workspace, grid, n_elem, dW, accumulate);
+  EGNN_LAUNCH_CHECK(fn);
+  return 0;
+}
+
 }  // namespace egnn

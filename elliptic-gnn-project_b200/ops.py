@@ -73,15 +73,20 @@ def spmm(g: Graph, view: str, mode: int, x: torch.Tensor, out_dtype: torch.dtype
     return out
 
 
-def _gemm(A, a_sm, a_sk, B, b_sk, b_sn, C, M, N, K, bias, accumulate, split_k=1, impl=0):
+GEMM_IMPL = 0  # 0 auto (tcgen05 for bf16 where supported), 1 force SIMT, 2 force tcgen05
+
+
+def _gemm(A, a_sm, a_sk, B, b_sk, b_sn, C, M, N, K, bias, accumulate, split_k=1, impl=None, row_div=None,
+          need_ws=False):
     L = lib()
-    nws = L.egnn_gemm_workspace_floats(M, N, K, split_k)
+    nws = L.egnn_gemm_workspace_floats(M, N, K, split_k) if (need_ws or split_k > 1 or M <= 8) else 0
     ws = torch.empty(nws, dtype=torch.float32, device=C.device) if nws else None
     check(L.egnn_gemm(ptr(A), dt(A), a_sm, a_sk, ptr(B), dt(B), b_sk, b_sn, ptr(C), dt(C), _ld(C), M, N, K,
-                      ptr(bias), int(accumulate), split_k, ptr(ws), impl, stream()))
+                      ptr(bias), ptr(row_div), int(accumulate), split_k, ptr(ws),
+                      GEMM_IMPL if impl is None else impl, stream()))
 
 
-def linear_fwd(x, W, bias=None, out=None, accumulate=False, out_dtype=None, impl=0):
+def linear_fwd(x, W, bias=None, out=None, accumulate=False, out_dtype=None, impl=None):
     """out[M,N] (+)= x[M,K] @ W[N,K]^T (+ bias)."""
     x, W = _rows(x), _rows(W)
     M, K = x.shape
@@ -92,18 +97,23 @@ def linear_fwd(x, W, bias=None, out=None, accumulate=False, out_dtype=None, impl
     return out
 
 
-def linear_dgrad(g, W, out=None, accumulate=False, out_dtype=None):
-    """out[M,K] (+)= g[M,N] @ W[N,K]."""
+def linear_dgrad(g, W, out=None, accumulate=False, out_dtype=None, row_div=None, impl=None):
+    """out[M,K] (+)= g[M,N] @ W[N,K]; `row_div` = CSR row pointer whose row counts divide the rows
+    of the result (SAGE mean backward: dsum = dm / cnt, fused into the GEMM epilogue)."""
     g, W = _rows(g), _rows(W)
     M, N = g.shape
     K = W.size(1)
     if out is None:
         out = torch.empty((M, K), dtype=out_dtype or g.dtype, device=g.device)
-    _gemm(g, _ld(g), 1, W, _ld(W), 1, out, M, K, N, None, accumulate)
+    if g.dtype == torch.bfloat16 and W.dtype == torch.bfloat16 and (GEMM_IMPL if impl is None else impl) != 1:
+        Wt = W.t().contiguous()  # [K, N]: contraction-contiguous B operand for the tcgen05 kernel
+        _gemm(g, _ld(g), 1, Wt, 1, _ld(Wt), out, M, K, N, None, accumulate, row_div=row_div, impl=impl)
+    else:
+        _gemm(g, _ld(g), 1, W, _ld(W), 1, out, M, K, N, None, accumulate, row_div=row_div, impl=impl)
     return out
 
 
-def linear_wgrad(g, x):
+def linear_wgrad(g, x, impl=None):
     """dW[N,K] = g[M,N]^T @ x[M,K], fp32, deterministic split over the node axis."""
     g, x = _rows(g), _rows(x)
     M, N = g.shape
@@ -111,7 +121,7 @@ def linear_wgrad(g, x):
     out = torch.empty((N, K), dtype=torch.float32, device=g.device)
     tiles = -(-N // 128) * -(-K // 64)
     split = max(1, min(-(-M // 512), -(-2 * 148 // tiles)))
-    _gemm(g, 1, _ld(g), x, _ld(x), 1, out, N, K, M, None, False, split_k=split)
+    _gemm(g, 1, _ld(g), x, _ld(x), 1, out, N, K, M, None, False, split_k=split, impl=impl, need_ws=True)
     return out
 
 
@@ -165,9 +175,9 @@ class SageConvFn(torch.autograd.Function):
         db = colsum(dz).float()
         dx = None
         if ctx.needs_input_grad[0]:
-            dm = linear_dgrad(dz, wl)
+            dm = linear_dgrad(dz, wl, row_div=g.csr_ptr)   # dm / in-degree, fused in the GEMM epilogue
             dx = linear_dgrad(dz, wr)
-            spmm(g, "csc", _lib.SPMM_DIV_NBR, dm, dx.dtype, out=dx, accumulate=True)
+            spmm(g, "csc", _lib.SPMM_SUM, dm, dx.dtype, out=dx, accumulate=True)
             if dx.dtype != ctx.x_dtype:
                 dx = cast(dx, ctx.x_dtype)
         return dx, dwl, db, dwr, None, None

@@ -112,16 +112,19 @@ int egnn_spmm(int mode, const int32_t* ptr, const int32_t* col, const float* w,
  * A[m*a_sm + k*a_sk], element (k,n) of op(B) at B[k*b_sk + n*b_sn]; C row-major with ld_c.
  * Covers Linear forward (x W^T), dgrad (g W) and wgrad (g^T x) of torch_geometric's
  * nn.dense.Linear / torch.nn.Linear (src/models/gnn.py:141-144 and the convs' lin*).
- * fp32 accumulate always.  impl: 0 = auto, 1 = SIMT FFMA, 2 = tcgen05 (bf16 inputs,
- * K-major A and B only; error if the shape is not supported).
+ * fp32 accumulate always.  row_div_ptr (optional CSR row pointer, int32 [M+1]): row m of the
+ * result is divided by max(ptr[m+1]-ptr[m], 1) -- the 1/deg of SAGE's mean backward, fused.
+ * impl: 0 = auto, 1 = SIMT FFMA (exact-fp32 parity path), 2 = tcgen05 only (bf16 operands, either
+ * both contiguous along the contraction -- forward/dgrad -- or both contiguous along the other
+ * dimension with fp32 dense C -- wgrad; error if the shape is not supported).
  * split_k > 1 (and every M <= 8 reduction) needs egnn_gemm_workspace_floats(...) floats of
  * workspace; partials are reduced in a fixed order (deterministic).
  */
 size_t egnn_gemm_workspace_floats(int64_t M, int64_t N, int64_t K, int split_k);
 int egnn_gemm(const void* A, int a_dtype, int64_t a_sm, int64_t a_sk, const void* B, int b_dtype,
               int64_t b_sk, int64_t b_sn, void* C, int c_dtype, int64_t ld_c, int64_t M,
-              int64_t N, int64_t K, const float* bias, int accumulate, int split_k,
-              float* workspace, int impl, void* stream);
+              int64_t N, int64_t K, const float* bias, const int32_t* row_div_ptr, int accumulate,
+              int split_k, float* workspace, int impl, void* stream);
 
 /* cast / copy with optional column padding: out[r, 0:F] = in[r, 0:F], out[r, F:ld_out] = 0 */
 int egnn_cast(const void* in, int in_dtype, int64_t ld_in, void* out, int out_dtype,

@@ -184,6 +184,8 @@ def test_net_train_step_fp32(egnn, small_graph, name, with_dropout):
                      lr=cfg["lr"], weight_decay=cfg["wd"], grad_clip=1.0, amp=False, cw=cw)
     opt_ref = torch.optim.Adam(ref.parameters(), lr=cfg["lr"], weight_decay=cfg["wd"])
     for it in range(2):
+        if it > 0:  # re-synchronise so every iteration checks the kernels, not the Adam-amplified drift
+            ref.load_state_dict({k: v.detach().cpu() for k, v in ours.state_dict().items()})
         loss_o = step.run()
         grads_o = {n: p.grad.detach().clone() for n, p in ours.named_parameters()}
         masks = None

@@ -1,0 +1,85 @@
+"""K6 tensor-core path: the tcgen05/TMA bf16 kernels against an fp64 matmul of the same
+bf16-rounded operands (fp32 accumulation: only summation-order error remains) and against
+the SIMT path; plus epilogue options (bias, accumulate, row-count division, fp32/bf16 out)."""
+import pytest
+import torch
+
+from util import assert_close
+
+pytestmark = pytest.mark.gpu
+
+TOL = 2e-6  # fp32 accumulation of exact bf16 products, relative to ||ref||_inf
+
+
+def _mk(shape, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(shape, generator=g).bfloat16().cuda()
+
+
+@pytest.mark.parametrize("M", [1, 127, 128, 129, 5000, 203769])
+@pytest.mark.parametrize("K,N", [(168, 64), (64, 64), (64, 168), (40, 32), (336, 128), (64, 8), (72, 24), (256, 256)])
+def test_tn_fwd_matches_fp64(egnn, M, K, N):
+    from egnn_b200 import ops
+    if M == 203769 and (K, N) not in ((168, 64), (64, 168)):
+        pytest.skip("full-size case kept to the bench shapes")
+    a, w = _mk((M, K), 1), _mk((N, K), 2)
+    ref = (a.double() @ w.double().t())
+    out = ops.linear_fwd(a, w, out_dtype=torch.float32, impl=2)
+    assert_close(out, ref, TOL, "tcgen05 fwd fp32 out")
+    out_simt = ops.linear_fwd(a, w, out_dtype=torch.float32, impl=1)
+    assert_close(out, out_simt, 2 * TOL, "tcgen05 vs SIMT")
+    outb = ops.linear_fwd(a, w, out_dtype=torch.bfloat16, impl=2)
+    assert torch.equal(outb, out.bfloat16()) or (outb.float() - ref.float()).abs().max() <= ref.abs().max() * 2 ** -8
+
+
+def test_tn_epilogues(egnn):
+    from egnn_b200 import ops
+    M, K, N = 3000, 168, 64
+    a, w = _mk((M, K), 3), _mk((N, K), 4)
+    bias = torch.randn(N, device="cuda")
+    ref = a.double() @ w.double().t() + bias.double()
+    out = ops.linear_fwd(a, w, bias=bias, out_dtype=torch.float32, impl=2)
+    assert_close(out, ref, TOL, "bias")
+    base = torch.randn(M, N, device="cuda")
+    acc = base.clone()
+    ops.linear_fwd(a, w, out=acc, accumulate=True, impl=2)
+    assert_close(acc, base.double() + a.double() @ w.double().t(), TOL, "accumulate fp32")
+    accb = base.bfloat16()
+    ops.linear_fwd(a, w, out=accb, accumulate=True, impl=2)
+    assert_close(accb.float(), base.bfloat16().double() + a.double() @ w.double().t(), 2 ** -7, "accumulate bf16")
+    # row-count division through a CSR pointer
+    cnt = torch.randint(0, 5, (M,))
+    ptr = torch.zeros(M + 1, dtype=torch.int32)
+    ptr[1:] = torch.cumsum(cnt, 0)
+    g, wt = _mk((M, N), 5), _mk((N, K), 6)
+    d = ops.linear_dgrad(g, wt, out_dtype=torch.float32, row_div=ptr.cuda(), impl=2)
+    refd = (g.double() @ wt.double()) / cnt.clamp(min=1).double().cuda().unsqueeze(1)
+    assert_close(d, refd, TOL, "dgrad + row_div")
+    d1 = ops.linear_dgrad(g, wt, out_dtype=torch.float32, row_div=ptr.cuda(), impl=1)
+    assert_close(d1, refd, TOL, "SIMT dgrad + row_div")
+
+
+@pytest.mark.parametrize("M", [1, 63, 64, 65, 6000, 203769])
+@pytest.mark.parametrize("N,K", [(64, 168), (64, 64), (128, 128), (8, 64), (32, 168), (128, 256), (16, 40)])
+def test_wgrad_matches_fp64(egnn, M, N, K):
+    from egnn_b200 import ops
+    if M == 203769 and (N, K) not in ((64, 168), (64, 64)):
+        pytest.skip("full-size case kept to the bench shapes")
+    g, x = _mk((M, N), 7), _mk((M, K), 8)
+    ref = g.double().t() @ x.double()
+    if M < 1024:
+        out = ops.linear_wgrad(g, x)  # short reductions stay on the SIMT path
+    else:
+        out = ops.linear_wgrad(g, x, impl=2)
+        again = ops.linear_wgrad(g, x, impl=2)
+        assert torch.equal(out, again)  # deterministic partial reduction
+    assert_close(out, ref, 5e-6, "wgrad")
+
+
+def test_unsupported_layout_fails_loudly(egnn):
+    from egnn_b200 import ops
+    a, w = torch.randn(100, 30, device="cuda").bfloat16(), torch.randn(8, 30, device="cuda").bfloat16()
+    with pytest.raises(RuntimeError, match="tcgen05"):
+        ops.linear_fwd(a, w, impl=2)  # lda = 30 is not a multiple of 8 (TMA needs 16-byte strides)
+    out = ops.linear_fwd(a, w)        # auto falls back to the SIMT *CUDA* kernel, never to CPU
+    assert_close(out.float(), a.double() @ w.double().t(), 2 ** -7, "auto")
