@@ -363,10 +363,26 @@ __global__ void __launch_bounds__(kThreads) collect_long_rows(const int* __restr
   if (ptr[i + 1] - ptr[i] > threshold) list[atomicAdd(n_long, 1)] = (int)i;
 }
 
+// key for the longest-rows-first schedule, applied inside tiles of 32768 consecutive rows so that a
+// wave of CTAs still works on one timestep's feature rows (L2 locality) while every tile starts
+// with its longest rows: key = tile << 7 | (64 - min(deg, 64)); stable sort => deterministic
+__global__ void __launch_bounds__(kThreads) degree_keys(const int* __restrict__ ptr, int64_t n_nodes,
+                                                        int* __restrict__ keys, int* __restrict__ n_dev) {
+  int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i == 0) *n_dev = (int)n_nodes;
+  if (i >= n_nodes) return;
+  int d = ptr[i + 1] - ptr[i];
+  keys[i] = (int)((i >> 15) << 7) | (64 - (d < 64 ? d : 64));
+}
+__global__ void __launch_bounds__(kThreads) copy_ints(const int* __restrict__ src, int64_t n, int* __restrict__ dst) {
+  int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+
 inline size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
 
 struct Workspace {
-  int *src32, *dst32, *keysA, *keysB, *valsA, *valsB, *inv, *keep, *counts, *table, *tile_sums;
+  int *src32, *dst32, *keysA, *keysB, *valsA, *valsB, *inv, *keep, *counts, *table, *tile_sums, *deg_keys, *n_dev;
   size_t bytes;
 };
 
@@ -378,17 +394,20 @@ Workspace carve(char* base, int64_t n_nodes, int64_t E_log, int64_t cap) {
     off += align_up((size_t)n_int * sizeof(int));
     return p;
   };
-  int64_t nblk = ceil_div(cap, kSortTile);
+  int64_t sort_n = cap > n_nodes ? cap : n_nodes;  // the row-order sort re-uses the radix buffers
+  int64_t nblk = ceil_div(sort_n, kSortTile);
   int64_t table_n = 256 * nblk;
   int64_t longest = cap;
   if (n_nodes + 1 > longest) longest = n_nodes + 1;
   if (table_n > longest) longest = table_n;
   w.src32 = take(cap);
   w.dst32 = take(cap);
-  w.keysA = take(cap);
-  w.keysB = take(cap);
-  w.valsA = take(cap);
-  w.valsB = take(cap);
+  w.keysA = take(sort_n);
+  w.keysB = take(sort_n);
+  w.valsA = take(sort_n);
+  w.valsB = take(sort_n);
+  w.deg_keys = take(n_nodes);
+  w.n_dev = take(4);
   w.inv = take(cap);
   w.keep = take(E_log + 1);
   w.counts = take(n_nodes + 2);
@@ -439,7 +458,7 @@ extern "C" int egnn_graph_build(const int64_t* ei, int64_t E, int64_t n_nodes, i
                                 int want_norm, int32_t* info, int32_t* csr_ptr, int32_t* csr_src,
                                 int32_t* csr_eid, int32_t* csc_ptr, int32_t* csc_dst,
                                 int32_t* csc_pos, int32_t* csr_long, int32_t* csc_long,
-                                int64_t* ei2, float* dis, float* w_edge,
+                                int32_t* csr_order, int32_t* csc_order, int64_t* ei2, float* dis, float* w_edge,
                                 float* w_csr, float* w_csc, void* workspace,
                                 size_t workspace_bytes, void* stream) {
   const char* fn = "egnn_graph_build";
@@ -501,6 +520,28 @@ extern "C" int egnn_graph_build(const int64_t* ei, int64_t E, int64_t n_nodes, i
       collect_long_rows<<<(unsigned)ceil_div(n_nodes, kThreads), kThreads, 0, st>>>(ptr, n_nodes, 64, long_list,
                                                                                   info + 2 + view);
       EGNN_LAUNCH_CHECK("collect_long_rows");
+    }
+    int* order = view == 0 ? csr_order : csc_order;
+    if (order) {
+      const unsigned gN = (unsigned)ceil_div(n_nodes, kThreads);
+      degree_keys<<<gN, kThreads, 0, st>>>(ptr, n_nodes, w.deg_keys, w.n_dev);
+      EGNN_LAUNCH_CHECK("degree_keys");
+      // consume the edge permutation before the radix buffers are re-used
+      if (view == 0) {
+        gather_csr<<<gC, kThreads, 0, st>>>(perm, w.src32, n_ptr, cap1, csr_src, csr_eid, w.inv);
+        EGNN_LAUNCH_CHECK("gather_csr");
+      } else {
+        gather_csc<<<gC, kThreads, 0, st>>>(perm, w.dst32, w.inv, n_ptr, cap1, csc_dst, csc_pos);
+        EGNN_LAUNCH_CHECK("gather_csc");
+      }
+      int* rperm = nullptr;
+      int obits = 7;
+      while (((int64_t)1 << (obits - 7)) < ceil_div(n_nodes, 32768)) ++obits;
+      rc = radix_sort_perm(w.deg_keys, w.n_dev, n_nodes, obits, w, &rperm, st);
+      if (rc) return rc;
+      copy_ints<<<gN, kThreads, 0, st>>>(rperm, n_nodes, order);
+      EGNN_LAUNCH_CHECK("copy_ints");
+      continue;
     }
     if (view == 0) {
       gather_csr<<<gC, kThreads, 0, st>>>(perm, w.src32, n_ptr, cap1, csr_src, csr_eid, w.inv);

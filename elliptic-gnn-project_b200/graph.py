@@ -33,6 +33,8 @@ class Graph:
     csc_pos: torch.Tensor          # int32[cap]  position in CSR order
     csr_long: torch.Tensor         # int32[cap/64+1]
     csc_long: torch.Tensor
+    csr_order: torch.Tensor        # int32[N] destination rows by descending in-degree (SpMM schedule)
+    csc_order: torch.Tensor        # int32[N] source rows by descending out-degree
     ei2: Optional[torch.Tensor] = None     # int64[2,cap] expanded edge list (debug/parity)
     dis: Optional[torch.Tensor] = None     # float[N]   deg^-1/2
     w_edge: Optional[torch.Tensor] = None  # float[cap] gcn_norm in ei2 order
@@ -82,6 +84,7 @@ def build_graph(edge_index: torch.Tensor, num_nodes: int, symmetrize: bool = Fal
         csr_ptr=torch.empty(N + 1, **i32), csr_src=torch.empty(cap, **i32), csr_eid=torch.empty(cap, **i32),
         csc_ptr=torch.empty(N + 1, **i32), csc_dst=torch.empty(cap, **i32), csc_pos=torch.empty(cap, **i32),
         csr_long=torch.empty(cap // 64 + 1, **i32), csc_long=torch.empty(cap // 64 + 1, **i32),
+        csr_order=torch.empty(N, **i32), csc_order=torch.empty(N, **i32),
         ei2=torch.empty(2, cap, dtype=torch.int64, device=dev) if keep_edge_list else None,
         dis=torch.empty(N, dtype=torch.float32, device=dev) if norm else None,
         w_edge=torch.empty(cap, dtype=torch.float32, device=dev) if (norm and keep_edge_list) else None,
@@ -93,7 +96,7 @@ def build_graph(edge_index: torch.Tensor, num_nodes: int, symmetrize: bool = Fal
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     check(L.egnn_graph_build(ptr(ei), E, N, flags, int(want_norm), ptr(g.info), ptr(g.csr_ptr), ptr(g.csr_src),
                              ptr(g.csr_eid), ptr(g.csc_ptr), ptr(g.csc_dst), ptr(g.csc_pos), ptr(g.csr_long),
-                             ptr(g.csc_long), ptr(g.ei2), ptr(g.dis), ptr(g.w_edge), ptr(g.w_csr),
+                             ptr(g.csc_long), ptr(g.csr_order), ptr(g.csc_order), ptr(g.ei2), ptr(g.dis), ptr(g.w_edge), ptr(g.w_csr),
                              ptr(g.w_csc), ptr(ws), ws_bytes, stream()))
     if validate and not torch.cuda.is_current_stream_capturing():
         bad = int(g.info[1].item())

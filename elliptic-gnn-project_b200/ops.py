@@ -62,12 +62,12 @@ def spmm(g: Graph, view: str, mode: int, x: torch.Tensor, out_dtype: torch.dtype
     if out is None:
         out = torch.empty((n, x.size(1)), dtype=out_dtype, device=x.device)
     if view == "csr":
-        p, c, w, long_rows, vi, nbr = g.csr_ptr, g.csr_src, g.w_csr, g.csr_long, 0, g.csc_ptr
+        p, c, w, long_rows, vi, nbr, order = g.csr_ptr, g.csr_src, g.w_csr, g.csr_long, 0, g.csc_ptr, g.csr_order
     else:
-        p, c, w, long_rows, vi, nbr = g.csc_ptr, g.csc_dst, g.w_csc, g.csc_long, 1, g.csr_ptr
+        p, c, w, long_rows, vi, nbr, order = g.csc_ptr, g.csc_dst, g.w_csc, g.csc_long, 1, g.csr_ptr, g.csc_order
     n_long = g.info.data_ptr() + 4 * (2 + vi)
     check(lib().egnn_spmm(mode, ptr(p), ptr(c), ptr(w) if mode == _lib.SPMM_WEIGHTED else None,
-                          ptr(nbr) if mode == _lib.SPMM_DIV_NBR else None, ptr(long_rows), n_long, ptr(x),
+                          ptr(nbr) if mode == _lib.SPMM_DIV_NBR else None, ptr(long_rows), n_long, ptr(order), ptr(x),
                           dt(x), _ld(x), ptr(out), dt(out), _ld(out), n, x.size(1), ptr(bias), act,
                           int(accumulate), stream()))
     return out

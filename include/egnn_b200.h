@@ -72,6 +72,8 @@ uint64_t egnn_launch_count(void);
  *   csc_pos   int32 [cap] : position of that edge in CSR order (addresses per-edge arrays)
  *   csr_long  int32 [cap/64+1] or NULL : destination rows with more than 64 in-edges (any order)
  *   csc_long  int32 [cap/64+1] or NULL : source rows with more than 64 out-edges (any order)
+ *   csr_order int32 [N] or NULL : destination rows sorted by DESCENDING in-degree (stable); the
+ *   csc_order int32 [N] or NULL   SpMM walks rows in this order (longest rows first: no tail)
  *   ei2       int64 [2,cap] or NULL : the expanded edge list itself (parity checks)
  *   dis       float [N]   or NULL : deg^-1/2 = rn(1/rn(sqrt(deg))), 0 where deg == 0
  *   w_edge    float [cap] or NULL : gcn_norm weights in ei2 order
@@ -83,7 +85,8 @@ size_t egnn_graph_workspace_bytes(int64_t n_nodes, int64_t n_edges_in, int flags
 int egnn_graph_build(const int64_t* ei, int64_t n_edges_in, int64_t n_nodes, int flags,
                      int want_norm, int32_t* info, int32_t* csr_ptr, int32_t* csr_src,
                      int32_t* csr_eid, int32_t* csc_ptr, int32_t* csc_dst, int32_t* csc_pos,
-                     int32_t* csr_long, int32_t* csc_long, int64_t* ei2, float* dis, float* w_edge, float* w_csr, float* w_csc,
+                     int32_t* csr_long, int32_t* csc_long, int32_t* csr_order, int32_t* csc_order,
+                     int64_t* ei2, float* dis, float* w_edge, float* w_csr, float* w_csc,
                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------- K2/K3: SpMM --------- */
@@ -98,12 +101,14 @@ int egnn_graph_build(const int64_t* ei, int64_t n_edges_in, int64_t n_nodes, int
  *            row c by max(nbr_ptr[c+1]-nbr_ptr[c],1)) else NULL
  *   long_rows/n_long  (both NULL or both set) list of rows with more than 64 entries and its
  *            device-side length, from egnn_graph_build; those rows take the whole-CTA path
+ *   row_order int32 [n_rows] or NULL: processing order of the rows (egnn_graph_build's
+ *            descending-degree order); results do not depend on it
  *   bias     float [F] or NULL, added after the reduction; act = EGNN_ACT_*
  *   accumulate != 0: out += result (one rounding in out dtype after an fp32 add)
  */
 int egnn_spmm(int mode, const int32_t* ptr, const int32_t* col, const float* w,
               const int32_t* nbr_ptr, const int32_t* long_rows, const int32_t* n_long,
-              const void* in, int in_dtype, int64_t ld_in, void* out,
+              const int32_t* row_order, const void* in, int in_dtype, int64_t ld_in, void* out,
               int out_dtype, int64_t ld_out, int64_t n_rows, int64_t n_feat, const float* bias,
               int act, int accumulate, void* stream);
 

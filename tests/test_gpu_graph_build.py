@@ -45,6 +45,12 @@ def _check(egnn, ei_cpu, n, symmetrize, self_loops):
     assert np.array_equal(bits(g.w_edge[:E2].cpu().numpy()), bits(w))
     assert np.array_equal(bits(g.w_csr[:E2].cpu().numpy()), bits(w[csr_eid]))
     assert np.array_equal(bits(g.w_csc[:E2].cpu().numpy()), bits(w[csc_eid]))
+    # longest-rows-first schedule inside 32768-row tiles (a stable permutation)
+    for ptr_, order in ((g.csr_ptr, g.csr_order), (g.csc_ptr, g.csc_order)):
+        d = np.minimum(np.diff(ptr_.cpu().numpy()), 64)
+        key = (np.arange(n) >> 15) * 128 + (64 - d)   # descending degree inside 32768-row tiles
+        want = np.argsort(key, kind="stable")
+        assert np.array_equal(order.cpu().numpy(), want)
     # long-row lists
     for view, ptr_ in ((0, g.csr_ptr), (1, g.csc_ptr)):
         d = np.diff(ptr_.cpu().numpy())
