@@ -36,18 +36,18 @@ SIGNATURES = {
                          _vp, _i32, _i32, _vp]),
     "egnn_gemm_workspace_floats": (_sz, [_i64, _i64, _i64, _i32]),
     "egnn_gemm": (_i32, [_vp, _i32, _i64, _i64, _vp, _i32, _i64, _i64, _vp, _i32, _i64, _i64, _i64, _i64,
-                         _vp, _vp, _i32, _i32, _vp, _i32, _vp]),
+                         _vp, _vp, _i64, _i32, _i32, _vp, _i32, _vp]),
     "egnn_cast": (_i32, [_vp, _i32, _i64, _vp, _i32, _i64, _i64, _i64, _vp]),
-    "egnn_inject_time": (_i32, [_vp, _i64, _vp, _vp, _i64, _i64, _vp, _vp, _i64, _i64, _i64, _vp]),
+    "egnn_inject_time": (_i32, [_vp, _i64, _vp, _vp, _i64, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _vp]),
     "egnn_colreduce_workspace_bytes": (_sz, [_i64]),
     "egnn_colreduce": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "egnn_bn_finalize": (_i32, [_vp, _vp, _f64, _i64, _f32, _f32, _vp, _vp, _vp, _vp, _vp]),
     "egnn_bn_act_dropout_res_fwd": (_i32, [_vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i32,
-                                           _f32, _u64, _vp, _u32, _i64, _vp]),
+                                           _f32, _u64, _vp, _u32, _i64, _i64, _i64, _vp]),
     "egnn_bn_act_dropout_bwd_reduce": (_i32, [_vp, _vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i32,
-                                              _f32, _u64, _vp, _u32, _i64, _vp, _vp, _vp, _vp]),
+                                              _f32, _u64, _vp, _u32, _i64, _vp, _vp, _vp, _i64, _vp]),
     "egnn_bn_act_dropout_bwd_apply": (_i32, [_vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i32,
-                                             _f32, _u64, _vp, _u32, _i64, _vp, _vp, _f64, _vp]),
+                                             _f32, _u64, _vp, _u32, _i64, _vp, _vp, _f64, _vp, _vp, _i64, _vp]),
     "egnn_dropout_mask": (_i32, [_vp, _i64, _i64, _f32, _u64, _vp, _u32, _i64, _vp]),
     "egnn_gat_scores": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "egnn_gat_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _f32, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _vp]),
@@ -57,6 +57,12 @@ SIGNATURES = {
                                 _i64, _vp]),
     "egnn_gat_att_grad": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp]),
     "egnn_ce_workspace_floats": (_sz, [_i64]),
+    "egnn_skinny_project": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _i32, _vp, _vp]),
+    "egnn_sage_out_fwd": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _i64, _vp]),
+    "egnn_sage_out_bwd": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _i64, _vp]),
+    "egnn_skinny_wgrad_workspace_floats": (_sz, [_i64, _i64, _i32]),
+    "egnn_skinny_wgrad": (_i32, [_vp, _i32, _i64, _vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "egnn_skinny_dgrad": (_i32, [_vp, _vp, _i32, _vp, _i32, _i64, _i64, _i64, _vp]),
     "egnn_masked_ce": (_i32, [_vp, _i32, _i64, _vp, _vp, _i64, _vp, _f64, _vp, _vp, _vp, _vp]),
     "egnn_adam_workspace_floats": (_sz, [_i64]),
     "egnn_clip_adam_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _vp, _vp,

@@ -6,6 +6,8 @@
 #include "common.cuh"
 #include "philox.cuh"
 
+#include <initializer_list>
+
 namespace egnn {
 namespace {
 
@@ -55,31 +57,41 @@ __global__ void __launch_bounds__(kThreads) cast_kernel(const TI* __restrict__ i
 }
 
 // ---- time-feature injection ----------------------------------------------------------------
+constexpr int kInjectRows = 32;  // rows per block
 __global__ void __launch_bounds__(kThreads) inject_time_kernel(
     const float* __restrict__ x, int64_t ld_x, const int64_t* __restrict__ t,
     const float* __restrict__ table, int64_t T, int D, float* __restrict__ o32,
-    __nv_bfloat16* __restrict__ o16, int64_t ld_out, int64_t n_rows, int F) {
+    __nv_bfloat16* __restrict__ o16, int64_t ld_out, int64_t ld_out16, int64_t n_rows, int F) {
   const int W2 = (int)(ld_out / 2);  // ld_out is even (multiple of 4)
-  int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  if (i >= n_rows * W2) return;
-  int64_t r = i / W2;
-  int c = (int)(i - r * W2) * 2;
-  float v[2];
-#pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    int cc = c + k;
-    if (cc < F) {
-      v[k] = __ldg(x + r * ld_x + cc);
-    } else if (cc < F + D) {
-      int64_t ti = t[r] - 1;
-      ti = ti < 0 ? 0 : (ti > T - 1 ? T - 1 : ti);
-      v[k] = __ldg(table + ti * D + (cc - F));
+  const int64_t row0 = (int64_t)blockIdx.x * kInjectRows;
+  const int nr = (int)min((int64_t)kInjectRows, n_rows - row0);
+  const bool x2 = (ld_x % 2 == 0) && ((uintptr_t)x % 8 == 0);  // 8-byte loads of x pairs
+  for (int j = threadIdx.x; j < nr * W2; j += kThreads) {
+    const int rr = j / W2;
+    const int c = (j - rr * W2) * 2;
+    const int64_t r = row0 + rr;
+    float v[2];
+    if (x2 && c + 1 < F) {
+      const float2 p = __ldg(reinterpret_cast<const float2*>(x + r * ld_x + c));
+      v[0] = p.x; v[1] = p.y;
     } else {
-      v[k] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int cc = c + k;
+        if (cc < F) {
+          v[k] = __ldg(x + r * ld_x + cc);
+        } else if (cc < F + D) {
+          int64_t ti = t[r] - 1;
+          ti = ti < 0 ? 0 : (ti > T - 1 ? T - 1 : ti);
+          v[k] = __ldg(table + ti * D + (cc - F));
+        } else {
+          v[k] = 0.f;
+        }
+      }
     }
+    if (o32) *reinterpret_cast<float2*>(o32 + r * ld_out + c) = make_float2(v[0], v[1]);
+    if (o16) *reinterpret_cast<uint32_t*>(o16 + r * ld_out16 + c) = pack_bf16x2(v[0], v[1]);
   }
-  if (o32) *reinterpret_cast<float2*>(o32 + r * ld_out + c) = make_float2(v[0], v[1]);
-  if (o16) *reinterpret_cast<uint32_t*>(o16 + r * ld_out + c) = pack_bf16x2(v[0], v[1]);
 }
 
 // ---- fused BN / activation / dropout element math ------------------------------------------
@@ -319,6 +331,328 @@ int run_colreduce(const Prod& prod, int64_t n_rows, int F, double* out0, double*
   return 0;
 }
 
+// ---- fast path: 8 columns per thread, column constants in registers, rows looped ---------------
+// Used when F % 8 == 0, F/8 is a power of two <= 256 and every pointer is 16-byte aligned with
+// ld % 8 == 0 (the hidden widths 32 / 64 / 128 of the reference configs).  A thread owns 8 fixed
+// columns and walks rows; per-column BatchNorm constants are loaded once.  Same element math as
+// act_eval (the generic kernels remain the fallback for ragged shapes).
+template <typename T>
+__device__ __forceinline__ void ld8f(const T* p, float (&v)[8]);
+template <>
+__device__ __forceinline__ void ld8f<float>(const float* p, float (&v)[8]) {
+  float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void ld8f<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+  F8 r = ld8(p);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = r.v[i];
+}
+__device__ __forceinline__ void st8f(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *(reinterpret_cast<float4*>(p) + 1) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void st8f(__nv_bfloat16* p, const float (&v)[8]) {
+  F8 r;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r.v[i] = v[i];
+  st8(p, r);
+}
+
+// raw 8-element loads (held packed while the next iteration's loads are in flight)
+template <typename T>
+struct Raw8;
+template <>
+struct Raw8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) {
+    a = __ldg(reinterpret_cast<const float4*>(p));
+    b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  }
+  __device__ __forceinline__ void unpack(float (&v)[8]) const {
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+};
+template <>
+struct Raw8<__nv_bfloat16> {
+  uint4 q;
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) { q = __ldg(reinterpret_cast<const uint4*>(p)); }
+  __device__ __forceinline__ void unpack(float (&v)[8]) const {
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+};
+
+constexpr int kFastMaxF = 512;  // widths served by the fast kernels (column constants in shared memory)
+
+// per-column BatchNorm constants staged in shared memory (keeps the streaming loops under 64 registers)
+struct ColConsts {
+  float mean[kFastMaxF], rstd[kFastMaxF], gamma[kFastMaxF], beta[kFastMaxF];
+};
+__device__ __forceinline__ void stage_consts(const ActCtx& C, int F, ColConsts& k) {
+  for (int i = threadIdx.x; i < F; i += kThreads) {
+    k.mean[i] = C.mean ? C.mean[i] : 0.f;
+    k.rstd[i] = C.mean ? C.rstd[i] : 1.f;
+    k.gamma[i] = C.mean ? C.gamma[i] : 1.f;
+    k.beta[i] = C.mean ? C.beta[i] : 0.f;
+  }
+}
+// y = dropout(act(bn(z))), dfac = dy/du, xhat for 8 columns starting at c (c % 8 == 0) of row r
+__device__ __forceinline__ void act_eval8(const ActCtx& C, const ColConsts& k, uint64_t seed, int64_t r, int c,
+                                          const float (&z)[8], float (&y)[8], float (&dfac)[8],
+                                          float (&xhat)[8]) {
+  uint32_t words[8];
+  if (C.drop) {
+    Philox4 w0 = dropout_words(seed, C.layer, C.row0 + r, (uint32_t)(c >> 2));
+    Philox4 w1 = dropout_words(seed, C.layer, C.row0 + r, (uint32_t)(c >> 2) + 1u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { words[i] = w0.v[i]; words[4 + i] = w1.v[i]; }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float u = z[i];
+    xhat[i] = 0.f;
+    if (C.mean) {
+      xhat[i] = (z[i] - k.mean[c + i]) * k.rstd[c + i];
+      u = xhat[i] * k.gamma[c + i] + k.beta[c + i];
+    }
+    float a = u, da = 1.f;
+    if (C.act == EGNN_ACT_RELU) {
+      a = u > 0.f ? u : 0.f;
+      da = u > 0.f ? 1.f : 0.f;
+    } else if (C.act == EGNN_ACT_ELU) {
+      float e = expm1f(u);
+      a = u > 0.f ? u : e;
+      da = u > 0.f ? 1.f : e + 1.f;
+    }
+    float ks = 1.f;
+    if (C.drop) ks = words[i] >= C.thr ? C.scale : 0.f;
+    y[i] = a * ks;
+    dfac[i] = da * ks;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) bn_act_fwd_fast(const T* __restrict__ z, const T* __restrict__ res,
+                                                            T* __restrict__ yout, int64_t ld, int64_t ld_res,
+                                                            int64_t ld_y,
+                                                            int64_t n_rows, int F, int cg_shift,
+                                                            int64_t rows_per_block, ActCtx C) {
+  __shared__ ColConsts k;
+  stage_consts(C, F, k);
+  __syncthreads();
+  const int CG = 1 << cg_shift, RL = kThreads >> cg_shift;
+  const int c = (threadIdx.x & (CG - 1)) * 8, rl = threadIdx.x >> cg_shift;
+  const uint64_t seed = C.seed + (C.seed_off ? (uint64_t)*C.seed_off : 0ull);
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(n_rows, r0 + rows_per_block);
+  Raw8<T> zr, rr, zn, rn;
+  int64_t r = r0 + rl;
+  if (r < r1) {
+    zr.load(z + r * ld + c);
+    if (res) rr.load(res + r * ld_res + c);
+  }
+#pragma unroll 1
+  for (; r < r1; r += RL) {
+    if (r + RL < r1) {  // next row's loads in flight while this row is processed
+      zn.load(z + (r + RL) * ld + c);
+      if (res) rn.load(res + (r + RL) * ld_res + c);
+    }
+    float zv[8], rv[8], y[8], d[8], xh[8];
+    zr.unpack(zv);
+    if (res) rr.unpack(rv);
+    zr = zn; rr = rn;
+    act_eval8(C, k, seed, r, c, zv, y, d, xh);
+    if (res) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) y[i] += rv[i];
+    }
+    st8f(yout + r * ld_y + c, y);
+  }
+}
+
+// partial[(blk*2 + which)*F + col] (double), which: 0 = sum g, 1 = sum g*xhat
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 3) bn_act_bwd_reduce_fast(const T* __restrict__ dy, int64_t ld_dy,
+                                                                   const T* __restrict__ z, int64_t ld,
+                                                                   int64_t n_rows, int F, int cg_shift,
+                                                                   int64_t rows_per_block, ActCtx C,
+                                                                   double* __restrict__ partial) {
+  __shared__ ColConsts k;
+  __shared__ float sm[kThreads][17];
+  stage_consts(C, F, k);
+  __syncthreads();
+  const int CG = 1 << cg_shift, RL = kThreads >> cg_shift;
+  const int cgi = threadIdx.x & (CG - 1), c = cgi * 8, rl = threadIdx.x >> cg_shift;
+  const uint64_t seed = C.seed + (C.seed_off ? (uint64_t)*C.seed_off : 0ull);
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(n_rows, r0 + rows_per_block);
+  float a0[8], a1[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a0[i] = a1[i] = 0.f;
+  Raw8<T> zr, gr, zn, gn;
+  int64_t r = r0 + rl;
+  if (r < r1) { zr.load(z + r * ld + c); gr.load(dy + r * ld_dy + c); }
+#pragma unroll 1
+  for (; r < r1; r += RL) {
+    if (r + RL < r1) { zn.load(z + (r + RL) * ld + c); gn.load(dy + (r + RL) * ld_dy + c); }
+    float zv[8], g[8], y[8], d[8], xh[8];
+    zr.unpack(zv); gr.unpack(g);
+    zr = zn; gr = gn;
+    act_eval8(C, k, seed, r, c, zv, y, d, xh);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float gg = g[i] * d[i];
+      a0[i] += gg;
+      a1[i] = fmaf(gg, xh[i], a1[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { sm[threadIdx.x][i] = a0[i]; sm[threadIdx.x][8 + i] = a1[i]; }
+  __syncthreads();
+  // 16 values per column group, summed over the row lanes in a fixed order by 16 threads per group
+  for (int item = threadIdx.x; item < CG * 16; item += kThreads) {
+    const int g_ = item >> 4, i = item & 15;
+    double s = 0.0;
+    for (int l = 0; l < RL; ++l) s += (double)sm[l * CG + g_][i];
+    partial[((int64_t)blockIdx.x * 2 + (i >> 3)) * F + g_ * 8 + (i & 7)] = s;
+  }
+}
+
+// dz = gamma*rstd*(g - mean(g) - xhat*mean(g*xhat)) (or g without BN); optionally the per-block
+// column sums of the dz values written (the conv-bias gradient) -> dzsum_partial[blk*F + col]
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 3) bn_act_bwd_apply_fast(const T* __restrict__ dy, int64_t ld_dy,
+                                                                  const T* __restrict__ z, int64_t ld_z,
+                                                                  T* __restrict__ dz, int64_t ld, int64_t n_rows, int F, int cg_shift,
+                                                                  int64_t rows_per_block, ActCtx C,
+                                                                  const double* __restrict__ sum_g,
+                                                                  const double* __restrict__ sum_gx, double inv_n,
+                                                                  double* __restrict__ dzsum_partial) {
+  __shared__ ColConsts k;
+  __shared__ float s_mg[kFastMaxF], s_mgx[kFastMaxF];
+  __shared__ float sm[kThreads][9];
+  stage_consts(C, F, k);
+  for (int i = threadIdx.x; i < F; i += kThreads) {
+    s_mg[i] = C.mean ? (float)(sum_g[i] * inv_n) : 0.f;
+    s_mgx[i] = C.mean ? (float)(sum_gx[i] * inv_n) : 0.f;
+  }
+  __syncthreads();
+  const int CG = 1 << cg_shift, RL = kThreads >> cg_shift;
+  const int cgi = threadIdx.x & (CG - 1), c = cgi * 8, rl = threadIdx.x >> cg_shift;
+  const uint64_t seed = C.seed + (C.seed_off ? (uint64_t)*C.seed_off : 0ull);
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(n_rows, r0 + rows_per_block);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  Raw8<T> zr, gr, zn, gn;
+  int64_t r = r0 + rl;
+  if (r < r1) { zr.load(z + r * ld_z + c); gr.load(dy + r * ld_dy + c); }
+#pragma unroll 1
+  for (; r < r1; r += RL) {
+    if (r + RL < r1) { zn.load(z + (r + RL) * ld_z + c); gn.load(dy + (r + RL) * ld_dy + c); }
+    float zv[8], g[8], y[8], d[8], xh[8], o[8];
+    zr.unpack(zv); gr.unpack(g);
+    zr = zn; gr = gn;
+    act_eval8(C, k, seed, r, c, zv, y, d, xh);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float gg = g[i] * d[i];
+      if (C.mean) gg = k.gamma[c + i] * k.rstd[c + i] * (gg - s_mg[c + i] - xh[i] * s_mgx[c + i]);
+      o[i] = gg;
+    }
+    st8f(dz + r * ld + c, o);
+    if (dzsum_partial) {
+      // sum what the consumer will read (the value after rounding to T)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += to_f32(from_f32<T>(o[i]));
+    }
+  }
+  if (dzsum_partial) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sm[threadIdx.x][i] = acc[i];
+    __syncthreads();
+    for (int item = threadIdx.x; item < CG * 8; item += kThreads) {
+      const int g_ = item >> 3, i = item & 7;
+      double s = 0.0;
+      for (int l = 0; l < RL; ++l) s += (double)sm[l * CG + g_][i];
+      dzsum_partial[(int64_t)blockIdx.x * F + g_ * 8 + i] = s;
+    }
+  }
+}
+
+// column statistics of a matrix (BatchNorm forward): partial[(blk*2+which)*F + col]
+template <typename T>
+__global__ void __launch_bounds__(kThreads) colstats_fast(const T* __restrict__ a, int64_t ld, int64_t n_rows,
+                                                          int F, int cg_shift, int64_t rows_per_block,
+                                                          double* __restrict__ partial) {
+  __shared__ float sm[kThreads][17];
+  const int CG = 1 << cg_shift, RL = kThreads >> cg_shift;
+  const int cgi = threadIdx.x & (CG - 1), c = cgi * 8, rl = threadIdx.x >> cg_shift;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(n_rows, r0 + rows_per_block);
+  float a0[8], a1[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a0[i] = a1[i] = 0.f;
+#pragma unroll 4
+  for (int64_t r = r0 + rl; r < r1; r += RL) {
+    float v[8];
+    ld8f<T>(a + r * ld + c, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a0[i] += v[i]; a1[i] = fmaf(v[i], v[i], a1[i]); }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { sm[threadIdx.x][i] = a0[i]; sm[threadIdx.x][8 + i] = a1[i]; }
+  __syncthreads();
+  for (int item = threadIdx.x; item < CG * 16; item += kThreads) {
+    const int g_ = item >> 4, i = item & 15;
+    double s = 0.0;
+    for (int l = 0; l < RL; ++l) s += (double)sm[l * CG + g_][i];
+    partial[((int64_t)blockIdx.x * 2 + (i >> 3)) * F + g_ * 8 + (i & 7)] = s;
+  }
+}
+
+struct FastPlan {
+  bool ok;
+  int cg_shift;
+  int64_t rpb;
+  int nblk;
+};
+// rows per block: a multiple of the row lanes, <= kMaxPartBlocks blocks, ~8 rows per thread
+inline FastPlan fast_plan(int64_t n_rows, int64_t F, int64_t ld, int dtype, std::initializer_list<const void*> ptrs) {
+  FastPlan p{false, 0, 0, 0};
+  if (F % 8 != 0 || ld % 8 != 0 || F > kFastMaxF) return p;
+  int cg = (int)(F / 8), sh = 0;
+  while ((1 << sh) < cg) ++sh;
+  if ((1 << sh) != cg) return p;
+  const size_t es = dtype == EGNN_F32 ? 4 : 2;
+  for (const void* q : ptrs)
+    if (q && (uintptr_t)q % (8 * es) != 0) return p;
+  const int RL = kThreads >> sh;
+  int64_t rpb = (int64_t)RL * 8;
+  if (ceil_div(n_rows, rpb) > kMaxPartBlocks) rpb = ceil_div(ceil_div(n_rows, kMaxPartBlocks), RL) * RL;
+  p.ok = true; p.cg_shift = sh; p.rpb = rpb; p.nblk = (int)ceil_div(n_rows > 0 ? n_rows : 1, rpb);
+  return p;
+}
+
+// one block per column: fixed-order sum of nblk doubles
+__global__ void __launch_bounds__(kThreads) colsum_final(const double* __restrict__ partial, int nblk, int F,
+                                                         float* __restrict__ out) {
+  __shared__ double sm[kThreads];
+  const int col = blockIdx.x;
+  double s = 0;
+  for (int b = threadIdx.x; b < nblk; b += kThreads) s += partial[(int64_t)b * F + col];
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = kThreads / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[col] = (float)sm[0];
+}
+
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, const double* __restrict__ sumsq,
                                    double count, int F, float eps, float momentum,
                                    float* __restrict__ mean, float* __restrict__ rstd,
@@ -502,16 +836,19 @@ extern "C" int egnn_cast(const void* in, int in_dtype, int64_t ld_in, void* out,
 
 extern "C" int egnn_inject_time(const float* x, int64_t ld_x, const int64_t* t, const float* table,
                                 int64_t T, int64_t D, float* out_f32, void* out_bf16, int64_t ld_out,
-                                int64_t n_rows, int64_t n_feat, void* stream) {
+                                int64_t ld_out_bf16, int64_t n_rows, int64_t n_feat, void* stream) {
   const char* fn = "egnn_inject_time";
+  if (ld_out_bf16 <= 0) ld_out_bf16 = ld_out;
+  EGNN_REQUIRE(ld_out_bf16 % 2 == 0 && ld_out_bf16 >= ld_out, fn, "bad ld_out_bf16");
   EGNN_REQUIRE(x && (out_f32 || out_bf16), fn, "null pointer");
   EGNN_REQUIRE(D == 0 || (t && table && T > 0), fn, "time table / indices missing");
   EGNN_REQUIRE(ld_out % 4 == 0 && ld_out >= n_feat + D, fn, "ld_out must be a multiple of 4 and >= F+D");
   if (n_rows == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  unsigned grid = (unsigned)ceil_div(n_rows * (ld_out / 2), kThreads);
+  unsigned grid = (unsigned)ceil_div(n_rows, kInjectRows);
   inject_time_kernel<<<grid, kThreads, 0, st>>>(x, ld_x, t, table, T, (int)D, out_f32,
-                                                (__nv_bfloat16*)out_bf16, ld_out, n_rows, (int)n_feat);
+                                                (__nv_bfloat16*)out_bf16, ld_out, ld_out_bf16, n_rows,
+                                                (int)n_feat);
   EGNN_LAUNCH_CHECK(fn);
   return 0;
 }
@@ -526,6 +863,20 @@ extern "C" int egnn_colreduce(const void* a, int dtype, int64_t ld, int64_t n_ro
   EGNN_REQUIRE(a && sums && workspace, fn, "null pointer");
   EGNN_REQUIRE(n_feat > 0 && ld >= n_feat, fn, "bad shape");
   cudaStream_t st = (cudaStream_t)stream;
+  FastPlan fp = fast_plan(n_rows, n_feat, ld, dtype, {a});
+  if (fp.ok) {
+    double* partial = reinterpret_cast<double*>(workspace);
+    if (dtype == EGNN_F32)
+      colstats_fast<float><<<fp.nblk, kThreads, 0, st>>>((const float*)a, ld, n_rows, (int)n_feat, fp.cg_shift,
+                                                         fp.rpb, partial);
+    else
+      colstats_fast<__nv_bfloat16><<<fp.nblk, kThreads, 0, st>>>((const __nv_bfloat16*)a, ld, n_rows, (int)n_feat,
+                                                                 fp.cg_shift, fp.rpb, partial);
+    EGNN_LAUNCH_CHECK(fn);
+    colreduce_final<<<dim3((unsigned)n_feat, 2), kThreads, 0, st>>>(partial, fp.nblk, (int)n_feat, sums, sumsq);
+    EGNN_LAUNCH_CHECK(fn);
+    return 0;
+  }
   bool v = vec_ok(a, dtype, ld, n_feat);
   if (dtype == EGNN_F32)
     return run_colreduce(PlainProd<float>{(const float*)a, ld, (int)n_feat, v}, n_rows, (int)n_feat, sums,
@@ -571,16 +922,33 @@ extern "C" int egnn_bn_act_dropout_res_fwd(const void* z, const void* res, void*
                                            int64_t n_rows, int64_t n_feat, const float* mean,
                                            const float* rstd, const float* gamma, const float* beta,
                                            int act, float p, uint64_t seed, const int64_t* seed_off, uint32_t layer,
-                                           int64_t row0, void* stream) {
+                                           int64_t row0, int64_t ld_res, int64_t ld_y, void* stream) {
   const char* fn = "egnn_bn_act_dropout_res_fwd";
+  if (ld_y <= 0) ld_y = ld;
+  if (ld_res <= 0) ld_res = ld;
+  EGNN_REQUIRE(ld_y >= n_feat && ld_res >= n_feat, fn, "ld_y / ld_res < n_feat");
   EGNN_REQUIRE(z && y, fn, "null pointer");
   EGNN_REQUIRE(!mean || (rstd && gamma && beta), fn, "incomplete BatchNorm arguments");
   EGNN_REQUIRE(p >= 0.f && p < 1.f, fn, "dropout p must be in [0,1)");
   if (n_rows == 0) return 0;
   ActCtx C = make_ctx(mean, rstd, gamma, beta, act, p, seed, seed_off, layer, row0);
+  cudaStream_t st = (cudaStream_t)stream;
+  FastPlan fp = fast_plan(n_rows, n_feat, ld, dtype, {z, res, y});
+  if (fp.ok && ld_y % 8 == 0 && ld_res % 8 == 0) {
+    const unsigned nb = (unsigned)ceil_div(n_rows, fp.rpb);
+    if (dtype == EGNN_F32)
+      bn_act_fwd_fast<float><<<nb, kThreads, 0, st>>>((const float*)z, (const float*)res, (float*)y, ld, ld_res, ld_y, n_rows,
+                                                      (int)n_feat, fp.cg_shift, fp.rpb, C);
+    else
+      bn_act_fwd_fast<__nv_bfloat16><<<nb, kThreads, 0, st>>>((const __nv_bfloat16*)z, (const __nv_bfloat16*)res,
+                                                              (__nv_bfloat16*)y, ld, ld_res, ld_y, n_rows, (int)n_feat,
+                                                              fp.cg_shift, fp.rpb, C);
+    EGNN_LAUNCH_CHECK(fn);
+    return 0;
+  }
+  EGNN_REQUIRE(ld_y == ld && ld_res == ld, fn, "separate leading dimensions need the 8-column fast path");
   bool v = vec_ok(z, dtype, ld, n_feat) && vec_ok(res, dtype, ld, n_feat) && vec_ok(y, dtype, ld, n_feat);
   unsigned grid = (unsigned)ceil_div(n_rows * ceil_div(n_feat, 4), kThreads);
-  cudaStream_t st = (cudaStream_t)stream;
   if (dtype == EGNN_F32)
     bn_act_fwd_kernel<float><<<grid, kThreads, 0, st>>>((const float*)z, (const float*)res, (float*)y, ld,
                                                         n_rows, (int)n_feat, v, C);
@@ -596,12 +964,29 @@ extern "C" int egnn_bn_act_dropout_bwd_reduce(const void* dy, const void* z, int
                                               const float* rstd, const float* gamma, const float* beta,
                                               int act, float p, uint64_t seed, const int64_t* seed_off,
                                               uint32_t layer, int64_t row0, double* sum_g, double* sum_gx, void* workspace,
-                                              void* stream) {
+                                              int64_t ld_z, void* stream) {
   const char* fn = "egnn_bn_act_dropout_bwd_reduce";
+  if (ld_z <= 0) ld_z = ld;
   EGNN_REQUIRE(dy && z && sum_g && sum_gx && workspace && mean && rstd && gamma && beta, fn, "null pointer");
   ActCtx C = make_ctx(mean, rstd, gamma, beta, act, p, seed, seed_off, layer, row0);
-  bool v = vec_ok(z, dtype, ld, n_feat) && vec_ok(dy, dtype, ld, n_feat);
   cudaStream_t st = (cudaStream_t)stream;
+  FastPlan fp = fast_plan(n_rows, n_feat, ld, dtype, {z, dy});
+  if (!(fp.ok && ld_z % 8 == 0) && ld_z != ld) return fail(fn, "separate ld_z needs the 8-column fast path");
+  if (fp.ok && ld_z % 8 == 0) {
+    double* partial = reinterpret_cast<double*>(workspace);
+    if (dtype == EGNN_F32)
+      bn_act_bwd_reduce_fast<float><<<fp.nblk, kThreads, 0, st>>>((const float*)dy, ld, (const float*)z, ld_z, n_rows,
+                                                                  (int)n_feat, fp.cg_shift, fp.rpb, C, partial);
+    else
+      bn_act_bwd_reduce_fast<__nv_bfloat16><<<fp.nblk, kThreads, 0, st>>>(
+          (const __nv_bfloat16*)dy, ld, (const __nv_bfloat16*)z, ld_z, n_rows, (int)n_feat, fp.cg_shift, fp.rpb, C,
+          partial);
+    EGNN_LAUNCH_CHECK(fn);
+    colreduce_final<<<dim3((unsigned)n_feat, 2), kThreads, 0, st>>>(partial, fp.nblk, (int)n_feat, sum_g, sum_gx);
+    EGNN_LAUNCH_CHECK(fn);
+    return 0;
+  }
+  bool v = vec_ok(z, dtype, ld, n_feat) && vec_ok(dy, dtype, ld, n_feat);
   if (dtype == EGNN_F32)
     return run_colreduce(BnBwdProd<float>{(const float*)dy, (const float*)z, ld, (int)n_feat, v, C}, n_rows,
                          (int)n_feat, sum_g, sum_gx, workspace, st, fn);
@@ -615,17 +1000,38 @@ extern "C" int egnn_bn_act_dropout_bwd_apply(const void* dy, const void* z, void
                                              const float* rstd, const float* gamma, const float* beta,
                                              int act, float p, uint64_t seed, const int64_t* seed_off, uint32_t layer,
                                              int64_t row0, const double* sum_g, const double* sum_gx, double n_total,
-                                             void* stream) {
+                                             float* dz_colsum, void* workspace, int64_t ld_z, void* stream) {
   const char* fn = "egnn_bn_act_dropout_bwd_apply";
+  if (ld_z <= 0) ld_z = ld;
+  EGNN_REQUIRE(!dz_colsum || workspace, fn, "dz_colsum needs a workspace (egnn_colreduce_workspace_bytes)");
   EGNN_REQUIRE(dy && z && dz, fn, "null pointer");
   EGNN_REQUIRE(!mean || (rstd && gamma && beta && sum_g && sum_gx && n_total > 0), fn,
                "incomplete BatchNorm arguments");
   if (n_rows == 0) return 0;
   ActCtx C = make_ctx(mean, rstd, gamma, beta, act, p, seed, seed_off, layer, row0);
-  bool v = vec_ok(z, dtype, ld, n_feat) && vec_ok(dy, dtype, ld, n_feat) && vec_ok(dz, dtype, ld, n_feat);
-  unsigned grid = (unsigned)ceil_div(n_rows * ceil_div(n_feat, 4), kThreads);
   cudaStream_t st = (cudaStream_t)stream;
   double inv_n = mean ? 1.0 / n_total : 0.0;
+  FastPlan fp = fast_plan(n_rows, n_feat, ld, dtype, {z, dy, dz});
+  if (!(fp.ok && ld_z % 8 == 0) && ld_z != ld) return fail(fn, "separate ld_z needs the 8-column fast path");
+  if (fp.ok && ld_z % 8 == 0) {
+    double* partial = dz_colsum ? reinterpret_cast<double*>(workspace) : nullptr;
+    if (dtype == EGNN_F32)
+      bn_act_bwd_apply_fast<float><<<fp.nblk, kThreads, 0, st>>>((const float*)dy, ld, (const float*)z, ld_z, (float*)dz,
+                                                                 ld, n_rows, (int)n_feat, fp.cg_shift, fp.rpb, C,
+                                                                 sum_g, sum_gx, inv_n, partial);
+    else
+      bn_act_bwd_apply_fast<__nv_bfloat16><<<fp.nblk, kThreads, 0, st>>>(
+          (const __nv_bfloat16*)dy, ld, (const __nv_bfloat16*)z, ld_z, (__nv_bfloat16*)dz, ld, n_rows, (int)n_feat,
+          fp.cg_shift, fp.rpb, C, sum_g, sum_gx, inv_n, partial);
+    EGNN_LAUNCH_CHECK(fn);
+    if (dz_colsum) {
+      colsum_final<<<(unsigned)n_feat, kThreads, 0, st>>>(partial, fp.nblk, (int)n_feat, dz_colsum);
+      EGNN_LAUNCH_CHECK(fn);
+    }
+    return 0;
+  }
+  bool v = vec_ok(z, dtype, ld, n_feat) && vec_ok(dy, dtype, ld, n_feat) && vec_ok(dz, dtype, ld, n_feat);
+  unsigned grid = (unsigned)ceil_div(n_rows * ceil_div(n_feat, 4), kThreads);
   if (dtype == EGNN_F32)
     bn_act_bwd_apply_kernel<float><<<grid, kThreads, 0, st>>>((const float*)dy, (const float*)z, (float*)dz,
                                                               ld, n_rows, (int)n_feat, v, C, sum_g, sum_gx,
@@ -635,6 +1041,14 @@ extern "C" int egnn_bn_act_dropout_bwd_apply(const void* dy, const void* z, void
         (const __nv_bfloat16*)dy, (const __nv_bfloat16*)z, (__nv_bfloat16*)dz, ld, n_rows, (int)n_feat, v, C,
         sum_g, sum_gx, inv_n);
   EGNN_LAUNCH_CHECK(fn);
+  if (dz_colsum) {  // generic shapes: a separate deterministic column reduction of dz
+    double* sums = reinterpret_cast<double*>(workspace);
+    char* ws2 = reinterpret_cast<char*>(workspace) + 8 * sizeof(double) * (size_t)(((n_feat + 3) / 4) * 4);
+    int rc = egnn_colreduce(dz, dtype, ld, n_rows, n_feat, sums, nullptr, ws2, stream);
+    if (rc) return rc;
+    colsum_final<<<(unsigned)n_feat, kThreads, 0, st>>>(sums, 1, (int)n_feat, dz_colsum);
+    EGNN_LAUNCH_CHECK(fn);
+  }
   return 0;
 }
 

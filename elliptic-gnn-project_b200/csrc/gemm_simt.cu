@@ -24,6 +24,7 @@ struct GemmParams {
   void* C;
   const float* bias;
   const int32_t* row_div_ptr;
+  int64_t row_div_cols;  // columns [0, row_div_cols) are divided (<= 0: all)
   float* ws;
   int64_t a_sm, a_sk, b_sk, b_sn, ld_c;
   int64_t M, N, K;
@@ -33,7 +34,7 @@ struct GemmParams {
 
 __device__ __forceinline__ void store_c(const GemmParams& P, int64_t m, int64_t n, float v) {
   if (P.bias) v += P.bias[n];
-  if (P.row_div_ptr) {
+  if (P.row_div_ptr && (P.row_div_cols <= 0 || n < P.row_div_cols)) {
     int d = P.row_div_ptr[m + 1] - P.row_div_ptr[m];
     v = __fdiv_rn(v, (float)(d > 1 ? d : 1));
   }
@@ -218,7 +219,7 @@ int run(GemmParams& P, cudaStream_t st) {
 
 int gemm_tcgen05_dispatch(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int c_dtype,
                           int64_t ld_c, int64_t M, int64_t N, int64_t K, const float* bias, int accumulate,
-                          const int32_t* row_div_ptr, cudaStream_t st);  // gemm_tcgen05.cu
+                          const int32_t* row_div_ptr, int64_t row_div_cols, cudaStream_t st);  // gemm_tcgen05.cu
 bool gemm_tcgen05_supported(int64_t lda, int64_t ldb, int64_t ld_c, int64_t M, int64_t N, int64_t K,
                             const void* A, const void* B, const void* C);
 size_t wgrad_tcgen05_workspace_floats(int64_t N_out, int64_t K_in);
@@ -241,7 +242,8 @@ extern "C" size_t egnn_gemm_workspace_floats(int64_t M, int64_t N, int64_t K, in
 extern "C" int egnn_gemm(const void* A, int a_dtype, int64_t a_sm, int64_t a_sk, const void* B,
                          int b_dtype, int64_t b_sk, int64_t b_sn, void* C, int c_dtype, int64_t ld_c,
                          int64_t M, int64_t N, int64_t K, const float* bias, const int32_t* row_div_ptr,
-                         int accumulate, int split_k, float* workspace, int impl, void* stream) {
+                         int64_t row_div_cols, int accumulate, int split_k, float* workspace, int impl,
+                         void* stream) {
   const char* fn = "egnn_gemm";
   EGNN_REQUIRE(A && B && C, fn, "null pointer");
   EGNN_REQUIRE(M >= 0 && N > 0 && K > 0, fn, "bad shape");
@@ -260,11 +262,11 @@ extern "C" int egnn_gemm(const void* A, int a_dtype, int64_t a_sm, int64_t a_sk,
                      wgrad_tcgen05_supported(A, a_sk, B, b_sk, K, M, N);
   if (impl == 2 && !(tc_tn || tc_wg)) return fail(fn, "shape/dtype/layout not supported by the tcgen05 path");
   if (impl != 1 && tc_tn)
-    return gemm_tcgen05_dispatch(A, a_sm, B, b_sn, C, c_dtype, ld_c, M, N, K, bias, accumulate, row_div_ptr, st);
+    return gemm_tcgen05_dispatch(A, a_sm, B, b_sn, C, c_dtype, ld_c, M, N, K, bias, accumulate, row_div_ptr, row_div_cols, st);
   if (impl != 1 && tc_wg)
     return wgrad_tcgen05_dispatch(A, a_sk, B, b_sk, (float*)C, K, M, N, accumulate, workspace, st);
   GemmParams P;
-  P.A = A; P.B = B; P.C = C; P.bias = bias; P.row_div_ptr = row_div_ptr; P.ws = workspace;
+  P.A = A; P.B = B; P.C = C; P.bias = bias; P.row_div_ptr = row_div_ptr; P.row_div_cols = row_div_cols; P.ws = workspace;
   P.a_sm = a_sm; P.a_sk = a_sk; P.b_sk = b_sk; P.b_sn = b_sn; P.ld_c = ld_c;
   P.M = M; P.N = N; P.K = K; P.k_per_split = K;
   P.c_dtype = c_dtype; P.accumulate = accumulate; P.split_k = split_k;

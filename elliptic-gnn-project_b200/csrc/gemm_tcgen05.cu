@@ -126,6 +126,7 @@ struct Epilogue {
   const int32_t* row_div_ptr;  // optional: divide row m by max(ptr[m+1]-ptr[m], 1)
   int64_t ld_c;
   int c_dtype, accumulate;
+  int row_div_cols;  // only columns [0, row_div_cols) are divided (<= 0: all)
 };
 
 // ------------------------------------------------------------------ forward / dgrad --------
@@ -233,6 +234,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         rdiv = (float)(d > 1 ? d : 1);
       }
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * Npad);
+      const int div_cols = ep.row_div_cols > 0 ? ep.row_div_cols : N;
       for (int c0 = 0; c0 < N; c0 += 8) {
         float v[8];
         tmem_ld8(t_addr + c0, v);
@@ -241,7 +243,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             if (ep.bias && j < nv) v[j] += ep.bias[c0 + j];
-            if (ep.row_div_ptr) v[j] = __fdiv_rn(v[j], rdiv);
+            if (ep.row_div_ptr && c0 + j < div_cols) v[j] = __fdiv_rn(v[j], rdiv);
           }
           if (ep.c_dtype == EGNN_F32) {
             float* c = reinterpret_cast<float*>(ep.C) + row * ep.ld_c + c0;
@@ -460,7 +462,7 @@ bool gemm_tcgen05_supported(int64_t lda, int64_t ldb, int64_t ld_c, int64_t M, i
 
 int gemm_tcgen05_dispatch(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int c_dtype,
                           int64_t ld_c, int64_t M, int64_t N, int64_t K, const float* bias, int accumulate,
-                          const int32_t* row_div_ptr, cudaStream_t st) {
+                          const int32_t* row_div_ptr, int64_t row_div_cols, cudaStream_t st) {
   const char* fn = "egnn_gemm(tcgen05)";
   const int Npad = (int)((N + 15) / 16 * 16);
   const int KC = (int)((K + BK - 1) / BK);
@@ -475,7 +477,7 @@ int gemm_tcgen05_dispatch(const void* A, int64_t lda, const void* B, int64_t ldb
   }
   int n_tiles = (int)((M + BM - 1) / BM);
   int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
-  Epilogue ep{C, bias, row_div_ptr, ld_c, c_dtype, accumulate};
+  Epilogue ep{C, bias, row_div_ptr, ld_c, c_dtype, accumulate, (int)row_div_cols};
   gemm_tn_kernel<kStagesTN><<<grid, kThreads, smem, st>>>(tmA, tmW, (int)M, (int)N, Npad, (int)K, ep);
   EGNN_LAUNCH_CHECK(fn);
   return 0;

@@ -97,7 +97,7 @@ class _LinearFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, bf16: bool):
         cd = torch.bfloat16 if bf16 else torch.float32
-        xg = x if x.dtype == cd else ops.cast(x, cd)
+        xg = ops.to_compute(x, cd)
         wc = w if w.dtype == cd else ops.cast(w, cd)
         ctx.x_dtype = x.dtype
         ctx.save_for_backward(xg, wc)
@@ -172,7 +172,7 @@ class SAGEResBNNet(nn.Module, _DropoutMixin):
         if self.time_embed_dim <= 0 or t_idx is None:
             return x
         table = self.time_emb.weight if self.time_embed_type == "learned" else self._sin_table
-        return ops.InjectTimeFn.apply(x, t_idx, table, self.in_dim)
+        return ops.inject_time(x, t_idx, table, self.in_dim)
 
     def forward(self, x, edge_index: Union[torch.Tensor, Graph], t_idx: Optional[torch.Tensor] = None):
         x = self._inject_time(x, t_idx)
@@ -183,9 +183,11 @@ class SAGEResBNNet(nn.Module, _DropoutMixin):
             drop.advance()
         for li, conv in enumerate(self.convs[:-1]):
             h_in = h
-            z = conv(h, edge_index)
             proj = self.res_projs[li]
-            res = h_in if isinstance(proj, nn.Identity) else proj(h_in)
+            if isinstance(proj, nn.Identity):
+                z, res = conv(h, edge_index), h_in
+            else:   # residual projection shares the conv's GEMM (one pass over h_in)
+                z, res = conv.forward_with_res(h, edge_index, proj.weight)
             if self.use_bn:
                 bn = self.bns[li]
                 if self.training and bn.track_running_stats:

@@ -74,7 +74,18 @@ class SAGEConv(nn.Module):
     def forward(self, x: torch.Tensor, edge_index: Union[torch.Tensor, Graph]) -> torch.Tensor:
         _check_input(x, self.in_channels)
         g = _graph_of(edge_index, x.size(0), self_loops=False)
-        return ops.SageConvFn.apply(x, self.lin_l.weight, self.lin_l.bias, self.lin_r.weight, g,
+        if ops.sage_out_supported(x, self.out_channels):
+            # narrow output (the logits layer): project first, aggregate at width out_channels
+            return ops.SageOutFn.apply(ops._rows(x), self.lin_l.weight, self.lin_l.bias, self.lin_r.weight, g)
+        return ops.SageConvFn.apply(x, self.lin_l.weight, self.lin_l.bias, self.lin_r.weight, None, g,
+                                    ops.amp_bf16())
+
+    def forward_with_res(self, x: torch.Tensor, edge_index: Union[torch.Tensor, Graph], res_weight: torch.Tensor):
+        """(conv(x, edge_index), x @ res_weight.T): SAGEResBNNet's residual projection
+        (`src/models/gnn.py:141-144,192`) folded into the conv's GEMM."""
+        _check_input(x, self.in_channels)
+        g = _graph_of(edge_index, x.size(0), self_loops=False)
+        return ops.SageConvFn.apply(x, self.lin_l.weight, self.lin_l.bias, self.lin_r.weight, res_weight, g,
                                     ops.amp_bf16())
 
 

@@ -45,6 +45,40 @@ def _ld(t: torch.Tensor) -> int:
 
 
 # ------------------------------------------------------------------------------ raw ops --
+def to_compute(x: torch.Tensor, cd: torch.dtype) -> torch.Tensor:
+    """x in the compute dtype: x itself, its pre-computed twin (an op that produced x may have
+    written a bf16 copy in the same pass, see InjectTimeFn), or a cast."""
+    if x.dtype == cd:
+        return x
+    tw = getattr(x, "_egnn_twin", None)
+    if tw is not None and tw.dtype == cd and tw.shape == x.shape:
+        return tw
+    return cast(x, cd)
+
+
+def alloc_cat(n_rows: int, width: int, dtype: torch.dtype, device):
+    """An activation buffer with room for its own aggregation: buf = [agg | h], [n_rows, 2*width].
+    Returns (buf, h) where h = buf[:, width:] carries `_egnn_cat = buf`; the next SAGEConv writes
+    mean_j h_j into buf[:, :width] and runs ONE GEMM over the concatenated operand."""
+    buf = torch.empty((n_rows, 2 * width), dtype=dtype, device=device)
+    h = buf[:, width:]
+    h._egnn_cat = buf
+    return buf, h
+
+
+def _fast8(F: int, *tensors) -> bool:
+    """Shapes served by the 8-column streaming kernels (which also take per-tensor row strides)."""
+    g = F // 8
+    if F % 8 or F > 512 or g & (g - 1):
+        return False
+    for t in tensors:
+        if t is None:
+            continue
+        if t.stride(-1) != 1 or t.data_ptr() % 32 or (t.size(0) > 1 and t.stride(0) % 8):
+            return False
+    return True
+
+
 def cast(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     x = _rows(x)
     out = torch.empty(x.shape, dtype=dtype, device=x.device)
@@ -77,12 +111,12 @@ GEMM_IMPL = 0  # 0 auto (tcgen05 for bf16 where supported), 1 force SIMT, 2 forc
 
 
 def _gemm(A, a_sm, a_sk, B, b_sk, b_sn, C, M, N, K, bias, accumulate, split_k=1, impl=None, row_div=None,
-          need_ws=False):
+          need_ws=False, row_div_cols=0):
     L = lib()
     nws = L.egnn_gemm_workspace_floats(M, N, K, split_k) if (need_ws or split_k > 1 or M <= 8) else 0
     ws = torch.empty(nws, dtype=torch.float32, device=C.device) if nws else None
     check(L.egnn_gemm(ptr(A), dt(A), a_sm, a_sk, ptr(B), dt(B), b_sk, b_sn, ptr(C), dt(C), _ld(C), M, N, K,
-                      ptr(bias), ptr(row_div), int(accumulate), split_k, ptr(ws),
+                      ptr(bias), ptr(row_div), int(row_div_cols), int(accumulate), split_k, ptr(ws),
                       GEMM_IMPL if impl is None else impl, stream()))
 
 
@@ -97,7 +131,7 @@ def linear_fwd(x, W, bias=None, out=None, accumulate=False, out_dtype=None, impl
     return out
 
 
-def linear_dgrad(g, W, out=None, accumulate=False, out_dtype=None, row_div=None, impl=None):
+def linear_dgrad(g, W, out=None, accumulate=False, out_dtype=None, row_div=None, impl=None, row_div_cols=0):
     """out[M,K] (+)= g[M,N] @ W[N,K]; `row_div` = CSR row pointer whose row counts divide the rows
     of the result (SAGE mean backward: dsum = dm / cnt, fused into the GEMM epilogue)."""
     g, W = _rows(g), _rows(W)
@@ -107,9 +141,11 @@ def linear_dgrad(g, W, out=None, accumulate=False, out_dtype=None, row_div=None,
         out = torch.empty((M, K), dtype=out_dtype or g.dtype, device=g.device)
     if g.dtype == torch.bfloat16 and W.dtype == torch.bfloat16 and (GEMM_IMPL if impl is None else impl) != 1:
         Wt = W.t().contiguous()  # [K, N]: contraction-contiguous B operand for the tcgen05 kernel
-        _gemm(g, _ld(g), 1, Wt, 1, _ld(Wt), out, M, K, N, None, accumulate, row_div=row_div, impl=impl)
+        _gemm(g, _ld(g), 1, Wt, 1, _ld(Wt), out, M, K, N, None, accumulate, row_div=row_div, impl=impl,
+              row_div_cols=row_div_cols)
     else:
-        _gemm(g, _ld(g), 1, W, _ld(W), 1, out, M, K, N, None, accumulate, row_div=row_div, impl=impl)
+        _gemm(g, _ld(g), 1, W, _ld(W), 1, out, M, K, N, None, accumulate, row_div=row_div, impl=impl,
+              row_div_cols=row_div_cols)
     return out
 
 
@@ -145,42 +181,183 @@ def dropout_mask(n_rows: int, n_feat: int, p: float, seed: int, layer: int, row0
     return m
 
 
+# Column sums of a gradient matrix produced as a by-product of the kernel that wrote it (the
+# BatchNorm backward), handed to the consumer (the conv's bias gradient) without another pass
+# over the matrix.  Keyed by the matrix' storage pointer; consumed once.
+_COLSUM_SIDE: dict = {}
+
+
+def _publish_colsum(t: torch.Tensor, s: torch.Tensor):
+    _COLSUM_SIDE.clear()
+    _COLSUM_SIDE[(t.data_ptr(), tuple(t.shape), t.dtype)] = s
+
+
+def _take_colsum(t: torch.Tensor) -> Optional[torch.Tensor]:
+    return _COLSUM_SIDE.pop((t.data_ptr(), tuple(t.shape), t.dtype), None)
+
+
 # --------------------------------------------------------------------------- SAGEConv ----
 class SageConvFn(torch.autograd.Function):
-    """PyG SAGEConv(mean, root_weight, bias): lin_l(mean_j x_j) + lin_r(x)  (SURVEY.md A.2)."""
+    """PyG SAGEConv(mean, root_weight, bias): lin_l(mean_j x_j) + lin_r(x)  (SURVEY.md A.2), optionally
+    with the residual projection res = x W_res^T of SAGEResBNNet (gnn.py:141-144,192) folded into
+    the same GEMM.
+
+    bf16 path with a concatenated activation buffer (`alloc_cat`): the mean aggregation is written
+    next to x, so the layer is ONE tensor-core GEMM  [m | x] . [[W_l, W_r], [0, W_res]]^T (+ bias),
+    the weight gradient one GEMM dz^T [m | x], and the input gradient one GEMM
+    dz . [W_l | W_r] -> [dm/deg | dx_root] followed by the transposed aggregation accumulating
+    into its right half."""
 
     @staticmethod
-    def forward(ctx, x, w_l, b_l, w_r, g: Graph, bf16: bool):
+    def forward(ctx, x, w_l, b_l, w_r, w_res, g: Graph, bf16: bool):
         cd = torch.bfloat16 if bf16 else torch.float32
+        xg = to_compute(x, cd)
         x = _rows(x)
+        K, No = x.size(1), w_l.size(0)
+        cat = getattr(xg, "_egnn_cat", None) if bf16 else None
+        if cat is not None and getattr(xg, "_egnn_cat_used", False):
+            cat = None          # the aggregation slot already serves another consumer of this tensor
+        ctx.g, ctx.x_dtype, ctx.dims = g, x.dtype, (K, No, 0 if w_res is None else w_res.size(0))
+        ctx.has_res = w_res is not None
+        if cat is not None and cat.dtype == cd and cat.size(1) == 2 * K:
+            xg._egnn_cat_used = True
+            spmm(g, "csr", _lib.SPMM_MEAN, x, cd, out=cat[:, :K])
+            w32 = torch.cat([w_l, w_r], dim=1)
+            bias = b_l
+            if w_res is not None:
+                Nr = w_res.size(0)
+                w32 = torch.cat([w32, torch.cat([w_res.new_zeros((Nr, K)), w_res], dim=1)], dim=0)
+                bias = torch.cat([b_l, b_l.new_zeros(Nr)])
+            wcat = cast(w32, cd)                      # [No (+Nr), 2K]
+            zc = linear_fwd(cat, wcat, bias=bias, out_dtype=cd)
+            ctx.cat_path = True
+            ctx.save_for_backward(cat, wcat)
+            if w_res is None:
+                return zc
+            return zc[:, :No], zc[:, No:]
         m = spmm(g, "csr", _lib.SPMM_MEAN, x, cd)
-        xg = x if x.dtype == cd else cast(x, cd)
         wl = w_l if w_l.dtype == cd else cast(w_l, cd)
         wr = w_r if w_r.dtype == cd else cast(w_r, cd)
         z = linear_fwd(m, wl, bias=b_l, out_dtype=cd)
         linear_fwd(xg, wr, out=z, accumulate=True)
-        ctx.g, ctx.x_dtype = g, x.dtype
-        ctx.save_for_backward(m, xg, wl, wr)
-        return z
+        ctx.cat_path = False
+        if w_res is None:
+            ctx.save_for_backward(m, xg, wl, wr)
+            return z
+        wres = w_res if w_res.dtype == cd else cast(w_res, cd)
+        ctx.save_for_backward(m, xg, wl, wr, wres)
+        return z, linear_fwd(xg, wres, out_dtype=cd)
 
     @staticmethod
-    def backward(ctx, dz):
-        m, xg, wl, wr = ctx.saved_tensors
+    def backward(ctx, dz, dres=None):
         g = ctx.g
+        K, No, Nr = ctx.dims
         dz = _rows(dz)
+        db = _take_colsum(dz)
+        dwres = None
+        if ctx.cat_path:
+            cat, wcat = ctx.saved_tensors
+            cd = cat.dtype
+            if dz.dtype != cd:
+                dz = cast(dz, cd)
+            if 2 * K <= 256:
+                dwc = linear_wgrad(dz, cat)
+                dwl, dwr = dwc[:, :K], dwc[:, K:]
+            else:
+                dwl, dwr = linear_wgrad(dz, cat[:, :K]), linear_wgrad(dz, cat[:, K:])
+            if ctx.has_res:
+                dres = _rows(dres)
+                if dres.dtype != cd:
+                    dres = cast(dres, cd)
+                dwres = linear_wgrad(dres, cat[:, K:])
+            if db is None:
+                db = colsum(dz).float()
+            dx = None
+            if ctx.needs_input_grad[0]:
+                # [dm / in-degree | dx_root] = dz . [W_l | W_r]; then dx = dx_root + A^T (dm / deg)
+                out = linear_dgrad(dz, wcat[:No], row_div=g.csr_ptr, row_div_cols=K)
+                if ctx.has_res:
+                    linear_dgrad(dres, wcat[No:, K:], out=out[:, K:], accumulate=True)
+                spmm(g, "csc", _lib.SPMM_SUM, out[:, :K], cd, out=out[:, K:], accumulate=True)
+                dx = out[:, K:]
+                if dx.dtype != ctx.x_dtype:
+                    dx = cast(dx, ctx.x_dtype)
+            return dx, dwl, db, dwr, dwres, None, None
+        if ctx.has_res:
+            m, xg, wl, wr, wres = ctx.saved_tensors
+        else:
+            m, xg, wl, wr = ctx.saved_tensors
         if dz.dtype != m.dtype:
             dz = cast(dz, m.dtype)
         dwl = linear_wgrad(dz, m)
         dwr = linear_wgrad(dz, xg)
-        db = colsum(dz).float()
+        if db is None:
+            db = colsum(dz).float()
+        if ctx.has_res:
+            dres = _rows(dres)
+            if dres.dtype != m.dtype:
+                dres = cast(dres, m.dtype)
+            dwres = linear_wgrad(dres, xg)
         dx = None
         if ctx.needs_input_grad[0]:
             dm = linear_dgrad(dz, wl, row_div=g.csr_ptr)   # dm / in-degree, fused in the GEMM epilogue
             dx = linear_dgrad(dz, wr)
+            if ctx.has_res:
+                linear_dgrad(dres, wres, out=dx, accumulate=True)
             spmm(g, "csc", _lib.SPMM_SUM, dm, dx.dtype, out=dx, accumulate=True)
             if dx.dtype != ctx.x_dtype:
                 dx = cast(dx, ctx.x_dtype)
-        return dx, dwl, db, dwr, None, None
+        return dx, dwl, db, dwr, dwres, None, None
+
+
+class SageOutFn(torch.autograd.Function):
+    """SAGEConv with <= 4 output channels (the `hidden -> 2` logits layer, gnn.py:44,128),
+    evaluated project-first: p = h [W_l; W_r]^T, out = (mean_j p_j[:C] + b) + p_i[C:]  -- three
+    passes over h for forward + backward instead of ten (csrc/sage_out.cu).  fp32 weights, fp32
+    accumulation and fp32 logits whatever the activation dtype."""
+
+    @staticmethod
+    def forward(ctx, x, w_l, b_l, w_r, g: Graph):
+        x = _rows(x)
+        N, K = x.shape
+        C = w_l.size(0)
+        L = lib()
+        wcat = torch.cat([w_l.detach().float(), w_r.detach().float()], dim=0).contiguous()  # [2C, K]
+        p = torch.empty((N, 2 * C), dtype=torch.float32, device=x.device)
+        check(L.egnn_skinny_project(ptr(x), dt(x), _ld(x), N, K, ptr(wcat), 2 * C, ptr(p), stream()))
+        out = torch.empty((N, C), dtype=torch.float32, device=x.device)
+        bias = b_l.detach().float().contiguous() if b_l is not None else None
+        check(L.egnn_sage_out_fwd(ptr(g.csr_ptr), ptr(g.csr_src), ptr(p), ptr(bias), C, ptr(out), N, stream()))
+        ctx.g, ctx.C = g, C
+        ctx.save_for_backward(x, wcat)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, wcat = ctx.saved_tensors
+        g, C = ctx.g, ctx.C
+        N, K = x.shape
+        L = lib()
+        dout = _rows(dout).contiguous()
+        dp = torch.empty((N, 2 * C), dtype=torch.float32, device=x.device)
+        check(L.egnn_sage_out_bwd(ptr(g.csc_ptr), ptr(g.csc_dst), ptr(g.csr_ptr), ptr(dout), dt(dout), C, ptr(dp),
+                                  N, stream()))
+        dw = torch.empty((2 * C, K), dtype=torch.float32, device=x.device)
+        dsum = torch.empty(2 * C, dtype=torch.float32, device=x.device)
+        ws = torch.empty(L.egnn_skinny_wgrad_workspace_floats(N, K, 2 * C), dtype=torch.float32, device=x.device)
+        check(L.egnn_skinny_wgrad(ptr(x), dt(x), _ld(x), ptr(dp), 2 * C, N, K, ptr(dw), ptr(dsum), ptr(ws),
+                                  stream()))
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((N, K), dtype=x.dtype, device=x.device)
+            check(L.egnn_skinny_dgrad(ptr(dp), ptr(wcat), 2 * C, ptr(dx), dt(dx), K, N, K, stream()))
+        return dx, dw[:C], dsum[C:], dw[C:], None
+
+
+def sage_out_supported(x: torch.Tensor, out_channels: int) -> bool:
+    K = x.size(1)
+    return (out_channels in (1, 2, 4) and K % 8 == 0 and K <= 1024 and x.dtype in (torch.float32, torch.bfloat16)
+            and x.stride(-1) == 1 and x.data_ptr() % 32 == 0 and (x.size(0) <= 1 or x.stride(0) % 8 == 0))
 
 
 # ---------------------------------------------------------------------------- GCNConv ----
@@ -317,10 +494,17 @@ class BnActDropResFn(torch.autograd.Function):
     def forward(ctx, z, res, gamma, beta, running_mean, running_var, training: bool, act: int, p: float,
                 drop: Optional[DropoutState], layer: int, row0: int, eps: float, momentum: float,
                 reducer: Optional[StatsReducer]):
-        z = _rows(z).contiguous()
+        z = _rows(z)
         N, F = z.shape
         L = lib()
         dev = z.device
+        res = _rows(res) if res is not None else None
+        if res is not None and res.dtype != z.dtype:
+            res = cast(res, z.dtype)
+        strided_ok = _fast8(F, z, res)   # the 8-column kernels take per-tensor row strides
+        if not strided_ok:
+            z = z.contiguous()
+            res = res.contiguous() if res is not None else None
         use_bn = gamma is not None
         mean = rstd = None
         n_total = float(reducer.n_total) if (reducer is not None and reducer.n_total) else float(N)
@@ -338,17 +522,15 @@ class BnActDropResFn(torch.autograd.Function):
                 mean = running_mean
                 rstd = torch.rsqrt(running_var + eps)
         p_eff = float(p) if (training and p > 0) else 0.0
-        if res is not None:
-            res = _rows(res)
-            if res.dtype != z.dtype:
-                res = cast(res, z.dtype)
-            res = res.contiguous()
-        y = torch.empty_like(z)
+        if strided_ok and z.dtype == torch.bfloat16:
+            _, y = alloc_cat(N, F, z.dtype, dev)   # [agg | y]: the next SAGEConv aggregates in place
+        else:
+            y = torch.empty((N, F), dtype=z.dtype, device=dev)
         seed = drop.seed if drop is not None else 0
         soff = drop.offset if drop is not None else None
-        check(L.egnn_bn_act_dropout_res_fwd(ptr(z), ptr(res), ptr(y), dt(z), F, N, F, ptr(mean), ptr(rstd),
+        check(L.egnn_bn_act_dropout_res_fwd(ptr(z), ptr(res), ptr(y), dt(z), _ld(z), N, F, ptr(mean), ptr(rstd),
                                             ptr(gamma), ptr(beta), act, p_eff, seed, ptr(soff), layer, row0,
-                                            stream()))
+                                            _ld(res) if res is not None else 0, _ld(y), stream()))
         ctx.cfg = (use_bn, act, p_eff, seed, layer, row0, n_total, reducer, res is not None)
         ctx.soff = soff
         ctx.save_for_backward(z, mean, rstd, gamma, beta)
@@ -365,27 +547,30 @@ class BnActDropResFn(torch.autograd.Function):
         if dy.dtype != z.dtype:
             dy = cast(dy, z.dtype)
         dy = dy.contiguous()
-        dz = torch.empty_like(z)
+        dz = torch.empty((N, F), dtype=z.dtype, device=z.device)
         dgamma = dbeta = None
         if use_bn:
             sg = torch.empty((2, F), dtype=torch.float64, device=z.device)
             ws = torch.empty(L.egnn_colreduce_workspace_bytes(F), dtype=torch.uint8, device=z.device)
             check(L.egnn_bn_act_dropout_bwd_reduce(ptr(dy), ptr(z), dt(z), F, N, F, ptr(mean), ptr(rstd),
                                                    ptr(gamma), ptr(beta), act, p_eff, seed, ptr(soff), layer,
-                                                   row0, sg[0].data_ptr(), sg[1].data_ptr(), ptr(ws),
+                                                   row0, sg[0].data_ptr(), sg[1].data_ptr(), ptr(ws), _ld(z),
                                                    stream()))
             if reducer is not None:
                 reducer.reduce_(sg)
+            dzsum = torch.empty(F, dtype=torch.float32, device=z.device)
+            ws2 = torch.empty(L.egnn_colreduce_workspace_bytes(F) + 64 * F, dtype=torch.uint8, device=z.device)
             check(L.egnn_bn_act_dropout_bwd_apply(ptr(dy), ptr(z), ptr(dz), dt(z), F, N, F, ptr(mean),
                                                   ptr(rstd), ptr(gamma), ptr(beta), act, p_eff, seed,
                                                   ptr(soff), layer, row0, sg[0].data_ptr(), sg[1].data_ptr(),
-                                                  n_total, stream()))
+                                                  n_total, ptr(dzsum), ptr(ws2), _ld(z), stream()))
+            _publish_colsum(dz, dzsum)
             sgf = sg.float()
             dbeta, dgamma = sgf[0], sgf[1]
         else:
             check(L.egnn_bn_act_dropout_bwd_apply(ptr(dy), ptr(z), ptr(dz), dt(z), F, N, F, None, None, None,
                                                   None, act, p_eff, seed, ptr(soff), layer, row0, None, None,
-                                                  1.0, stream()))
+                                                  1.0, None, None, _ld(z), stream()))
         dres = dy if has_res else None
         return (dz, dres, dgamma, dbeta) + (None,) * 11
 
@@ -402,7 +587,7 @@ class InjectTimeFn(torch.autograd.Function):
     """[x | table[clamp(t-1)]] zero-padded to a multiple of 4 columns (gnn.py:168-179)."""
 
     @staticmethod
-    def forward(ctx, x, t, table, width: int):
+    def forward(ctx, x, t, table, width: int, want_twin: bool = False):
         x = _rows(x)
         if x.dtype != torch.float32:
             raise TypeError("node features must be float32")
@@ -410,8 +595,14 @@ class InjectTimeFn(torch.autograd.Function):
         T, D = table.shape
         tb = table.detach().contiguous().float()
         out = torch.empty((N, width), dtype=torch.float32, device=x.device)
-        check(lib().egnn_inject_time(ptr(x), _ld(x), ptr(t.contiguous()), ptr(tb), T, D, ptr(out), None, width,
-                                     N, F, stream()))
+        # under bf16 autocast the same pass also writes the bf16 copy the GEMMs consume
+        twin = None
+        if want_twin:
+            twin = (alloc_cat(N, width, torch.bfloat16, x.device)[1] if width % 8 == 0
+                    else torch.empty((N, width), dtype=torch.bfloat16, device=x.device))
+        check(lib().egnn_inject_time(ptr(x), _ld(x), ptr(t.contiguous()), ptr(tb), T, D, ptr(out), ptr(twin), width,
+                                     _ld(twin) if twin is not None else 0, N, F, stream()))
+        InjectTimeFn.last_twin = twin
         ctx.dims = (F, D, T)
         ctx.save_for_backward(t)
         return out
@@ -427,7 +618,16 @@ class InjectTimeFn(torch.autograd.Function):
             idx = torch.clamp(t.long() - 1, 0, T - 1)
             dtab = torch.zeros((T, D), dtype=torch.float32, device=dout.device)
             dtab.index_add_(0, idx, dout[:, F:F + D].float())
-        return dx, None, dtab, None
+        return dx, None, dtab, None, None
+
+
+def inject_time(x, t, table, width: int):
+    want_twin = amp_bf16()
+    out = InjectTimeFn.apply(x, t, table, width, want_twin)
+    if want_twin:
+        out._egnn_twin = InjectTimeFn.last_twin
+        InjectTimeFn.last_twin = None
+    return out
 
 
 # ------------------------------------------------------------------------------- loss ----

@@ -118,7 +118,8 @@ int egnn_spmm(int mode, const int32_t* ptr, const int32_t* col, const float* w,
  * Covers Linear forward (x W^T), dgrad (g W) and wgrad (g^T x) of torch_geometric's
  * nn.dense.Linear / torch.nn.Linear (src/models/gnn.py:141-144 and the convs' lin*).
  * fp32 accumulate always.  row_div_ptr (optional CSR row pointer, int32 [M+1]): row m of the
- * result is divided by max(ptr[m+1]-ptr[m], 1) -- the 1/deg of SAGE's mean backward, fused.
+ * result is divided by max(ptr[m+1]-ptr[m], 1) -- the 1/deg of SAGE's mean backward, fused; only
+ * columns [0, row_div_cols) are divided when row_div_cols > 0 (the [dm | dx_root] concatenated dgrad).
  * impl: 0 = auto, 1 = SIMT FFMA (exact-fp32 parity path), 2 = tcgen05 only (bf16 operands, either
  * both contiguous along the contraction -- forward/dgrad -- or both contiguous along the other
  * dimension with fp32 dense C -- wgrad; error if the shape is not supported).
@@ -128,8 +129,31 @@ int egnn_spmm(int mode, const int32_t* ptr, const int32_t* col, const float* w,
 size_t egnn_gemm_workspace_floats(int64_t M, int64_t N, int64_t K, int split_k);
 int egnn_gemm(const void* A, int a_dtype, int64_t a_sm, int64_t a_sk, const void* B, int b_dtype,
               int64_t b_sk, int64_t b_sn, void* C, int c_dtype, int64_t ld_c, int64_t M,
-              int64_t N, int64_t K, const float* bias, const int32_t* row_div_ptr, int accumulate,
-              int split_k, float* workspace, int impl, void* stream);
+              int64_t N, int64_t K, const float* bias, const int32_t* row_div_ptr, int64_t row_div_cols,
+              int accumulate, int split_k, float* workspace, int impl, void* stream);
+
+/* ---------------------------------------------------------------- narrow-output SAGEConv -- */
+/* The `hidden -> num_classes` SAGEConv of every SAGE net (src/models/gnn.py:44,128: PyG
+ * SAGEConv(hidden, 2), A.2) evaluated project-first -- aggregation and projection commute:
+ *   p = h . [W_l ; W_r]^T  [N, P = 2C];  out_i = (mean_{j->i} p_j[0:C] + b) + p_i[C:2C].
+ * egnn_skinny_project : out[r, 0:P] = sum_k a[r,k] * W[p,k]     W float [P, K] row-major, P in {2,4,8}
+ * egnn_sage_out_fwd   : the width-C gather + combine over the CSR-by-destination view, C in {1,2,4}
+ * egnn_sage_out_bwd   : dp[j] = [ sum_{j->i} dout_i / max(deg_in(i),1) | dout_j ]  (CSC view)
+ * egnn_skinny_wgrad   : dW[p,k] = sum_r dp[r,p]*a[r,k]; dsum[p] = sum_r dp[r,p] (may be NULL);
+ *                       deterministic two-level reduction, workspace from ..._workspace_floats
+ * egnn_skinny_dgrad   : dh[r,k] = sum_p dp[r,p] * W[p,k]
+ * a / dh: dtype EGNN_F32 | EGNN_BF16, rows of K elements with leading dimension ld. */
+int egnn_skinny_project(const void* a, int dtype, int64_t ld, int64_t n_rows, int64_t K,
+                        const float* W, int P, float* out, void* stream);
+int egnn_sage_out_fwd(const int32_t* csr_ptr, const int32_t* csr_src, const float* p, const float* bias,
+                      int C, float* out, int64_t n_rows, void* stream);
+int egnn_sage_out_bwd(const int32_t* csc_ptr, const int32_t* csc_dst, const int32_t* csr_ptr,
+                      const void* dout, int dtype, int C, float* dp, int64_t n_rows, void* stream);
+size_t egnn_skinny_wgrad_workspace_floats(int64_t n_rows, int64_t K, int P);
+int egnn_skinny_wgrad(const void* a, int dtype, int64_t ld, const float* dp, int P, int64_t n_rows,
+                      int64_t K, float* dW, float* dsum, float* workspace, void* stream);
+int egnn_skinny_dgrad(const float* dp, const float* W, int P, void* dh, int dtype, int64_t ld,
+                      int64_t n_rows, int64_t K, void* stream);
 
 /* cast / copy with optional column padding: out[r, 0:F] = in[r, 0:F], out[r, F:ld_out] = 0 */
 int egnn_cast(const void* in, int in_dtype, int64_t ld_in, void* out, int out_dtype,
@@ -138,10 +162,11 @@ int egnn_cast(const void* in, int in_dtype, int64_t ld_in, void* out, int out_dt
 /* SAGEResBNNet._inject_time (src/models/gnn.py:168-179) / scalar-time append
  * (src/train_gnn.py:314-317): out[r] = [x[r, 0:F] | table[clamp(t[r]-1, 0, T-1), 0:D] | 0-pad].
  * table is float [T, D] (sin/cos LUT computed by the host with the reference's own torch
- * ops, or the learned nn.Embedding weight).  out_f32 / out_bf16 may each be NULL. */
+ * ops, or the learned nn.Embedding weight).  out_f32 / out_bf16 may each be NULL; the bf16 copy has
+ * its own leading dimension ld_out_bf16 (0 = ld_out). */
 int egnn_inject_time(const float* x, int64_t ld_x, const int64_t* t, const float* table,
                      int64_t T, int64_t D, float* out_f32, void* out_bf16, int64_t ld_out,
-                     int64_t n_rows, int64_t n_feat, void* stream);
+                     int64_t ld_out_bf16, int64_t n_rows, int64_t n_feat, void* stream);
 
 /* column reductions over rows: sums[c] = sum_r a[r,c] (and sumsq[c] = sum_r a[r,c]^2 when
  * sumsq != NULL), deterministic two-level tree, fp64 combine.  Used for bias gradients and
@@ -165,27 +190,33 @@ int egnn_bn_finalize(const double* sums, const double* sumsq, double count, int6
  *   kept values scaled by 1/(1-p); p == 0 disables it.  seed_off (device int64, may be NULL)
  *   is added to seed at run time so a captured CUDA graph draws a new mask on every replay
  *   (advance it with egnn_counter_add inside the graph).
- *   res may be NULL.  z/res/y share dtype `dtype`. */
+ *   res may be NULL.  z/res/y share dtype `dtype`; z has leading dimension ld, res ld_res and y
+ *   ld_y (0 = ld): the output may be the right half of a wider [h_agg | h] buffer. */
 int egnn_bn_act_dropout_res_fwd(const void* z, const void* res, void* y, int dtype, int64_t ld,
                                 int64_t n_rows, int64_t n_feat, const float* mean,
                                 const float* rstd, const float* gamma, const float* beta, int act,
                                 float p, uint64_t seed, const int64_t* seed_off, uint32_t layer,
-                                int64_t row0, void* stream);
+                                int64_t row0, int64_t ld_res, int64_t ld_y, void* stream);
 
 /* backward stage 1: g = dy * keep/(1-p) * act'(.) ; sums[c] = sum g, sums_xhat[c] = sum g*xhat
  * (BatchNorm dbeta, dgamma).  stage 2: dz = gamma*rstd*(g - sum_g/n - xhat*sum_gx/n) (or g
- * when mean == NULL).  n_total = global row count (multi-GPU passes the global N). */
+ * when mean == NULL).  n_total = global row count (multi-GPU passes the global N).  dy and dz
+ * have leading dimension ld, z has ld_z (0 = ld). */
 int egnn_bn_act_dropout_bwd_reduce(const void* dy, const void* z, int dtype, int64_t ld,
                                    int64_t n_rows, int64_t n_feat, const float* mean,
                                    const float* rstd, const float* gamma, const float* beta,
                                    int act, float p, uint64_t seed, const int64_t* seed_off,
-                                   uint32_t layer, int64_t row0, double* sum_g, double* sum_gx, void* workspace, void* stream);
+                                   uint32_t layer, int64_t row0, double* sum_g, double* sum_gx, void* workspace,
+                                   int64_t ld_z, void* stream);
+/* dz_colsum (float [n_feat], optional): column sums of the dz values written -- the gradient of the
+ * conv bias that feeds the BatchNorm -- produced in the same pass; needs `workspace` of
+ * egnn_colreduce_workspace_bytes(n_feat) + 8*8*n_feat bytes. */
 int egnn_bn_act_dropout_bwd_apply(const void* dy, const void* z, void* dz, int dtype, int64_t ld,
                                   int64_t n_rows, int64_t n_feat, const float* mean,
                                   const float* rstd, const float* gamma, const float* beta,
                                   int act, float p, uint64_t seed, const int64_t* seed_off,
                                   uint32_t layer, int64_t row0, const double* sum_g, const double* sum_gx, double n_total,
-                                  void* stream);
+                                  float* dz_colsum, void* workspace, int64_t ld_z, void* stream);
 
 /* *counter += inc on the device (one thread) */
 int egnn_counter_add(int64_t* counter, int64_t inc, void* stream);
