@@ -239,7 +239,7 @@ def run_ours(args):
         t64 = time_kernel(lambda b: ops.spmm(g, "csr", _lib.SPMM_MEAN, b, torch.bfloat16, out=out64), xs64)
         t64b = time_kernel(lambda b: ops.spmm(g, "csc", _lib.SPMM_DIV_NBR, b, torch.bfloat16, out=out64), xs64)
         b64 = spmm_bytes(N, 64, e_local, 2, 2)
-        roof = {"kernel": "spmm_vec<float,bf16,MEAN> F=168 (layer-0 aggregation)", "bound": "hbm",
+        roof = {"kernel": "egnn_spmm mean fp32->bf16 F=168 (layer-0 aggregation, spmm_pipe)", "bound": "hbm",
                 "achieved": round(b168 / t168 / 1e6, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(b168 / t168 / 1e6 / peak, 4), "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes": b168, "us": round(t168 * 1e3, 2)}
@@ -273,8 +273,14 @@ def run_ours(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        # leave without tearing NCCL down: destroy_process_group() with captured NCCL kernels still alive
+        # in a CUDA graph did not return on the 2-GPU box (round 1); every rank has printed / finished by now
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 # --------------------------------------------------------------------------- reference ------
@@ -378,8 +384,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--eager", action="store_true", help="do not capture a CUDA graph (profiling runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU baseline leg (profiling runs)")
+    ap.add_argument("--max-seconds", type=float, default=840.0, help="watchdog: hard-exit if the run hangs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    wd = threading.Timer(args.max_seconds, lambda: (sys.stderr.write("[bench] watchdog: run exceeded "
+                         f"{args.max_seconds:.0f} s, exiting\n"), sys.stderr.flush(), os._exit(3)))
+    wd.daemon = True
+    wd.start()
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -33,7 +33,7 @@ SIGNATURES = {
     "egnn_graph_workspace_bytes": (_sz, [_i64, _i64, _i32]),
     "egnn_graph_build": (_i32, [_vp, _i64, _i64, _i32, _i32] + [_vp] * 16 + [_vp, _sz, _vp]),
     "egnn_spmm": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _i32, _i64, _i64, _i64,
-                         _vp, _i32, _i32, _vp]),
+                         _vp, _i32, _i32, _vp, _i64, _vp]),
     "egnn_gemm_workspace_floats": (_sz, [_i64, _i64, _i64, _i32]),
     "egnn_gemm": (_i32, [_vp, _i32, _i64, _i64, _vp, _i32, _i64, _i64, _vp, _i32, _i64, _i64, _i64, _i64,
                          _vp, _vp, _i64, _i32, _i32, _vp, _i32, _vp]),
@@ -43,11 +43,11 @@ SIGNATURES = {
     "egnn_colreduce": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "egnn_bn_finalize": (_i32, [_vp, _vp, _f64, _i64, _f32, _f32, _vp, _vp, _vp, _vp, _vp]),
     "egnn_bn_act_dropout_res_fwd": (_i32, [_vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i32,
-                                           _f32, _u64, _vp, _u32, _i64, _i64, _i64, _vp]),
+                                           _f32, _u64, _vp, _u32, _i64, _i64, _i64, _vp, _vp]),
     "egnn_bn_act_dropout_bwd_reduce": (_i32, [_vp, _vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i32,
-                                              _f32, _u64, _vp, _u32, _i64, _vp, _vp, _vp, _i64, _vp]),
+                                              _f32, _u64, _vp, _u32, _i64, _vp, _vp, _vp, _i64, _vp, _vp]),
     "egnn_bn_act_dropout_bwd_apply": (_i32, [_vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i32,
-                                             _f32, _u64, _vp, _u32, _i64, _vp, _vp, _f64, _vp, _vp, _i64, _vp]),
+                                             _f32, _u64, _vp, _u32, _i64, _vp, _vp, _f64, _vp, _vp, _i64, _vp, _vp]),
     "egnn_dropout_mask": (_i32, [_vp, _i64, _i64, _f32, _u64, _vp, _u32, _i64, _vp]),
     "egnn_gat_scores": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "egnn_gat_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _f32, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _vp]),

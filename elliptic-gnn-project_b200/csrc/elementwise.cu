@@ -388,201 +388,283 @@ struct Raw8<__nv_bfloat16> {
   }
 };
 
-constexpr int kFastMaxF = 512;  // widths served by the fast kernels (column constants in shared memory)
-
-// per-column BatchNorm constants staged in shared memory (keeps the streaming loops under 64 registers)
-struct ColConsts {
-  float mean[kFastMaxF], rstd[kFastMaxF], gamma[kFastMaxF], beta[kFastMaxF];
+// ---- lean streaming kernels: 4 columns per thread, column constants in REGISTERS, 4 rows in flight ---
+// (the first 8-column version kept its constants in shared memory and was bound by LDS wavefronts:
+//  l1tex 68 %, 43 us for 78 MB, profiles/r01/ncu_kernels_after_fusion.txt).  Templated on BatchNorm
+// presence and the activation so the element math is ~12 instructions.  The dropout keep bits of a
+// (row, 4-column group) are one byte of `keep_bits` [n_rows, F/4] (low nibble): written by the forward,
+// read by the backward kernels instead of re-running Philox.
+template <typename T>
+struct Raw4;
+template <>
+struct Raw4<float> {
+  float4 a;
+  __device__ __forceinline__ void load(const float* p) { a = __ldg(reinterpret_cast<const float4*>(p)); }
+  __device__ __forceinline__ void unpack(float (&v)[4]) const { v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; }
 };
-__device__ __forceinline__ void stage_consts(const ActCtx& C, int F, ColConsts& k) {
-  for (int i = threadIdx.x; i < F; i += kThreads) {
-    k.mean[i] = C.mean ? C.mean[i] : 0.f;
-    k.rstd[i] = C.mean ? C.rstd[i] : 1.f;
-    k.gamma[i] = C.mean ? C.gamma[i] : 1.f;
-    k.beta[i] = C.mean ? C.beta[i] : 0.f;
+template <>
+struct Raw4<__nv_bfloat16> {
+  uint2 q;
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) { q = __ldg(reinterpret_cast<const uint2*>(p)); }
+  __device__ __forceinline__ void unpack(float (&v)[4]) const {
+    v[0] = __uint_as_float(q.x << 16); v[1] = __uint_as_float(q.x & 0xffff0000u);
+    v[2] = __uint_as_float(q.y << 16); v[3] = __uint_as_float(q.y & 0xffff0000u);
+  }
+};
+__device__ __forceinline__ void st4f(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void st4f(__nv_bfloat16* p, const float (&v)[4]) {
+  *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+}
+
+constexpr int kRowsInFlight = 4;
+
+struct Col4 {
+  float mean[4], rstd[4], gamma[4], beta[4];
+};
+template <bool BN>
+__device__ __forceinline__ void load_col4(const ActCtx& C, int c, Col4& k) {
+  if (BN) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      k.mean[i] = C.mean[c + i]; k.rstd[i] = C.rstd[c + i]; k.gamma[i] = C.gamma[c + i]; k.beta[i] = C.beta[c + i];
+    }
   }
 }
-// y = dropout(act(bn(z))), dfac = dy/du, xhat for 8 columns starting at c (c % 8 == 0) of row r
-__device__ __forceinline__ void act_eval8(const ActCtx& C, const ColConsts& k, uint64_t seed, int64_t r, int c,
-                                          const float (&z)[8], float (&y)[8], float (&dfac)[8],
-                                          float (&xhat)[8]) {
-  uint32_t words[8];
-  if (C.drop) {
-    Philox4 w0 = dropout_words(seed, C.layer, C.row0 + r, (uint32_t)(c >> 2));
-    Philox4 w1 = dropout_words(seed, C.layer, C.row0 + r, (uint32_t)(c >> 2) + 1u);
+// 4 keep bits of (row r, columns c..c+3) from Philox (same words as egnn_dropout_mask)
+__device__ __forceinline__ uint32_t keep_bits4(const ActCtx& C, uint64_t seed, int64_t r, int c) {
+  Philox4 w = dropout_words(seed, C.layer, C.row0 + r, (uint32_t)(c >> 2));
+  return (w.v[0] >= C.thr ? 1u : 0u) | (w.v[1] >= C.thr ? 2u : 0u) | (w.v[2] >= C.thr ? 4u : 0u) |
+         (w.v[3] >= C.thr ? 8u : 0u);
+}
+// u = bn(z); a = act(u); returns y = a*ks, dfac = act'(u)*ks, xhat
+template <bool BN, int ACT>
+__device__ __forceinline__ void act4(const Col4& k, float scale, uint32_t bits, const float (&z)[4], float (&y)[4],
+                                     float (&dfac)[4], float (&xhat)[4]) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { words[i] = w0.v[i]; words[4 + i] = w1.v[i]; }
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < 4; ++i) {
     float u = z[i];
     xhat[i] = 0.f;
-    if (C.mean) {
-      xhat[i] = (z[i] - k.mean[c + i]) * k.rstd[c + i];
-      u = xhat[i] * k.gamma[c + i] + k.beta[c + i];
+    if (BN) {
+      xhat[i] = (z[i] - k.mean[i]) * k.rstd[i];
+      u = xhat[i] * k.gamma[i] + k.beta[i];
     }
     float a = u, da = 1.f;
-    if (C.act == EGNN_ACT_RELU) {
+    if (ACT == EGNN_ACT_RELU) {
       a = u > 0.f ? u : 0.f;
       da = u > 0.f ? 1.f : 0.f;
-    } else if (C.act == EGNN_ACT_ELU) {
-      float e = expm1f(u);
+    } else if (ACT == EGNN_ACT_ELU) {
+      const float e = expm1f(u);
       a = u > 0.f ? u : e;
       da = u > 0.f ? 1.f : e + 1.f;
     }
-    float ks = 1.f;
-    if (C.drop) ks = words[i] >= C.thr ? C.scale : 0.f;
+    const float ks = (bits >> i) & 1u ? scale : 0.f;
     y[i] = a * ks;
     dfac[i] = da * ks;
   }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(kThreads) bn_act_fwd_fast(const T* __restrict__ z, const T* __restrict__ res,
+template <typename T, bool BN, int ACT>
+__global__ void __launch_bounds__(kThreads, 3) bn_act_fwd_lean(const T* __restrict__ z, const T* __restrict__ res,
                                                             T* __restrict__ yout, int64_t ld, int64_t ld_res,
-                                                            int64_t ld_y,
-                                                            int64_t n_rows, int F, int cg_shift,
-                                                            int64_t rows_per_block, ActCtx C) {
-  __shared__ ColConsts k;
-  stage_consts(C, F, k);
-  __syncthreads();
+                                                            int64_t ld_y, int64_t n_rows, int F, int cg_shift,
+                                                            int64_t rows_per_block, ActCtx C,
+                                                            uint8_t* __restrict__ keep_bits) {
   const int CG = 1 << cg_shift, RL = kThreads >> cg_shift;
-  const int c = (threadIdx.x & (CG - 1)) * 8, rl = threadIdx.x >> cg_shift;
+  const int cgi = threadIdx.x & (CG - 1), c = cgi * 4, rl = threadIdx.x >> cg_shift;
+  Col4 k;
+  load_col4<BN>(C, c, k);
   const uint64_t seed = C.seed + (C.seed_off ? (uint64_t)*C.seed_off : 0ull);
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(n_rows, r0 + rows_per_block);
-  Raw8<T> zr, rr, zn, rn;
-  int64_t r = r0 + rl;
-  if (r < r1) {
-    zr.load(z + r * ld + c);
-    if (res) rr.load(res + r * ld_res + c);
-  }
-#pragma unroll 1
-  for (; r < r1; r += RL) {
-    if (r + RL < r1) {  // next row's loads in flight while this row is processed
-      zn.load(z + (r + RL) * ld + c);
-      if (res) rn.load(res + (r + RL) * ld_res + c);
-    }
-    float zv[8], rv[8], y[8], d[8], xh[8];
-    zr.unpack(zv);
-    if (res) rr.unpack(rv);
-    zr = zn; rr = rn;
-    act_eval8(C, k, seed, r, c, zv, y, d, xh);
-    if (res) {
+  for (int64_t rb = r0 + rl; rb < r1; rb += (int64_t)RL * kRowsInFlight) {
+    Raw4<T> zr[kRowsInFlight], rr[kRowsInFlight];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) y[i] += rv[i];
+    for (int u = 0; u < kRowsInFlight; ++u) {
+      const int64_t r = rb + (int64_t)u * RL;
+      if (r < r1) {
+        zr[u].load(z + r * ld + c);
+        if (res) rr[u].load(res + r * ld_res + c);
+      }
     }
-    st8f(yout + r * ld_y + c, y);
+#pragma unroll
+    for (int u = 0; u < kRowsInFlight; ++u) {
+      const int64_t r = rb + (int64_t)u * RL;
+      if (r < r1) {
+        float zv[4], y[4], d[4], xh[4];
+        zr[u].unpack(zv);
+        const uint32_t bits = C.drop ? keep_bits4(C, seed, r, c) : 0xfu;
+        if (keep_bits) keep_bits[r * CG + cgi] = (uint8_t)bits;
+        act4<BN, ACT>(k, C.scale, bits, zv, y, d, xh);
+        if (res) {
+          float rv[4];
+          rr[u].unpack(rv);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) y[i] += rv[i];
+        }
+        st4f(yout + r * ld_y + c, y);
+      }
+    }
   }
 }
 
 // partial[(blk*2 + which)*F + col] (double), which: 0 = sum g, 1 = sum g*xhat
-template <typename T>
-__global__ void __launch_bounds__(kThreads, 3) bn_act_bwd_reduce_fast(const T* __restrict__ dy, int64_t ld_dy,
+template <typename T, bool BN, int ACT>
+__global__ void __launch_bounds__(kThreads, 3) bn_act_bwd_reduce_lean(const T* __restrict__ dy, int64_t ld_dy,
                                                                    const T* __restrict__ z, int64_t ld,
                                                                    int64_t n_rows, int F, int cg_shift,
                                                                    int64_t rows_per_block, ActCtx C,
-                                                                   double* __restrict__ partial) {
-  __shared__ ColConsts k;
-  __shared__ float sm[kThreads][17];
-  stage_consts(C, F, k);
-  __syncthreads();
+                                                                   double* __restrict__ partial,
+                                                                   const uint8_t* __restrict__ keep_bits) {
+  __shared__ float sm[kThreads][9];
   const int CG = 1 << cg_shift, RL = kThreads >> cg_shift;
-  const int cgi = threadIdx.x & (CG - 1), c = cgi * 8, rl = threadIdx.x >> cg_shift;
+  const int cgi = threadIdx.x & (CG - 1), c = cgi * 4, rl = threadIdx.x >> cg_shift;
+  Col4 k;
+  load_col4<BN>(C, c, k);
   const uint64_t seed = C.seed + (C.seed_off ? (uint64_t)*C.seed_off : 0ull);
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(n_rows, r0 + rows_per_block);
-  float a0[8], a1[8];
+  float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int64_t rb = r0 + rl; rb < r1; rb += (int64_t)RL * kRowsInFlight) {
+    Raw4<T> zr[kRowsInFlight], gr[kRowsInFlight];
+    uint32_t kb[kRowsInFlight];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) a0[i] = a1[i] = 0.f;
-  Raw8<T> zr, gr, zn, gn;
-  int64_t r = r0 + rl;
-  if (r < r1) { zr.load(z + r * ld + c); gr.load(dy + r * ld_dy + c); }
-#pragma unroll 1
-  for (; r < r1; r += RL) {
-    if (r + RL < r1) { zn.load(z + (r + RL) * ld + c); gn.load(dy + (r + RL) * ld_dy + c); }
-    float zv[8], g[8], y[8], d[8], xh[8];
-    zr.unpack(zv); gr.unpack(g);
-    zr = zn; gr = gn;
-    act_eval8(C, k, seed, r, c, zv, y, d, xh);
+    for (int u = 0; u < kRowsInFlight; ++u) {
+      const int64_t r = rb + (int64_t)u * RL;
+      if (r < r1) {
+        zr[u].load(z + r * ld + c);
+        gr[u].load(dy + r * ld_dy + c);
+        kb[u] = (C.drop && keep_bits) ? keep_bits[r * CG + cgi] : 0xfu;
+      }
+    }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float gg = g[i] * d[i];
-      a0[i] += gg;
-      a1[i] = fmaf(gg, xh[i], a1[i]);
+    for (int u = 0; u < kRowsInFlight; ++u) {
+      const int64_t r = rb + (int64_t)u * RL;
+      if (r < r1) {
+        float zv[4], g[4], y[4], d[4], xh[4];
+        zr[u].unpack(zv);
+        gr[u].unpack(g);
+        const uint32_t bits = (C.drop && !keep_bits) ? keep_bits4(C, seed, r, c) : kb[u];
+        act4<BN, ACT>(k, C.scale, bits, zv, y, d, xh);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float gg = g[i] * d[i];
+          a0[i] += gg;
+          a1[i] = fmaf(gg, xh[i], a1[i]);
+        }
+      }
     }
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { sm[threadIdx.x][i] = a0[i]; sm[threadIdx.x][8 + i] = a1[i]; }
+  for (int i = 0; i < 4; ++i) { sm[threadIdx.x][i] = a0[i]; sm[threadIdx.x][4 + i] = a1[i]; }
   __syncthreads();
-  // 16 values per column group, summed over the row lanes in a fixed order by 16 threads per group
-  for (int item = threadIdx.x; item < CG * 16; item += kThreads) {
-    const int g_ = item >> 4, i = item & 15;
+  for (int item = threadIdx.x; item < CG * 8; item += kThreads) {
+    const int g_ = item >> 3, i = item & 7;
     double s = 0.0;
     for (int l = 0; l < RL; ++l) s += (double)sm[l * CG + g_][i];
-    partial[((int64_t)blockIdx.x * 2 + (i >> 3)) * F + g_ * 8 + (i & 7)] = s;
+    partial[((int64_t)blockIdx.x * 2 + (i >> 2)) * F + g_ * 4 + (i & 3)] = s;
   }
 }
 
 // dz = gamma*rstd*(g - mean(g) - xhat*mean(g*xhat)) (or g without BN); optionally the per-block
 // column sums of the dz values written (the conv-bias gradient) -> dzsum_partial[blk*F + col]
-template <typename T>
-__global__ void __launch_bounds__(kThreads, 3) bn_act_bwd_apply_fast(const T* __restrict__ dy, int64_t ld_dy,
+template <typename T, bool BN, int ACT>
+__global__ void __launch_bounds__(kThreads, 3) bn_act_bwd_apply_lean(const T* __restrict__ dy, int64_t ld_dy,
                                                                   const T* __restrict__ z, int64_t ld_z,
-                                                                  T* __restrict__ dz, int64_t ld, int64_t n_rows, int F, int cg_shift,
-                                                                  int64_t rows_per_block, ActCtx C,
-                                                                  const double* __restrict__ sum_g,
+                                                                  T* __restrict__ dz, int64_t ld, int64_t n_rows,
+                                                                  int F, int cg_shift, int64_t rows_per_block,
+                                                                  ActCtx C, const double* __restrict__ sum_g,
                                                                   const double* __restrict__ sum_gx, double inv_n,
-                                                                  double* __restrict__ dzsum_partial) {
-  __shared__ ColConsts k;
-  __shared__ float s_mg[kFastMaxF], s_mgx[kFastMaxF];
-  __shared__ float sm[kThreads][9];
-  stage_consts(C, F, k);
-  for (int i = threadIdx.x; i < F; i += kThreads) {
-    s_mg[i] = C.mean ? (float)(sum_g[i] * inv_n) : 0.f;
-    s_mgx[i] = C.mean ? (float)(sum_gx[i] * inv_n) : 0.f;
-  }
-  __syncthreads();
+                                                                  double* __restrict__ dzsum_partial,
+                                                                  const uint8_t* __restrict__ keep_bits) {
+  __shared__ float sm[kThreads][5];
   const int CG = 1 << cg_shift, RL = kThreads >> cg_shift;
-  const int cgi = threadIdx.x & (CG - 1), c = cgi * 8, rl = threadIdx.x >> cg_shift;
+  const int cgi = threadIdx.x & (CG - 1), c = cgi * 4, rl = threadIdx.x >> cg_shift;
+  Col4 k;
+  load_col4<BN>(C, c, k);
+  float c1[4], c2[4], c3[4];  // dz = c1*gg - c2 - xhat*c3
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (BN) {
+      const float gr = k.gamma[i] * k.rstd[i];
+      c1[i] = gr;
+      c2[i] = gr * (float)(sum_g[c + i] * inv_n);
+      c3[i] = gr * (float)(sum_gx[c + i] * inv_n);
+    } else {
+      c1[i] = 1.f; c2[i] = 0.f; c3[i] = 0.f;
+    }
+  }
   const uint64_t seed = C.seed + (C.seed_off ? (uint64_t)*C.seed_off : 0ull);
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(n_rows, r0 + rows_per_block);
-  float acc[8];
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int64_t rb = r0 + rl; rb < r1; rb += (int64_t)RL * kRowsInFlight) {
+    Raw4<T> zr[kRowsInFlight], gr[kRowsInFlight];
+    uint32_t kb[kRowsInFlight];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-  Raw8<T> zr, gr, zn, gn;
-  int64_t r = r0 + rl;
-  if (r < r1) { zr.load(z + r * ld_z + c); gr.load(dy + r * ld_dy + c); }
-#pragma unroll 1
-  for (; r < r1; r += RL) {
-    if (r + RL < r1) { zn.load(z + (r + RL) * ld_z + c); gn.load(dy + (r + RL) * ld_dy + c); }
-    float zv[8], g[8], y[8], d[8], xh[8], o[8];
-    zr.unpack(zv); gr.unpack(g);
-    zr = zn; gr = gn;
-    act_eval8(C, k, seed, r, c, zv, y, d, xh);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float gg = g[i] * d[i];
-      if (C.mean) gg = k.gamma[c + i] * k.rstd[c + i] * (gg - s_mg[c + i] - xh[i] * s_mgx[c + i]);
-      o[i] = gg;
+    for (int u = 0; u < kRowsInFlight; ++u) {
+      const int64_t r = rb + (int64_t)u * RL;
+      if (r < r1) {
+        zr[u].load(z + r * ld_z + c);
+        gr[u].load(dy + r * ld_dy + c);
+        kb[u] = (C.drop && keep_bits) ? keep_bits[r * CG + cgi] : 0xfu;
+      }
     }
-    st8f(dz + r * ld + c, o);
-    if (dzsum_partial) {
-      // sum what the consumer will read (the value after rounding to T)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += to_f32(from_f32<T>(o[i]));
+    for (int u = 0; u < kRowsInFlight; ++u) {
+      const int64_t r = rb + (int64_t)u * RL;
+      if (r < r1) {
+        float zv[4], g[4], y[4], d[4], xh[4], o[4];
+        zr[u].unpack(zv);
+        gr[u].unpack(g);
+        const uint32_t bits = (C.drop && !keep_bits) ? keep_bits4(C, seed, r, c) : kb[u];
+        act4<BN, ACT>(k, C.scale, bits, zv, y, d, xh);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float gg = g[i] * d[i];
+          o[i] = BN ? (c1[i] * gg - c2[i]) - xh[i] * c3[i] : gg;
+        }
+        st4f(dz + r * ld + c, o);
+        if (dzsum_partial) {  // sum what the consumer will read (the value after rounding to T)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[i] += to_f32(from_f32<T>(o[i]));
+        }
+      }
     }
   }
   if (dzsum_partial) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) sm[threadIdx.x][i] = acc[i];
+    for (int i = 0; i < 4; ++i) sm[threadIdx.x][i] = acc[i];
     __syncthreads();
-    for (int item = threadIdx.x; item < CG * 8; item += kThreads) {
-      const int g_ = item >> 3, i = item & 7;
+    for (int item = threadIdx.x; item < CG * 4; item += kThreads) {
+      const int g_ = item >> 2, i = item & 3;
       double s = 0.0;
       for (int l = 0; l < RL; ++l) s += (double)sm[l * CG + g_][i];
-      dzsum_partial[(int64_t)blockIdx.x * F + g_ * 8 + i] = s;
+      dzsum_partial[(int64_t)blockIdx.x * F + g_ * 4 + i] = s;
     }
   }
 }
+
+// host-side dispatch over (dtype, BatchNorm, activation)
+#define EGNN_LEAN_DISPATCH(KERNEL, GRID, ...)                                                            \
+  do {                                                                                                   \
+    const bool bn_ = C.mean != nullptr;                                                                  \
+    if (dtype == EGNN_F32) {                                                                             \
+      using TT = float;                                                                                  \
+      if (bn_ && C.act == EGNN_ACT_RELU) KERNEL<TT, true, EGNN_ACT_RELU><<<GRID, kThreads, 0, st>>>(__VA_ARGS__);   \
+      else if (bn_ && C.act == EGNN_ACT_NONE) KERNEL<TT, true, EGNN_ACT_NONE><<<GRID, kThreads, 0, st>>>(__VA_ARGS__); \
+      else if (bn_) KERNEL<TT, true, EGNN_ACT_ELU><<<GRID, kThreads, 0, st>>>(__VA_ARGS__);             \
+      else if (C.act == EGNN_ACT_RELU) KERNEL<TT, false, EGNN_ACT_RELU><<<GRID, kThreads, 0, st>>>(__VA_ARGS__);  \
+      else if (C.act == EGNN_ACT_NONE) KERNEL<TT, false, EGNN_ACT_NONE><<<GRID, kThreads, 0, st>>>(__VA_ARGS__);  \
+      else KERNEL<TT, false, EGNN_ACT_ELU><<<GRID, kThreads, 0, st>>>(__VA_ARGS__);                     \
+    } else {                                                                                             \
+      using TT = __nv_bfloat16;                                                                          \
+      if (bn_ && C.act == EGNN_ACT_RELU) KERNEL<TT, true, EGNN_ACT_RELU><<<GRID, kThreads, 0, st>>>(__VA_ARGS__);   \
+      else if (bn_ && C.act == EGNN_ACT_NONE) KERNEL<TT, true, EGNN_ACT_NONE><<<GRID, kThreads, 0, st>>>(__VA_ARGS__); \
+      else if (bn_) KERNEL<TT, true, EGNN_ACT_ELU><<<GRID, kThreads, 0, st>>>(__VA_ARGS__);             \
+      else if (C.act == EGNN_ACT_RELU) KERNEL<TT, false, EGNN_ACT_RELU><<<GRID, kThreads, 0, st>>>(__VA_ARGS__);  \
+      else if (C.act == EGNN_ACT_NONE) KERNEL<TT, false, EGNN_ACT_NONE><<<GRID, kThreads, 0, st>>>(__VA_ARGS__);  \
+      else KERNEL<TT, false, EGNN_ACT_ELU><<<GRID, kThreads, 0, st>>>(__VA_ARGS__);                     \
+    }                                                                                                    \
+  } while (0)
 
 // column statistics of a matrix (BatchNorm forward): partial[(blk*2+which)*F + col]
 template <typename T>
@@ -614,6 +696,7 @@ __global__ void __launch_bounds__(kThreads) colstats_fast(const T* __restrict__ 
   }
 }
 
+constexpr int kFastMaxF = 2048;
 struct FastPlan {
   bool ok;
   int cg_shift;
@@ -633,6 +716,27 @@ inline FastPlan fast_plan(int64_t n_rows, int64_t F, int64_t ld, int dtype, std:
   const int RL = kThreads >> sh;
   int64_t rpb = (int64_t)RL * 8;
   if (ceil_div(n_rows, rpb) > kMaxPartBlocks) rpb = ceil_div(ceil_div(n_rows, kMaxPartBlocks), RL) * RL;
+  p.ok = true; p.cg_shift = sh; p.rpb = rpb; p.nblk = (int)ceil_div(n_rows > 0 ? n_rows : 1, rpb);
+  return p;
+}
+
+// plan of the 4-column lean kernels: F/4 a power of two <= 256, 4-element aligned pointers / strides
+inline FastPlan lean_plan(int64_t n_rows, int64_t F, int dtype, std::initializer_list<int64_t> lds,
+                          std::initializer_list<const void*> ptrs) {
+  FastPlan p{false, 0, 0, 0};
+  if (F % 4 != 0 || F > 4 * kThreads) return p;
+  int cg = (int)(F / 4), sh = 0;
+  while ((1 << sh) < cg) ++sh;
+  if ((1 << sh) != cg) return p;
+  const size_t es = dtype == EGNN_F32 ? 4 : 2;
+  for (int64_t l : lds)
+    if (l % 4 != 0) return p;
+  for (const void* q : ptrs)
+    if (q && (uintptr_t)q % (4 * es) != 0) return p;
+  const int RL = kThreads >> sh;
+  int64_t rpb = (int64_t)RL * kRowsInFlight * 2;
+  if (ceil_div(n_rows, rpb) > kMaxPartBlocks)
+    rpb = ceil_div(ceil_div(n_rows, kMaxPartBlocks), RL * kRowsInFlight) * RL * kRowsInFlight;
   p.ok = true; p.cg_shift = sh; p.rpb = rpb; p.nblk = (int)ceil_div(n_rows > 0 ? n_rows : 1, rpb);
   return p;
 }
@@ -922,7 +1026,8 @@ extern "C" int egnn_bn_act_dropout_res_fwd(const void* z, const void* res, void*
                                            int64_t n_rows, int64_t n_feat, const float* mean,
                                            const float* rstd, const float* gamma, const float* beta,
                                            int act, float p, uint64_t seed, const int64_t* seed_off, uint32_t layer,
-                                           int64_t row0, int64_t ld_res, int64_t ld_y, void* stream) {
+                                           int64_t row0, int64_t ld_res, int64_t ld_y, uint8_t* keep_bits,
+                                           void* stream) {
   const char* fn = "egnn_bn_act_dropout_res_fwd";
   if (ld_y <= 0) ld_y = ld;
   if (ld_res <= 0) ld_res = ld;
@@ -933,20 +1038,15 @@ extern "C" int egnn_bn_act_dropout_res_fwd(const void* z, const void* res, void*
   if (n_rows == 0) return 0;
   ActCtx C = make_ctx(mean, rstd, gamma, beta, act, p, seed, seed_off, layer, row0);
   cudaStream_t st = (cudaStream_t)stream;
-  FastPlan fp = fast_plan(n_rows, n_feat, ld, dtype, {z, res, y});
-  if (fp.ok && ld_y % 8 == 0 && ld_res % 8 == 0) {
-    const unsigned nb = (unsigned)ceil_div(n_rows, fp.rpb);
-    if (dtype == EGNN_F32)
-      bn_act_fwd_fast<float><<<nb, kThreads, 0, st>>>((const float*)z, (const float*)res, (float*)y, ld, ld_res, ld_y, n_rows,
-                                                      (int)n_feat, fp.cg_shift, fp.rpb, C);
-    else
-      bn_act_fwd_fast<__nv_bfloat16><<<nb, kThreads, 0, st>>>((const __nv_bfloat16*)z, (const __nv_bfloat16*)res,
-                                                              (__nv_bfloat16*)y, ld, ld_res, ld_y, n_rows, (int)n_feat,
-                                                              fp.cg_shift, fp.rpb, C);
+  FastPlan fp = lean_plan(n_rows, n_feat, dtype, {ld, res ? ld_res : 4, ld_y}, {z, res, y});
+  if (fp.ok) {
+    EGNN_LEAN_DISPATCH(bn_act_fwd_lean, fp.nblk, (const TT*)z, (const TT*)res, (TT*)y, ld, ld_res, ld_y, n_rows,
+                       (int)n_feat, fp.cg_shift, fp.rpb, C, keep_bits);
     EGNN_LAUNCH_CHECK(fn);
     return 0;
   }
-  EGNN_REQUIRE(ld_y == ld && ld_res == ld, fn, "separate leading dimensions need the 8-column fast path");
+  EGNN_REQUIRE(ld_y == ld && ld_res == ld && !keep_bits, fn,
+               "separate leading dimensions / keep_bits need the 4-column streaming path");
   bool v = vec_ok(z, dtype, ld, n_feat) && vec_ok(res, dtype, ld, n_feat) && vec_ok(y, dtype, ld, n_feat);
   unsigned grid = (unsigned)ceil_div(n_rows * ceil_div(n_feat, 4), kThreads);
   if (dtype == EGNN_F32)
@@ -964,28 +1064,23 @@ extern "C" int egnn_bn_act_dropout_bwd_reduce(const void* dy, const void* z, int
                                               const float* rstd, const float* gamma, const float* beta,
                                               int act, float p, uint64_t seed, const int64_t* seed_off,
                                               uint32_t layer, int64_t row0, double* sum_g, double* sum_gx, void* workspace,
-                                              int64_t ld_z, void* stream) {
+                                              int64_t ld_z, const uint8_t* keep_bits, void* stream) {
   const char* fn = "egnn_bn_act_dropout_bwd_reduce";
   if (ld_z <= 0) ld_z = ld;
   EGNN_REQUIRE(dy && z && sum_g && sum_gx && workspace && mean && rstd && gamma && beta, fn, "null pointer");
   ActCtx C = make_ctx(mean, rstd, gamma, beta, act, p, seed, seed_off, layer, row0);
   cudaStream_t st = (cudaStream_t)stream;
-  FastPlan fp = fast_plan(n_rows, n_feat, ld, dtype, {z, dy});
-  if (!(fp.ok && ld_z % 8 == 0) && ld_z != ld) return fail(fn, "separate ld_z needs the 8-column fast path");
-  if (fp.ok && ld_z % 8 == 0) {
+  FastPlan fp = lean_plan(n_rows, n_feat, dtype, {ld, ld_z}, {z, dy});
+  if (fp.ok) {
     double* partial = reinterpret_cast<double*>(workspace);
-    if (dtype == EGNN_F32)
-      bn_act_bwd_reduce_fast<float><<<fp.nblk, kThreads, 0, st>>>((const float*)dy, ld, (const float*)z, ld_z, n_rows,
-                                                                  (int)n_feat, fp.cg_shift, fp.rpb, C, partial);
-    else
-      bn_act_bwd_reduce_fast<__nv_bfloat16><<<fp.nblk, kThreads, 0, st>>>(
-          (const __nv_bfloat16*)dy, ld, (const __nv_bfloat16*)z, ld_z, n_rows, (int)n_feat, fp.cg_shift, fp.rpb, C,
-          partial);
+    EGNN_LEAN_DISPATCH(bn_act_bwd_reduce_lean, fp.nblk, (const TT*)dy, ld, (const TT*)z, ld_z, n_rows, (int)n_feat,
+                       fp.cg_shift, fp.rpb, C, partial, keep_bits);
     EGNN_LAUNCH_CHECK(fn);
     colreduce_final<<<dim3((unsigned)n_feat, 2), kThreads, 0, st>>>(partial, fp.nblk, (int)n_feat, sum_g, sum_gx);
     EGNN_LAUNCH_CHECK(fn);
     return 0;
   }
+  if (ld_z != ld || keep_bits) return fail(fn, "separate ld_z / keep_bits need the 4-column streaming path");
   bool v = vec_ok(z, dtype, ld, n_feat) && vec_ok(dy, dtype, ld, n_feat);
   if (dtype == EGNN_F32)
     return run_colreduce(BnBwdProd<float>{(const float*)dy, (const float*)z, ld, (int)n_feat, v, C}, n_rows,
@@ -1000,7 +1095,8 @@ extern "C" int egnn_bn_act_dropout_bwd_apply(const void* dy, const void* z, void
                                              const float* rstd, const float* gamma, const float* beta,
                                              int act, float p, uint64_t seed, const int64_t* seed_off, uint32_t layer,
                                              int64_t row0, const double* sum_g, const double* sum_gx, double n_total,
-                                             float* dz_colsum, void* workspace, int64_t ld_z, void* stream) {
+                                             float* dz_colsum, void* workspace, int64_t ld_z,
+                                             const uint8_t* keep_bits, void* stream) {
   const char* fn = "egnn_bn_act_dropout_bwd_apply";
   if (ld_z <= 0) ld_z = ld;
   EGNN_REQUIRE(!dz_colsum || workspace, fn, "dz_colsum needs a workspace (egnn_colreduce_workspace_bytes)");
@@ -1011,18 +1107,11 @@ extern "C" int egnn_bn_act_dropout_bwd_apply(const void* dy, const void* z, void
   ActCtx C = make_ctx(mean, rstd, gamma, beta, act, p, seed, seed_off, layer, row0);
   cudaStream_t st = (cudaStream_t)stream;
   double inv_n = mean ? 1.0 / n_total : 0.0;
-  FastPlan fp = fast_plan(n_rows, n_feat, ld, dtype, {z, dy, dz});
-  if (!(fp.ok && ld_z % 8 == 0) && ld_z != ld) return fail(fn, "separate ld_z needs the 8-column fast path");
-  if (fp.ok && ld_z % 8 == 0) {
+  FastPlan fp = lean_plan(n_rows, n_feat, dtype, {ld, ld_z}, {z, dy, dz});
+  if (fp.ok) {
     double* partial = dz_colsum ? reinterpret_cast<double*>(workspace) : nullptr;
-    if (dtype == EGNN_F32)
-      bn_act_bwd_apply_fast<float><<<fp.nblk, kThreads, 0, st>>>((const float*)dy, ld, (const float*)z, ld_z, (float*)dz,
-                                                                 ld, n_rows, (int)n_feat, fp.cg_shift, fp.rpb, C,
-                                                                 sum_g, sum_gx, inv_n, partial);
-    else
-      bn_act_bwd_apply_fast<__nv_bfloat16><<<fp.nblk, kThreads, 0, st>>>(
-          (const __nv_bfloat16*)dy, ld, (const __nv_bfloat16*)z, ld_z, (__nv_bfloat16*)dz, ld, n_rows, (int)n_feat,
-          fp.cg_shift, fp.rpb, C, sum_g, sum_gx, inv_n, partial);
+    EGNN_LEAN_DISPATCH(bn_act_bwd_apply_lean, fp.nblk, (const TT*)dy, ld, (const TT*)z, ld_z, (TT*)dz, ld, n_rows,
+                       (int)n_feat, fp.cg_shift, fp.rpb, C, sum_g, sum_gx, inv_n, partial, keep_bits);
     EGNN_LAUNCH_CHECK(fn);
     if (dz_colsum) {
       colsum_final<<<(unsigned)n_feat, kThreads, 0, st>>>(partial, fp.nblk, (int)n_feat, dz_colsum);
@@ -1030,6 +1119,7 @@ extern "C" int egnn_bn_act_dropout_bwd_apply(const void* dy, const void* z, void
     }
     return 0;
   }
+  if (ld_z != ld || keep_bits) return fail(fn, "separate ld_z / keep_bits need the 4-column streaming path");
   bool v = vec_ok(z, dtype, ld, n_feat) && vec_ok(dy, dtype, ld, n_feat) && vec_ok(dz, dtype, ld, n_feat);
   unsigned grid = (unsigned)ceil_div(n_rows * ceil_div(n_feat, 4), kThreads);
   if (dtype == EGNN_F32)

@@ -29,6 +29,8 @@ namespace egnn {
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kThreadsTN = 384;   // gemm_tn_kernel: warps 0-3 control, 4-11 epilogue (two per TMEM sub-partition)
+constexpr int kEpiWarps = 8;
 constexpr int BM = 128;          // UMMA M (cta_group::1)
 constexpr int BK = 64;           // bf16 elements per 128-byte swizzled row
 constexpr int kStageBytesA = BM * BK * 2;  // 16 KB
@@ -92,6 +94,17 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
@@ -129,10 +142,94 @@ struct Epilogue {
   int row_div_cols;  // only columns [0, row_div_cols) are divided (<= 0: all)
 };
 
+// Epilogue of gemm_tn_kernel for one warp: FLAGS bit 0 = +bias, bit 1 = /row count, bit 2 = += C.
+template <typename TC, int FLAGS>
+__device__ __forceinline__ void epilogue_loop(const Epilogue& ep, const float* s_bias, uint64_t* t_full,
+                                              uint64_t* t_empty, uint32_t tmem_base, int Npad, int M, int N,
+                                              int n_tiles, int q, int half, int lane) {
+  constexpr bool kBias = FLAGS & 1, kDiv = (FLAGS & 2) != 0, kAcc = (FLAGS & 4) != 0;
+  const int div_cols = ep.row_div_cols > 0 ? ep.row_div_cols : N;
+  TC* __restrict__ Cbase = reinterpret_cast<TC*>(ep.C);
+  const bool vec_ok = (ep.ld_c % 8 == 0) && ((uintptr_t)ep.C % 16 == 0);
+  int it = 0;
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const uint32_t use = (uint32_t)(it >> 1);
+    mbar_wait(&t_full[buf], use & 1);
+    tcgen05_fence_after();
+    const int64_t row = (int64_t)t * BM + q * 32 + lane;
+    const bool row_ok = row < M;
+    float rdiv = 1.f, rinv = 1.f;
+    if (kDiv && row_ok) {
+      int d = ep.row_div_ptr[row + 1] - ep.row_div_ptr[row];
+      rdiv = (float)(d > 1 ? d : 1);
+      rinv = __frcp_rn(rdiv);
+    }
+    const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * Npad);
+    for (int c0 = half * 16; c0 < N; c0 += 32) {
+      float v[16];
+      tmem_ld16(t_addr + c0, v);
+      if (!row_ok) continue;
+      const int nv = min(16, N - c0);
+      TC* c = Cbase + row * ep.ld_c + c0;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (kBias) v[j] += s_bias[c0 + j];
+        if (kDiv) {
+          // bf16 result: x * rn(1/deg) differs from the IEEE quotient by < 1 ulp(fp32), invisible after
+          // rounding to 8 mantissa bits; fp32 result keeps the exact division (parity with CPU torch)
+          if (c0 + j < div_cols) v[j] = sizeof(TC) == 2 ? v[j] * rinv : __fdiv_rn(v[j], rdiv);
+        }
+      }
+      if (nv == 16 && vec_ok) {
+        if (sizeof(TC) == 4) {
+          float* cf = reinterpret_cast<float*>(c);
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            float4 o = make_float4(v[4 * h], v[4 * h + 1], v[4 * h + 2], v[4 * h + 3]);
+            if (kAcc) {
+              const float4 old = *reinterpret_cast<const float4*>(cf + 4 * h);
+              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+            }
+            *reinterpret_cast<float4*>(cf + 4 * h) = o;
+          }
+        } else {
+          __nv_bfloat16* cb = reinterpret_cast<__nv_bfloat16*>(c);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            F8 r;
+            if (kAcc) {
+              const F8 old = ld8(cb + 8 * h);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) r.v[j] = v[8 * h + j] + old.v[j];
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) r.v[j] = v[8 * h + j];
+            }
+            st8(cb + 8 * h, r);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (j < nv) {
+            float o = v[j];
+            if (kAcc) o += to_f32(c[j]);
+            c[j] = from_f32<TC>(o);
+          }
+        }
+      }
+    }
+    tcgen05_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&t_empty[buf]);
+  }
+}
+
 // ------------------------------------------------------------------ forward / dgrad --------
 // smem map (dynamic, 1024-aligned): [W chunks: KC * Npad*128][A ring: S * 16 KB][barriers]
 template <int kStages>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreadsTN, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, int M, int N,
                int Npad, int K, Epilogue ep) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -151,13 +248,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (M + BM - 1) / BM;
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);  // [256 + 16] floats behind the barriers
+  for (int i = threadIdx.x; i < 256 + 16; i += kThreadsTN) s_bias[i] = (ep.bias && i < N) ? ep.bias[i] : 0.f;
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < 2 * Npad) tmem_cols <<= 1;
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(w_full, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(&t_full[b], 1); mbar_init(&t_empty[b], 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&t_full[b], 1); mbar_init(&t_empty[b], kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -219,68 +318,23 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp >= 4) {
-    const int q = warp & 3;  // TMEM sub-partition of this warp
-    int it = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-      const int buf = it & 1;
-      const uint32_t use = (uint32_t)(it >> 1);
-      mbar_wait(&t_full[buf], use & 1);
-      tcgen05_fence_after();
-      const int64_t row = (int64_t)t * BM + q * 32 + lane;
-      const bool row_ok = row < M;
-      float rdiv = 1.f;
-      if (ep.row_div_ptr && row_ok) {
-        int d = ep.row_div_ptr[row + 1] - ep.row_div_ptr[row];
-        rdiv = (float)(d > 1 ? d : 1);
-      }
-      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * Npad);
-      const int div_cols = ep.row_div_cols > 0 ? ep.row_div_cols : N;
-      for (int c0 = 0; c0 < N; c0 += 8) {
-        float v[8];
-        tmem_ld8(t_addr + c0, v);
-        if (row_ok) {
-          const int nv = min(8, N - c0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (ep.bias && j < nv) v[j] += ep.bias[c0 + j];
-            if (ep.row_div_ptr && c0 + j < div_cols) v[j] = __fdiv_rn(v[j], rdiv);
-          }
-          if (ep.c_dtype == EGNN_F32) {
-            float* c = reinterpret_cast<float*>(ep.C) + row * ep.ld_c + c0;
-            if (nv == 8 && (((uintptr_t)c) & 15) == 0) {
-              if (ep.accumulate) {
-                float4 o0 = *reinterpret_cast<float4*>(c), o1 = *reinterpret_cast<float4*>(c + 4);
-                v[0] += o0.x; v[1] += o0.y; v[2] += o0.z; v[3] += o0.w;
-                v[4] += o1.x; v[5] += o1.y; v[6] += o1.z; v[7] += o1.w;
-              }
-              *reinterpret_cast<float4*>(c) = make_float4(v[0], v[1], v[2], v[3]);
-              *reinterpret_cast<float4*>(c + 4) = make_float4(v[4], v[5], v[6], v[7]);
-            } else {
-              for (int j = 0; j < nv; ++j) c[j] = ep.accumulate ? c[j] + v[j] : v[j];
-            }
-          } else {
-            __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(ep.C) + row * ep.ld_c + c0;
-            if (nv == 8 && (((uintptr_t)c) & 15) == 0) {
-              if (ep.accumulate) {
-                F8 o = ld8(c);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] += o.v[j];
-              }
-              F8 r;
-#pragma unroll
-              for (int j = 0; j < 8; ++j) r.v[j] = v[j];
-              st8(c, r);
-            } else {
-              for (int j = 0; j < nv; ++j)
-                c[j] = __float2bfloat16_rn(ep.accumulate ? __bfloat162float(c[j]) + v[j] : v[j]);
-            }
-          }
-        }
-      }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&t_empty[buf]);
+    // 8 epilogue warps: warp w reads TMEM lanes 32*(w&3).. (its sub-partition) and every second
+    // 16-column chunk, so each scheduler has two epilogue warps to interleave
+    const int q = warp & 3, half = (warp - 4) >> 2;
+    const int flags = (ep.bias ? 1 : 0) | (ep.row_div_ptr ? 2 : 0) | (ep.accumulate ? 4 : 0);
+#define EGNN_EPI_CASE(F)                                                                                      \
+  case F:                                                                                                     \
+    if (ep.c_dtype == EGNN_F32)                                                                               \
+      epilogue_loop<float, F>(ep, s_bias, t_full, t_empty, tmem_base, Npad, M, N, n_tiles, q, half, lane);    \
+    else                                                                                                      \
+      epilogue_loop<__nv_bfloat16, F>(ep, s_bias, t_full, t_empty, tmem_base, Npad, M, N, n_tiles, q, half,   \
+                                      lane);                                                                  \
+    break;
+    switch (flags) {
+      EGNN_EPI_CASE(0) EGNN_EPI_CASE(1) EGNN_EPI_CASE(2) EGNN_EPI_CASE(3)
+      EGNN_EPI_CASE(4) EGNN_EPI_CASE(5) EGNN_EPI_CASE(6) EGNN_EPI_CASE(7)
     }
+#undef EGNN_EPI_CASE
   }
 
   tcgen05_fence_before();
@@ -443,6 +497,7 @@ bool make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int6
 }
 
 constexpr int kStagesTN = 6;
+constexpr size_t kMaxDynSmemTN = 227 * 1024;
 constexpr int kStagesWG = 4;
 
 }  // namespace
@@ -456,8 +511,8 @@ bool gemm_tcgen05_supported(int64_t lda, int64_t ldb, int64_t ld_c, int64_t M, i
   if (M >= (int64_t)1 << 31) return false;
   const int Npad = (int)((N + 15) / 16 * 16);
   const int KC = (int)((K + BK - 1) / BK);
-  size_t smem = (size_t)KC * Npad * 128 + (size_t)kStagesTN * kStageBytesA + 256 + 1024;
-  return smem <= 227 * 1024 && 2 * Npad <= 512;
+  size_t smem = (size_t)KC * Npad * 128 + (size_t)kStagesTN * kStageBytesA + 256 + 1088 + 1024;
+  return smem <= kMaxDynSmemTN && 2 * Npad <= 512;
 }
 
 int gemm_tcgen05_dispatch(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int c_dtype,
@@ -469,16 +524,16 @@ int gemm_tcgen05_dispatch(const void* A, int64_t lda, const void* B, int64_t ldb
   CUtensorMap tmA, tmW;
   if (!make_map(&tmA, A, M, K, lda, BM) || !make_map(&tmW, B, N, K, ldb, Npad))
     return fail(fn, "cuTensorMapEncodeTiled failed");
-  size_t smem = (size_t)KC * Npad * 128 + (size_t)kStagesTN * kStageBytesA + 256 + 1024;
+  size_t smem = (size_t)KC * Npad * 128 + (size_t)kStagesTN * kStageBytesA + 256 + 1088 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(gemm_tn_kernel<kStagesTN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(gemm_tn_kernel<kStagesTN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmemTN);
     attr_set = true;
   }
   int n_tiles = (int)((M + BM - 1) / BM);
   int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
   Epilogue ep{C, bias, row_div_ptr, ld_c, c_dtype, accumulate, (int)row_div_cols};
-  gemm_tn_kernel<kStagesTN><<<grid, kThreads, smem, st>>>(tmA, tmW, (int)M, (int)N, Npad, (int)K, ep);
+  gemm_tn_kernel<kStagesTN><<<grid, kThreadsTN, smem, st>>>(tmA, tmW, (int)M, (int)N, Npad, (int)K, ep);
   EGNN_LAUNCH_CHECK(fn);
   return 0;
 }

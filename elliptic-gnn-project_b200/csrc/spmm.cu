@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(kThreads) spmm_scalar(Params P) {
       if (P.bias) a = __fadd_rn(a, __ldg(P.bias + f));
       a = apply_act(a, P.act);
       TO* o = out + row * P.ld_out + f;
-      if (P.accumulate) a = __fadd_rn(to_f32(*o), a);
+      if (P.accumulate) a = __fadd_rn(to_f32(reinterpret_cast<const TO*>(P.add_in)[row * P.ld_add + f]), a);
       *o = from_f32<TO>(a);
     }
   }
@@ -220,7 +220,7 @@ extern "C" int egnn_spmm(int mode, const int32_t* ptr, const int32_t* col, const
                          const int32_t* nbr_ptr, const int32_t* long_rows, const int32_t* n_long,
                          const int32_t* row_order, const void* in, int in_dtype, int64_t ld_in, void* out, int out_dtype,
                          int64_t ld_out, int64_t n_rows, int64_t n_feat, const float* bias, int act,
-                         int accumulate, void* stream) {
+                         int accumulate, const void* addend, int64_t ld_addend, void* stream) {
   const char* fn = "egnn_spmm";
   EGNN_REQUIRE(ptr && col && in && out, fn, "null pointer");
   EGNN_REQUIRE(n_rows >= 0 && n_feat > 0 && n_feat <= (1 << 20), fn, "bad shape");
@@ -235,12 +235,17 @@ extern "C" int egnn_spmm(int mode, const int32_t* ptr, const int32_t* col, const
   P.long_rows = long_rows; P.n_long = n_long; P.row_order = row_order;
   P.in = in; P.out = out; P.bias = bias;
   P.ld_in = ld_in; P.ld_out = ld_out; P.n_rows = n_rows; P.n_feat = (int)n_feat;
-  P.mean = (mode == EGNN_SPMM_MEAN); P.act = act; P.accumulate = accumulate;
+  P.mean = (mode == EGNN_SPMM_MEAN); P.act = act;
+  P.accumulate = (accumulate || addend) ? 1 : 0;
+  P.add_in = addend ? addend : out;
+  P.ld_add = addend ? ld_addend : ld_out;
+  EGNN_REQUIRE(!addend || ld_addend >= n_feat, fn, "ld_addend < n_feat");
   const size_t in_es = in_dtype == EGNN_F32 ? 4 : 2, out_es = out_dtype == EGNN_F32 ? 4 : 2;
   // 4-feature vector accesses need 4-element-aligned rows and 16 B (fp32) / 8 B (bf16) bases
   bool vec_ok = (n_feat % 4 == 0) && (ld_in % 4 == 0) && (ld_out % 4 == 0) &&
                 ((uintptr_t)in % (4 * in_es) == 0) && ((uintptr_t)out % (4 * out_es) == 0) &&
-                (!bias || (uintptr_t)bias % 16 == 0);
+                (!bias || (uintptr_t)bias % 16 == 0) &&
+                (!addend || (ld_addend % 4 == 0 && (uintptr_t)addend % (4 * out_es) == 0));
   if (!vec_ok) { P.long_rows = nullptr; P.n_long = nullptr; }
   cudaStream_t st = (cudaStream_t)stream;
   if (vec_ok && mode != EGNN_SPMM_DIV_NBR) {

@@ -30,7 +30,9 @@ struct Params {
   int n_feat;      // total features
   int mean;        // divide by max(rowlen,1) after the reduction
   int act;
-  int accumulate;
+  int accumulate;       // out = add_in + result (add_in == out for an in-place accumulate)
+  const void* add_in;
+  int64_t ld_add;
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -77,7 +79,7 @@ __device__ __forceinline__ void epilogue_store(const Params& P, int64_t row, int
   a.z = apply_act(a.z, P.act); a.w = apply_act(a.w, P.act);
   TO* o = reinterpret_cast<TO*>(P.out) + row * P.ld_out + f;
   if (P.accumulate) {
-    F4 old = ld4(o);
+    F4 old = ld4(reinterpret_cast<const TO*>(P.add_in) + row * P.ld_add + f);
     a.x = __fadd_rn(old.x, a.x); a.y = __fadd_rn(old.y, a.y);
     a.z = __fadd_rn(old.z, a.z); a.w = __fadd_rn(old.w, a.w);
   }

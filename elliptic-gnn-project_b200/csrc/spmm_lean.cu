@@ -79,13 +79,13 @@ __device__ __forceinline__ void mean_scale(Acc<VEC>& a, int deg) {
 }
 
 template <typename TO, int VEC>
-__device__ __forceinline__ void generic_epilogue(const Params& P, TO* o, int f, Acc<VEC>& a) {
+__device__ __forceinline__ void generic_epilogue(const Params& P, TO* o, const TO* add, int f, Acc<VEC>& a) {
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
     float v = a.v[i];
     if (P.bias) v = __fadd_rn(v, __ldg(P.bias + f + i));
     v = apply_act(v, P.act);
-    if (P.accumulate) v = __fadd_rn(to_f32(o[i]), v);
+    if (P.accumulate) v = __fadd_rn(to_f32(add[i]), v);
     a.v[i] = v;
   }
   stv(o, a);
@@ -164,14 +164,229 @@ __global__ void __launch_bounds__(kThreads) spmm_lean(Params P) {
     }
   }
   TO* o = reinterpret_cast<TO*>(P.out) + row * P.ld_out + VEC * lane;
+  const TO* add = reinterpret_cast<const TO*>(P.add_in) + row * P.ld_add + VEC * lane;
 #pragma unroll
   for (int k = 0; k < VPL; ++k) {
     if (k < VPL - 1 || on[k]) {
       if (P.mean) mean_scale<sizeof(TO) == 4, VEC>(acc[k], deg);
       if (LEAN) stv(o + k * G * VEC, acc[k]);
-      else generic_epilogue<TO, VEC>(P, o + k * G * VEC, VEC * (lane + k * G), acc[k]);
+      else generic_epilogue<TO, VEC>(P, o + k * G * VEC, add + k * G * VEC, VEC * (lane + k * G), acc[k]);
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Pipelined persistent variant (the production forward / transposed kernel).
+//
+// The lean kernel above still pays three dependent global latencies per row (row pointers -> column
+// indices -> feature rows) inside every lane group, and with mean degree 2.3 only the last of them
+// carries feature bytes.  Here a CTA walks tiles of kTileRows consecutive rows and keeps a three-deep
+// software pipeline in shared memory with cp.async (LDGSTS): while the lane groups gather tile i, the
+// row pointers of tile i+2 and the column indices (and edge weights) of tile i+1 are already in
+// flight.  The gather phase therefore starts from shared-memory indices and every resident warp
+// spends its time with feature loads outstanding.  Tiles are handed out by a global counter (two
+// tiles of look-ahead), rows inside a tile by a shared-memory counter, so degree skew does not idle
+// lane groups.  Per-row arithmetic is unchanged: sequential fp32 adds in stored edge order.
+constexpr int kTileRows = 32;
+constexpr int kColCap = 768;      // staged column indices per tile; longer tiles read the rest from global
+constexpr int kCounterSlots = 16;
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+struct PipeSmem {
+  int ptr[3][kTileRows + 1];
+  int col[2][kColCap];
+  int tile[4];
+  int next_row[2];
+};
+
+template <typename TI, typename TO, int MODE, int VEC, int G, int VPL, int BATCH, bool LEAN>
+__global__ void __launch_bounds__(kThreads) spmm_pipe(Params P, int* __restrict__ counters, int n_tiles) {
+  __shared__ PipeSmem S;
+  __shared__ float s_w[MODE == M_WEIGHTED ? 2 : 1][MODE == M_WEIGHTED ? kColCap : 1];
+  __shared__ __align__(16) float s_stage[kStageEdges][kSliceFeat];  // long-row path only
+  __shared__ float s_scale[kStageEdges];
+  __shared__ int s_lcol[kStageEdges];
+  const int tid = threadIdx.x;
+  const bool has_long = P.long_rows != nullptr;
+  if (has_long && blockIdx.x < kLongCtas) {
+    long_row_path<TI, TO, MODE>(P, blockIdx.x, s_stage, s_scale, s_lcol);
+    __syncthreads();
+  }
+  int* work = counters;        // next tile to hand out
+  int* done = counters + 1;    // CTAs that have finished (the last one resets the slot)
+
+  auto issue_ptr = [&](int t, int buf) {
+    const int64_t r0 = (int64_t)t * kTileRows;
+    for (int i = tid; i <= kTileRows; i += kThreads) {
+      int64_t r = r0 + i;
+      cp_async4(&S.ptr[buf][i], P.ptr + (r <= P.n_rows ? r : P.n_rows));
+    }
+  };
+  auto issue_col = [&](int pbuf, int cbuf) {
+    const int base = S.ptr[pbuf][0];
+    int n = S.ptr[pbuf][kTileRows] - base;
+    n = n < kColCap ? n : kColCap;
+    for (int i = tid; i < n; i += kThreads) {
+      cp_async4(&S.col[cbuf][i], P.col + base + i);
+      if (MODE == M_WEIGHTED) cp_async4(&s_w[MODE == M_WEIGHTED ? cbuf : 0][i], P.w + base + i);
+    }
+  };
+
+  // ---- prologue: three tile ids, row pointers of tiles 0 and 1, column indices of tile 0
+  if (tid == 0) {
+    S.tile[0] = atomicAdd(work, 1);
+    S.tile[1] = atomicAdd(work, 1);
+    S.tile[2] = atomicAdd(work, 1);
+    S.next_row[0] = 0;
+    S.next_row[1] = 0;
+  }
+  __syncthreads();
+  if (S.tile[0] < n_tiles) issue_ptr(S.tile[0], 0);
+  if (S.tile[1] < n_tiles) issue_ptr(S.tile[1], 1);
+  cp_async_commit_wait_all();
+  __syncthreads();
+  if (S.tile[0] < n_tiles) issue_col(0, 0);
+  cp_async_commit_wait_all();
+  __syncthreads();
+
+  const int g = tid / G, lane = tid % G;
+  const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (((tid & 31) / G) * G));
+  const TI* __restrict__ in = reinterpret_cast<const TI*>(P.in) + VEC * lane;
+  bool on[VPL];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) on[k] = VEC * (lane + k * G) < P.n_feat;
+
+  for (int it = 0;; ++it) {
+    const int t = S.tile[it & 3];
+    if (t >= n_tiles) break;  // block-uniform
+    const int pb = it % 3, cb = it & 1;
+    const int t1 = S.tile[(it + 1) & 3], t2 = S.tile[(it + 2) & 3];
+    if (t2 < n_tiles) issue_ptr(t2, (it + 2) % 3);
+    if (t1 < n_tiles) issue_col((it + 1) % 3, cb ^ 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (tid == 0) {
+      S.tile[(it + 3) & 3] = atomicAdd(work, 1);
+      S.next_row[cb ^ 1] = 0;
+    }
+    const int64_t r0 = (int64_t)t * kTileRows;
+    const int rows_here = (int)min((int64_t)kTileRows, P.n_rows - r0);
+    const int base = S.ptr[pb][0];
+    for (;;) {
+      int rr = 0;
+      if (lane == 0) rr = atomicAdd(&S.next_row[cb], 1);
+      rr = __shfl_sync(gmask, rr, 0, G);
+      if (rr >= rows_here) break;
+      const int p0 = S.ptr[pb][rr], p1 = S.ptr[pb][rr + 1];
+      const int deg = p1 - p0;
+      if (has_long && deg > kLongRow) continue;
+      const int64_t row = r0 + rr;
+      Acc<VEC> acc[VPL];
+#pragma unroll
+      for (int k = 0; k < VPL; ++k)
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[k].v[i] = 0.f;
+      for (int p = p0; p < p1; p += BATCH) {
+        int c[BATCH];
+        float w[BATCH];
+#pragma unroll
+        for (int b = 0; b < BATCH; ++b) {
+          const int q = p + b, off = q - base;
+          const bool ok = q < p1;
+          c[b] = ok ? (off < kColCap ? S.col[cb][off] : __ldg(P.col + q)) : -1;
+          if (MODE == M_WEIGHTED)
+            w[b] = ok ? (off < kColCap ? s_w[MODE == M_WEIGHTED ? cb : 0][off] : __ldg(P.w + q)) : 0.f;
+        }
+        Acc<VEC> x[BATCH][VPL];
+#pragma unroll
+        for (int b = 0; b < BATCH; ++b) {
+          if (c[b] >= 0) {
+            const TI* src = in + (int64_t)c[b] * P.ld_in;
+#pragma unroll
+            for (int k = 0; k < VPL; ++k)
+              if (k < VPL - 1 || on[k]) x[b][k] = ldg_vec<TI, VEC>(src + k * G * VEC);
+          }
+        }
+#pragma unroll
+        for (int b = 0; b < BATCH; ++b) {
+          if (c[b] >= 0) {
+#pragma unroll
+            for (int k = 0; k < VPL; ++k) {
+              if (k < VPL - 1 || on[k]) {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                  float tv = x[b][k].v[i];
+                  if (MODE == M_WEIGHTED) tv = __fmul_rn(w[b], tv);
+                  acc[k].v[i] = __fadd_rn(acc[k].v[i], tv);
+                }
+              }
+            }
+          }
+        }
+      }
+      TO* o = reinterpret_cast<TO*>(P.out) + row * P.ld_out + VEC * lane;
+      const TO* add = reinterpret_cast<const TO*>(P.add_in) + row * P.ld_add + VEC * lane;
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        if (k < VPL - 1 || on[k]) {
+          if (P.mean) mean_scale<sizeof(TO) == 4, VEC>(acc[k], deg);
+          if (LEAN) stv(o + k * G * VEC, acc[k]);
+          else generic_epilogue<TO, VEC>(P, o + k * G * VEC, add + k * G * VEC, VEC * (lane + k * G), acc[k]);
+        }
+      }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+  }
+  // the last CTA to leave resets the counter slot for the next launch that uses it
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(done, 1) == (int)gridDim.x - 1) {
+      *work = 0;
+      *done = 0;
+      __threadfence();
+    }
+  }
+}
+
+int* pipe_counters() {  // kCounterSlots x {work, done}, zero-initialised once per device
+  static int* buf[64] = {nullptr};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return nullptr;
+  if (!buf[dev]) {
+    if (cudaMalloc(&buf[dev], kCounterSlots * 2 * sizeof(int)) != cudaSuccess) return nullptr;
+    cudaMemset(buf[dev], 0, kCounterSlots * 2 * sizeof(int));
+  }
+  return buf[dev];
+}
+
+template <typename TI, typename TO, int MODE, int VEC, int G, int VPL, int BATCH>
+int launch_pipe(const Params& P, cudaStream_t st) {
+  static std::atomic<unsigned> slot{0};
+  int* ctr = pipe_counters();
+  if (!ctr) return -2;
+  ctr += 2 * (slot.fetch_add(1) % kCounterSlots);
+  const int n_tiles = (int)ceil_div(P.n_rows, kTileRows);
+  const bool lean = !P.bias && P.act == EGNN_ACT_NONE && !P.accumulate;
+  int per_sm = 0;
+  if (lean) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spmm_pipe<TI, TO, MODE, VEC, G, VPL, BATCH, true>, kThreads, 0);
+  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spmm_pipe<TI, TO, MODE, VEC, G, VPL, BATCH, false>, kThreads, 0);
+  if (per_sm < 1) per_sm = 1;
+  int grid = kNumSMs * per_sm;
+  const int min_grid = P.long_rows ? kLongCtas : 1;
+  if (grid > n_tiles) grid = n_tiles > min_grid ? n_tiles : min_grid;
+  if (lean) spmm_pipe<TI, TO, MODE, VEC, G, VPL, BATCH, true><<<grid, kThreads, 0, st>>>(P, ctr, n_tiles);
+  else spmm_pipe<TI, TO, MODE, VEC, G, VPL, BATCH, false><<<grid, kThreads, 0, st>>>(P, ctr, n_tiles);
+  EGNN_LAUNCH_CHECK("egnn_spmm(pipe)");
+  return 0;
 }
 
 template <typename TI, typename TO, int MODE, int VEC, int G, int VPL, int BATCH>
@@ -186,6 +401,11 @@ int launch_exp(const Params& P, cudaStream_t st) {
 template <typename TI, typename TO, int MODE, int VEC, int G, int VPL>
 int launch_cfg(const Params& P, cudaStream_t st) {
   constexpr int BATCH = 2;
+  static const bool use_lean = [] { const char* e = getenv("EGNN_SPMM_IMPL"); return e && e[0] == 'l'; }();
+  if (!use_lean) {
+    int rc = launch_pipe<TI, TO, MODE, VEC, G, VPL, BATCH>(P, st);
+    if (rc != -2) return rc;
+  }
   constexpr int rows = kThreads / G;
   const int long_ctas = P.long_rows ? kLongCtas : 0;
   dim3 grid((unsigned)(ceil_div(P.n_rows, rows) + long_ctas), 1);
@@ -225,7 +445,8 @@ int launch(const Params& P, cudaStream_t st) {
 template <int MODE>
 int by_dtype(const Params& P, int in_dt, int out_dt, cudaStream_t st) {
   const bool v8 = in_dt == EGNN_BF16 && P.n_feat % 8 == 0 && P.ld_in % 8 == 0 && P.ld_out % 8 == 0 &&
-                  ((uintptr_t)P.in % 16 == 0) && ((uintptr_t)P.out % 16 == 0);
+                  ((uintptr_t)P.in % 16 == 0) && ((uintptr_t)P.out % 16 == 0) &&
+                  (!P.accumulate || (P.ld_add % 8 == 0 && (uintptr_t)P.add_in % 16 == 0));
   if (in_dt == EGNN_F32 && out_dt == EGNN_F32) return launch<float, float, MODE, 4>(P, st);
   if (in_dt == EGNN_F32 && out_dt == EGNN_BF16) return launch<float, __nv_bfloat16, MODE, 4>(P, st);
   if (in_dt == EGNN_BF16 && out_dt == EGNN_BF16)

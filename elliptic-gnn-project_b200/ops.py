@@ -66,15 +66,16 @@ def alloc_cat(n_rows: int, width: int, dtype: torch.dtype, device):
     return buf, h
 
 
-def _fast8(F: int, *tensors) -> bool:
-    """Shapes served by the 8-column streaming kernels (which also take per-tensor row strides)."""
-    g = F // 8
-    if F % 8 or F > 512 or g & (g - 1):
+def _lean4(F: int, *tensors) -> bool:
+    """Shapes served by the 4-column streaming kernels (which also take per-tensor row strides):
+    F/4 a power of two <= 256, 4-element aligned pointers and row strides."""
+    g = F // 4
+    if F % 4 or g > 256 or g & (g - 1):
         return False
     for t in tensors:
         if t is None:
             continue
-        if t.stride(-1) != 1 or t.data_ptr() % 32 or (t.size(0) > 1 and t.stride(0) % 8):
+        if t.stride(-1) != 1 or t.data_ptr() % (4 * t.element_size()) or (t.size(0) > 1 and t.stride(0) % 4):
             return False
     return True
 
@@ -88,7 +89,8 @@ def cast(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
 
 
 def spmm(g: Graph, view: str, mode: int, x: torch.Tensor, out_dtype: torch.dtype, *, bias=None,
-         act: int = ACT_NONE, out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+         act: int = ACT_NONE, out: Optional[torch.Tensor] = None, accumulate: bool = False,
+         addend: Optional[torch.Tensor] = None) -> torch.Tensor:
     x = _rows(x)
     n = g.n_nodes
     if x.size(0) != n:
@@ -103,7 +105,7 @@ def spmm(g: Graph, view: str, mode: int, x: torch.Tensor, out_dtype: torch.dtype
     check(lib().egnn_spmm(mode, ptr(p), ptr(c), ptr(w) if mode == _lib.SPMM_WEIGHTED else None,
                           ptr(nbr) if mode == _lib.SPMM_DIV_NBR else None, ptr(long_rows), n_long, ptr(order), ptr(x),
                           dt(x), _ld(x), ptr(out), dt(out), _ld(out), n, x.size(1), ptr(bias), act,
-                          int(accumulate), stream()))
+                          int(accumulate), ptr(addend), _ld(addend) if addend is not None else 0, stream()))
     return out
 
 
@@ -278,8 +280,8 @@ class SageConvFn(torch.autograd.Function):
                 out = linear_dgrad(dz, wcat[:No], row_div=g.csr_ptr, row_div_cols=K)
                 if ctx.has_res:
                     linear_dgrad(dres, wcat[No:, K:], out=out[:, K:], accumulate=True)
-                spmm(g, "csc", _lib.SPMM_SUM, out[:, :K], cd, out=out[:, K:], accumulate=True)
-                dx = out[:, K:]
+                # dx (contiguous) = dx_root + A^T (dm / deg)
+                dx = spmm(g, "csc", _lib.SPMM_SUM, out[:, :K], cd, addend=out[:, K:])
                 if dx.dtype != ctx.x_dtype:
                     dx = cast(dx, ctx.x_dtype)
             return dx, dwl, db, dwr, dwres, None, None
@@ -501,7 +503,7 @@ class BnActDropResFn(torch.autograd.Function):
         res = _rows(res) if res is not None else None
         if res is not None and res.dtype != z.dtype:
             res = cast(res, z.dtype)
-        strided_ok = _fast8(F, z, res)   # the 8-column kernels take per-tensor row strides
+        strided_ok = _lean4(F, z, res)   # the streaming kernels take per-tensor row strides
         if not strided_ok:
             z = z.contiguous()
             res = res.contiguous() if res is not None else None
@@ -522,15 +524,19 @@ class BnActDropResFn(torch.autograd.Function):
                 mean = running_mean
                 rstd = torch.rsqrt(running_var + eps)
         p_eff = float(p) if (training and p > 0) else 0.0
-        if strided_ok and z.dtype == torch.bfloat16:
+        if strided_ok and z.dtype == torch.bfloat16 and F % 8 == 0:
             _, y = alloc_cat(N, F, z.dtype, dev)   # [agg | y]: the next SAGEConv aggregates in place
         else:
             y = torch.empty((N, F), dtype=z.dtype, device=dev)
         seed = drop.seed if drop is not None else 0
         soff = drop.offset if drop is not None else None
+        # dropout keep bits (1 bit / element) saved for the backward, which then skips Philox
+        kb = (torch.empty((N, F // 4), dtype=torch.uint8, device=dev)
+              if (strided_ok and p_eff > 0 and z.requires_grad) else None)
         check(L.egnn_bn_act_dropout_res_fwd(ptr(z), ptr(res), ptr(y), dt(z), _ld(z), N, F, ptr(mean), ptr(rstd),
                                             ptr(gamma), ptr(beta), act, p_eff, seed, ptr(soff), layer, row0,
-                                            _ld(res) if res is not None else 0, _ld(y), stream()))
+                                            _ld(res) if res is not None else 0, _ld(y), ptr(kb), stream()))
+        ctx.kb = kb
         ctx.cfg = (use_bn, act, p_eff, seed, layer, row0, n_total, reducer, res is not None)
         ctx.soff = soff
         ctx.save_for_backward(z, mean, rstd, gamma, beta)
@@ -555,7 +561,7 @@ class BnActDropResFn(torch.autograd.Function):
             check(L.egnn_bn_act_dropout_bwd_reduce(ptr(dy), ptr(z), dt(z), F, N, F, ptr(mean), ptr(rstd),
                                                    ptr(gamma), ptr(beta), act, p_eff, seed, ptr(soff), layer,
                                                    row0, sg[0].data_ptr(), sg[1].data_ptr(), ptr(ws), _ld(z),
-                                                   stream()))
+                                                   ptr(ctx.kb), stream()))
             if reducer is not None:
                 reducer.reduce_(sg)
             dzsum = torch.empty(F, dtype=torch.float32, device=z.device)
@@ -563,14 +569,14 @@ class BnActDropResFn(torch.autograd.Function):
             check(L.egnn_bn_act_dropout_bwd_apply(ptr(dy), ptr(z), ptr(dz), dt(z), F, N, F, ptr(mean),
                                                   ptr(rstd), ptr(gamma), ptr(beta), act, p_eff, seed,
                                                   ptr(soff), layer, row0, sg[0].data_ptr(), sg[1].data_ptr(),
-                                                  n_total, ptr(dzsum), ptr(ws2), _ld(z), stream()))
+                                                  n_total, ptr(dzsum), ptr(ws2), _ld(z), ptr(ctx.kb), stream()))
             _publish_colsum(dz, dzsum)
             sgf = sg.float()
             dbeta, dgamma = sgf[0], sgf[1]
         else:
             check(L.egnn_bn_act_dropout_bwd_apply(ptr(dy), ptr(z), ptr(dz), dt(z), F, N, F, None, None, None,
                                                   None, act, p_eff, seed, ptr(soff), layer, row0, None, None,
-                                                  1.0, None, None, _ld(z), stream()))
+                                                  1.0, None, None, _ld(z), ptr(ctx.kb), stream()))
         dres = dy if has_res else None
         return (dz, dres, dgamma, dbeta) + (None,) * 11
 

@@ -104,13 +104,14 @@ int egnn_graph_build(const int64_t* ei, int64_t n_edges_in, int64_t n_nodes, int
  *   row_order int32 [n_rows] or NULL: processing order of the rows (egnn_graph_build's
  *            descending-degree order); results do not depend on it
  *   bias     float [F] or NULL, added after the reduction; act = EGNN_ACT_*
- *   accumulate != 0: out += result (one rounding in out dtype after an fp32 add)
+ *   accumulate != 0: out += result (one rounding in out dtype after an fp32 add);
+ *   addend != NULL: out = addend + result instead (addend has the out dtype, leading dimension ld_addend)
  */
 int egnn_spmm(int mode, const int32_t* ptr, const int32_t* col, const float* w,
               const int32_t* nbr_ptr, const int32_t* long_rows, const int32_t* n_long,
               const int32_t* row_order, const void* in, int in_dtype, int64_t ld_in, void* out,
               int out_dtype, int64_t ld_out, int64_t n_rows, int64_t n_feat, const float* bias,
-              int act, int accumulate, void* stream);
+              int act, int accumulate, const void* addend, int64_t ld_addend, void* stream);
 
 /* ---------------------------------------------------------------- K6: dense ----------- */
 /* C[M,N] (+)= op(A)[M,K] . op(B)[K,N] (+ bias[N]).  Element (m,k) of op(A) is at
@@ -191,12 +192,15 @@ int egnn_bn_finalize(const double* sums, const double* sumsq, double count, int6
  *   is added to seed at run time so a captured CUDA graph draws a new mask on every replay
  *   (advance it with egnn_counter_add inside the graph).
  *   res may be NULL.  z/res/y share dtype `dtype`; z has leading dimension ld, res ld_res and y
- *   ld_y (0 = ld): the output may be the right half of a wider [h_agg | h] buffer. */
+ *   ld_y (0 = ld): the output may be the right half of a wider [h_agg | h] buffer.
+ *   keep_bits (optional, uint8 [n_rows, n_feat/4], n_feat % 4 == 0): receives the dropout keep bits drawn
+ *   (bit i of byte (r, c/4) = column c+i kept, low nibble); passing them to the backward kernels skips the Philox
+ *   recomputation there.  The bits ARE the Philox mask of egnn_dropout_mask. */
 int egnn_bn_act_dropout_res_fwd(const void* z, const void* res, void* y, int dtype, int64_t ld,
                                 int64_t n_rows, int64_t n_feat, const float* mean,
                                 const float* rstd, const float* gamma, const float* beta, int act,
                                 float p, uint64_t seed, const int64_t* seed_off, uint32_t layer,
-                                int64_t row0, int64_t ld_res, int64_t ld_y, void* stream);
+                                int64_t row0, int64_t ld_res, int64_t ld_y, uint8_t* keep_bits, void* stream);
 
 /* backward stage 1: g = dy * keep/(1-p) * act'(.) ; sums[c] = sum g, sums_xhat[c] = sum g*xhat
  * (BatchNorm dbeta, dgamma).  stage 2: dz = gamma*rstd*(g - sum_g/n - xhat*sum_gx/n) (or g
@@ -207,7 +211,7 @@ int egnn_bn_act_dropout_bwd_reduce(const void* dy, const void* z, int dtype, int
                                    const float* rstd, const float* gamma, const float* beta,
                                    int act, float p, uint64_t seed, const int64_t* seed_off,
                                    uint32_t layer, int64_t row0, double* sum_g, double* sum_gx, void* workspace,
-                                   int64_t ld_z, void* stream);
+                                   int64_t ld_z, const uint8_t* keep_bits, void* stream);
 /* dz_colsum (float [n_feat], optional): column sums of the dz values written -- the gradient of the
  * conv bias that feeds the BatchNorm -- produced in the same pass; needs `workspace` of
  * egnn_colreduce_workspace_bytes(n_feat) + 8*8*n_feat bytes. */
@@ -216,7 +220,8 @@ int egnn_bn_act_dropout_bwd_apply(const void* dy, const void* z, void* dz, int d
                                   const float* rstd, const float* gamma, const float* beta,
                                   int act, float p, uint64_t seed, const int64_t* seed_off,
                                   uint32_t layer, int64_t row0, const double* sum_g, const double* sum_gx, double n_total,
-                                  float* dz_colsum, void* workspace, int64_t ld_z, void* stream);
+                                  float* dz_colsum, void* workspace, int64_t ld_z, const uint8_t* keep_bits,
+                                  void* stream);
 
 /* *counter += inc on the device (one thread) */
 int egnn_counter_add(int64_t* counter, int64_t inc, void* stream);
