@@ -455,14 +455,31 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   }
 }
 
+// block = 64 output elements x 4 partial lanes; lane q sums partials q, q+4, ... with four independent
+// accumulators (loads in flight), then the four lanes are combined in a fixed order: deterministic
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int n_part,
                                                            int64_t n_elem, float* __restrict__ out,
                                                            int accumulate) {
-  int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (i >= n_elem) return;
-  float s = 0.f;
-  for (int p = 0; p < n_part; ++p) s += partial[(size_t)p * n_elem + i];
-  out[i] = accumulate ? out[i] + s : s;
+  __shared__ float sm[4][64];
+  const int el = threadIdx.x & 63, q = threadIdx.x >> 6;
+  const int64_t i = (int64_t)blockIdx.x * 64 + el;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (i < n_elem) {
+    int p = q;
+    for (; p + 12 < n_part; p += 16) {
+      s0 += partial[(size_t)p * n_elem + i];
+      s1 += partial[(size_t)(p + 4) * n_elem + i];
+      s2 += partial[(size_t)(p + 8) * n_elem + i];
+      s3 += partial[(size_t)(p + 12) * n_elem + i];
+    }
+    for (; p < n_part; p += 4) s0 += partial[(size_t)p * n_elem + i];
+  }
+  sm[q][el] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (q == 0 && i < n_elem) {
+    const float s = (sm[0][el] + sm[1][el]) + (sm[2][el] + sm[3][el]);
+    out[i] = accumulate ? out[i] + s : s;
+  }
 }
 
 // ------------------------------------------------------------------ host side ---------------
@@ -573,7 +590,7 @@ int wgrad_tcgen05_dispatch(const void* G, int64_t ldg, const void* X, int64_t ld
                                                             workspace);
   EGNN_LAUNCH_CHECK(fn);
   int64_t n_elem = N_out * K_in;
-  wgrad_reduce_kernel<<<(unsigned)ceil_div(n_elem, 256), 256, 0, st>>>(workspace, grid, n_elem, dW, accumulate);
+  wgrad_reduce_kernel<<<(unsigned)ceil_div(n_elem, 64), 256, 0, st>>>(workspace, grid, n_elem, dW, accumulate);
   EGNN_LAUNCH_CHECK(fn);
   return 0;
 }

@@ -97,80 +97,70 @@ __global__ void __launch_bounds__(kThreads) skinny_project_kernel(const T* __res
   }
 }
 
-// Row gathers at width C.  One thread per row for rows of up to kShortRow entries (entries read in
-// predicated batches of 4: index loads, then value loads, then the ordered adds); longer rows (hubs,
-// up to several hundred entries) are processed by the whole warp, lanes striding the entries and a
-// fixed xor-tree combining the 32 partial sums -- deterministic, and a hub no longer serialises
-// hundreds of dependent loads in one thread.
-constexpr int kShortRow = 16;
+// Width-C gathers in two uniform passes (no per-row dependent chains, whatever the degree skew: the
+// synthetic generator's preferential attachment puts a timestep's hubs into the same warp):
+//   pass 1, one thread per ENTRY of the sorted view: term[e] = value gathered for entry e;
+//   pass 2, one thread per ROW: sequential fp32 sum of its contiguous terms in stored order.
+template <int C>
+__global__ void __launch_bounds__(kThreads) sage_out_fwd_terms(const int32_t* __restrict__ ptr,
+                                                               const int32_t* __restrict__ col,
+                                                               const float* __restrict__ p,
+                                                               float* __restrict__ term, int64_t n_rows) {
+  const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (e >= __ldg(ptr + n_rows)) return;
+  const float* src = p + (int64_t)__ldg(col + e) * (2 * C);
+#pragma unroll
+  for (int c = 0; c < C; ++c) term[e * C + c] = __ldg(src + c);
+}
 
-template <int C, typename Term>
-__device__ __forceinline__ void gather_row(int p0, int p1, bool valid, Term term, float (&acc)[C]) {
-  const int lane = threadIdx.x & 31;
-  const int deg = valid ? p1 - p0 : 0;
+template <typename TD, int C>
+__global__ void __launch_bounds__(kThreads) sage_out_bwd_terms(const int32_t* __restrict__ csc_ptr,
+                                                               const int32_t* __restrict__ csc_dst,
+                                                               const int32_t* __restrict__ csr_ptr,
+                                                               const TD* __restrict__ dout,
+                                                               float* __restrict__ term, int64_t n_rows) {
+  const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (e >= __ldg(csc_ptr + n_rows)) return;
+  const int i = __ldg(csc_dst + e);
+  const int d = __ldg(csr_ptr + i + 1) - __ldg(csr_ptr + i);
+  const float cnt = (float)(d > 1 ? d : 1);
+#pragma unroll
+  for (int c = 0; c < C; ++c) term[e * C + c] = __fdiv_rn(to_f32(dout[(int64_t)i * C + c]), cnt);
+}
+
+template <int C>
+__device__ __forceinline__ void sum_terms(const float* __restrict__ term, int p0, int p1, float (&acc)[C]) {
 #pragma unroll
   for (int c = 0; c < C; ++c) acc[c] = 0.f;
-  if (deg <= kShortRow) {
-    for (int e = p0; e < p0 + deg; e += 4) {
-      float v[4][C];
+  int e = p0;
+  for (; e + 4 <= p1; e += 4) {  // four independent loads in flight, added in stored order
+    float v[4][C];
 #pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        if (e + b < p0 + deg) term(e + b, v[b]);
-        else {
+    for (int b = 0; b < 4; ++b)
 #pragma unroll
-          for (int c = 0; c < C; ++c) v[b][c] = 0.f;
-        }
-      }
+      for (int c = 0; c < C; ++c) v[b][c] = __ldg(term + (int64_t)(e + b) * C + c);
 #pragma unroll
-      for (int b = 0; b < 4; ++b)
-        if (e + b < p0 + deg) {
+    for (int b = 0; b < 4; ++b)
 #pragma unroll
-          for (int c = 0; c < C; ++c) acc[c] = __fadd_rn(acc[c], v[b][c]);
-        }
-    }
+      for (int c = 0; c < C; ++c) acc[c] = __fadd_rn(acc[c], v[b][c]);
   }
-  unsigned long_mask = __ballot_sync(0xffffffffu, deg > kShortRow);
-  while (long_mask) {
-    const int src = __ffs(long_mask) - 1;
-    long_mask &= long_mask - 1;
-    const int q0 = __shfl_sync(0xffffffffu, p0, src), q1 = __shfl_sync(0xffffffffu, p1, src);
-    float part[C];
+  for (; e < p1; ++e)
 #pragma unroll
-    for (int c = 0; c < C; ++c) part[c] = 0.f;
-    for (int e = q0 + lane; e < q1; e += 32) {
-      float v[C];
-      term(e, v);
-#pragma unroll
-      for (int c = 0; c < C; ++c) part[c] = __fadd_rn(part[c], v[c]);
-    }
-#pragma unroll
-    for (int c = 0; c < C; ++c)
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) part[c] = __fadd_rn(part[c], __shfl_xor_sync(0xffffffffu, part[c], o));
-    if (lane == src) {
-#pragma unroll
-      for (int c = 0; c < C; ++c) acc[c] = part[c];
-    }
-  }
+    for (int c = 0; c < C; ++c) acc[c] = __fadd_rn(acc[c], __ldg(term + (int64_t)e * C + c));
 }
 
 // ---- out[i, c] = (mean_{j->i} p[j, c] + b[c]) + p[i, C + c] ----------------------------------
 template <int C>
 __global__ void __launch_bounds__(kThreads) sage_out_fwd_kernel(const int32_t* __restrict__ ptr,
-                                                                const int32_t* __restrict__ col,
+                                                                const float* __restrict__ term,
                                                                 const float* __restrict__ p,
                                                                 const float* __restrict__ bias,
                                                                 float* __restrict__ out, int64_t n_rows) {
   const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  const bool valid = i < n_rows;
-  const int p0 = valid ? __ldg(ptr + i) : 0, p1 = valid ? __ldg(ptr + i + 1) : 0;
+  if (i >= n_rows) return;
+  const int p0 = __ldg(ptr + i), p1 = __ldg(ptr + i + 1);
   float acc[C];
-  gather_row<C>(p0, p1, valid, [&](int e, float (&v)[C]) {
-    const float* src = p + (int64_t)__ldg(col + e) * (2 * C);
-#pragma unroll
-    for (int c = 0; c < C; ++c) v[c] = __ldg(src + c);
-  }, acc);
-  if (!valid) return;
+  sum_terms<C>(term, p0, p1, acc);
   const int deg = p1 - p0;
   const float cnt = (float)(deg > 1 ? deg : 1);
 #pragma unroll
@@ -184,22 +174,14 @@ __global__ void __launch_bounds__(kThreads) sage_out_fwd_kernel(const int32_t* _
 // ---- dp[j, 0:C] = sum_{j->i} dout[i, :] / max(deg_in(i), 1);  dp[j, C:2C] = dout[j, :] ---------
 template <typename TD, int C>
 __global__ void __launch_bounds__(kThreads) sage_out_bwd_kernel(const int32_t* __restrict__ csc_ptr,
-                                                                const int32_t* __restrict__ csc_dst,
-                                                                const int32_t* __restrict__ csr_ptr,
+                                                                const float* __restrict__ term,
                                                                 const TD* __restrict__ dout,
                                                                 float* __restrict__ dp, int64_t n_rows) {
   const int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  const bool valid = j < n_rows;
-  const int p0 = valid ? __ldg(csc_ptr + j) : 0, p1 = valid ? __ldg(csc_ptr + j + 1) : 0;
+  if (j >= n_rows) return;
+  const int p0 = __ldg(csc_ptr + j), p1 = __ldg(csc_ptr + j + 1);
   float acc[C];
-  gather_row<C>(p0, p1, valid, [&](int e, float (&v)[C]) {
-    const int i = __ldg(csc_dst + e);
-    const int d = __ldg(csr_ptr + i + 1) - __ldg(csr_ptr + i);
-    const float cnt = (float)(d > 1 ? d : 1);
-#pragma unroll
-    for (int c = 0; c < C; ++c) v[c] = __fdiv_rn(to_f32(dout[(int64_t)i * C + c]), cnt);
-  }, acc);
-  if (!valid) return;
+  sum_terms<C>(term, p0, p1, acc);
 #pragma unroll
   for (int c = 0; c < C; ++c) {
     dp[j * (2 * C) + c] = acc[c];
@@ -269,23 +251,35 @@ __global__ void __launch_bounds__(kThreads) skinny_wgrad_kernel(const T* __restr
 
 // final: dW[p,k] = sum_blk partial (double combine, fixed order); dsum[p] likewise.
 // block = 32 output columns x 8 block lanes; lane bl sums blocks bl, bl+8, ... then a fixed tree.
+// block = 8 output columns x 32 block lanes; lane bl sums blocks bl, bl+32, ... (four independent
+// accumulators keep the loads in flight), then a fixed-order combine over the 32 lanes.
 __global__ void __launch_bounds__(kThreads) skinny_wgrad_final(const float* __restrict__ partial, int nblk, int P,
                                                                int K, int Kp, float* __restrict__ dW,
                                                                float* __restrict__ dsum) {
-  __shared__ double sm[8][33];
-  const int kl = threadIdx.x & 31, bl = threadIdx.x >> 5;
-  const int k = blockIdx.x * 32 + kl, p = blockIdx.y;
+  __shared__ double sm[32][9];
+  const int kl = threadIdx.x & 7, bl = threadIdx.x >> 3;
+  const int k = blockIdx.x * 8 + kl, p = blockIdx.y;
   const bool ok = k <= K;  // k == K is the dsum column
   const int src = k < K ? k : Kp;
-  double s = 0;
-  if (ok)
-    for (int b = bl; b < nblk; b += 8) s += (double)partial[((int64_t)b * P + p) * (Kp + 8) + src];
-  sm[bl][kl] = s;
+  const int64_t stride = (int64_t)P * (Kp + 8);
+  const float* base = partial + (int64_t)p * (Kp + 8) + src;
+  double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+  if (ok) {
+    int b = bl;
+    for (; b + 96 < nblk; b += 128) {
+      s0 += (double)base[(int64_t)b * stride];
+      s1 += (double)base[(int64_t)(b + 32) * stride];
+      s2 += (double)base[(int64_t)(b + 64) * stride];
+      s3 += (double)base[(int64_t)(b + 96) * stride];
+    }
+    for (; b < nblk; b += 32) s0 += (double)base[(int64_t)b * stride];
+  }
+  sm[bl][kl] = (s0 + s1) + (s2 + s3);
   __syncthreads();
   if (bl == 0 && ok) {
     double t = 0;
 #pragma unroll
-    for (int l = 0; l < 8; ++l) t += sm[l][kl];
+    for (int l = 0; l < 32; ++l) t += sm[l][kl];
     if (k < K) dW[p * K + k] = (float)t;
     else if (dsum) dsum[p] = (float)t;
   }
@@ -362,31 +356,44 @@ extern "C" int egnn_skinny_project(const void* a, int dtype, int64_t ld, int64_t
 }
 
 extern "C" int egnn_sage_out_fwd(const int32_t* csr_ptr, const int32_t* csr_src, const float* p,
-                                 const float* bias, int C, float* out, int64_t n_rows, void* stream) {
+                                 const float* bias, int C, float* out, int64_t n_rows, float* edge_tmp,
+                                 int64_t edge_cap, void* stream) {
   const char* fn = "egnn_sage_out_fwd";
-  EGNN_REQUIRE(csr_ptr && csr_src && p && out, fn, "null pointer");
+  EGNN_REQUIRE(csr_ptr && csr_src && p && out && edge_tmp, fn, "null pointer");
   if (n_rows == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned grid = (unsigned)ceil_div(n_rows, kThreads);
+  const unsigned egrid = (unsigned)ceil_div(edge_cap > 0 ? edge_cap : 1, kThreads);
+#define LAUNCH(CC)                                                                                   \
+  sage_out_fwd_terms<CC><<<egrid, kThreads, 0, st>>>(csr_ptr, csr_src, p, edge_tmp, n_rows);         \
+  EGNN_LAUNCH_CHECK(fn);                                                                             \
+  sage_out_fwd_kernel<CC><<<grid, kThreads, 0, st>>>(csr_ptr, edge_tmp, p, bias, out, n_rows)
   switch (C) {
-    case 1: sage_out_fwd_kernel<1><<<grid, kThreads, 0, st>>>(csr_ptr, csr_src, p, bias, out, n_rows); break;
-    case 2: sage_out_fwd_kernel<2><<<grid, kThreads, 0, st>>>(csr_ptr, csr_src, p, bias, out, n_rows); break;
-    case 4: sage_out_fwd_kernel<4><<<grid, kThreads, 0, st>>>(csr_ptr, csr_src, p, bias, out, n_rows); break;
+    case 1: LAUNCH(1); break;
+    case 2: LAUNCH(2); break;
+    case 4: LAUNCH(4); break;
     default: return fail(fn, "C must be 1, 2 or 4");
   }
+#undef LAUNCH
   EGNN_LAUNCH_CHECK(fn);
   return 0;
 }
 
 extern "C" int egnn_sage_out_bwd(const int32_t* csc_ptr, const int32_t* csc_dst, const int32_t* csr_ptr,
-                                 const void* dout, int dtype, int C, float* dp, int64_t n_rows, void* stream) {
+                                 const void* dout, int dtype, int C, float* dp, int64_t n_rows, float* edge_tmp,
+                                 int64_t edge_cap, void* stream) {
   const char* fn = "egnn_sage_out_bwd";
-  EGNN_REQUIRE(csc_ptr && csc_dst && csr_ptr && dout && dp, fn, "null pointer");
+  EGNN_REQUIRE(csc_ptr && csc_dst && csr_ptr && dout && dp && edge_tmp, fn, "null pointer");
   if (n_rows == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned grid = (unsigned)ceil_div(n_rows, kThreads);
-#define LAUNCH(T, CC) sage_out_bwd_kernel<T, CC><<<grid, kThreads, 0, st>>>( \
-      csc_ptr, csc_dst, csr_ptr, reinterpret_cast<const T*>(dout), dp, n_rows)
+  const unsigned egrid = (unsigned)ceil_div(edge_cap > 0 ? edge_cap : 1, kThreads);
+#define LAUNCH(T, CC)                                                                                          \
+  sage_out_bwd_terms<T, CC><<<egrid, kThreads, 0, st>>>(csc_ptr, csc_dst, csr_ptr,                             \
+                                                        reinterpret_cast<const T*>(dout), edge_tmp, n_rows);   \
+  EGNN_LAUNCH_CHECK(fn);                                                                                       \
+  sage_out_bwd_kernel<T, CC><<<grid, kThreads, 0, st>>>(csc_ptr, edge_tmp, reinterpret_cast<const T*>(dout), dp, \
+                                                        n_rows)
   if (dtype == EGNN_F32) {
     switch (C) { case 1: LAUNCH(float, 1); break; case 2: LAUNCH(float, 2); break; case 4: LAUNCH(float, 4); break;
       default: return fail(fn, "C must be 1, 2 or 4"); }
@@ -438,7 +445,7 @@ extern "C" int egnn_skinny_wgrad(const void* a, int dtype, int64_t ld, const flo
   else return fail(fn, "bad dtype");
 #undef LAUNCH
   EGNN_LAUNCH_CHECK(fn);
-  skinny_wgrad_final<<<dim3((unsigned)ceil_div(K + 1, 32), (unsigned)P), kThreads, 0, st>>>(
+  skinny_wgrad_final<<<dim3((unsigned)ceil_div(K + 1, 8), (unsigned)P), kThreads, 0, st>>>(
       workspace, w.nblk, P, (int)K, w.Kp, dW, dsum);
   EGNN_LAUNCH_CHECK(fn);
   return 0;

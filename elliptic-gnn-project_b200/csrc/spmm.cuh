@@ -90,7 +90,7 @@ __device__ __forceinline__ void epilogue_store(const Params& P, int64_t row, int
 // work item = (long row, 32-feature slice); 128 source rows staged per round in shared memory by
 // all threads (memory-level parallelism), then thread t adds feature t over the staged rows
 // sequentially -- the same summation order as the sub-warp path.
-template <typename TI, typename TO, int MODE>
+template <typename TI, typename TO, int MODE, int NT = kThreads>
 __device__ __forceinline__ void long_row_path(const Params& P, int bx, float (*s_stage)[kSliceFeat],
                                               float* s_scale, int* s_col) {
   const TI* __restrict__ in = reinterpret_cast<const TI*>(P.in);
@@ -114,7 +114,7 @@ __device__ __forceinline__ void long_row_path(const Params& P, int bx, float (*s
             s_scale[threadIdx.x] = edge_scale<MODE>(P, pb + threadIdx.x, c);
           }
           __syncthreads();
-          for (int i = threadIdx.x; i < ne * nv; i += kThreads) {
+          for (int i = threadIdx.x; i < ne * nv; i += NT) {
             int e = i / nv, v = i - e * nv;
             F4 x = ld4(in + (int64_t)s_col[e] * P.ld_in + f0 + 4 * v);
             *reinterpret_cast<float4*>(&s_stage[e][4 * v]) = make_float4(x.x, x.y, x.z, x.w);
@@ -142,6 +142,7 @@ __device__ __forceinline__ void long_row_path(const Params& P, int bx, float (*s
 
 }  // namespace spmm_detail
 
-// spmm_tile.cu: returns -2 when the configuration is not covered (caller falls back to spmm_vec)
+// spmm_lean.cu (lane groups, production): returns -2 when the configuration is not covered and the caller
+// falls through to the chunked kernels of spmm.cu
 int spmm_tile_launch(const spmm_detail::Params& P, int in_dt, int out_dt, bool weighted, cudaStream_t st);
 }  // namespace egnn

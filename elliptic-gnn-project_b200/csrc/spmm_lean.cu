@@ -401,8 +401,8 @@ int launch_exp(const Params& P, cudaStream_t st) {
 template <typename TI, typename TO, int MODE, int VEC, int G, int VPL>
 int launch_cfg(const Params& P, cudaStream_t st) {
   constexpr int BATCH = 2;
-  static const bool use_lean = [] { const char* e = getenv("EGNN_SPMM_IMPL"); return e && e[0] == 'l'; }();
-  if (!use_lean) {
+  static const bool use_pipe = [] { const char* e = getenv("EGNN_SPMM_IMPL"); return e && e[0] == 'p'; }();
+  if (use_pipe) {
     int rc = launch_pipe<TI, TO, MODE, VEC, G, VPL, BATCH>(P, st);
     if (rc != -2) return rc;
   }

@@ -80,6 +80,26 @@ def _lean4(F: int, *tensors) -> bool:
     return True
 
 
+def pad_features(x: torch.Tensor, width: int, want_twin: bool):
+    """Raw fp32 node features zero-padded to `width` columns (a multiple of 8: 16-byte rows for the
+    vectorised gathers and the TMA descriptors; e.g. the reference's 167 = 166 + scalar time,
+    `src/train_gnn.py:314-317`), plus -- under bf16 autocast -- the bf16 copy inside an [agg | h]
+    buffer, both written by one pass of the time-injection kernel with an empty time table."""
+    x = _rows(x)
+    N, F = x.shape
+    out = torch.empty((N, width), dtype=torch.float32, device=x.device)
+    twin = alloc_cat(N, width, torch.bfloat16, x.device)[1] if want_twin else None
+    check(lib().egnn_inject_time(ptr(x), _ld(x), None, None, 0, 0, ptr(out), ptr(twin), width,
+                                 _ld(twin) if twin is not None else 0, N, F, stream()))
+    if twin is not None:
+        out._egnn_twin = twin
+    return out
+
+
+def _pad_cols(w: torch.Tensor, pad: int) -> torch.Tensor:
+    return torch.cat([w, w.new_zeros((w.size(0), pad))], dim=1) if pad else w
+
+
 def cast(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     x = _rows(x)
     out = torch.empty(x.shape, dtype=dtype, device=x.device)
@@ -213,6 +233,12 @@ class SageConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w_l, b_l, w_r, w_res, g: Graph, bf16: bool):
         cd = torch.bfloat16 if bf16 else torch.float32
+        pad = (-x.size(1)) % 8 if x.dtype == torch.float32 else 0
+        if pad:   # e.g. 167 raw columns: pad once so that gathers and GEMM operands have 16-byte rows
+            x = pad_features(x, x.size(1) + pad, want_twin=bf16)
+            w_l, w_r = _pad_cols(w_l, pad), _pad_cols(w_r, pad)
+            w_res = _pad_cols(w_res, pad) if w_res is not None else None
+        ctx.pad = pad
         xg = to_compute(x, cd)
         x = _rows(x)
         K, No = x.size(1), w_l.size(0)
@@ -284,7 +310,7 @@ class SageConvFn(torch.autograd.Function):
                 dx = spmm(g, "csc", _lib.SPMM_SUM, out[:, :K], cd, addend=out[:, K:])
                 if dx.dtype != ctx.x_dtype:
                     dx = cast(dx, ctx.x_dtype)
-            return dx, dwl, db, dwr, dwres, None, None
+            return SageConvFn._strip(ctx.pad, dx, dwl, db, dwr, dwres)
         if ctx.has_res:
             m, xg, wl, wr, wres = ctx.saved_tensors
         else:
@@ -309,6 +335,13 @@ class SageConvFn(torch.autograd.Function):
             spmm(g, "csc", _lib.SPMM_SUM, dm, dx.dtype, out=dx, accumulate=True)
             if dx.dtype != ctx.x_dtype:
                 dx = cast(dx, ctx.x_dtype)
+        return SageConvFn._strip(ctx.pad, dx, dwl, db, dwr, dwres)
+
+    @staticmethod
+    def _strip(pad, dx, dwl, db, dwr, dwres):
+        if pad:
+            cut = lambda t: None if t is None else t[:, :t.size(1) - pad]
+            dx, dwl, dwr, dwres = cut(dx), cut(dwl), cut(dwr), cut(dwres)
         return dx, dwl, db, dwr, dwres, None, None
 
 
@@ -329,7 +362,9 @@ class SageOutFn(torch.autograd.Function):
         check(L.egnn_skinny_project(ptr(x), dt(x), _ld(x), N, K, ptr(wcat), 2 * C, ptr(p), stream()))
         out = torch.empty((N, C), dtype=torch.float32, device=x.device)
         bias = b_l.detach().float().contiguous() if b_l is not None else None
-        check(L.egnn_sage_out_fwd(ptr(g.csr_ptr), ptr(g.csr_src), ptr(p), ptr(bias), C, ptr(out), N, stream()))
+        tmp = torch.empty((g.cap, C), dtype=torch.float32, device=x.device)
+        check(L.egnn_sage_out_fwd(ptr(g.csr_ptr), ptr(g.csr_src), ptr(p), ptr(bias), C, ptr(out), N, ptr(tmp),
+                                  g.cap, stream()))
         ctx.g, ctx.C = g, C
         ctx.save_for_backward(x, wcat)
         return out
@@ -342,8 +377,9 @@ class SageOutFn(torch.autograd.Function):
         L = lib()
         dout = _rows(dout).contiguous()
         dp = torch.empty((N, 2 * C), dtype=torch.float32, device=x.device)
+        tmp = torch.empty((g.cap, C), dtype=torch.float32, device=x.device)
         check(L.egnn_sage_out_bwd(ptr(g.csc_ptr), ptr(g.csc_dst), ptr(g.csr_ptr), ptr(dout), dt(dout), C, ptr(dp),
-                                  N, stream()))
+                                  N, ptr(tmp), g.cap, stream()))
         dw = torch.empty((2 * C, K), dtype=torch.float32, device=x.device)
         dsum = torch.empty(2 * C, dtype=torch.float32, device=x.device)
         ws = torch.empty(L.egnn_skinny_wgrad_workspace_floats(N, K, 2 * C), dtype=torch.float32, device=x.device)
@@ -370,7 +406,11 @@ class GcnConvFn(torch.autograd.Function):
     def forward(ctx, x, w, b, g: Graph, bf16: bool):
         cd = torch.bfloat16 if bf16 else torch.float32
         x = _rows(x)
-        xg = x if x.dtype == cd else cast(x, cd)
+        pad = (-x.size(1)) % 8 if (bf16 and x.dtype == torch.float32) else 0
+        if pad:
+            x, w = pad_features(x, x.size(1) + pad, want_twin=True), _pad_cols(w, pad)
+        ctx.pad = pad
+        xg = to_compute(x, cd)
         wc = w if w.dtype == cd else cast(w, cd)
         h = linear_fwd(xg, wc, out_dtype=cd)
         out = spmm(g, "csr", _lib.SPMM_WEIGHTED, h, torch.float32, bias=b)
@@ -393,6 +433,9 @@ class GcnConvFn(torch.autograd.Function):
             dx = linear_dgrad(dh, wc)
             if dx.dtype != ctx.x_dtype:
                 dx = cast(dx, ctx.x_dtype)
+        if ctx.pad:
+            dw = dw[:, :dw.size(1) - ctx.pad]
+            dx = dx[:, :dx.size(1) - ctx.pad] if dx is not None else None
         return dx, dw, db, None, None
 
 
@@ -406,7 +449,11 @@ class GatConvFn(torch.autograd.Function):
         cd = torch.bfloat16 if bf16 else torch.float32
         x = _rows(x)
         N = x.size(0)
-        xg = x if x.dtype == cd else cast(x, cd)
+        pad = (-x.size(1)) % 8 if (bf16 and x.dtype == torch.float32) else 0
+        if pad:
+            x, w = pad_features(x, x.size(1) + pad, want_twin=True), _pad_cols(w, pad)
+        ctx.pad = pad
+        xg = to_compute(x, cd)
         wc = w if w.dtype == cd else cast(w, cd)
         xs = linear_fwd(xg, wc, out_dtype=torch.float32)  # [N, H*C]; attention path stays fp32
         dev = x.device
@@ -456,6 +503,9 @@ class GatConvFn(torch.autograd.Function):
             dx = linear_dgrad(dxs, wc, out_dtype=xg.dtype)
             if dx.dtype != ctx.x_dtype:
                 dx = cast(dx, ctx.x_dtype)
+        if ctx.pad:
+            dw = dw[:, :dw.size(1) - ctx.pad]
+            dx = dx[:, :dx.size(1) - ctx.pad] if dx is not None else None
         return (dx, dw, datt[0].view(1, H, C), datt[1].view(1, H, C), dbias, None, None, None, None, None,
                 None)
 

@@ -140,6 +140,8 @@ int egnn_gemm(const void* A, int a_dtype, int64_t a_sm, int64_t a_sk, const void
  * egnn_skinny_project : out[r, 0:P] = sum_k a[r,k] * W[p,k]     W float [P, K] row-major, P in {2,4,8}
  * egnn_sage_out_fwd   : the width-C gather + combine over the CSR-by-destination view, C in {1,2,4}
  * egnn_sage_out_bwd   : dp[j] = [ sum_{j->i} dout_i / max(deg_in(i),1) | dout_j ]  (CSC view)
+ *                       both gathers run as two uniform passes (one thread per entry, then one thread per
+ *                       row summing its contiguous terms in stored order); edge_tmp = float [edge_cap, C]
  * egnn_skinny_wgrad   : dW[p,k] = sum_r dp[r,p]*a[r,k]; dsum[p] = sum_r dp[r,p] (may be NULL);
  *                       deterministic two-level reduction, workspace from ..._workspace_floats
  * egnn_skinny_dgrad   : dh[r,k] = sum_p dp[r,p] * W[p,k]
@@ -147,9 +149,10 @@ int egnn_gemm(const void* A, int a_dtype, int64_t a_sm, int64_t a_sk, const void
 int egnn_skinny_project(const void* a, int dtype, int64_t ld, int64_t n_rows, int64_t K,
                         const float* W, int P, float* out, void* stream);
 int egnn_sage_out_fwd(const int32_t* csr_ptr, const int32_t* csr_src, const float* p, const float* bias,
-                      int C, float* out, int64_t n_rows, void* stream);
+                      int C, float* out, int64_t n_rows, float* edge_tmp, int64_t edge_cap, void* stream);
 int egnn_sage_out_bwd(const int32_t* csc_ptr, const int32_t* csc_dst, const int32_t* csr_ptr,
-                      const void* dout, int dtype, int C, float* dp, int64_t n_rows, void* stream);
+                      const void* dout, int dtype, int C, float* dp, int64_t n_rows, float* edge_tmp,
+                      int64_t edge_cap, void* stream);
 size_t egnn_skinny_wgrad_workspace_floats(int64_t n_rows, int64_t K, int P);
 int egnn_skinny_wgrad(const void* a, int dtype, int64_t ld, const float* dp, int P, int64_t n_rows,
                       int64_t K, float* dW, float* dsum, float* workspace, void* stream);
