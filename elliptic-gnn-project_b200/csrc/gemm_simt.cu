@@ -235,7 +235,7 @@ extern "C" size_t egnn_gemm_workspace_floats(int64_t M, int64_t N, int64_t K, in
   (void)K;
   size_t need = split_k > 1 ? (size_t)split_k * (size_t)M * (size_t)N : 0;
   if (M <= 8) need = std::max(need, (size_t)(kNumSMs * 4 + 1) * (size_t)M * (size_t)N);  // skinny wgrad chunks
-  if (M <= 256 && N <= 256) need = std::max(need, wgrad_tcgen05_workspace_floats(M, N));     // tcgen05 wgrad
+  if (M <= 256 && N <= 384) need = std::max(need, wgrad_tcgen05_workspace_floats(M, N));     // tcgen05 wgrad
   return need;
 }
 

@@ -346,7 +346,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------ wgrad ------------------
-// dW^T tile: UMMA M axis = K_in (two 128-wide M tiles when K_in > 128), N axis = N_out.
+// dW^T tile: UMMA M axis = K_in (up to three 128-wide M tiles), N axis = N_out.
 // smem stage = [X blocks: MB * 8 KB][G blocks: NB * 8 KB], each block = 64 nodes x 64 columns.
 template <int kStages>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -354,7 +354,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                   int N_out, int Nopad, int K_in, float* __restrict__ partial) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~uintptr_t(1023));
-  const int MT = K_in > 128 ? 2 : 1;   // 128-wide M tiles over K_in
+  const int MT = (K_in + 127) / 128;   // 128-wide M tiles over K_in (<= 3)
   const int MB = MT * 2;               // 64-column X blocks per stage
   const int NB = (Nopad + 63) / 64;    // 64-column G blocks per stage
   const int stage_bytes = (MB + NB) * 8192;
@@ -559,11 +559,11 @@ size_t wgrad_tcgen05_workspace_floats(int64_t N_out, int64_t K_in) { return (siz
 
 bool wgrad_tcgen05_supported(const void* G, int64_t ldg, const void* X, int64_t ldx, int64_t M_rows, int64_t N_out,
                              int64_t K_in) {
-  if (N_out < 8 || N_out > 256 || K_in < 8 || K_in > 256 || M_rows < 1 || M_rows >= (int64_t)1 << 31) return false;
+  if (N_out < 8 || N_out > 256 || K_in < 8 || K_in > 384 || M_rows < 1 || M_rows >= (int64_t)1 << 31) return false;
   if (ldg % 8 || ldx % 8) return false;
   if (((uintptr_t)G | (uintptr_t)X) & 15) return false;
   const int Nopad = (int)((N_out + 15) / 16 * 16);
-  const int MT = K_in > 128 ? 2 : 1;
+  const int MT = (int)((K_in + 127) / 128);
   const int stage = (MT * 2 + (Nopad + 63) / 64) * 8192;
   return (size_t)kStagesWG * stage + 256 + 1024 <= 227 * 1024 && MT * Nopad <= 512;
 }
@@ -573,7 +573,7 @@ int wgrad_tcgen05_dispatch(const void* G, int64_t ldg, const void* X, int64_t ld
                            int64_t N_out, int64_t K_in, int accumulate, float* workspace, cudaStream_t st) {
   const char* fn = "egnn_gemm(tcgen05 wgrad)";
   const int Nopad = (int)((N_out + 15) / 16 * 16);
-  const int MT = K_in > 128 ? 2 : 1;
+  const int MT = (int)((K_in + 127) / 128);
   const int stage = (MT * 2 + (Nopad + 63) / 64) * 8192;
   CUtensorMap tmX, tmG;
   if (!make_map(&tmX, X, M_rows, K_in, ldx, 64) || !make_map(&tmG, G, M_rows, N_out, ldg, 64))

@@ -288,7 +288,7 @@ class SageConvFn(torch.autograd.Function):
             cd = cat.dtype
             if dz.dtype != cd:
                 dz = cast(dz, cd)
-            if 2 * K <= 256:
+            if 2 * K <= 384:
                 dwc = linear_wgrad(dz, cat)
                 dwl, dwr = dwc[:, :K], dwc[:, K:]
             else:
