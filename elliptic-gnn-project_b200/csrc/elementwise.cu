@@ -57,26 +57,31 @@ __global__ void __launch_bounds__(kThreads) cast_kernel(const TI* __restrict__ i
 }
 
 // ---- time-feature injection ----------------------------------------------------------------
-constexpr int kInjectRows = 32;  // rows per block
+constexpr int kInjectRows = 48;  // rows per block
+// 4 output columns per thread; a thread walks the block's (row, column group) items with an incremental
+// index (no per-item division).  x rows are only 8-byte aligned (ld_x = 166), so they are read as float2.
 __global__ void __launch_bounds__(kThreads) inject_time_kernel(
     const float* __restrict__ x, int64_t ld_x, const int64_t* __restrict__ t,
     const float* __restrict__ table, int64_t T, int D, float* __restrict__ o32,
     __nv_bfloat16* __restrict__ o16, int64_t ld_out, int64_t ld_out16, int64_t n_rows, int F) {
-  const int W2 = (int)(ld_out / 2);  // ld_out is even (multiple of 4)
+  const int W4 = (int)(ld_out / 4);  // ld_out is a multiple of 4
   const int64_t row0 = (int64_t)blockIdx.x * kInjectRows;
   const int nr = (int)min((int64_t)kInjectRows, n_rows - row0);
-  const bool x2 = (ld_x % 2 == 0) && ((uintptr_t)x % 8 == 0);  // 8-byte loads of x pairs
-  for (int j = threadIdx.x; j < nr * W2; j += kThreads) {
-    const int rr = j / W2;
-    const int c = (j - rr * W2) * 2;
+  const bool x2 = (ld_x % 2 == 0) && ((uintptr_t)x % 8 == 0);
+  const int dq = kThreads / W4, dm = kThreads - dq * W4;  // advance of (row, group) per 256 items
+  int rr = threadIdx.x / W4, cg = threadIdx.x - rr * W4;
+  for (; rr < nr; rr += dq, cg += dm) {
+    if (cg >= W4) { cg -= W4; ++rr; if (rr >= nr) break; }
+    const int c = cg * 4;
     const int64_t r = row0 + rr;
-    float v[2];
-    if (x2 && c + 1 < F) {
-      const float2 p = __ldg(reinterpret_cast<const float2*>(x + r * ld_x + c));
-      v[0] = p.x; v[1] = p.y;
+    float v[4];
+    if (x2 && c + 3 < F) {
+      const float2 p0 = __ldg(reinterpret_cast<const float2*>(x + r * ld_x + c));
+      const float2 p1 = __ldg(reinterpret_cast<const float2*>(x + r * ld_x + c + 2));
+      v[0] = p0.x; v[1] = p0.y; v[2] = p1.x; v[3] = p1.y;
     } else {
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
+      for (int k = 0; k < 4; ++k) {
         const int cc = c + k;
         if (cc < F) {
           v[k] = __ldg(x + r * ld_x + cc);
@@ -89,8 +94,9 @@ __global__ void __launch_bounds__(kThreads) inject_time_kernel(
         }
       }
     }
-    if (o32) *reinterpret_cast<float2*>(o32 + r * ld_out + c) = make_float2(v[0], v[1]);
-    if (o16) *reinterpret_cast<uint32_t*>(o16 + r * ld_out16 + c) = pack_bf16x2(v[0], v[1]);
+    if (o32) *reinterpret_cast<float4*>(o32 + r * ld_out + c) = make_float4(v[0], v[1], v[2], v[3]);
+    if (o16)
+      *reinterpret_cast<uint2*>(o16 + r * ld_out16 + c) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
   }
 }
 
@@ -734,9 +740,10 @@ inline FastPlan lean_plan(int64_t n_rows, int64_t F, int dtype, std::initializer
   for (const void* q : ptrs)
     if (q && (uintptr_t)q % (4 * es) != 0) return p;
   const int RL = kThreads >> sh;
-  int64_t rpb = (int64_t)RL * kRowsInFlight * 2;
-  if (ceil_div(n_rows, rpb) > kMaxPartBlocks)
-    rpb = ceil_div(ceil_div(n_rows, kMaxPartBlocks), RL * kRowsInFlight) * RL * kRowsInFlight;
+  // at most one wave of blocks at 3 resident blocks per SM (no partially filled second wave)
+  const int64_t unit = (int64_t)RL * kRowsInFlight;
+  int64_t rpb = ceil_div(ceil_div(n_rows > 0 ? n_rows : 1, (int64_t)kNumSMs * 3), unit) * unit;
+  if (rpb < unit * 2) rpb = unit * 2;
   p.ok = true; p.cg_shift = sh; p.rpb = rpb; p.nblk = (int)ceil_div(n_rows > 0 ? n_rows : 1, rpb);
   return p;
 }
@@ -943,7 +950,10 @@ extern "C" int egnn_inject_time(const float* x, int64_t ld_x, const int64_t* t, 
                                 int64_t ld_out_bf16, int64_t n_rows, int64_t n_feat, void* stream) {
   const char* fn = "egnn_inject_time";
   if (ld_out_bf16 <= 0) ld_out_bf16 = ld_out;
-  EGNN_REQUIRE(ld_out_bf16 % 2 == 0 && ld_out_bf16 >= ld_out, fn, "bad ld_out_bf16");
+  EGNN_REQUIRE(ld_out_bf16 % 4 == 0 && ld_out_bf16 >= ld_out, fn, "bad ld_out_bf16");
+  EGNN_REQUIRE((!out_f32 || (uintptr_t)out_f32 % 16 == 0) && (!out_bf16 || (uintptr_t)out_bf16 % 8 == 0) &&
+                   ld_out / 4 <= kThreads,
+               fn, "outputs must be 16-byte (fp32) / 8-byte (bf16) aligned, ld_out <= 1024");
   EGNN_REQUIRE(x && (out_f32 || out_bf16), fn, "null pointer");
   EGNN_REQUIRE(D == 0 || (t && table && T > 0), fn, "time table / indices missing");
   EGNN_REQUIRE(ld_out % 4 == 0 && ld_out >= n_feat + D, fn, "ld_out must be a multiple of 4 and >= F+D");
