@@ -48,23 +48,38 @@ class FlatClipAdam:
         self.grad_norm = torch.zeros(1, dtype=torch.float32, device=dev)
         self.ws = torch.empty(lib().egnn_adam_workspace_floats(n), dtype=torch.float32, device=dev)
         off = 0
+        self.views = []
         for p in self.params:
             k = p.numel()
             self.flat_param[off:off + k].copy_(p.data.reshape(-1))
             p.data = self.flat_param[off:off + k].view_as(p.data)
-            p.grad = self.flat_grad[off:off + k].view_as(p.data)
+            self.views.append(self.flat_grad[off:off + k].view_as(p.data))
+            p.grad = self.views[-1]
             off += k
         self.lr, self.wd, self.betas, self.eps, self.max_norm = lr, weight_decay, betas, eps, max_norm
 
-    def zero_grad(self, set_to_none: bool = False):
-        self.flat_grad.zero_()
-        off = 0
-        for p in self.params:  # re-attach views (autograd may have replaced a None grad)
-            k = p.numel()
-            v = self.flat_grad[off:off + k].view_as(p.data)
-            if p.grad is None or p.grad.data_ptr() != v.data_ptr():
-                p.grad = v
-            off += k
+    def zero_grad(self, set_to_none: bool = True):
+        """Drop the .grad references: autograd then hands each parameter its gradient tensor as is
+        (no `grad += new` kernel per parameter); `gather_grads()` packs them into the flat buffer."""
+        for p in self.params:
+            p.grad = None
+
+    def gather_grads(self):
+        """flat_grad <- the gradients autograd produced, in ONE multi-tensor copy; afterwards every
+        p.grad is a view of the flat buffer again (what clip / Adam / the all-reduce operate on)."""
+        src, dst, missing = [], [], []
+        for p, v in zip(self.params, self.views):
+            if p.grad is None:
+                missing.append(v)
+            else:
+                src.append(p.grad.reshape(v.shape).to(torch.float32))
+                dst.append(v)
+        if dst:
+            torch._foreach_copy_(dst, src)
+        for v in missing:
+            v.zero_()
+        for p, v in zip(self.params, self.views):
+            p.grad = v
 
     def step(self):
         check(lib().egnn_clip_adam_step(ptr(self.flat_param), ptr(self.flat_grad), ptr(self.exp_avg),
@@ -104,6 +119,7 @@ class TrainStep:
             logits = m(self.x, self.edge_index, t)
         loss = ops.masked_weighted_ce(logits, self.y, self.train_idx, self.cw, self.n_train_total)
         loss.backward()
+        self.opt.gather_grads()
         if self.grad_reducer is not None:
             self.grad_reducer(self.opt.flat_grad)
         self.opt.step()

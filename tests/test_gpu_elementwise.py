@@ -121,7 +121,8 @@ def test_clip_adam_matches_torch(egnn):
         opt.zero_grad()
         for p, pr, g in zip(ps, ps_ref, grads):
             pr.grad = g.clone()
-            p.grad.copy_(g.cuda())
+            p.grad = g.cuda()
+        opt.gather_grads()   # one multi-tensor copy into the flat gradient buffer
         total = torch.nn.utils.clip_grad_norm_(ps_ref, 1.0)
         opt_ref.step()
         opt.step()
