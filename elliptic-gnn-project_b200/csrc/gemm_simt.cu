@@ -265,6 +265,15 @@ extern "C" int egnn_gemm(const void* A, int a_dtype, int64_t a_sm, int64_t a_sk,
     return gemm_tcgen05_dispatch(A, a_sm, B, b_sn, C, c_dtype, ld_c, M, N, K, bias, accumulate, row_div_ptr, row_div_cols, st);
   if (impl != 1 && tc_wg)
     return wgrad_tcgen05_dispatch(A, a_sk, B, b_sk, (float*)C, K, M, N, accumulate, workspace, st);
+  if (both_bf16 && (M >= 65536 || K >= 65536)) {  // a large bf16 product that misses the tensor-core path: say so once
+    static bool warned = false;
+    if (!warned) {
+      warned = true;
+      fprintf(stderr, "[egnn_b200] note: bf16 GEMM M=%lld N=%lld K=%lld (a_sm=%lld a_sk=%lld) runs on the SIMT kernel "
+                      "(shape/layout outside the tcgen05 kernels)\n",
+              (long long)M, (long long)N, (long long)K, (long long)a_sm, (long long)a_sk);
+    }
+  }
   GemmParams P;
   P.A = A; P.B = B; P.C = C; P.bias = bias; P.row_div_ptr = row_div_ptr; P.row_div_cols = row_div_cols; P.ws = workspace;
   P.a_sm = a_sm; P.a_sk = a_sk; P.b_sk = b_sk; P.b_sn = b_sn; P.ld_c = ld_c;

@@ -565,7 +565,7 @@ bool wgrad_tcgen05_supported(const void* G, int64_t ldg, const void* X, int64_t 
   const int Nopad = (int)((N_out + 15) / 16 * 16);
   const int MT = (int)((K_in + 127) / 128);
   const int stage = (MT * 2 + (Nopad + 63) / 64) * 8192;
-  return (size_t)kStagesWG * stage + 256 + 1024 <= 227 * 1024 && MT * Nopad <= 512;
+  return (size_t)2 * stage + 256 + 1024 <= 227 * 1024 && MT * Nopad <= 512;  // at least a 2-deep ring
 }
 
 // dW[N_out, K_in] (fp32, ld = K_in) (+)= G[M,N_out]^T X[M,K_in]; workspace >= wgrad_tcgen05_workspace_floats
@@ -578,16 +578,25 @@ int wgrad_tcgen05_dispatch(const void* G, int64_t ldg, const void* X, int64_t ld
   CUtensorMap tmX, tmG;
   if (!make_map(&tmX, X, M_rows, K_in, ldx, 64) || !make_map(&tmG, G, M_rows, N_out, ldg, 64))
     return fail(fn, "cuTensorMapEncodeTiled failed");
-  size_t smem = (size_t)kStagesWG * stage + 256 + 1024;
+  // deepest TMA ring that fits: 4 stages for the 64-wide layers, 3 / 2 for the wide concatenated operands
+  int stages = kStagesWG;
+  while (stages > 2 && (size_t)stages * stage + 256 + 1024 > 227 * 1024) --stages;
+  size_t smem = (size_t)stages * stage + 256 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(gemm_wgrad_kernel<kStagesWG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(gemm_wgrad_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(gemm_wgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(gemm_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
   int n_slabs = (int)((M_rows + 63) / 64);
   int grid = n_slabs < kNumSMs ? n_slabs : kNumSMs;
-  gemm_wgrad_kernel<kStagesWG><<<grid, kThreads, smem, st>>>(tmX, tmG, (int)M_rows, (int)N_out, Nopad, (int)K_in,
-                                                            workspace);
+  if (stages == 4)
+    gemm_wgrad_kernel<4><<<grid, kThreads, smem, st>>>(tmX, tmG, (int)M_rows, (int)N_out, Nopad, (int)K_in, workspace);
+  else if (stages == 3)
+    gemm_wgrad_kernel<3><<<grid, kThreads, smem, st>>>(tmX, tmG, (int)M_rows, (int)N_out, Nopad, (int)K_in, workspace);
+  else
+    gemm_wgrad_kernel<2><<<grid, kThreads, smem, st>>>(tmX, tmG, (int)M_rows, (int)N_out, Nopad, (int)K_in, workspace);
   EGNN_LAUNCH_CHECK(fn);
   int64_t n_elem = N_out * K_in;
   wgrad_reduce_kernel<<<(unsigned)ceil_div(n_elem, 64), 256, 0, st>>>(workspace, grid, n_elem, dW, accumulate);

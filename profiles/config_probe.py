@@ -27,6 +27,7 @@ ap.add_argument("--arch", default="sage_l3")
 ap.add_argument("--replicas", type=int, default=1)
 ap.add_argument("--fp32", action="store_true")
 ap.add_argument("--steps", type=int, default=20)
+ap.add_argument("--profile", action="store_true", help="per-kernel device time of eager steps (torch.profiler)")
 args = ap.parse_args()
 cfg = CFGS[args.arch]
 torch.cuda.set_device(0)
@@ -48,6 +49,25 @@ step = TrainStep(model, x.cuda(), ei.cuda(), gr.timestep.cuda(), gr.y.cuda(), gr
 del x, gr
 step.run()
 torch.cuda.synchronize()
+if args.profile:
+    import collections
+    from torch.profiler import ProfilerActivity, profile
+    step.run()
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        for _ in range(2):
+            step.run()
+        torch.cuda.synchronize()
+    evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for e in evs:
+        agg[e.name[:110]][0] += 1
+        agg[e.name[:110]][1] += e.device_time
+    tot = sum(v[1] for v in agg.values())
+    print(f"# {len(evs) // 2} kernels/step, {tot / 2:.1f} us device time per step (eager)")
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:25]:
+        print(f"{v[1] / 2:10.1f} us {v[0] // 2:4d}x {v[1] / tot * 100:5.1f}%  {k}")
+    sys.exit(0)
 step.capture(warmup=2)
 for _ in range(3):
     step.run()

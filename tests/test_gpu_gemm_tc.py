@@ -60,7 +60,7 @@ def test_tn_epilogues(egnn):
 
 
 @pytest.mark.parametrize("M", [1, 63, 64, 65, 6000, 203769])
-@pytest.mark.parametrize("N,K", [(64, 168), (64, 64), (128, 128), (8, 64), (32, 168), (128, 256), (16, 40), (64, 336), (64, 384)])
+@pytest.mark.parametrize("N,K", [(64, 168), (64, 64), (128, 128), (8, 64), (32, 168), (128, 256), (16, 40), (64, 336), (64, 384), (128, 336), (256, 256)])
 def test_wgrad_matches_fp64(egnn, M, N, K):
     from egnn_b200 import ops
     if M == 203769 and (N, K) not in ((64, 168), (64, 64), (64, 336)):
