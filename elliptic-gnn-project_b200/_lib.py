@@ -37,6 +37,7 @@ SIGNATURES = {
     "egnn_gemm_workspace_floats": (_sz, [_i64, _i64, _i64, _i32]),
     "egnn_gemm": (_i32, [_vp, _i32, _i64, _i64, _vp, _i32, _i64, _i64, _vp, _i32, _i64, _i64, _i64, _i64,
                          _vp, _vp, _i64, _i32, _i32, _vp, _i32, _vp]),
+    "egnn_pack_sage_weights": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp]),
     "egnn_cast": (_i32, [_vp, _i32, _i64, _vp, _i32, _i64, _i64, _i64, _vp]),
     "egnn_inject_time": (_i32, [_vp, _i64, _vp, _vp, _i64, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _vp]),
     "egnn_colreduce_workspace_bytes": (_sz, [_i64]),

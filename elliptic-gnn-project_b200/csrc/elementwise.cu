@@ -945,6 +945,38 @@ extern "C" int egnn_cast(const void* in, int in_dtype, int64_t ld_in, void* out,
   return 0;
 }
 
+// out[r, :] (bf16, [No + Nr, 2*Kp]) = r < No ? [w_l[r] | 0 | w_r[r] | 0] : [0 | w_res[r - No] | 0];  bias_out = [b_l | 0]
+__global__ void __launch_bounds__(kThreads) pack_sage_weights_kernel(
+    const float* __restrict__ w_l, const float* __restrict__ w_r, const float* __restrict__ w_res,
+    const float* __restrict__ b_l, int No, int Nr, int K, int Kp, __nv_bfloat16* __restrict__ out,
+    float* __restrict__ bias_out) {
+  const int i = blockIdx.x * kThreads + threadIdx.x;
+  const int W = 2 * Kp;
+  if (i < No + Nr && bias_out) bias_out[i] = (i < No && b_l) ? b_l[i] : 0.f;
+  if (i >= (No + Nr) * W) return;
+  const int r = i / W, c = i - r * W;
+  const int half = c >= Kp, k = c - half * Kp;
+  float v = 0.f;
+  if (k < K) {
+    if (r < No) v = half ? w_r[r * K + k] : w_l[r * K + k];
+    else if (half) v = w_res[(r - No) * K + k];
+  }
+  out[i] = __float2bfloat16_rn(v);
+}
+
+extern "C" int egnn_pack_sage_weights(const float* w_l, const float* w_r, const float* w_res, const float* b_l,
+                                      int64_t n_out, int64_t n_res, int64_t K, int64_t K_padded, void* out_bf16,
+                                      float* bias_out, void* stream) {
+  const char* fn = "egnn_pack_sage_weights";
+  EGNN_REQUIRE(w_l && w_r && out_bf16 && (n_res == 0 || w_res), fn, "null pointer");
+  EGNN_REQUIRE(n_out > 0 && K > 0 && K_padded >= K && (n_out + n_res) * 2 * K_padded < (1 << 30), fn, "bad shape");
+  const int64_t total = (n_out + n_res) * 2 * K_padded;
+  pack_sage_weights_kernel<<<(unsigned)ceil_div(total, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+      w_l, w_r, w_res, b_l, (int)n_out, (int)n_res, (int)K, (int)K_padded, (__nv_bfloat16*)out_bf16, bias_out);
+  EGNN_LAUNCH_CHECK(fn);
+  return 0;
+}
+
 extern "C" int egnn_inject_time(const float* x, int64_t ld_x, const int64_t* t, const float* table,
                                 int64_t T, int64_t D, float* out_f32, void* out_bf16, int64_t ld_out,
                                 int64_t ld_out_bf16, int64_t n_rows, int64_t n_feat, void* stream) {

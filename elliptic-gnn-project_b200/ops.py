@@ -233,11 +233,10 @@ class SageConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w_l, b_l, w_r, w_res, g: Graph, bf16: bool):
         cd = torch.bfloat16 if bf16 else torch.float32
-        pad = (-x.size(1)) % 8 if x.dtype == torch.float32 else 0
+        K0 = x.size(1)
+        pad = (-K0) % 8 if x.dtype == torch.float32 else 0
         if pad:   # e.g. 167 raw columns: pad once so that gathers and GEMM operands have 16-byte rows
-            x = pad_features(x, x.size(1) + pad, want_twin=bf16)
-            w_l, w_r = _pad_cols(w_l, pad), _pad_cols(w_r, pad)
-            w_res = _pad_cols(w_res, pad) if w_res is not None else None
+            x = pad_features(x, K0 + pad, want_twin=bf16)
         ctx.pad = pad
         xg = to_compute(x, cd)
         x = _rows(x)
@@ -250,19 +249,22 @@ class SageConvFn(torch.autograd.Function):
         if cat is not None and cat.dtype == cd and cat.size(1) == 2 * K:
             xg._egnn_cat_used = True
             spmm(g, "csr", _lib.SPMM_MEAN, x, cd, out=cat[:, :K])
-            w32 = torch.cat([w_l, w_r], dim=1)
-            bias = b_l
-            if w_res is not None:
-                Nr = w_res.size(0)
-                w32 = torch.cat([w32, torch.cat([w_res.new_zeros((Nr, K)), w_res], dim=1)], dim=0)
-                bias = torch.cat([b_l, b_l.new_zeros(Nr)])
-            wcat = cast(w32, cd)                      # [No (+Nr), 2K]
+            Nr = 0 if w_res is None else w_res.size(0)
+            wcat = torch.empty((No + Nr, 2 * K), dtype=cd, device=x.device)     # [[W_l | W_r], [0 | W_res]]
+            bias = torch.empty(No + Nr, dtype=torch.float32, device=x.device)
+            check(lib().egnn_pack_sage_weights(ptr(w_l.contiguous()), ptr(w_r.contiguous()),
+                                               ptr(w_res.contiguous()) if w_res is not None else None,
+                                               ptr(b_l.contiguous()) if b_l is not None else None, No, Nr, K0, K,
+                                               ptr(wcat), ptr(bias), stream()))
             zc = linear_fwd(cat, wcat, bias=bias, out_dtype=cd)
             ctx.cat_path = True
             ctx.save_for_backward(cat, wcat)
             if w_res is None:
                 return zc
             return zc[:, :No], zc[:, No:]
+        if pad:
+            w_l, w_r = _pad_cols(w_l, pad), _pad_cols(w_r, pad)
+            w_res = _pad_cols(w_res, pad) if w_res is not None else None
         m = spmm(g, "csr", _lib.SPMM_MEAN, x, cd)
         wl = w_l if w_l.dtype == cd else cast(w_l, cd)
         wr = w_r if w_r.dtype == cd else cast(w_r, cd)
@@ -496,11 +498,14 @@ class GatConvFn(torch.autograd.Function):
         check(L.egnn_gat_att_grad(ptr(xs), ptr(da_s), ptr(da_d), N, H, C, datt[0].data_ptr(),
                                   datt[1].data_ptr(), ptr(ws), stream()))
         datt = datt.float()
-        dw = linear_wgrad(dxs, xg)
+        # under bf16 autocast the Linear's backward runs in bf16 (PyG: grad of an autocast matmul): cast the fp32
+        # attention-path gradient once so that wgrad / dgrad take the tensor-core kernels
+        dxs_c = dxs if dxs.dtype == xg.dtype else cast(dxs, xg.dtype)
+        dw = linear_wgrad(dxs_c, xg)
         dbias = colsum(dout).float()
         dx = None
         if ctx.needs_input_grad[0]:
-            dx = linear_dgrad(dxs, wc, out_dtype=xg.dtype)
+            dx = linear_dgrad(dxs_c, wc, out_dtype=xg.dtype)
             if dx.dtype != ctx.x_dtype:
                 dx = cast(dx, ctx.x_dtype)
         if ctx.pad:

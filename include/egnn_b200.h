@@ -159,6 +159,14 @@ int egnn_skinny_wgrad(const void* a, int dtype, int64_t ld, const float* dp, int
 int egnn_skinny_dgrad(const float* dp, const float* W, int P, void* dh, int dtype, int64_t ld,
                       int64_t n_rows, int64_t K, void* stream);
 
+/* SAGE layer operand for the concatenated GEMM (ops.SageConvFn): one launch builds the bf16 matrix
+ * [[W_l | W_r], [0 | W_res]] (each block zero-padded from K to K_padded columns; W_res optional, n_res rows)
+ * and the matching bias [b_l | 0] from the fp32 parameters lin_l.weight / lin_r.weight / res_projs.weight
+ * (src/models/gnn.py:125-128,141-144). */
+int egnn_pack_sage_weights(const float* w_l, const float* w_r, const float* w_res, const float* b_l,
+                           int64_t n_out, int64_t n_res, int64_t K, int64_t K_padded, void* out_bf16,
+                           float* bias_out, void* stream);
+
 /* cast / copy with optional column padding: out[r, 0:F] = in[r, 0:F], out[r, F:ld_out] = 0 */
 int egnn_cast(const void* in, int in_dtype, int64_t ld_in, void* out, int out_dtype,
               int64_t ld_out, int64_t n_rows, int64_t n_feat, void* stream);
