@@ -91,8 +91,12 @@ __device__ __forceinline__ void generic_epilogue(const Params& P, TO* o, const T
   stv(o, a);
 }
 
+// minimum resident CTAs per SM: the kernel is bound by rows in flight (ncu: issue active 31 %, DRAM 28 %,
+// 52 registers -> 4 CTAs), so the register budget is capped to buy occupancy
+constexpr int lean_min_blocks(int vpl, int batch, int vec) { return (vpl >= 3 && batch == 1 && vec == 4) ? 6 : 1; }
+
 template <typename TI, typename TO, int MODE, int VEC, int G, int VPL, int BATCH, bool LEAN>
-__global__ void __launch_bounds__(kThreads) spmm_lean(Params P) {
+__global__ void __launch_bounds__(kThreads, lean_min_blocks(VPL, BATCH, VEC)) spmm_lean(Params P) {
   constexpr int kRows = kThreads / G;
   __shared__ __align__(16) float s_stage[kStageEdges][kSliceFeat];  // used by the long-row CTAs only
   __shared__ float s_scale[kStageEdges];
@@ -400,7 +404,7 @@ int launch_exp(const Params& P, cudaStream_t st) {
 
 template <typename TI, typename TO, int MODE, int VEC, int G, int VPL>
 int launch_cfg(const Params& P, cudaStream_t st) {
-  constexpr int BATCH = 2;
+  constexpr int BATCH = VPL >= 3 ? 1 : 2;  // wide rows: one edge per batch keeps the kernel at 6 CTAs per SM
   static const bool use_pipe = [] { const char* e = getenv("EGNN_SPMM_IMPL"); return e && e[0] == 'p'; }();
   if (use_pipe) {
     int rc = launch_pipe<TI, TO, MODE, VEC, G, VPL, BATCH>(P, st);
