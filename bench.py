@@ -290,6 +290,8 @@ def run_ours(args):
                                    "symmetrize_edges, dropout 0.2, bf16 autocast, full-batch",
                        "nodes_per_gpu": lg.num_nodes, "edges_total": e_total, "replicas": world,
                        "parallelism": f"timestep-sharded dp{world}", "cuda_graph": graphed,
+                       "collectives": ("peer-memory all-reduce kernel (csrc/p2p.cu) for BatchNorm statistics and "
+                                       "gradients" if ctx.p2p else ("nccl" if world > 1 else "none")),
                        "l2": "inputs larger than L2 (x alone 135 MB; ~1 GB touched per step)"},
             "clocks": clocks,
             "e2e": {"value": round(e_total / (ms_e2e_step * 1e-3) / 1e9, 4), "unit": UNIT,

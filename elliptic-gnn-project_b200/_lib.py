@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libegnn_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
-F32, BF16 = 0, 1
+F32, BF16, F64 = 0, 1, 2
 G_SYMMETRIZE, G_SELF_LOOPS = 1, 2
 SPMM_SUM, SPMM_MEAN, SPMM_DIV_NBR, SPMM_WEIGHTED = 0, 1, 2, 3
 ACT_NONE, ACT_RELU, ACT_ELU = 0, 1, 2
@@ -64,6 +64,8 @@ SIGNATURES = {
     "egnn_skinny_wgrad_workspace_floats": (_sz, [_i64, _i64, _i32]),
     "egnn_skinny_wgrad": (_i32, [_vp, _i32, _i64, _vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp]),
     "egnn_skinny_dgrad": (_i32, [_vp, _vp, _i32, _vp, _i32, _i64, _i64, _i64, _vp]),
+    "egnn_p2p_allreduce_buffer_bytes": (_sz, [_i32, _i64, _i32]),
+    "egnn_p2p_allreduce": (_i32, [_vp, _vp, _i64, _i32, _i64, _vp, _i32, _i32, _vp, _vp, _vp]),
     "egnn_masked_ce": (_i32, [_vp, _i32, _i64, _vp, _vp, _i64, _vp, _f64, _vp, _vp, _vp, _vp]),
     "egnn_adam_workspace_floats": (_sz, [_i64]),
     "egnn_clip_adam_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _vp, _vp,

@@ -14,6 +14,8 @@ with re-based ids: zero halo, zero feature exchange.  Collectives (NCCL over NVL
 """
 from __future__ import annotations
 
+import os
+import sys
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
 
@@ -115,6 +117,53 @@ def make_shard(gr: EllipticGraph, rank: int, world: int, feat_cost: float = 1.0)
     return Shard(rank=rank, world=world, row0=lo, n_local=hi - lo, n_global=gr.num_nodes, graph=local)
 
 
+class P2PAllReduce:
+    """In-place sum over the ranks of a small fp32 / fp64 vector as ONE hand-written kernel over NVLink peer
+    memory (csrc/p2p.cu: push into the peers' symmetric buffers, per-chunk flags, sum in rank order) instead
+    of a NCCL call.  The symmetric buffer and the device array of peer pointers come from
+    torch.distributed._symmetric_memory (allocation + rendezvous only)."""
+
+    def __init__(self, n_max: int, dtype: torch.dtype, group, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        self.code = {torch.float32: _lib.F32, torch.float64: _lib.F64}[dtype]
+        self.dtype, self.n_max, self.group = dtype, int(n_max), group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        nbytes = _lib.lib().egnn_p2p_allreduce_buffer_bytes(self.world, self.n_max, self.code)
+        self.buf = symm_mem.empty((nbytes + 7) // 8, dtype=torch.int64, device=device)
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.peer_ptrs = int(self.hdl.buffer_ptrs_dev)
+        self.epoch = torch.zeros(1, dtype=torch.int64, device=device)
+        self.err = torch.zeros(1, dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)      # every rank's flags are zero before anyone pushes
+
+    def supports(self, t: torch.Tensor) -> bool:
+        return t.dtype == self.dtype and t.is_contiguous() and 0 < t.numel() <= self.n_max
+
+    def __call__(self, t: torch.Tensor) -> torch.Tensor:
+        from ._lib import check, lib, stream
+        check(lib().egnn_p2p_allreduce(t.data_ptr(), t.data_ptr(), t.numel(), self.code, self.n_max, self.peer_ptrs,
+                                       self.rank, self.world, self.epoch.data_ptr(), self.err.data_ptr(), stream()))
+        return t
+
+    def check(self):
+        if int(self.err.item()):
+            raise RuntimeError("egnn_p2p_allreduce: a peer did not arrive (timeout inside the kernel)")
+
+
+class P2PStatsReducer(StatsReducer):
+    """BatchNorm-statistics all-reduce through the peer-memory kernel (NCCL for anything it does not cover)."""
+
+    def __init__(self, n_total: int, group, device):
+        super().__init__(n_total=n_total, group=group)
+        self.ar = P2PAllReduce(1024, torch.float64, group, device)
+
+    def reduce_(self, buf: torch.Tensor) -> torch.Tensor:
+        return self.ar(buf) if self.ar.supports(buf) else super().reduce_(buf)
+
+
 class ShardedContext:
     """What a rank needs to step its shard so that the result equals the single-GPU step on the
     whole graph (up to the order of the cross-rank sums)."""
@@ -133,6 +182,16 @@ class ShardedContext:
             self.class_weight = torch.tensor([(pos + neg) / (2.0 * neg), (pos + neg) / (2.0 * pos)],
                                              dtype=torch.float32)
         self.stats_reducer = StatsReducer(n_total=shard.n_global, group=group)
+        self.p2p = False
+        self._grad_ar = None
+        if dist.is_initialized() and dist.get_world_size(group) > 1 and torch.device(device).type == "cuda" \
+                and os.environ.get("EGNN_P2P", "1") != "0":
+            try:
+                self.stats_reducer = P2PStatsReducer(shard.n_global, group, device)
+                self.p2p = True
+            except Exception as ex:   # no symmetric-memory support on this box: NCCL all-reduce instead
+                print(f"[egnn_b200] peer-memory BatchNorm all-reduce unavailable ({type(ex).__name__}: {ex}); "
+                      "using NCCL", file=sys.stderr, flush=True)
 
     def attach(self, model):
         model.stats_reducer = self.stats_reducer
@@ -140,6 +199,12 @@ class ShardedContext:
         return model
 
     def reduce_grads(self, flat_grad: torch.Tensor):
-        if dist.is_initialized():
-            dist.all_reduce(flat_grad, group=self.group)
+        if not dist.is_initialized():
+            return flat_grad
+        if self.p2p and self._grad_ar is None and flat_grad.dtype == torch.float32 \
+                and flat_grad.numel() <= 131072 and not torch.cuda.is_current_stream_capturing():
+            self._grad_ar = P2PAllReduce(flat_grad.numel(), torch.float32, self.group, flat_grad.device)
+        if self._grad_ar is not None and self._grad_ar.supports(flat_grad):
+            return self._grad_ar(flat_grad)
+        dist.all_reduce(flat_grad, group=self.group)
         return flat_grad

@@ -30,7 +30,7 @@ extern "C" {
 
 #define EGNN_ABI_VERSION 1
 
-enum { EGNN_F32 = 0, EGNN_BF16 = 1 };
+enum { EGNN_F32 = 0, EGNN_BF16 = 1, EGNN_F64 = 2 /* egnn_p2p_allreduce only */ };
 
 /* graph-build flags */
 enum {
@@ -270,6 +270,21 @@ int egnn_gat_bwd_src(const int32_t* csc_ptr, const int32_t* csc_dst, const int32
  * workspace: egnn_colreduce_workspace_bytes(H*C). */
 int egnn_gat_att_grad(const float* xs, const float* da_s, const float* da_d, int64_t n_rows, int H,
                       int C, double* datt_src, double* datt_dst, void* workspace, void* stream);
+
+/* ---------------------------------------------------------------- multi-GPU ----------- */
+/* One-shot all-reduce (sum) over NVLink peer memory of the small vectors the timestep-sharded step exchanges: the
+ * BatchNorm statistics (nn.BatchNorm1d over ALL nodes, src/models/gnn.py:134,189; fp64) and the flat
+ * weight-gradient buffer (fp32).  Each rank stores its vector into a slot of every peer's symmetric buffer,
+ * publishes a system-scope flag per 2048-element chunk, waits for the peers' flags in its own memory and sums
+ * the slots in rank order (bit-identical on every rank).  n <= n_max <= 131 072; dtype EGNN_F32 | EGNN_F64.
+ * peer_bufs_dev: DEVICE array of `world` base pointers, entry r = rank r's buffer of
+ * egnn_p2p_allreduce_buffer_bytes(world, n_max, dtype) bytes, zero-initialised, mapped into this process (the
+ * Python layer gets them from torch.distributed._symmetric_memory).  epoch: device int64, local, starts at 0
+ * (CUDA-graph replayable).  error_flag (optional, device int): set to 1 if a peer did not arrive within ~2 s.
+ * in == out is allowed.  Every rank must make the same sequence of calls on a given buffer. */
+size_t egnn_p2p_allreduce_buffer_bytes(int world, int64_t n_max, int dtype);
+int egnn_p2p_allreduce(const void* in, void* out, int64_t n, int dtype, int64_t n_max, void* const* peer_bufs_dev,
+                       int rank, int world, int64_t* epoch, int* error_flag, void* stream);
 
 /* ---------------------------------------------------------------- step tail ----------- */
 /* Masked weighted cross-entropy over precomputed train-row indices:
