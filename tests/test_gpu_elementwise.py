@@ -150,3 +150,25 @@ def test_inject_time_bitexact(egnn):
     tab = (torch.arange(1, T + 1).float() / float(tt.max())).unsqueeze(1)
     got = ops.InjectTimeFn.apply(x.cuda(), tt.cuda(), tab.cuda(), 168).cpu()
     assert torch.equal(got[:, :167], torch.cat([x, tn], dim=1)) and (got[:, 167] == 0).all()
+
+
+def test_p2p_allreduce_single_rank_protocol(egnn):
+    """csrc/p2p.cu with world_size 1 (the only size a 1-GPU box can run): the rank pushes into its own buffer,
+    flags itself and sums one slot -- exercises the epoch / parity / chunk-flag protocol over several calls,
+    for fp64 statistics and a multi-chunk fp32 gradient vector.  The 2/4/8-rank behaviour is checked by
+    profiles/shard_check.py on a multi-GPU box."""
+    from egnn_b200 import _lib
+    L = _lib.lib()
+    for dtype, code, n_max, n in ((torch.float64, _lib.F64, 1024, 128), (torch.float32, _lib.F32, 41090, 41090)):
+        nbytes = L.egnn_p2p_allreduce_buffer_bytes(1, n_max, code)
+        buf = torch.zeros((nbytes + 7) // 8, dtype=torch.int64, device="cuda")
+        ptrs = torch.tensor([buf.data_ptr()], dtype=torch.int64, device="cuda")
+        epoch = torch.zeros(1, dtype=torch.int64, device="cuda")
+        err = torch.zeros(1, dtype=torch.int32, device="cuda")
+        for it in range(5):
+            x = torch.randn(n, dtype=dtype, device="cuda")
+            want = x.clone()
+            _lib.check(L.egnn_p2p_allreduce(x.data_ptr(), x.data_ptr(), n, code, n_max, ptrs.data_ptr(), 0, 1,
+                                            epoch.data_ptr(), err.data_ptr(), _lib.stream()))
+            assert torch.equal(x, want)
+        assert int(epoch.item()) == 5 and int(err.item()) == 0
