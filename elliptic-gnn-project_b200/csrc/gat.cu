@@ -46,26 +46,118 @@ __global__ void __launch_bounds__(kThreads) gat_fwd_kernel(const int* __restrict
   if (row >= n_rows) return;
   const int p0 = ptr[row], p1 = ptr[row + 1];
   const int F = H * C;
+  // segment softmax with ONE LANE PER ENTRY (32 entries per sweep; the usual row is one sweep): all score
+  // gathers of a row are issued together, max / sum are warp reductions, nothing walks the row serially
+  constexpr int kHMax = 8;
+  if (H <= kHMax) {
+    float ad[kHMax], mx[kHMax], den[kHMax], e0[kHMax];
+#pragma unroll
+    for (int h = 0; h < kHMax; ++h) {
+      ad[h] = h < H ? __ldg(a_d + row * H + h) : 0.f;
+      mx[h] = -INFINITY;
+      den[h] = 0.f;
+      e0[h] = 0.f;
+    }
+    const bool single = p1 - p0 <= 32;
+    for (int base = p0; base < p1; base += 32) {  // pass A: scores and per-head max
+      const int p = base + lane;
+      const bool valid = p < p1;
+      const int64_t sj = valid ? __ldg(src + p) : 0;
+#pragma unroll
+      for (int h = 0; h < kHMax; ++h)
+        if (h < H) {
+          const float e = leaky(__ldg(a_s + sj * H + h) + ad[h], slope);
+          if (base == p0) e0[h] = e;
+          if (valid) mx[h] = fmaxf(mx[h], e);
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < kHMax; ++h)
+      if (h < H)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], o));
+    for (int base = p0; base < p1; base += 32) {  // pass B: exp and per-head sum (unnormalised alpha parked)
+      const int p = base + lane;
+      const bool valid = p < p1;
+      const int64_t sj = (valid && !single) ? __ldg(src + p) : 0;
+#pragma unroll
+      for (int h = 0; h < kHMax; ++h)
+        if (h < H) {
+          const float e = single ? e0[h] : leaky(__ldg(a_s + sj * H + h) + ad[h], slope);
+          const float ex = valid ? expf(e - mx[h]) : 0.f;
+          den[h] += ex;
+          if (valid) alpha[(int64_t)p * H + h] = ex;
+          if (single) e0[h] = ex;
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < kHMax; ++h)
+      if (h < H) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) den[h] += __shfl_xor_sync(0xffffffffu, den[h], o);
+        den[h] += 1e-16f;
+      }
+    for (int base = p0; base < p1; base += 32) {  // pass C: normalise
+      const int p = base + lane;
+      if (p < p1) {
+#pragma unroll
+        for (int h = 0; h < kHMax; ++h)
+          if (h < H) alpha[(int64_t)p * H + h] = __fdiv_rn(single ? e0[h] : alpha[(int64_t)p * H + h], den[h]);
+      }
+    }
+  } else {
   for (int h = lane; h < H; h += 32) {
     const float ad = a_d[row * H + h];
     float mx = -INFINITY;
-    for (int p = p0; p < p1; ++p) mx = fmaxf(mx, leaky(a_s[(int64_t)src[p] * H + h] + ad, slope));
+    int p = p0;
+    for (; p + 4 <= p1; p += 4) {  // four (src -> a_s) chains in flight: a hub row is hundreds of entries long
+      float v[4];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) v[b] = __ldg(a_s + (int64_t)__ldg(src + p + b) * H + h);
+#pragma unroll
+      for (int b = 0; b < 4; ++b) mx = fmaxf(mx, leaky(v[b] + ad, slope));
+    }
+    for (; p < p1; ++p) mx = fmaxf(mx, leaky(__ldg(a_s + (int64_t)__ldg(src + p) * H + h) + ad, slope));
     float den = 0.f;
-    for (int p = p0; p < p1; ++p) {
-      float e = expf(leaky(a_s[(int64_t)src[p] * H + h] + ad, slope) - mx);
+    p = p0;
+    for (; p + 4 <= p1; p += 4) {
+      float v[4];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) v[b] = __ldg(a_s + (int64_t)__ldg(src + p + b) * H + h);
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const float e = expf(leaky(v[b] + ad, slope) - mx);
+        alpha[(int64_t)(p + b) * H + h] = e;
+        den = __fadd_rn(den, e);
+      }
+    }
+    for (; p < p1; ++p) {
+      const float e = expf(leaky(__ldg(a_s + (int64_t)__ldg(src + p) * H + h) + ad, slope) - mx);
       alpha[(int64_t)p * H + h] = e;
       den = __fadd_rn(den, e);
     }
     den = den + 1e-16f;
-    for (int p = p0; p < p1; ++p) alpha[(int64_t)p * H + h] = __fdiv_rn(alpha[(int64_t)p * H + h], den);
+    for (p = p0; p < p1; ++p) alpha[(int64_t)p * H + h] = __fdiv_rn(alpha[(int64_t)p * H + h], den);
+  }
   }
   __syncwarp();
   if (concat) {
     for (int f = lane; f < F; f += 32) {
       const int h = f / C;
       float acc = 0.f;
-      for (int p = p0; p < p1; ++p)
-        acc = __fadd_rn(acc, __fmul_rn(alpha[(int64_t)p * H + h], xs[(int64_t)src[p] * F + f]));
+      int p = p0;
+      for (; p + 4 <= p1; p += 4) {
+        float a[4], x[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          a[b] = alpha[(int64_t)(p + b) * H + h];
+          x[b] = __ldg(xs + (int64_t)__ldg(src + p + b) * F + f);
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc = __fadd_rn(acc, __fmul_rn(a[b], x[b]));
+      }
+      for (; p < p1; ++p)
+        acc = __fadd_rn(acc, __fmul_rn(alpha[(int64_t)p * H + h], __ldg(xs + (int64_t)__ldg(src + p) * F + f)));
       out[row * F + f] = acc + (bias ? bias[f] : 0.f);
     }
   } else {
@@ -73,8 +165,19 @@ __global__ void __launch_bounds__(kThreads) gat_fwd_kernel(const int* __restrict
       float tot = 0.f;
       for (int h = 0; h < H; ++h) {
         float acc = 0.f;
-        for (int p = p0; p < p1; ++p)
-          acc = __fadd_rn(acc, __fmul_rn(alpha[(int64_t)p * H + h], xs[(int64_t)src[p] * F + h * C + c]));
+        int p = p0;
+        for (; p + 4 <= p1; p += 4) {
+          float a[4], x[4];
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            a[b] = alpha[(int64_t)(p + b) * H + h];
+            x[b] = __ldg(xs + (int64_t)__ldg(src + p + b) * F + h * C + c);
+          }
+#pragma unroll
+          for (int b = 0; b < 4; ++b) acc = __fadd_rn(acc, __fmul_rn(a[b], x[b]));
+        }
+        for (; p < p1; ++p)
+          acc = __fadd_rn(acc, __fmul_rn(alpha[(int64_t)p * H + h], __ldg(xs + (int64_t)__ldg(src + p) * F + h * C + c)));
         tot = __fadd_rn(tot, acc);
       }
       out[row * C + c] = __fdiv_rn(tot, (float)H) + (bias ? bias[c] : 0.f);
@@ -97,22 +200,57 @@ __global__ void __launch_bounds__(kThreads) gat_bwd_dst_kernel(
   const float* dorow = concat ? dout + row * F + h * C : dout + row * C;
   const float dscale = concat ? 1.f : 1.f / (float)H;
   float s = 0.f;
-  for (int p = p0; p < p1; ++p) {
-    const float* xj = xs + (int64_t)src[p] * F + h * C;
-    float g = 0.f;
-    for (int c = 0; c < C; ++c) g = fmaf(dorow[c] * dscale, xj[c], g);
-    dpre[(int64_t)p * H + h] = g;
-    s = fmaf(alpha[(int64_t)p * H + h], g, s);
+  {
+    int p = p0;
+    for (; p + 4 <= p1; p += 4) {  // four gathers in flight
+      const float* xj[4];
+      float g[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int b = 0; b < 4; ++b) xj[b] = xs + (int64_t)__ldg(src + p + b) * F + h * C;
+      for (int c = 0; c < C; ++c) {
+        const float d = dorow[c] * dscale;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) g[b] = fmaf(d, __ldg(xj[b] + c), g[b]);
+      }
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        dpre[(int64_t)(p + b) * H + h] = g[b];
+        s = fmaf(alpha[(int64_t)(p + b) * H + h], g[b], s);
+      }
+    }
+    for (; p < p1; ++p) {
+      const float* xj = xs + (int64_t)__ldg(src + p) * F + h * C;
+      float g = 0.f;
+      for (int c = 0; c < C; ++c) g = fmaf(dorow[c] * dscale, __ldg(xj + c), g);
+      dpre[(int64_t)p * H + h] = g;
+      s = fmaf(alpha[(int64_t)p * H + h], g, s);
+    }
   }
   const float ad = a_d[t];
   float acc = 0.f;
-  for (int p = p0; p < p1; ++p) {
-    float g = dpre[(int64_t)p * H + h];
-    float de = alpha[(int64_t)p * H + h] * (g - s);
-    float pre = a_s[(int64_t)src[p] * H + h] + ad;
-    float dp = pre > 0.f ? de : de * slope;
-    dpre[(int64_t)p * H + h] = dp;
-    acc += dp;
+  {
+    int p = p0;
+    for (; p + 4 <= p1; p += 4) {
+      float as4[4];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) as4[b] = __ldg(a_s + (int64_t)__ldg(src + p + b) * H + h);
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const float g = dpre[(int64_t)(p + b) * H + h];
+        const float de = alpha[(int64_t)(p + b) * H + h] * (g - s);
+        const float dp = (as4[b] + ad) > 0.f ? de : de * slope;
+        dpre[(int64_t)(p + b) * H + h] = dp;
+        acc += dp;
+      }
+    }
+    for (; p < p1; ++p) {
+      float g = dpre[(int64_t)p * H + h];
+      float de = alpha[(int64_t)p * H + h] * (g - s);
+      float pre = __ldg(a_s + (int64_t)__ldg(src + p) * H + h) + ad;
+      float dp = pre > 0.f ? de : de * slope;
+      dpre[(int64_t)p * H + h] = dp;
+      acc += dp;
+    }
   }
   da_d[t] = acc;
 }
@@ -128,21 +266,63 @@ __global__ void __launch_bounds__(kThreads) gat_bwd_src_kernel(
   if (row >= n_rows) return;
   const int q0 = ptr[row], q1 = ptr[row + 1];
   const int F = H * C;
-  for (int h = lane; h < H; h += 32) {
-    float acc = 0.f;
-    for (int q = q0; q < q1; ++q) acc += dpre[(int64_t)pos[q] * H + h];
-    da_s[row * H + h] = acc;
+  constexpr int kHMax = 8;
+  float das[kHMax];
+#pragma unroll
+  for (int h = 0; h < kHMax; ++h) das[h] = 0.f;
+  if (H <= kHMax) {  // one lane per entry, warp-reduced: no serial walk over the row
+    for (int base = q0; base < q1; base += 32) {
+      const int q = base + lane;
+      if (q < q1) {
+        const int64_t pq = __ldg(pos + q);
+#pragma unroll
+        for (int h = 0; h < kHMax; ++h)
+          if (h < H) das[h] += __ldg(dpre + pq * H + h);
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < kHMax; ++h)
+      if (h < H) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) das[h] += __shfl_xor_sync(0xffffffffu, das[h], o);
+        if (lane == h) da_s[row * H + h] = das[h];
+      }
+  } else {
+    for (int h = lane; h < H; h += 32) {
+      float acc = 0.f;
+      for (int q = q0; q < q1; ++q) acc += __ldg(dpre + (int64_t)__ldg(pos + q) * H + h);
+      da_s[row * H + h] = acc;
+    }
   }
   __syncwarp();
   const float dscale = concat ? 1.f : 1.f / (float)H;
   for (int f = lane; f < F; f += 32) {
     const int h = f / C, c = f - h * C;
     float acc = 0.f;
-    for (int q = q0; q < q1; ++q) {
+    int q = q0;
+    for (; q + 4 <= q1; q += 4) {
+      float d[4], a[4];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int64_t dq = __ldg(dst + q + b);
+        d[b] = concat ? __ldg(dout + dq * F + f) : __ldg(dout + dq * C + c) * dscale;
+        a[b] = __ldg(alpha + (int64_t)__ldg(pos + q + b) * H + h);
+      }
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc = fmaf(a[b], d[b], acc);
+    }
+    for (; q < q1; ++q) {
       const float d = concat ? dout[(int64_t)dst[q] * F + f] : dout[(int64_t)dst[q] * C + c] * dscale;
       acc = fmaf(alpha[(int64_t)pos[q] * H + h], d, acc);
     }
-    acc = fmaf(da_s[row * H + h], att_src[f], acc);
+    float das_h = 0.f;
+    if (H <= kHMax) {
+#pragma unroll
+      for (int k = 0; k < kHMax; ++k) das_h = k == h ? das[k] : das_h;
+    } else {
+      das_h = da_s[row * H + h];
+    }
+    acc = fmaf(das_h, att_src[f], acc);
     acc = fmaf(da_d[row * H + h], att_dst[f], acc);
     dxs[row * F + f] = acc;
   }
