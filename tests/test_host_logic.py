@@ -93,3 +93,29 @@ def test_synthetic_graph_contract():
     assert rep.num_nodes == 60000 and rep.edge_index.size(1) == 69000
     assert torch.equal(rep.edge_index[:, 23000:46000], ei + 20000)
     assert (rep.timestep[rep.edge_index[0]] == rep.timestep[rep.edge_index[1]]).all()
+
+
+def test_product_package_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under the product package (Python or CUDA) may import, call or
+    even name it; only tests/, __graft_entry__.smoke() and bench.py's CPU legs do."""
+    import glob
+    pkg = os.path.join(ROOT, "elliptic-gnn-project_b200")
+    for path in glob.glob(os.path.join(pkg, "**", "*"), recursive=True):
+        if os.path.isdir(path) or path.endswith((".so", ".o", ".pyc", ".log")) or "/build/" in path:
+            continue
+        text = open(path, errors="ignore").read()
+        if path.endswith(".py"):
+            assert "pyg_restated" not in text and "graph_build_np" not in text, path
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), path
+            assert "importlib" not in text and "__import__" not in text, path
+        else:   # CUDA / C sources: comments may cite the NumPy twin, but nothing may include or link it
+            assert not re.search(r"#\s*include\s*[<\"][^>\"]*oracle", text), path
+
+
+def test_ops_fail_loudly_without_the_extension(monkeypatch, egnn):
+    """No silent fallback: if libegnn_b200.so is missing, the first op raises with build instructions."""
+    from egnn_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", os.path.join(ROOT, "does_not_exist", "libegnn_b200.so"))
+    with pytest.raises(RuntimeError, match="must be built"):
+        _lib.lib()
