@@ -444,22 +444,27 @@ __device__ __forceinline__ uint32_t keep_bits4(const ActCtx& C, uint64_t seed, i
   return (w.v[0] >= C.thr ? 1u : 0u) | (w.v[1] >= C.thr ? 2u : 0u) | (w.v[2] >= C.thr ? 4u : 0u) |
          (w.v[3] >= C.thr ? 8u : 0u);
 }
-// u = bn(z); a = act(u); returns y = a*ks, dfac = act'(u)*ks, xhat
-template <bool BN, int ACT>
+// u = bn(z); a = act(u); returns y = a*ks, dfac = act'(u)*ks, xhat.  bits: low nibble = dropout keep bits; with
+// STORED_GATE (backward, ReLU, bits saved by the forward) the high nibble holds the ReLU gates u > 0, so the
+// backward needs neither gamma / beta nor the affine map; `gate_out` receives the gates computed here.
+template <bool BN, int ACT, bool STORED_GATE = false>
 __device__ __forceinline__ void act4(const Col4& k, float scale, uint32_t bits, const float (&z)[4], float (&y)[4],
-                                     float (&dfac)[4], float (&xhat)[4]) {
+                                     float (&dfac)[4], float (&xhat)[4], uint32_t* gate_out = nullptr) {
+  uint32_t gates = 0u;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     float u = z[i];
     xhat[i] = 0.f;
     if (BN) {
       xhat[i] = (z[i] - k.mean[i]) * k.rstd[i];
-      u = xhat[i] * k.gamma[i] + k.beta[i];
+      if (!STORED_GATE) u = xhat[i] * k.gamma[i] + k.beta[i];
     }
     float a = u, da = 1.f;
     if (ACT == EGNN_ACT_RELU) {
-      a = u > 0.f ? u : 0.f;
-      da = u > 0.f ? 1.f : 0.f;
+      const bool on = STORED_GATE ? ((bits >> (4 + i)) & 1u) != 0u : u > 0.f;
+      gates |= (on ? 1u : 0u) << i;
+      a = on ? u : 0.f;
+      da = on ? 1.f : 0.f;
     } else if (ACT == EGNN_ACT_ELU) {
       const float e = expm1f(u);
       a = u > 0.f ? u : e;
@@ -469,6 +474,7 @@ __device__ __forceinline__ void act4(const Col4& k, float scale, uint32_t bits, 
     y[i] = a * ks;
     dfac[i] = da * ks;
   }
+  if (gate_out) *gate_out = gates;
 }
 
 template <typename T, bool BN, int ACT>
@@ -500,8 +506,9 @@ __global__ void __launch_bounds__(kThreads, 3) bn_act_fwd_lean(const T* __restri
         float zv[4], y[4], d[4], xh[4];
         zr[u].unpack(zv);
         const uint32_t bits = C.drop ? keep_bits4(C, seed, r, c) : 0xfu;
-        if (keep_bits) keep_bits[r * CG + cgi] = (uint8_t)bits;
-        act4<BN, ACT>(k, C.scale, bits, zv, y, d, xh);
+        uint32_t gates;
+        act4<BN, ACT>(k, C.scale, bits, zv, y, d, xh, &gates);
+        if (keep_bits) keep_bits[r * CG + cgi] = (uint8_t)(bits | (gates << 4));  // keep bits | ReLU gates
         if (res) {
           float rv[4];
           rr[u].unpack(rv);
@@ -515,8 +522,8 @@ __global__ void __launch_bounds__(kThreads, 3) bn_act_fwd_lean(const T* __restri
 }
 
 // partial[(blk*2 + which)*F + col] (double), which: 0 = sum g, 1 = sum g*xhat
-template <typename T, bool BN, int ACT>
-__global__ void __launch_bounds__(kThreads, 3) bn_act_bwd_reduce_lean(const T* __restrict__ dy, int64_t ld_dy,
+template <typename T, bool BN, int ACT, bool KB>
+__global__ void __launch_bounds__(kThreads, 4) bn_act_bwd_reduce_lean(const T* __restrict__ dy, int64_t ld_dy,
                                                                    const T* __restrict__ z, int64_t ld,
                                                                    int64_t n_rows, int F, int cg_shift,
                                                                    int64_t rows_per_block, ActCtx C,
@@ -539,7 +546,7 @@ __global__ void __launch_bounds__(kThreads, 3) bn_act_bwd_reduce_lean(const T* _
       if (r < r1) {
         zr[u].load(z + r * ld + c);
         gr[u].load(dy + r * ld_dy + c);
-        kb[u] = (C.drop && keep_bits) ? keep_bits[r * CG + cgi] : 0xfu;
+        kb[u] = KB ? keep_bits[r * CG + cgi] : 0xfu;
       }
     }
 #pragma unroll
@@ -549,8 +556,8 @@ __global__ void __launch_bounds__(kThreads, 3) bn_act_bwd_reduce_lean(const T* _
         float zv[4], g[4], y[4], d[4], xh[4];
         zr[u].unpack(zv);
         gr[u].unpack(g);
-        const uint32_t bits = (C.drop && !keep_bits) ? keep_bits4(C, seed, r, c) : kb[u];
-        act4<BN, ACT>(k, C.scale, bits, zv, y, d, xh);
+        const uint32_t bits = (!KB && C.drop) ? keep_bits4(C, seed, r, c) : kb[u];
+        act4<BN, ACT, KB && ACT == EGNN_ACT_RELU>(k, C.scale, bits, zv, y, d, xh);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float gg = g[i] * d[i];
@@ -573,8 +580,8 @@ __global__ void __launch_bounds__(kThreads, 3) bn_act_bwd_reduce_lean(const T* _
 
 // dz = gamma*rstd*(g - mean(g) - xhat*mean(g*xhat)) (or g without BN); optionally the per-block
 // column sums of the dz values written (the conv-bias gradient) -> dzsum_partial[blk*F + col]
-template <typename T, bool BN, int ACT>
-__global__ void __launch_bounds__(kThreads, 3) bn_act_bwd_apply_lean(const T* __restrict__ dy, int64_t ld_dy,
+template <typename T, bool BN, int ACT, bool KB>
+__global__ void __launch_bounds__(kThreads, 4) bn_act_bwd_apply_lean(const T* __restrict__ dy, int64_t ld_dy,
                                                                   const T* __restrict__ z, int64_t ld_z,
                                                                   T* __restrict__ dz, int64_t ld, int64_t n_rows,
                                                                   int F, int cg_shift, int64_t rows_per_block,
@@ -611,7 +618,7 @@ __global__ void __launch_bounds__(kThreads, 3) bn_act_bwd_apply_lean(const T* __
       if (r < r1) {
         zr[u].load(z + r * ld_z + c);
         gr[u].load(dy + r * ld_dy + c);
-        kb[u] = (C.drop && keep_bits) ? keep_bits[r * CG + cgi] : 0xfu;
+        kb[u] = KB ? keep_bits[r * CG + cgi] : 0xfu;
       }
     }
 #pragma unroll
@@ -621,8 +628,8 @@ __global__ void __launch_bounds__(kThreads, 3) bn_act_bwd_apply_lean(const T* __
         float zv[4], g[4], y[4], d[4], xh[4], o[4];
         zr[u].unpack(zv);
         gr[u].unpack(g);
-        const uint32_t bits = (C.drop && !keep_bits) ? keep_bits4(C, seed, r, c) : kb[u];
-        act4<BN, ACT>(k, C.scale, bits, zv, y, d, xh);
+        const uint32_t bits = (!KB && C.drop) ? keep_bits4(C, seed, r, c) : kb[u];
+        act4<BN, ACT, KB && ACT == EGNN_ACT_RELU>(k, C.scale, bits, zv, y, d, xh);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float gg = g[i] * d[i];
@@ -648,6 +655,34 @@ __global__ void __launch_bounds__(kThreads, 3) bn_act_bwd_apply_lean(const T* __
     }
   }
 }
+
+// host-side dispatch over (dtype, BatchNorm, activation); the backward kernels are also specialised on whether
+// the forward's keep bits are supplied (the Philox recomputation is then compiled out: fewer registers)
+#define EGNN_LEAN_KB_T(KERNEL, TT_, HAVE_KB, GRID, ...)                                                    \
+  {                                                                                                        \
+    using TT = TT_;                                                                                        \
+    const int sel_ = (C.mean != nullptr ? 0 : 6) +                                                         \
+                     (C.act == EGNN_ACT_RELU ? 0 : C.act == EGNN_ACT_NONE ? 2 : 4) + ((HAVE_KB) ? 0 : 1);  \
+    switch (sel_) {                                                                                        \
+      case 0: KERNEL<TT, true, EGNN_ACT_RELU, true><<<GRID, kThreads, 0, st>>>(__VA_ARGS__); break;        \
+      case 1: KERNEL<TT, true, EGNN_ACT_RELU, false><<<GRID, kThreads, 0, st>>>(__VA_ARGS__); break;       \
+      case 2: KERNEL<TT, true, EGNN_ACT_NONE, true><<<GRID, kThreads, 0, st>>>(__VA_ARGS__); break;        \
+      case 3: KERNEL<TT, true, EGNN_ACT_NONE, false><<<GRID, kThreads, 0, st>>>(__VA_ARGS__); break;       \
+      case 4: KERNEL<TT, true, EGNN_ACT_ELU, true><<<GRID, kThreads, 0, st>>>(__VA_ARGS__); break;         \
+      case 5: KERNEL<TT, true, EGNN_ACT_ELU, false><<<GRID, kThreads, 0, st>>>(__VA_ARGS__); break;        \
+      case 6: KERNEL<TT, false, EGNN_ACT_RELU, true><<<GRID, kThreads, 0, st>>>(__VA_ARGS__); break;       \
+      case 7: KERNEL<TT, false, EGNN_ACT_RELU, false><<<GRID, kThreads, 0, st>>>(__VA_ARGS__); break;      \
+      case 8: KERNEL<TT, false, EGNN_ACT_NONE, true><<<GRID, kThreads, 0, st>>>(__VA_ARGS__); break;       \
+      case 9: KERNEL<TT, false, EGNN_ACT_NONE, false><<<GRID, kThreads, 0, st>>>(__VA_ARGS__); break;      \
+      case 10: KERNEL<TT, false, EGNN_ACT_ELU, true><<<GRID, kThreads, 0, st>>>(__VA_ARGS__); break;       \
+      default: KERNEL<TT, false, EGNN_ACT_ELU, false><<<GRID, kThreads, 0, st>>>(__VA_ARGS__); break;      \
+    }                                                                                                      \
+  }
+#define EGNN_LEAN_DISPATCH_KB(KERNEL, HAVE_KB, GRID, ...)                                  \
+  do {                                                                                     \
+    if (dtype == EGNN_F32) EGNN_LEAN_KB_T(KERNEL, float, HAVE_KB, GRID, __VA_ARGS__)       \
+    else EGNN_LEAN_KB_T(KERNEL, __nv_bfloat16, HAVE_KB, GRID, __VA_ARGS__)                 \
+  } while (0)
 
 // host-side dispatch over (dtype, BatchNorm, activation)
 #define EGNN_LEAN_DISPATCH(KERNEL, GRID, ...)                                                            \
@@ -1115,8 +1150,8 @@ extern "C" int egnn_bn_act_dropout_bwd_reduce(const void* dy, const void* z, int
   FastPlan fp = lean_plan(n_rows, n_feat, dtype, {ld, ld_z}, {z, dy});
   if (fp.ok) {
     double* partial = reinterpret_cast<double*>(workspace);
-    EGNN_LEAN_DISPATCH(bn_act_bwd_reduce_lean, fp.nblk, (const TT*)dy, ld, (const TT*)z, ld_z, n_rows, (int)n_feat,
-                       fp.cg_shift, fp.rpb, C, partial, keep_bits);
+    EGNN_LEAN_DISPATCH_KB(bn_act_bwd_reduce_lean, keep_bits != nullptr, fp.nblk, (const TT*)dy, ld, (const TT*)z, ld_z,
+                          n_rows, (int)n_feat, fp.cg_shift, fp.rpb, C, partial, keep_bits);
     EGNN_LAUNCH_CHECK(fn);
     colreduce_final<<<dim3((unsigned)n_feat, 2), kThreads, 0, st>>>(partial, fp.nblk, (int)n_feat, sum_g, sum_gx);
     EGNN_LAUNCH_CHECK(fn);
@@ -1152,8 +1187,9 @@ extern "C" int egnn_bn_act_dropout_bwd_apply(const void* dy, const void* z, void
   FastPlan fp = lean_plan(n_rows, n_feat, dtype, {ld, ld_z}, {z, dy, dz});
   if (fp.ok) {
     double* partial = dz_colsum ? reinterpret_cast<double*>(workspace) : nullptr;
-    EGNN_LEAN_DISPATCH(bn_act_bwd_apply_lean, fp.nblk, (const TT*)dy, ld, (const TT*)z, ld_z, (TT*)dz, ld, n_rows,
-                       (int)n_feat, fp.cg_shift, fp.rpb, C, sum_g, sum_gx, inv_n, partial, keep_bits);
+    EGNN_LEAN_DISPATCH_KB(bn_act_bwd_apply_lean, keep_bits != nullptr, fp.nblk, (const TT*)dy, ld, (const TT*)z, ld_z,
+                          (TT*)dz, ld, n_rows, (int)n_feat, fp.cg_shift, fp.rpb, C, sum_g, sum_gx, inv_n, partial,
+                          keep_bits);
     EGNN_LAUNCH_CHECK(fn);
     if (dz_colsum) {
       colsum_final<<<(unsigned)n_feat, kThreads, 0, st>>>(partial, fp.nblk, (int)n_feat, dz_colsum);

@@ -585,9 +585,10 @@ class BnActDropResFn(torch.autograd.Function):
             y = torch.empty((N, F), dtype=z.dtype, device=dev)
         seed = drop.seed if drop is not None else 0
         soff = drop.offset if drop is not None else None
-        # dropout keep bits (1 bit / element) saved for the backward, which then skips Philox
+        # per 4 columns one byte saved for the backward: low nibble = dropout keep bits (the backward skips Philox),
+        # high nibble = ReLU gates (the backward skips the affine map)
         kb = (torch.empty((N, F // 4), dtype=torch.uint8, device=dev)
-              if (strided_ok and p_eff > 0 and z.requires_grad) else None)
+              if (strided_ok and training and z.requires_grad) else None)
         check(L.egnn_bn_act_dropout_res_fwd(ptr(z), ptr(res), ptr(y), dt(z), _ld(z), N, F, ptr(mean), ptr(rstd),
                                             ptr(gamma), ptr(beta), act, p_eff, seed, ptr(soff), layer, row0,
                                             _ld(res) if res is not None else 0, _ld(y), ptr(kb), stream()))

@@ -205,7 +205,7 @@ int egnn_bn_finalize(const double* sums, const double* sumsq, double count, int6
  *   res may be NULL.  z/res/y share dtype `dtype`; z has leading dimension ld, res ld_res and y
  *   ld_y (0 = ld): the output may be the right half of a wider [h_agg | h] buffer.
  *   keep_bits (optional, uint8 [n_rows, n_feat/4], n_feat % 4 == 0): receives the dropout keep bits drawn
- *   (bit i of byte (r, c/4) = column c+i kept, low nibble); passing them to the backward kernels skips the Philox
+ *   (bit i of byte (r, c/4) = column c+i kept, low nibble; bit 4+i = ReLU gate of column c+i when act = ReLU); passing them to the backward kernels skips the Philox
  *   recomputation there.  The bits ARE the Philox mask of egnn_dropout_mask. */
 int egnn_bn_act_dropout_res_fwd(const void* z, const void* res, void* y, int dtype, int64_t ld,
                                 int64_t n_rows, int64_t n_feat, const float* mean,
