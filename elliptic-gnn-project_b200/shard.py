@@ -136,8 +136,26 @@ class P2PAllReduce:
         self.peer_ptrs = int(self.hdl.buffer_ptrs_dev)
         self.epoch = torch.zeros(1, dtype=torch.int64, device=device)
         self.err = torch.zeros(1, dtype=torch.int32, device=device)
-        torch.cuda.synchronize(device)
-        dist.barrier(group=group)      # every rank's flags are zero before anyone pushes
+        torch.cuda.synchronize(device)   # flags are zero; the caller's consensus all-reduce orders this before any push
+
+    @staticmethod
+    def create_on_all_ranks(n_max: int, dtype: torch.dtype, group, device):
+        """Build the reducer on every rank or on none: a rank whose symmetric-memory set-up failed must not leave
+        the others waiting on its flags, so the outcome is agreed on with one NCCL MIN all-reduce (which also
+        orders every rank's zero-initialisation before the first push)."""
+        ar, why = None, ""
+        try:
+            ar = P2PAllReduce(n_max, dtype, group, device)
+        except Exception as ex:      # no symmetric-memory support on this box / driver
+            why = f"{type(ex).__name__}: {ex}"
+        ok = torch.tensor([1 if ar is not None else 0], dtype=torch.int32, device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            if dist.get_rank(group) == 0:
+                print(f"[egnn_b200] peer-memory all-reduce unavailable ({why or 'failed on another rank'}); using NCCL",
+                      file=sys.stderr, flush=True)
+            return None
+        return ar
 
     def supports(self, t: torch.Tensor) -> bool:
         return t.dtype == self.dtype and t.is_contiguous() and 0 < t.numel() <= self.n_max
@@ -156,9 +174,9 @@ class P2PAllReduce:
 class P2PStatsReducer(StatsReducer):
     """BatchNorm-statistics all-reduce through the peer-memory kernel (NCCL for anything it does not cover)."""
 
-    def __init__(self, n_total: int, group, device):
+    def __init__(self, n_total: int, group, ar: "P2PAllReduce"):
         super().__init__(n_total=n_total, group=group)
-        self.ar = P2PAllReduce(1024, torch.float64, group, device)
+        self.ar = ar
 
     def reduce_(self, buf: torch.Tensor) -> torch.Tensor:
         return self.ar(buf) if self.ar.supports(buf) else super().reduce_(buf)
@@ -184,14 +202,13 @@ class ShardedContext:
         self.stats_reducer = StatsReducer(n_total=shard.n_global, group=group)
         self.p2p = False
         self._grad_ar = None
+        self._grad_ar_tried = False
         if dist.is_initialized() and dist.get_world_size(group) > 1 and torch.device(device).type == "cuda" \
                 and os.environ.get("EGNN_P2P", "1") != "0":
-            try:
-                self.stats_reducer = P2PStatsReducer(shard.n_global, group, device)
+            ar = P2PAllReduce.create_on_all_ranks(1024, torch.float64, group, device)
+            if ar is not None:
+                self.stats_reducer = P2PStatsReducer(shard.n_global, group, ar)
                 self.p2p = True
-            except Exception as ex:   # no symmetric-memory support on this box: NCCL all-reduce instead
-                print(f"[egnn_b200] peer-memory BatchNorm all-reduce unavailable ({type(ex).__name__}: {ex}); "
-                      "using NCCL", file=sys.stderr, flush=True)
 
     def attach(self, model):
         model.stats_reducer = self.stats_reducer
@@ -201,9 +218,11 @@ class ShardedContext:
     def reduce_grads(self, flat_grad: torch.Tensor):
         if not dist.is_initialized():
             return flat_grad
-        if self.p2p and self._grad_ar is None and flat_grad.dtype == torch.float32 \
+        if self.p2p and self._grad_ar is None and not self._grad_ar_tried and flat_grad.dtype == torch.float32 \
                 and flat_grad.numel() <= 131072 and not torch.cuda.is_current_stream_capturing():
-            self._grad_ar = P2PAllReduce(flat_grad.numel(), torch.float32, self.group, flat_grad.device)
+            self._grad_ar_tried = True     # the first (eager) step of every rank gets here together
+            self._grad_ar = P2PAllReduce.create_on_all_ranks(flat_grad.numel(), torch.float32, self.group,
+                                                             flat_grad.device)
         if self._grad_ar is not None and self._grad_ar.supports(flat_grad):
             return self._grad_ar(flat_grad)
         dist.all_reduce(flat_grad, group=self.group)
