@@ -11,6 +11,8 @@
 // which are pure streaming reductions.
 #include <algorithm>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace egnn {
@@ -115,6 +117,158 @@ __global__ void __launch_bounds__(kThreads) gemm_simt(GemmParams P) {
   }
 }
 
+// fp32 fast path (the exact-fp32 parity / eval mode): A [M,K] and W [N,K] both contiguous along K (Linear forward,
+// and dgrad through a pre-transposed weight), 16-byte aligned rows.  Same 128x64x16 tiling and 8x4 micro-tile as the
+// generic kernel, but 128-bit global loads, register prefetch of the next K slab while the current one is
+// multiplied, and double-buffered shared memory (one barrier per slab).  FFMA only: TF32 would break rel 1e-5.
+__global__ void __launch_bounds__(kThreads) gemm_simt_f32_kmajor(GemmParams P) {
+  __shared__ __align__(16) float As[2][BK][BM + 4];
+  __shared__ __align__(16) float Bs[2][BK][BN + 4];
+  const float* __restrict__ A = reinterpret_cast<const float*>(P.A);
+  const float* __restrict__ B = reinterpret_cast<const float*>(P.B);
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int64_t m0 = (int64_t)blockIdx.x * BM, n0 = (int64_t)blockIdx.y * BN;
+  const int K = (int)P.K;
+  // this thread's slab loads: two float4 of A (rows ar0, ar0 + 64), one float4 of W
+  const int ar0 = tid >> 2, akq = (tid & 3) * 4;
+  const int64_t am0 = m0 + ar0, am1 = m0 + ar0 + 64, bn = n0 + ar0;
+  const float* pa0 = A + (am0 < P.M ? am0 : 0) * P.a_sm + akq;
+  const float* pa1 = A + (am1 < P.M ? am1 : 0) * P.a_sm + akq;
+  const float* pb = B + (bn < P.N ? bn : 0) * P.b_sn + akq;
+  const bool va0 = am0 < P.M, va1 = am1 < P.M, vb = bn < P.N;
+  float4 ra0, ra1, rb;
+  auto gload = [&](int k0) {
+    const bool kin = k0 + akq < K;  // K % 4 == 0: a float4 is entirely inside or outside
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    ra0 = (va0 && kin) ? __ldg(reinterpret_cast<const float4*>(pa0 + k0)) : z;
+    ra1 = (va1 && kin) ? __ldg(reinterpret_cast<const float4*>(pa1 + k0)) : z;
+    rb = (vb && kin && ar0 < BN) ? __ldg(reinterpret_cast<const float4*>(pb + k0)) : z;
+  };
+  auto sstore = [&](int buf) {
+    As[buf][akq + 0][ar0] = ra0.x; As[buf][akq + 1][ar0] = ra0.y; As[buf][akq + 2][ar0] = ra0.z; As[buf][akq + 3][ar0] = ra0.w;
+    As[buf][akq + 0][ar0 + 64] = ra1.x; As[buf][akq + 1][ar0 + 64] = ra1.y;
+    As[buf][akq + 2][ar0 + 64] = ra1.z; As[buf][akq + 3][ar0 + 64] = ra1.w;
+    if (ar0 < BN) {
+      Bs[buf][akq + 0][ar0] = rb.x; Bs[buf][akq + 1][ar0] = rb.y; Bs[buf][akq + 2][ar0] = rb.z; Bs[buf][akq + 3][ar0] = rb.w;
+    }
+  };
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    const bool more = k0 + BK < K;
+    if (more) gload(k0 + BK);  // in flight while this slab is multiplied
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 8 + 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (more) {
+      sstore(buf ^ 1);
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t m = m0 + ty * 8 + i;
+    if (m >= P.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t n = n0 + tx * 4 + j;
+      if (n < P.N) store_c(P, m, n, acc[i][j]);
+    }
+  }
+}
+
+// fp32 weight-gradient shape: C[M,N] = sum_k A(m,k) B(k,n) with BOTH operands contiguous along the non-contracted
+// axis (A = G^T: element (m,k) at A[k*a_sk + m];  B = X: element (k,n) at B[k*b_sk + n]) and a long contraction
+// (the node axis), split over blockIdx.z.  128-bit loads straight into the [k][m] / [k][n] shared tiles, register
+// prefetch and double buffering as above; partial sums go to the split-K workspace (fixed-order reduce).
+__global__ void __launch_bounds__(kThreads) gemm_simt_f32_mnmajor(GemmParams P) {
+  __shared__ __align__(16) float As[2][BK][BM + 4];
+  __shared__ __align__(16) float Bs[2][BK][BN + 4];
+  const float* __restrict__ A = reinterpret_cast<const float*>(P.A);
+  const float* __restrict__ B = reinterpret_cast<const float*>(P.B);
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int64_t m0 = (int64_t)blockIdx.x * BM, n0 = (int64_t)blockIdx.y * BN;
+  const int64_t kb = (int64_t)blockIdx.z * P.k_per_split;
+  const int64_t ke = min(P.K, kb + P.k_per_split);
+  // slab loads: A 16 x 128 floats = 512 float4 (two per thread), B 16 x 64 floats = 256 float4 (one per thread)
+  const int ak0 = tid >> 5, am4 = (tid & 31) * 4;     // k rows ak0 and ak0 + 8
+  const int bk = tid >> 4, bn4 = (tid & 15) * 4;
+  const bool vam = m0 + am4 < P.M, vbn = n0 + bn4 < P.N;  // M % 4 == 0, N % 4 == 0
+  float4 ra0, ra1, rb;
+  auto gload = [&](int64_t k0) {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int64_t k_a0 = k0 + ak0, k_a1 = k0 + ak0 + 8, k_b = k0 + bk;
+    ra0 = (vam && k_a0 < ke) ? __ldg(reinterpret_cast<const float4*>(A + k_a0 * P.a_sk + m0 + am4)) : z;
+    ra1 = (vam && k_a1 < ke) ? __ldg(reinterpret_cast<const float4*>(A + k_a1 * P.a_sk + m0 + am4)) : z;
+    rb = (vbn && k_b < ke) ? __ldg(reinterpret_cast<const float4*>(B + k_b * P.b_sk + n0 + bn4)) : z;
+  };
+  auto sstore = [&](int buf) {
+    *reinterpret_cast<float4*>(&As[buf][ak0][am4]) = ra0;
+    *reinterpret_cast<float4*>(&As[buf][ak0 + 8][am4]) = ra1;
+    *reinterpret_cast<float4*>(&Bs[buf][bk][bn4]) = rb;
+  };
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  gload(kb);
+  sstore(0);
+  __syncthreads();
+  int buf = 0;
+  for (int64_t k0 = kb; k0 < ke; k0 += BK) {
+    const bool more = k0 + BK < ke;
+    if (more) gload(k0 + BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 8 + 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (more) {
+      sstore(buf ^ 1);
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t m = m0 + ty * 8 + i;
+    if (m >= P.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t n = n0 + tx * 4 + j;
+      if (n >= P.N) continue;
+      if (P.split_k > 1) P.ws[((int64_t)blockIdx.z * P.M + m) * P.N + n] = acc[i][j];
+      else store_c(P, m, n, acc[i][j]);
+    }
+  }
+}
+
 // fixed-order second stage of split-K
 __global__ void __launch_bounds__(kThreads) splitk_reduce(GemmParams P) {
   int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
@@ -200,13 +354,26 @@ int run(GemmParams& P, cudaStream_t st) {
     EGNN_LAUNCH_CHECK(fn);
     return 0;
   }
+  if (std::is_same<TA, float>::value && std::is_same<TB, float>::value && P.a_sk == 1 && P.b_sk == 1 &&
+      P.split_k <= 1 && P.K % 4 == 0 && P.a_sm % 4 == 0 && P.b_sn % 4 == 0 &&
+      (((uintptr_t)P.A | (uintptr_t)P.B) & 15) == 0 && P.K < (1 << 30)) {
+    dim3 grid((unsigned)ceil_div(P.M, BM), (unsigned)ceil_div(P.N, BN), 1);
+    gemm_simt_f32_kmajor<<<grid, kThreads, 0, st>>>(P);
+    EGNN_LAUNCH_CHECK(fn);
+    return 0;
+  }
   int split = P.split_k < 1 ? 1 : P.split_k;
   int64_t per = ceil_div(ceil_div(P.K, split), BK) * BK;
   split = (int)ceil_div(P.K, per);
   P.k_per_split = per;
   P.split_k = split;
   dim3 grid((unsigned)ceil_div(P.M, BM), (unsigned)ceil_div(P.N, BN), (unsigned)split);
-  gemm_simt<TA, TB><<<grid, kThreads, 0, st>>>(P);
+  if (std::is_same<TA, float>::value && std::is_same<TB, float>::value && P.a_sm == 1 && P.b_sn == 1 &&
+      P.M % 4 == 0 && P.N % 4 == 0 && P.a_sk % 4 == 0 && P.b_sk % 4 == 0 &&
+      (((uintptr_t)P.A | (uintptr_t)P.B) & 15) == 0 && (split == 1 || P.ws))
+    gemm_simt_f32_mnmajor<<<grid, kThreads, 0, st>>>(P);
+  else
+    gemm_simt<TA, TB><<<grid, kThreads, 0, st>>>(P);
   EGNN_LAUNCH_CHECK(fn);
   if (split > 1) {
     splitk_reduce<<<(unsigned)ceil_div(P.M * P.N, kThreads), kThreads, 0, st>>>(P);

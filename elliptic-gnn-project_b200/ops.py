@@ -161,8 +161,8 @@ def linear_dgrad(g, W, out=None, accumulate=False, out_dtype=None, row_div=None,
     K = W.size(1)
     if out is None:
         out = torch.empty((M, K), dtype=out_dtype or g.dtype, device=g.device)
-    if g.dtype == torch.bfloat16 and W.dtype == torch.bfloat16 and (GEMM_IMPL if impl is None else impl) != 1:
-        Wt = W.t().contiguous()  # [K, N]: contraction-contiguous B operand for the tcgen05 kernel
+    if g.dtype == W.dtype and g.dtype in (torch.bfloat16, torch.float32):
+        Wt = W.t().contiguous()  # [K, N]: contraction-contiguous B operand (tcgen05 kernel / fp32 128-bit-load kernel)
         _gemm(g, _ld(g), 1, Wt, 1, _ld(Wt), out, M, K, N, None, accumulate, row_div=row_div, impl=impl,
               row_div_cols=row_div_cols)
     else:
