@@ -327,3 +327,55 @@ def test_nets_on_degenerate_graphs(egnn, name, gname, amp):
             assert cos >= 0.97 and 0.85 <= float(a.norm() / b.norm()) <= 1.15, (name, gname, n1, cos)
         else:
             assert_close(p1.grad, p2.grad, 2.5 * tol, f"{name}/{gname} grad {n1}")
+
+
+class _MiniRefStyle(torch.nn.Module):
+    """A net written the way the reference writes them (`src/models/gnn.py`): library convs with ordinary torch ops
+    -- nn.BatchNorm1d, F.relu, F.dropout, a residual nn.Linear -- in between.  Only the conv class differs."""
+
+    def __init__(self, convs_mod, kind):
+        super().__init__()
+        mk = {"sage": lambda i, o: convs_mod.SAGEConv(i, o), "gcn": lambda i, o: convs_mod.GCNConv(i, o),
+              "gat": lambda i, o: convs_mod.GATConv(i, o // 4, heads=4) if o > 2 else convs_mod.GATConv(i, o, heads=1, concat=False)}[kind]
+        self.c1, self.c2, self.c3 = mk(166, 64), mk(64, 64), mk(64, 2)
+        self.bn = torch.nn.BatchNorm1d(64)
+        self.res = torch.nn.Linear(166, 64, bias=False)
+
+    def forward(self, x, ei):
+        h = torch.nn.functional.relu(self.bn(self.c1(x, ei))) + self.res(x)
+        h = torch.nn.functional.dropout(torch.nn.functional.elu(self.c2(h, ei)), p=0.0, training=self.training)
+        return self.c3(h, ei)
+
+
+@pytest.mark.parametrize("kind", ["sage", "gcn", "gat"])
+@pytest.mark.parametrize("amp", [False, True])
+def test_convs_drop_into_a_reference_style_module(egnn, small_graph, kind, amp):
+    """INTEGRATION.md's one-line switch: `from egnn_b200 import GCNConv, SAGEConv, GATConv` inside a module that
+    otherwise uses plain torch ops (autograd, nn.BatchNorm1d, autocast) -- logits and gradients against the same
+    module built on the oracle convs."""
+    gr = small_graph
+    ei = torch.cat([gr.edge_index, gr.edge_index.flip(0)], 1)
+    torch.manual_seed(5)
+    ours = _MiniRefStyle(egnn, kind)
+    ref = _MiniRefStyle(O, kind)
+    ref.load_state_dict(ours.state_dict())
+    ours = ours.cuda().train()
+    ref.train()
+    x = gr.x
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+        lo = ours(x.cuda(), ei.cuda())
+    lr_ = ref(x, ei)
+    w = torch.randn(lr_.shape, generator=torch.Generator().manual_seed(9))
+    (lo.float() * w.cuda()).sum().backward()
+    (lr_ * w).sum().backward()
+    tol = REL_BF16 if amp else 2 * REL_FP32
+    assert_close(lo, lr_, tol, f"{kind} logits")
+    for (n1, p1), (_, p2) in zip(ours.named_parameters(), ref.named_parameters()):
+        a, b = p1.grad.detach().double().cpu().flatten(), p2.grad.detach().double().flatten()
+        if b.abs().max() < 1e-5 * max(q.grad.abs().max() for q in ref.parameters()):
+            continue
+        if amp:
+            cos = float(torch.dot(a, b) / (a.norm() * b.norm()).clamp_min(1e-30))
+            assert cos >= 0.97, (kind, n1, cos)
+        else:
+            assert_close(p1.grad, p2.grad, 5 * REL_FP32, f"{kind} grad {n1}")
