@@ -61,6 +61,8 @@ SIGNATURES = {
     "egnn_skinny_project": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _i32, _vp, _vp]),
     "egnn_sage_out_fwd": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _i64, _vp, _i64, _vp]),
     "egnn_sage_out_bwd": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _i64, _vp, _i64, _vp]),
+    "egnn_gcn_out_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _vp, _i64, _vp]),
+    "egnn_gcn_out_bwd": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _i64, _vp, _i64, _vp]),
     "egnn_skinny_wgrad_workspace_floats": (_sz, [_i64, _i64, _i32]),
     "egnn_skinny_wgrad": (_i32, [_vp, _i32, _i64, _vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp]),
     "egnn_skinny_dgrad": (_i32, [_vp, _vp, _i32, _vp, _i32, _i64, _i64, _i64, _vp]),

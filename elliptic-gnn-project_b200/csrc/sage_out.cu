@@ -101,27 +101,37 @@ __global__ void __launch_bounds__(kThreads) skinny_project_kernel(const T* __res
 // synthetic generator's preferential attachment puts a timestep's hubs into the same warp):
 //   pass 1, one thread per ENTRY of the sorted view: term[e] = value gathered for entry e;
 //   pass 2, one thread per ROW: sequential fp32 sum of its contiguous terms in stored order.
+// `w` (GCN: gcn_norm weight of the entry, rounded product like PyG's w * x_j) or NULL (SAGE); p has row stride ldp
 template <int C>
 __global__ void __launch_bounds__(kThreads) sage_out_fwd_terms(const int32_t* __restrict__ ptr,
                                                                const int32_t* __restrict__ col,
-                                                               const float* __restrict__ p,
+                                                               const float* __restrict__ w,
+                                                               const float* __restrict__ p, int ldp,
                                                                float* __restrict__ term, int64_t n_rows) {
   const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   if (e >= __ldg(ptr + n_rows)) return;
-  const float* src = p + (int64_t)__ldg(col + e) * (2 * C);
+  const float* src = p + (int64_t)__ldg(col + e) * ldp;
+  const float we = w ? __ldg(w + e) : 1.f;
 #pragma unroll
-  for (int c = 0; c < C; ++c) term[e * C + c] = __ldg(src + c);
+  for (int c = 0; c < C; ++c) term[e * C + c] = w ? __fmul_rn(we, __ldg(src + c)) : __ldg(src + c);
 }
 
 template <typename TD, int C>
 __global__ void __launch_bounds__(kThreads) sage_out_bwd_terms(const int32_t* __restrict__ csc_ptr,
                                                                const int32_t* __restrict__ csc_dst,
                                                                const int32_t* __restrict__ csr_ptr,
+                                                               const float* __restrict__ w,
                                                                const TD* __restrict__ dout,
                                                                float* __restrict__ term, int64_t n_rows) {
   const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   if (e >= __ldg(csc_ptr + n_rows)) return;
   const int i = __ldg(csc_dst + e);
+  if (w) {  // GCN: dp_j += w_e * dout_i
+    const float we = __ldg(w + e);
+#pragma unroll
+    for (int c = 0; c < C; ++c) term[e * C + c] = __fmul_rn(we, to_f32(dout[(int64_t)i * C + c]));
+    return;
+  }
   const int d = __ldg(csr_ptr + i + 1) - __ldg(csr_ptr + i);
   const float cnt = (float)(d > 1 ? d : 1);
 #pragma unroll
@@ -155,12 +165,17 @@ __global__ void __launch_bounds__(kThreads) sage_out_fwd_kernel(const int32_t* _
                                                                 const float* __restrict__ term,
                                                                 const float* __restrict__ p,
                                                                 const float* __restrict__ bias,
-                                                                float* __restrict__ out, int64_t n_rows) {
+                                                                float* __restrict__ out, int64_t n_rows, int gcn) {
   const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   if (i >= n_rows) return;
   const int p0 = __ldg(ptr + i), p1 = __ldg(ptr + i + 1);
   float acc[C];
   sum_terms<C>(term, p0, p1, acc);
+  if (gcn) {  // GCNConv: weighted sum + bias (no mean, no root term)
+#pragma unroll
+    for (int c = 0; c < C; ++c) out[i * C + c] = bias ? __fadd_rn(acc[c], __ldg(bias + c)) : acc[c];
+    return;
+  }
   const int deg = p1 - p0;
   const float cnt = (float)(deg > 1 ? deg : 1);
 #pragma unroll
@@ -355,19 +370,37 @@ extern "C" int egnn_skinny_project(const void* a, int dtype, int64_t ld, int64_t
   return 0;
 }
 
+static int narrow_out_fwd(const char* fn, const int32_t* csr_ptr, const int32_t* csr_src, const float* w,
+                          const float* p, const float* bias, int C, float* out, int64_t n_rows, float* edge_tmp,
+                          int64_t edge_cap, void* stream);
+
 extern "C" int egnn_sage_out_fwd(const int32_t* csr_ptr, const int32_t* csr_src, const float* p,
                                  const float* bias, int C, float* out, int64_t n_rows, float* edge_tmp,
                                  int64_t edge_cap, void* stream) {
-  const char* fn = "egnn_sage_out_fwd";
+  return narrow_out_fwd("egnn_sage_out_fwd", csr_ptr, csr_src, nullptr, p, bias, C, out, n_rows, edge_tmp, edge_cap,
+                        stream);
+}
+
+extern "C" int egnn_gcn_out_fwd(const int32_t* csr_ptr, const int32_t* csr_src, const float* w_csr, const float* p,
+                                const float* bias, int C, float* out, int64_t n_rows, float* edge_tmp,
+                                int64_t edge_cap, void* stream) {
+  if (!w_csr) return fail("egnn_gcn_out_fwd", "null weights");
+  return narrow_out_fwd("egnn_gcn_out_fwd", csr_ptr, csr_src, w_csr, p, bias, C, out, n_rows, edge_tmp, edge_cap,
+                        stream);
+}
+
+static int narrow_out_fwd(const char* fn, const int32_t* csr_ptr, const int32_t* csr_src, const float* w,
+                          const float* p, const float* bias, int C, float* out, int64_t n_rows, float* edge_tmp,
+                          int64_t edge_cap, void* stream) {
   EGNN_REQUIRE(csr_ptr && csr_src && p && out && edge_tmp, fn, "null pointer");
   if (n_rows == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned grid = (unsigned)ceil_div(n_rows, kThreads);
   const unsigned egrid = (unsigned)ceil_div(edge_cap > 0 ? edge_cap : 1, kThreads);
 #define LAUNCH(CC)                                                                                   \
-  sage_out_fwd_terms<CC><<<egrid, kThreads, 0, st>>>(csr_ptr, csr_src, p, edge_tmp, n_rows);         \
+  sage_out_fwd_terms<CC><<<egrid, kThreads, 0, st>>>(csr_ptr, csr_src, w, p, w ? CC : 2 * CC, edge_tmp, n_rows); \
   EGNN_LAUNCH_CHECK(fn);                                                                             \
-  sage_out_fwd_kernel<CC><<<grid, kThreads, 0, st>>>(csr_ptr, edge_tmp, p, bias, out, n_rows)
+  sage_out_fwd_kernel<CC><<<grid, kThreads, 0, st>>>(csr_ptr, edge_tmp, p, bias, out, n_rows, w ? 1 : 0)
   switch (C) {
     case 1: LAUNCH(1); break;
     case 2: LAUNCH(2); break;
@@ -379,17 +412,36 @@ extern "C" int egnn_sage_out_fwd(const int32_t* csr_ptr, const int32_t* csr_src,
   return 0;
 }
 
+static int narrow_out_bwd(const char* fn, const int32_t* csc_ptr, const int32_t* csc_dst, const int32_t* csr_ptr,
+                          const float* w, const void* dout, int dtype, int C, float* dp, int64_t n_rows,
+                          float* edge_tmp, int64_t edge_cap, void* stream);
+
 extern "C" int egnn_sage_out_bwd(const int32_t* csc_ptr, const int32_t* csc_dst, const int32_t* csr_ptr,
                                  const void* dout, int dtype, int C, float* dp, int64_t n_rows, float* edge_tmp,
                                  int64_t edge_cap, void* stream) {
-  const char* fn = "egnn_sage_out_bwd";
+  if (!csr_ptr) return fail("egnn_sage_out_bwd", "null pointer");
+  return narrow_out_bwd("egnn_sage_out_bwd", csc_ptr, csc_dst, csr_ptr, nullptr, dout, dtype, C, dp, n_rows, edge_tmp,
+                        edge_cap, stream);
+}
+
+extern "C" int egnn_gcn_out_bwd(const int32_t* csc_ptr, const int32_t* csc_dst, const float* w_csc, const void* dout,
+                                int dtype, int C, float* dp, int64_t n_rows, float* edge_tmp, int64_t edge_cap,
+                                void* stream) {
+  if (!w_csc) return fail("egnn_gcn_out_bwd", "null weights");
+  return narrow_out_bwd("egnn_gcn_out_bwd", csc_ptr, csc_dst, csc_ptr, w_csc, dout, dtype, C, dp, n_rows, edge_tmp,
+                        edge_cap, stream);
+}
+
+static int narrow_out_bwd(const char* fn, const int32_t* csc_ptr, const int32_t* csc_dst, const int32_t* csr_ptr,
+                          const float* w, const void* dout, int dtype, int C, float* dp, int64_t n_rows,
+                          float* edge_tmp, int64_t edge_cap, void* stream) {
   EGNN_REQUIRE(csc_ptr && csc_dst && csr_ptr && dout && dp && edge_tmp, fn, "null pointer");
   if (n_rows == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned grid = (unsigned)ceil_div(n_rows, kThreads);
   const unsigned egrid = (unsigned)ceil_div(edge_cap > 0 ? edge_cap : 1, kThreads);
 #define LAUNCH(T, CC)                                                                                          \
-  sage_out_bwd_terms<T, CC><<<egrid, kThreads, 0, st>>>(csc_ptr, csc_dst, csr_ptr,                             \
+  sage_out_bwd_terms<T, CC><<<egrid, kThreads, 0, st>>>(csc_ptr, csc_dst, csr_ptr, w,                          \
                                                         reinterpret_cast<const T*>(dout), edge_tmp, n_rows);   \
   EGNN_LAUNCH_CHECK(fn);                                                                                       \
   sage_out_bwd_kernel<T, CC><<<grid, kThreads, 0, st>>>(csc_ptr, edge_tmp, reinterpret_cast<const T*>(dout), dp, \

@@ -106,6 +106,9 @@ class GCNConv(nn.Module):
     def forward(self, x: torch.Tensor, edge_index: Union[torch.Tensor, Graph]) -> torch.Tensor:
         _check_input(x, self.in_channels)
         g = _graph_of(edge_index, x.size(0), self_loops=True)
+        if self.out_channels in (2, 4) and ops.sage_out_supported(x, self.out_channels):
+            # narrow output (the logits layer): project first, aggregate at width out_channels
+            return ops.GcnOutFn.apply(ops._rows(x), self.lin.weight, self.bias, g)
         return ops.GcnConvFn.apply(x, self.lin.weight, self.bias, g, ops.amp_bf16())
 
 

@@ -441,6 +441,53 @@ class GcnConvFn(torch.autograd.Function):
         return dx, dw, db, None, None
 
 
+class GcnOutFn(torch.autograd.Function):
+    """GCNConv with <= 4 output channels (the `hidden -> 2` logits layer of GCNNet, gnn.py:23), evaluated through the
+    same narrow kernels as the SAGE logits layer: p = h W^T (one pass over h), out_i = sum_j rn(w_ji p_j) + b at
+    width C, and the mirrored backward (csrc/sage_out.cu).  fp32 weights / accumulation / logits."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, g: Graph):
+        x = _rows(x)
+        N, K = x.shape
+        C = w.size(0)
+        L = lib()
+        # [W ; 0]: the zero rows absorb the `dout` half of dp in the shared skinny wgrad / dgrad kernels
+        wcat = torch.cat([w.detach().float(), w.new_zeros((C, K), dtype=torch.float32)], dim=0).contiguous()
+        p = torch.empty((N, C), dtype=torch.float32, device=x.device)
+        check(L.egnn_skinny_project(ptr(x), dt(x), _ld(x), N, K, ptr(wcat), C, ptr(p), stream()))
+        out = torch.empty((N, C), dtype=torch.float32, device=x.device)
+        tmp = torch.empty((g.cap, C), dtype=torch.float32, device=x.device)
+        bias = b.detach().float().contiguous() if b is not None else None
+        check(L.egnn_gcn_out_fwd(ptr(g.csr_ptr), ptr(g.csr_src), ptr(g.w_csr), ptr(p), ptr(bias), C, ptr(out), N,
+                                 ptr(tmp), g.cap, stream()))
+        ctx.g, ctx.C = g, C
+        ctx.save_for_backward(x, wcat)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, wcat = ctx.saved_tensors
+        g, C = ctx.g, ctx.C
+        N, K = x.shape
+        L = lib()
+        dout = _rows(dout).contiguous()
+        dp = torch.empty((N, 2 * C), dtype=torch.float32, device=x.device)
+        tmp = torch.empty((g.cap, C), dtype=torch.float32, device=x.device)
+        check(L.egnn_gcn_out_bwd(ptr(g.csc_ptr), ptr(g.csc_dst), ptr(g.w_csc), ptr(dout), dt(dout), C, ptr(dp), N,
+                                 ptr(tmp), g.cap, stream()))
+        dw = torch.empty((2 * C, K), dtype=torch.float32, device=x.device)
+        dsum = torch.empty(2 * C, dtype=torch.float32, device=x.device)
+        ws = torch.empty(L.egnn_skinny_wgrad_workspace_floats(N, K, 2 * C), dtype=torch.float32, device=x.device)
+        check(L.egnn_skinny_wgrad(ptr(x), dt(x), _ld(x), ptr(dp), 2 * C, N, K, ptr(dw), ptr(dsum), ptr(ws),
+                                  stream()))
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((N, K), dtype=x.dtype, device=x.device)
+            check(L.egnn_skinny_dgrad(ptr(dp), ptr(wcat), 2 * C, ptr(dx), dt(dx), K, N, K, stream()))
+        return dx, dw[:C], dsum[C:], None
+
+
 # ---------------------------------------------------------------------------- GATConv ----
 class GatConvFn(torch.autograd.Function):
     """PyG GATConv (heads, concat | head-mean) on the self-loop graph."""

@@ -153,6 +153,14 @@ int egnn_sage_out_fwd(const int32_t* csr_ptr, const int32_t* csr_src, const floa
 int egnn_sage_out_bwd(const int32_t* csc_ptr, const int32_t* csc_dst, const int32_t* csr_ptr,
                       const void* dout, int dtype, int C, float* dp, int64_t n_rows, float* edge_tmp,
                       int64_t edge_cap, void* stream);
+/* The same project-first evaluation for the narrow GCNConv (`GCNConv(hidden, 2)`, src/models/gnn.py:23):
+ *   p = h W^T [N, C];  out_i = sum_{j->i} rn(w_ji * p_j) + b  over the self-loop CSR with the gcn_norm weights;
+ *   backward dp = [ sum_{j->i} rn(w_ji * dout_i) | dout_j ]  over the CSC view (weights in CSC order). */
+int egnn_gcn_out_fwd(const int32_t* csr_ptr, const int32_t* csr_src, const float* w_csr, const float* p,
+                     const float* bias, int C, float* out, int64_t n_rows, float* edge_tmp, int64_t edge_cap,
+                     void* stream);
+int egnn_gcn_out_bwd(const int32_t* csc_ptr, const int32_t* csc_dst, const float* w_csc, const void* dout, int dtype,
+                     int C, float* dp, int64_t n_rows, float* edge_tmp, int64_t edge_cap, void* stream);
 size_t egnn_skinny_wgrad_workspace_floats(int64_t n_rows, int64_t K, int P);
 int egnn_skinny_wgrad(const void* a, int dtype, int64_t ld, const float* dp, int P, int64_t n_rows,
                       int64_t K, float* dW, float* dsum, float* workspace, void* stream);
