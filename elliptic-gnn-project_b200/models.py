@@ -59,6 +59,8 @@ class GCNNet(_StackNet):
         for _ in range(layers - 2):
             self.convs.append(GCNConv(hidden_dim, hidden_dim))
         self.convs.append(GCNConv(hidden_dim, num_classes))
+        for conv in self.convs[:-1]:
+            conv._hidden_bf16 = True   # hidden activations in bf16 under bf16 autocast (see nn.GCNConv)
 
 
 class SAGENet(_StackNet):

@@ -97,6 +97,9 @@ class GCNConv(nn.Module):
         self.in_channels, self.out_channels = in_channels, out_channels
         self.lin = _Lin(in_channels, out_channels, bias=False, glorot=True)
         self.bias = nn.Parameter(torch.zeros(out_channels))
+        # set by egnn_b200.models.GCNNet on its hidden layers: emit bf16 under bf16 autocast (PyG's fp32 output is
+        # rounded to bf16 by the next layer's Linear anyway); a standalone GCNConv keeps PyG's fp32 output
+        self._hidden_bf16 = False
 
     def reset_parameters(self):
         self.lin.reset_parameters()
@@ -109,7 +112,7 @@ class GCNConv(nn.Module):
         if self.out_channels in (2, 4) and ops.sage_out_supported(x, self.out_channels):
             # narrow output (the logits layer): project first, aggregate at width out_channels
             return ops.GcnOutFn.apply(ops._rows(x), self.lin.weight, self.bias, g)
-        return ops.GcnConvFn.apply(x, self.lin.weight, self.bias, g, ops.amp_bf16())
+        return ops.GcnConvFn.apply(x, self.lin.weight, self.bias, g, ops.amp_bf16(), self._hidden_bf16)
 
 
 class GATConv(nn.Module):

@@ -405,7 +405,7 @@ class GcnConvFn(torch.autograd.Function):
     """PyG GCNConv: D^-1/2 (A+I) D^-1/2 (x W^T) + b on the self-loop graph."""
 
     @staticmethod
-    def forward(ctx, x, w, b, g: Graph, bf16: bool):
+    def forward(ctx, x, w, b, g: Graph, bf16: bool, out_bf16: bool = False):
         cd = torch.bfloat16 if bf16 else torch.float32
         x = _rows(x)
         pad = (-x.size(1)) % 8 if (bf16 and x.dtype == torch.float32) else 0
@@ -415,7 +415,10 @@ class GcnConvFn(torch.autograd.Function):
         xg = to_compute(x, cd)
         wc = w if w.dtype == cd else cast(w, cd)
         h = linear_fwd(xg, wc, out_dtype=cd)
-        out = spmm(g, "csr", _lib.SPMM_WEIGHTED, h, torch.float32, bias=b)
+        # PyG returns fp32 here even under autocast (fp32 weights promote the aggregation); a hidden layer of OUR
+        # nets may ask for the bf16 rounding the next Linear would apply anyway (out_bf16), which halves the
+        # activation traffic and removes two cast passes per layer
+        out = spmm(g, "csr", _lib.SPMM_WEIGHTED, h, torch.bfloat16 if (out_bf16 and bf16) else torch.float32, bias=b)
         ctx.g, ctx.x_dtype = g, x.dtype
         ctx.save_for_backward(xg, wc)
         return out
@@ -425,8 +428,6 @@ class GcnConvFn(torch.autograd.Function):
         xg, wc = ctx.saved_tensors
         g = ctx.g
         dout = _rows(dout)
-        if dout.dtype != torch.float32:
-            dout = cast(dout, torch.float32)
         dh = spmm(g, "csc", _lib.SPMM_WEIGHTED, dout, xg.dtype)
         dw = linear_wgrad(dh, xg)
         db = colsum(dout).float()
@@ -438,7 +439,7 @@ class GcnConvFn(torch.autograd.Function):
         if ctx.pad:
             dw = dw[:, :dw.size(1) - ctx.pad]
             dx = dx[:, :dx.size(1) - ctx.pad] if dx is not None else None
-        return dx, dw, db, None, None
+        return dx, dw, db, None, None, None
 
 
 class GcnOutFn(torch.autograd.Function):
