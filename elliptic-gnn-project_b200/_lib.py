@@ -32,8 +32,10 @@ SIGNATURES = {
     "egnn_counter_add": (_i32, [_vp, _i64, _vp]),
     "egnn_graph_workspace_bytes": (_sz, [_i64, _i64, _i32]),
     "egnn_graph_build": (_i32, [_vp, _i64, _i64, _i32, _i32] + [_vp] * 16 + [_vp, _sz, _vp]),
-    "egnn_spmm": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _i32, _i64, _i64, _i64,
-                         _vp, _i32, _i32, _vp, _i64, _vp]),
+    "egnn_spmm": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _i64, _vp, _i32, _i64, _i64,
+                         _i64, _vp, _i32, _i32, _vp, _i64, _vp]),
+    "egnn_spmm_partition_tasks": (_i64, [_i64, _i64]),
+    "egnn_spmm_partition": (_i32, [_vp, _i64, _vp, _i64, _vp]),
     "egnn_gemm_workspace_floats": (_sz, [_i64, _i64, _i64, _i32]),
     "egnn_gemm": (_i32, [_vp, _i32, _i64, _i64, _vp, _i32, _i64, _i64, _vp, _i32, _i64, _i64, _i64, _i64,
                          _vp, _vp, _i64, _i32, _i32, _vp, _i32, _vp]),

@@ -218,7 +218,8 @@ using namespace egnn;
 
 extern "C" int egnn_spmm(int mode, const int32_t* ptr, const int32_t* col, const float* w,
                          const int32_t* nbr_ptr, const int32_t* long_rows, const int32_t* n_long,
-                         const int32_t* row_order, const void* in, int in_dtype, int64_t ld_in, void* out, int out_dtype,
+                         const int32_t* row_order, const int32_t* part, int64_t n_tasks, const void* in, int in_dtype,
+                         int64_t ld_in, void* out, int out_dtype,
                          int64_t ld_out, int64_t n_rows, int64_t n_feat, const float* bias, int act,
                          int accumulate, const void* addend, int64_t ld_addend, void* stream) {
   const char* fn = "egnn_spmm";
@@ -233,6 +234,7 @@ extern "C" int egnn_spmm(int mode, const int32_t* ptr, const int32_t* col, const
   Params P;
   P.ptr = ptr; P.col = col; P.w = w; P.nbr_ptr = nbr_ptr;
   P.long_rows = long_rows; P.n_long = n_long; P.row_order = row_order;
+  P.part = part; P.n_tasks = part ? n_tasks : 0;
   P.in = in; P.out = out; P.bias = bias;
   P.ld_in = ld_in; P.ld_out = ld_out; P.n_rows = n_rows; P.n_feat = (int)n_feat;
   P.mean = (mode == EGNN_SPMM_MEAN); P.act = act;

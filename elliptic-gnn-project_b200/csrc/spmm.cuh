@@ -8,10 +8,15 @@ namespace spmm_detail {
 
 constexpr int kThreads = 256;
 constexpr int kLongRow = 64;    // rows with more edges go to the CTA path (if a list is given)
-constexpr int kLongCtas = 32;   // leading blocks that serve the long-row list
+// Leading blocks that serve the long-row list, one (row, 32-feature slice) item at a time.  4 per SM: with 32
+// (the first value) these CTAs were the critical path of EVERY aggregation kernel of round 1 -- 68 long rows x 6
+// slices on the base graph at ~5 us per item = 65 us of an ~80 us launch, whatever the main path did; blocks
+// with no item left return at once.
+constexpr int kLongCtas = 4 * 148;
 constexpr int kStageEdges = 128; // source rows staged per round in the CTA path
 constexpr int kSliceFeat = 32;   // features per CTA work item in the CTA path
 constexpr int kStageFeat = 256;  // max features per feature-chunk (G*VPL*4 <= 256)
+constexpr int kTaskCost = 32;    // cost units (rows + 2 * entries) per task of the streaming kernel's row partition
 
 enum { M_PLAIN = 0, M_DIV_NBR = 1, M_WEIGHTED = 2 };
 
@@ -23,6 +28,8 @@ struct Params {
   const int32_t* long_rows;
   const int32_t* n_long;
   const int32_t* row_order;  // optional: rows in descending-degree order (lean kernel schedule)
+  const int32_t* part;       // optional: cost-balanced row partition (egnn_spmm_partition), n_tasks + 1 row ids
+  int64_t n_tasks;
   const void* in;
   void* out;
   const float* bias;
@@ -145,4 +152,6 @@ __device__ __forceinline__ void long_row_path(const Params& P, int bx, float (*s
 // spmm_lean.cu (lane groups, production): returns -2 when the configuration is not covered and the caller
 // falls through to the chunked kernels of spmm.cu
 int spmm_tile_launch(const spmm_detail::Params& P, int in_dt, int out_dt, bool weighted, cudaStream_t st);
+// spmm_stream.cu (lane groups streaming the edges of R consecutive rows); -2 when not covered
+int spmm_stream_launch(const spmm_detail::Params& P, int in_dt, int out_dt, bool weighted, cudaStream_t st);
 }  // namespace egnn

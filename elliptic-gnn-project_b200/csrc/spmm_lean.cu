@@ -464,6 +464,18 @@ int by_dtype(const Params& P, int in_dt, int out_dt, cudaStream_t st) {
 }  // namespace
 
 int spmm_tile_launch(const spmm_detail::Params& P, int in_dt, int out_dt, bool weighted, cudaStream_t st) {
+  // production: the streaming lane-group kernel (spmm_stream.cu); EGNN_SPMM_IMPL=lean / pipe select the
+  // per-row kernels of this file (kept for 4-lane groups and as the measured baseline)
+#ifdef EGNN_SPMM_EXPERIMENT
+  const char* impl_env = getenv("EGNN_SPMM_IMPL");  // re-read on every launch so one probe process can sweep it
+  const bool use_stream = !impl_env || impl_env[0] == 's';
+#else
+  static const bool use_stream = [] { const char* e = getenv("EGNN_SPMM_IMPL"); return !e || e[0] == 's'; }();
+#endif
+  if (use_stream) {
+    int rc = spmm_stream_launch(P, in_dt, out_dt, weighted, st);
+    if (rc != -2) return rc;
+  }
   return weighted ? by_dtype<M_WEIGHTED>(P, in_dt, out_dt, st) : by_dtype<M_PLAIN>(P, in_dt, out_dt, st);
 }
 

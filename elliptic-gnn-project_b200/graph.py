@@ -35,6 +35,9 @@ class Graph:
     csc_long: torch.Tensor
     csr_order: torch.Tensor        # int32[N] destination rows by descending in-degree (SpMM schedule)
     csc_order: torch.Tensor        # int32[N] source rows by descending out-degree
+    csr_part: Optional[torch.Tensor] = None  # int32[n_tasks+1] cost-balanced row partition (streaming SpMM)
+    csc_part: Optional[torch.Tensor] = None
+    n_tasks: int = 0
     ei2: Optional[torch.Tensor] = None     # int64[2,cap] expanded edge list (debug/parity)
     dis: Optional[torch.Tensor] = None     # float[N]   deg^-1/2
     w_edge: Optional[torch.Tensor] = None  # float[cap] gcn_norm in ei2 order
@@ -92,12 +95,19 @@ def build_graph(edge_index: torch.Tensor, num_nodes: int, symmetrize: bool = Fal
         w_csc=torch.empty(cap, dtype=torch.float32, device=dev) if norm else None,
     )
     L = lib()
+    if g.csr_part is None:
+        g.n_tasks = int(L.egnn_spmm_partition_tasks(N, cap))
+        g.csr_part = torch.empty(g.n_tasks + 1, **i32)
+        g.csc_part = torch.empty(g.n_tasks + 1, **i32)
     ws_bytes = L.egnn_graph_workspace_bytes(N, E, flags)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     check(L.egnn_graph_build(ptr(ei), E, N, flags, int(want_norm), ptr(g.info), ptr(g.csr_ptr), ptr(g.csr_src),
                              ptr(g.csr_eid), ptr(g.csc_ptr), ptr(g.csc_dst), ptr(g.csc_pos), ptr(g.csr_long),
                              ptr(g.csc_long), ptr(g.csr_order), ptr(g.csc_order), ptr(g.ei2), ptr(g.dis), ptr(g.w_edge), ptr(g.w_csr),
                              ptr(g.w_csc), ptr(ws), ws_bytes, stream()))
+    # row partitions of both views for the streaming aggregation kernel (equal work per lane group)
+    check(L.egnn_spmm_partition(ptr(g.csr_ptr), N, ptr(g.csr_part), g.n_tasks, stream()))
+    check(L.egnn_spmm_partition(ptr(g.csc_ptr), N, ptr(g.csc_part), g.n_tasks, stream()))
     if validate and not torch.cuda.is_current_stream_capturing():
         bad = int(g.info[1].item())
         if bad:

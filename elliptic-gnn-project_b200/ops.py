@@ -119,11 +119,14 @@ def spmm(g: Graph, view: str, mode: int, x: torch.Tensor, out_dtype: torch.dtype
         out = torch.empty((n, x.size(1)), dtype=out_dtype, device=x.device)
     if view == "csr":
         p, c, w, long_rows, vi, nbr, order = g.csr_ptr, g.csr_src, g.w_csr, g.csr_long, 0, g.csc_ptr, g.csr_order
+        part = g.csr_part
     else:
         p, c, w, long_rows, vi, nbr, order = g.csc_ptr, g.csc_dst, g.w_csc, g.csc_long, 1, g.csr_ptr, g.csc_order
+        part = g.csc_part
     n_long = g.info.data_ptr() + 4 * (2 + vi)
     check(lib().egnn_spmm(mode, ptr(p), ptr(c), ptr(w) if mode == _lib.SPMM_WEIGHTED else None,
-                          ptr(nbr) if mode == _lib.SPMM_DIV_NBR else None, ptr(long_rows), n_long, ptr(order), ptr(x),
+                          ptr(nbr) if mode == _lib.SPMM_DIV_NBR else None, ptr(long_rows), n_long, ptr(order),
+                          ptr(part), g.n_tasks if part is not None else 0, ptr(x),
                           dt(x), _ld(x), ptr(out), dt(out), _ld(out), n, x.size(1), ptr(bias), act,
                           int(accumulate), ptr(addend), _ld(addend) if addend is not None else 0, stream()))
     return out

@@ -103,15 +103,27 @@ int egnn_graph_build(const int64_t* ei, int64_t n_edges_in, int64_t n_nodes, int
  *            device-side length, from egnn_graph_build; those rows take the whole-CTA path
  *   row_order int32 [n_rows] or NULL: processing order of the rows (egnn_graph_build's
  *            descending-degree order); results do not depend on it
+ *   part/n_tasks  int32 [n_tasks+1] or NULL/0: cost-balanced row partition from egnn_spmm_partition;
+ *            with it the streaming kernel runs (a lane group walks the entries of its consecutive rows
+ *            as one stream with a shared-memory ring of cp.async copies in flight); results do not depend on it
  *   bias     float [F] or NULL, added after the reduction; act = EGNN_ACT_*
  *   accumulate != 0: out += result (one rounding in out dtype after an fp32 add);
  *   addend != NULL: out = addend + result instead (addend has the out dtype, leading dimension ld_addend)
  */
 int egnn_spmm(int mode, const int32_t* ptr, const int32_t* col, const float* w,
               const int32_t* nbr_ptr, const int32_t* long_rows, const int32_t* n_long,
-              const int32_t* row_order, const void* in, int in_dtype, int64_t ld_in, void* out,
-              int out_dtype, int64_t ld_out, int64_t n_rows, int64_t n_feat, const float* bias,
-              int act, int accumulate, const void* addend, int64_t ld_addend, void* stream);
+              const int32_t* row_order, const int32_t* part, int64_t n_tasks, const void* in,
+              int in_dtype, int64_t ld_in, void* out, int out_dtype, int64_t ld_out, int64_t n_rows,
+              int64_t n_feat, const float* bias, int act, int accumulate, const void* addend,
+              int64_t ld_addend, void* stream);
+
+/* Row partition for the streaming SpMM kernel: cost(r) = r + 2 * ptr[r]; part[k] = first row whose cost
+ * prefix reaches 32 * k (k = 0..n_tasks; entries past the end of the matrix hold n_rows), so every task
+ * [part[k], part[k+1]) carries about the same work whatever the degree skew (the reference's scatter has no
+ * such notion; this replaces the dynamic load balancing of its atomics-based `scatter_add_`).
+ * egnn_spmm_partition_tasks(n_rows, nnz_cap) = n_tasks to allocate for a matrix with at most nnz_cap entries. */
+int64_t egnn_spmm_partition_tasks(int64_t n_rows, int64_t nnz_cap);
+int egnn_spmm_partition(const int32_t* ptr, int64_t n_rows, int32_t* part, int64_t n_tasks, void* stream);
 
 /* ---------------------------------------------------------------- K6: dense ----------- */
 /* C[M,N] (+)= op(A)[M,K] . op(B)[K,N] (+ bias[N]).  Element (m,k) of op(A) is at
