@@ -284,7 +284,7 @@ def run_ours(args):
         add64 = torch.randn(N, 64, device=dev).bfloat16()
         t64b = time_kernel(lambda b: ops.spmm(g, "csc", _lib.SPMM_SUM, b, torch.bfloat16, out=out64, addend=add64), xs64)
         b64 = spmm_bytes(N, 64, e_local, 2, 2)
-        roof = {"kernel": "egnn_spmm mean fp32->bf16 F=168 (layer-0 aggregation, spmm_lean)", "bound": "hbm",
+        roof = {"kernel": "egnn_spmm mean fp32->bf16 F=168 (layer-0 aggregation, spmm_stream)", "bound": "hbm",
                 "achieved": round(b168 / t168 / 1e6, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(b168 / t168 / 1e6 / peak, 4), "traffic": ncu_traffic(), "peak_source": peak_src,
                 "algorithmic_bytes": b168, "us": round(t168 * 1e3, 2)}

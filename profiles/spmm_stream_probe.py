@@ -42,12 +42,12 @@ cases = [("F168 f32->bf16 csr", 168, torch.float32, torch.bfloat16, 'csr', 3 if 
          ("F64 bf16 csr", 64, torch.bfloat16, torch.bfloat16, 'csr', 8 if rep == 1 else 1),
          ("F64 bf16 csc", 64, torch.bfloat16, torch.bfloat16, 'csc', 8 if rep == 1 else 1)]
 sweeps = [("lean", dict(EGNN_SPMM_IMPL="lean"))]
-for K in ("1", "2", "3"):
-    for cfg in ("2,0", "4,0", "6,0"):
-        sweeps.append((f"stream168 W={K} D,MINB={cfg}", dict(EGNN_SPMM_IMPL="stream", EGNN_STREAM_W=K, EGNN_STREAM_CFG=cfg, only=0)))
-for K in ("1", "2", "3"):
-    for cfg in ("4,0", "8,0", "12,0"):
-        sweeps.append((f"stream64 W={K} D,MINB={cfg}", dict(EGNN_SPMM_IMPL="stream", EGNN_STREAM_W=K, EGNN_STREAM_CFG=cfg, only=1)))
+for W in ("2",):
+    for cfg in ("16,3,4", "8,6,2", "8,6,3", "8,6,4", "4,11,2"):
+        sweeps.append((f"stream168 W={W} G,VPL,D={cfg}", dict(EGNN_SPMM_IMPL="stream", EGNN_STREAM_W=W, EGNN_STREAM_CFG=cfg, only=0)))
+for W in ("2",):
+    for cfg in ("8,1,8", "4,2,4", "4,2,6", "4,2,8"):
+        sweeps.append((f"stream64 W={W} G,VPL,D={cfg}", dict(EGNN_SPMM_IMPL="stream", EGNN_STREAM_W=W, EGNN_STREAM_CFG=cfg, only=1)))
 sweeps.append(("stream default", dict(EGNN_SPMM_IMPL="stream")))
 for name, env in sweeps:
     only = env.pop("only", None)
