@@ -34,6 +34,9 @@ SIGNATURES = {
     "egnn_graph_build": (_i32, [_vp, _i64, _i64, _i32, _i32] + [_vp] * 16 + [_vp, _sz, _vp]),
     "egnn_spmm": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _i64, _vp, _i32, _i64, _i64,
                          _i64, _vp, _i32, _i32, _vp, _i64, _vp]),
+    "egnn_ap_workspace_bytes": (_sz, [_i64]),
+    "egnn_average_precision": (_i32, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "egnn_early_stop_update": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp]),
     "egnn_spmm_partition_tasks": (_i64, [_i64, _i64]),
     "egnn_spmm_partition": (_i32, [_vp, _i64, _vp, _i64, _vp]),
     "egnn_gemm_workspace_floats": (_sz, [_i64, _i64, _i64, _i32]),

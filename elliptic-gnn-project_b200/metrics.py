@@ -1,0 +1,93 @@
+"""Epoch tail on the device: validation PR-AUC and early stopping without host round trips.
+
+Mirrors what the reference does on the host after every epoch (`/root/reference/src/train_gnn.py:387-411`):
+`eval_split` -> `pr_auc_illicit((y_val == 1).astype(int), p_val)` (`/root/reference/src/utils/metrics.py:11-13`,
+sklearn `average_precision_score`) -> `if pr_val > best_val: best_state = clone(state_dict)` / `bad += 1` ->
+`if bad >= patience: break`.  Here the score, the comparison and the best-parameter snapshot stay on the GPU
+(`csrc/metrics.cu`); the host reads `EarlyStopper.state` only when it decides to (e.g. every 10 epochs).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from ._lib import check, lib, ptr, stream
+
+
+def average_precision(y: torch.Tensor, mask: Optional[torch.Tensor] = None, *, logits: Optional[torch.Tensor] = None,
+                      scores: Optional[torch.Tensor] = None, scores_out: Optional[torch.Tensor] = None,
+                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """PR-AUC of the class `y == 1` over the rows selected by `mask` -> float64[4] ON THE DEVICE:
+    `[AP, selected rows, positives, distinct thresholds]`.  Give `logits` ([N, 2] fp32; the score is
+    `softmax(logits, 1)[:, 1]` as in `eval_split`) or `scores` ([N] fp32)."""
+    if (logits is None) == (scores is None):
+        raise ValueError("give exactly one of logits / scores")
+    src = logits if logits is not None else scores
+    if not src.is_cuda:
+        raise RuntimeError("egnn_b200 computes metrics on the GPU only (no CPU fallback)")
+    if src.dtype != torch.float32:
+        raise TypeError("logits / scores must be float32 (eval forwards are never under autocast)")
+    if y.dtype != torch.int64:
+        raise TypeError("y must be int64")
+    n = int(y.numel())
+    if logits is not None:
+        if logits.dim() != 2 or logits.size(1) < 2 or logits.size(0) != n or logits.stride(1) != 1:
+            raise ValueError("logits must be [N, >=2] with contiguous rows")
+    elif scores.numel() != n or not scores.is_contiguous():
+        raise ValueError("scores must be a contiguous [N] tensor")
+    if mask is not None:
+        if mask.numel() != n or mask.dtype not in (torch.bool, torch.uint8) or not mask.is_contiguous():
+            raise ValueError("mask must be a contiguous bool / uint8 [N] tensor")
+    if out is None:
+        out = torch.empty(4, dtype=torch.float64, device=src.device)
+    L = lib()
+    ws_bytes = L.egnn_ap_workspace_bytes(n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=src.device)
+    check(L.egnn_average_precision(ptr(logits), logits.stride(0) if logits is not None else 0, ptr(scores),
+                                   ptr(y.contiguous()), ptr(mask), n, ptr(scores_out), ptr(out), ptr(ws), ws_bytes,
+                                   stream()))
+    return out
+
+
+class EarlyStopper:
+    """`best_val` / `bad` / `best_state` of `/root/reference/src/train_gnn.py:375-411` as device state.
+
+    `state` (float64[5], device) = [best value, epochs since the best, epoch of the best, epochs seen, improved].
+    `update(ap)` enqueues the comparison and, when `flat_param` was given, the conditional snapshot of the flat
+    parameter buffer (`train.FlatClipAdam.flat_param`) into `best_param`; nothing is read back.  `should_stop()`
+    is the one host synchronisation (`bad >= patience`)."""
+
+    def __init__(self, patience: int = 20, flat_param: Optional[torch.Tensor] = None, device=None):
+        dev = flat_param.device if flat_param is not None else torch.device(device or "cuda")
+        self.patience = int(patience)
+        self.state = torch.tensor([-1.0, 0.0, 0.0, 0.0, 0.0], dtype=torch.float64, device=dev)
+        self.flat_param = flat_param
+        self.best_param = torch.empty_like(flat_param) if flat_param is not None else None
+
+    def update(self, ap: torch.Tensor) -> None:
+        n = int(self.flat_param.numel()) if self.flat_param is not None else 0
+        check(lib().egnn_early_stop_update(ptr(ap), ptr(self.state), ptr(self.flat_param), ptr(self.best_param), n,
+                                           stream()))
+
+    def should_stop(self) -> bool:
+        return float(self.state[1].item()) >= self.patience
+
+    @property
+    def best(self) -> float:
+        return float(self.state[0].item())
+
+    def restore_best(self) -> None:
+        """`model.load_state_dict(best_state)` (`src/train_gnn.py:416-417`) for the flat parameter buffer."""
+        if self.flat_param is not None and float(self.state[2].item()) > 0:
+            self.flat_param.copy_(self.best_param)
+
+
+@torch.no_grad()
+def eval_pr_auc(model, x, edge_index, timestep, y, mask, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """`eval_split` + `pr_auc_illicit` (`src/train_gnn.py:248-257,391`): fp32 eval forward, then the PR-AUC of the
+    illicit class over `mask`, all on the device."""
+    from .train import model_uses_time_embed
+    model.eval()
+    logits = model(x, edge_index, timestep if model_uses_time_embed(model) else None)
+    return average_precision(y, mask, logits=logits.float().contiguous(), out=out)

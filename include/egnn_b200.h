@@ -327,6 +327,29 @@ int egnn_clip_adam_step(float* param, const float* grad, float* exp_avg, float* 
                         float weight_decay, float max_norm, int64_t* step_count, float* grad_norm_out,
                         float* workspace, void* stream);
 
+/* ---------------------------------------------------------------- epoch tail -- */
+/* Validation PR-AUC on the device.  Replaces, per epoch, `eval_split`'s softmax -> .cpu().numpy() -> mask indexing
+ * (src/train_gnn.py:248-257) and `pr_auc_illicit` = sklearn `average_precision_score` (src/utils/metrics.py:11-13):
+ *   AP = sum over distinct score thresholds k, descending, of (R_k - R_{k-1}) * P_k  (ties share a threshold).
+ * Exactly one of `logits` (float [n_rows, >=2], leading dimension ld_logits; score = softmax(row)[1]) or `scores`
+ * (float [n_rows]) is given; y int64 [n_rows] (positive class: y == 1, as the caller's `(y_val == 1).astype(int)`,
+ * src/train_gnn.py:391); mask uint8/bool [n_rows] or NULL (all rows).  scores_out (float [n_rows] or NULL) receives
+ * the scores.  out double[4] (device) = {AP, selected rows, positives, distinct thresholds}; no selected row or no
+ * positive -> AP = 0.0 (the reference's `y_val.size == 0` guard / sklearn's no-positive convention).
+ * Counts are exact integers; AP is a fixed-order float64 sum (deterministic). */
+size_t egnn_ap_workspace_bytes(int64_t n_rows);
+int egnn_average_precision(const float* logits, int64_t ld_logits, const float* scores, const int64_t* y,
+                           const uint8_t* mask, int64_t n_rows, float* scores_out, double* out,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* Early-stopping bookkeeping without a host round trip (src/train_gnn.py:392-402: `if pr_val > best_val` ->
+ * best_state = CPU clone of the state dict; else bad += 1).  state double[5] (device) = {best value, epochs since
+ * the best, epoch of the best (1-based), epochs seen, improved flag}; initialise to {-1, 0, 0, 0, 0} (best_val = -1.0,
+ * src/train_gnn.py:375).  When the value improves, params[0..n_params) is copied to best_params (both float,
+ * 16-byte aligned, may be NULL together). */
+int egnn_early_stop_update(const double* ap, double* state, const float* params, float* best_params,
+                           int64_t n_params, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

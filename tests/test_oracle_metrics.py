@@ -1,0 +1,67 @@
+"""The epoch-tail oracle (oracle/metrics_np.py) pinned against the reference's own function (golden vectors made by
+importing /root/reference/src/utils/metrics.py, tests/golden/make_metrics_golden.py) and against scikit-learn."""
+import importlib.util
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import metrics_np as M
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _gen():
+    spec = importlib.util.spec_from_file_location("mk", os.path.join(HERE, "golden", "make_metrics_golden.py"))
+    return spec
+
+
+def _case(seed, n, pos_rate, quant):
+    r = np.random.default_rng(seed)
+    y = (r.random(n) < pos_rate).astype(np.int64)
+    s = (r.random(n) * 0.6 + 0.4 * y * r.random(n)).astype(np.float32)
+    if quant:
+        s = (np.round(s * quant) / quant).astype(np.float32)
+    return y, s
+
+
+def test_golden_vectors_from_the_reference_function():
+    g = json.load(open(os.path.join(HERE, "golden", "metrics_golden.json")))
+    assert len(g["cases"]) >= 9
+    for c in g["cases"]:
+        if c.get("reference_test"):
+            y, s = np.array(c["y"]), np.array(c["s"])
+        else:
+            y, s = _case(c["seed"], c["n"], c["pos_rate"], c["quant"])
+        ap = M.average_precision(y, s)[0]
+        assert ap == pytest.approx(c["ap"], rel=1e-13, abs=1e-15), c
+
+
+def test_against_sklearn_including_ties_and_degenerate_inputs():
+    sk = pytest.importorskip("sklearn.metrics")
+    rng = np.random.default_rng(11)
+    for n, q in [(1, 0), (2, 0), (17, 2), (300, 8), (5000, 0), (5000, 64)]:
+        y = (rng.random(n) < 0.3).astype(np.int64)
+        if y.sum() == 0:
+            y[0] = 1
+        s = rng.random(n).astype(np.float32)
+        if q:
+            s = (np.round(s * q) / q).astype(np.float32)
+        ap, cnt, pos, thr = M.average_precision(y, s)
+        assert ap == pytest.approx(float(sk.average_precision_score(y, s)), rel=1e-13)
+        assert (cnt, pos, thr) == (n, int(y.sum()), np.unique(s).size)
+    # all scores equal: one threshold, AP = prevalence
+    y = np.array([1, 0, 0, 1, 0])
+    assert M.average_precision(y, np.full(5, 0.5, np.float32))[0] == pytest.approx(0.4)
+    # no positives / empty selection -> 0.0 (sklearn warns and returns 0.0; the reference guards size == 0)
+    assert M.average_precision(np.zeros(4, np.int64), np.arange(4, dtype=np.float32))[0] == 0.0
+    assert M.average_precision(np.zeros(0, np.int64), np.zeros(0, np.float32)) == (0.0, 0, 0, 0)
+
+
+def test_early_stop_bookkeeping():
+    es = M.EarlyStop()
+    seq = [0.2, 0.3, 0.3, 0.25, 0.31, 0.1]
+    flags = [es.update(v) for v in seq]
+    assert flags == [True, True, False, False, True, False]          # strict `>` (src/train_gnn.py:394)
+    assert (es.best, es.bad, es.best_epoch, es.epoch) == (0.31, 1, 5, 6)
