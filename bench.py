@@ -246,11 +246,31 @@ def run_ours(args):
     ev1.record()
     barrier()
     ms_eval = ev0.elapsed_time(ev1) / 5
+    # ---- epoch tail on the device: validation PR-AUC from the eval logits + early-stopping
+    # bookkeeping with the best-parameter snapshot (the reference does these on the host, src/train_gnn.py:387-402)
+    from egnn_b200 import metrics as dev_metrics
+    _, ev_logits = eval_probs(model, devb["x"], devb["ei"], devb["t"])
+    ev_logits = ev_logits.float().contiguous()
+    val_mask = lg.val_mask.to(dev)
+    stopper = dev_metrics.EarlyStopper(patience=20, flat_param=step.opt.flat_param)
+    ap_out = torch.empty(4, dtype=torch.float64, device=dev)
+    for _ in range(2):
+        dev_metrics.average_precision(devb["y"], val_mask, logits=ev_logits, out=ap_out)
+        stopper.update(ap_out)
+    barrier()
+    ev0.record()
+    for _ in range(5):
+        dev_metrics.average_precision(devb["y"], val_mask, logits=ev_logits, out=ap_out)
+        stopper.update(ap_out)
+    ev1.record()
+    barrier()
+    ms_tail = ev0.elapsed_time(ev1) / 5
+    val_ap = [float(v) for v in ap_out.tolist()]
     model.train()
-    t = torch.tensor([ms, ms_e2e, ms_eval], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, ms_e2e, ms_eval, ms_tail], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e, ms_eval = (float(v) for v in t.tolist())
+    ms, ms_e2e, ms_eval, ms_tail = (float(v) for v in t.tolist())
     ms_step, ms_e2e_step = ms / args.steps, ms_e2e / e2e_steps
 
     # ---- roofline of the dominant sparse kernel (layer-0 mean SpMM, F=168, fp32 -> bf16), timed alone
@@ -300,7 +320,10 @@ def run_ours(args):
             "metric": METRIC, "value": round(e_total / (ms_step * 1e-3) / 1e9, 4), "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4),
             "epoch_ms": round(ms_step, 4), "eval_fwd_ms": round(ms_eval, 4),
-            "ref_epoch_ms": round(ms_step + ms_eval, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ref_epoch_ms": round(ms_step + ms_eval, 4), "epoch_tail_ms": round(ms_tail, 4),
+            "val_pr_auc": {"value": round(val_ap[0], 6), "rows": int(val_ap[1]), "positives": int(val_ap[2]),
+                           "where": "device (egnn_average_precision + egnn_early_stop_update)"},
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "rec_k8: SAGE-ResBN 168->64->64->2, BN, residual, sin-2 time embed, "
                                    "symmetrize_edges, dropout 0.2, bf16 autocast, full-batch",

@@ -9,4 +9,4 @@ from . import _lib  # noqa: F401
 from .graph import Graph, GraphCache, build_graph, cached_graph, symmetrize  # noqa: F401
 from .nn import GATConv, GCNConv, SAGEConv  # noqa: F401
 from .models import GATNet, GCNNet, SAGENet, SAGEResBNNet, build_model  # noqa: F401
-from . import ops, synthetic  # noqa: F401
+from . import metrics, ops, synthetic  # noqa: F401
