@@ -13,6 +13,7 @@ namespace egnn {
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kGatLanes = 8;  // lanes per row in the forward and the source pass (4 rows per warp)
 
 __global__ void __launch_bounds__(kThreads) gat_scores_kernel(const float* __restrict__ xs, int64_t n_rows,
                                                               int H, int C, const float* __restrict__ att_src,
@@ -34,6 +35,7 @@ __global__ void __launch_bounds__(kThreads) gat_scores_kernel(const float* __res
 
 __device__ __forceinline__ float leaky(float v, float slope) { return v > 0.f ? v : v * slope; }
 
+template <int G>
 __global__ void __launch_bounds__(kThreads) gat_fwd_kernel(const int* __restrict__ ptr, const int* __restrict__ src,
                                                            const float* __restrict__ xs,
                                                            const float* __restrict__ a_s,
@@ -41,10 +43,14 @@ __global__ void __launch_bounds__(kThreads) gat_fwd_kernel(const int* __restrict
                                                            int C, int concat, const float* __restrict__ bias,
                                                            float* alpha, float* __restrict__ out,
                                                            int64_t n_rows) {
-  const int lane = threadIdx.x & 31;
-  const int64_t row = ((int64_t)blockIdx.x * kThreads + threadIdx.x) >> 5;
-  if (row >= n_rows) return;
-  const int p0 = ptr[row], p1 = ptr[row + 1];
+  // G lanes per destination row (32 / G rows per warp): the mean row of the self-loop graph has 2-3 entries, so a
+  // whole warp per row left 90 % of the lanes idle and 203 769 warps queued behind eight dependent round trips
+  // each.  Rows past the end keep their lanes in the warp-wide shuffles with an empty range.
+  const int lane = threadIdx.x % G;
+  int64_t row = ((int64_t)blockIdx.x * kThreads + threadIdx.x) / G;
+  const bool live = row < n_rows;
+  if (!live) row = 0;
+  const int p0 = live ? ptr[row] : 0, p1 = live ? ptr[row + 1] : 0;
   const int F = H * C;
   // segment softmax with ONE LANE PER ENTRY (32 entries per sweep; the usual row is one sweep): all score
   // gathers of a row are issued together, max / sum are warp reductions, nothing walks the row serially
@@ -53,13 +59,14 @@ __global__ void __launch_bounds__(kThreads) gat_fwd_kernel(const int* __restrict
     float ad[kHMax], mx[kHMax], den[kHMax], e0[kHMax];
 #pragma unroll
     for (int h = 0; h < kHMax; ++h) {
-      ad[h] = h < H ? __ldg(a_d + row * H + h) : 0.f;
+      ad[h] = (h < H && live) ? __ldg(a_d + row * H + h) : 0.f;
       mx[h] = -INFINITY;
       den[h] = 0.f;
       e0[h] = 0.f;
     }
-    const bool single = p1 - p0 <= 32;
-    for (int base = p0; base < p1; base += 32) {  // pass A: scores and per-head max
+    const bool single = p1 - p0 <= G;
+#pragma unroll 4
+    for (int base = p0; base < p1; base += G) {  // pass A: scores and per-head max
       const int p = base + lane;
       const bool valid = p < p1;
       const int64_t sj = valid ? __ldg(src + p) : 0;
@@ -75,8 +82,9 @@ __global__ void __launch_bounds__(kThreads) gat_fwd_kernel(const int* __restrict
     for (int h = 0; h < kHMax; ++h)
       if (h < H)
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], o));
-    for (int base = p0; base < p1; base += 32) {  // pass B: exp and per-head sum (unnormalised alpha parked)
+        for (int o = G / 2; o > 0; o >>= 1) mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], o));
+#pragma unroll 4
+    for (int base = p0; base < p1; base += G) {  // pass B: exp and per-head sum (unnormalised alpha parked)
       const int p = base + lane;
       const bool valid = p < p1;
       const int64_t sj = (valid && !single) ? __ldg(src + p) : 0;
@@ -94,10 +102,11 @@ __global__ void __launch_bounds__(kThreads) gat_fwd_kernel(const int* __restrict
     for (int h = 0; h < kHMax; ++h)
       if (h < H) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) den[h] += __shfl_xor_sync(0xffffffffu, den[h], o);
+        for (int o = G / 2; o > 0; o >>= 1) den[h] += __shfl_xor_sync(0xffffffffu, den[h], o);
         den[h] += 1e-16f;
       }
-    for (int base = p0; base < p1; base += 32) {  // pass C: normalise
+#pragma unroll 4
+    for (int base = p0; base < p1; base += G) {  // pass C: normalise
       const int p = base + lane;
       if (p < p1) {
 #pragma unroll
@@ -106,7 +115,7 @@ __global__ void __launch_bounds__(kThreads) gat_fwd_kernel(const int* __restrict
       }
     }
   } else {
-  for (int h = lane; h < H; h += 32) {
+  for (int h = lane; live && h < H; h += G) {
     const float ad = a_d[row * H + h];
     float mx = -INFINITY;
     int p = p0;
@@ -141,43 +150,77 @@ __global__ void __launch_bounds__(kThreads) gat_fwd_kernel(const int* __restrict
   }
   }
   __syncwarp();
-  if (concat) {
-    for (int f = lane; f < F; f += 32) {
+  // Aggregation.  A hub row is hundreds of entries long and its lanes walk it alone, so the row's time is
+  // (entries / batch) dependent round trips: eight entries in flight per batch, and -- when every lane can own four
+  // contiguous features of one head (F = 4 G, C % 4 == 0: the 4 x 8 hidden layer) -- one 16-byte gather and one
+  // alpha per entry instead of four scalar walks over the row.  Products are rounded, adds sequential in stored
+  // order (the oracle's scatter order) in every variant.
+  constexpr int kB = 8;
+  if (concat && F == 4 * G && (C & 3) == 0) {
+    const int f0 = 4 * lane, h = f0 / C;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = p0; p < p1; p += kB) {
+      float a[kB];
+      float4 x[kB];
+#pragma unroll
+      for (int b = 0; b < kB; ++b) {
+        const bool ok = p + b < p1;
+        a[b] = ok ? alpha[(int64_t)(p + b) * H + h] : 0.f;
+        x[b] = ok ? __ldg(reinterpret_cast<const float4*>(xs + (int64_t)__ldg(src + p + b) * F + f0))
+                  : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int b = 0; b < kB; ++b) {
+        if (p + b < p1) {
+          acc.x = __fadd_rn(acc.x, __fmul_rn(a[b], x[b].x));
+          acc.y = __fadd_rn(acc.y, __fmul_rn(a[b], x[b].y));
+          acc.z = __fadd_rn(acc.z, __fmul_rn(a[b], x[b].z));
+          acc.w = __fadd_rn(acc.w, __fmul_rn(a[b], x[b].w));
+        }
+      }
+    }
+    if (live) {
+      float* o = out + row * F + f0;
+      o[0] = acc.x + (bias ? bias[f0] : 0.f);
+      o[1] = acc.y + (bias ? bias[f0 + 1] : 0.f);
+      o[2] = acc.z + (bias ? bias[f0 + 2] : 0.f);
+      o[3] = acc.w + (bias ? bias[f0 + 3] : 0.f);
+    }
+  } else if (concat) {
+    for (int f = lane; live && f < F; f += G) {
       const int h = f / C;
       float acc = 0.f;
-      int p = p0;
-      for (; p + 4 <= p1; p += 4) {
-        float a[4], x[4];
+      for (int p = p0; p < p1; p += kB) {
+        float a[kB], x[kB];
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          a[b] = alpha[(int64_t)(p + b) * H + h];
-          x[b] = __ldg(xs + (int64_t)__ldg(src + p + b) * F + f);
+        for (int b = 0; b < kB; ++b) {
+          const bool ok = p + b < p1;
+          a[b] = ok ? alpha[(int64_t)(p + b) * H + h] : 0.f;
+          x[b] = ok ? __ldg(xs + (int64_t)__ldg(src + p + b) * F + f) : 0.f;
         }
 #pragma unroll
-        for (int b = 0; b < 4; ++b) acc = __fadd_rn(acc, __fmul_rn(a[b], x[b]));
+        for (int b = 0; b < kB; ++b)
+          if (p + b < p1) acc = __fadd_rn(acc, __fmul_rn(a[b], x[b]));
       }
-      for (; p < p1; ++p)
-        acc = __fadd_rn(acc, __fmul_rn(alpha[(int64_t)p * H + h], __ldg(xs + (int64_t)__ldg(src + p) * F + f)));
       out[row * F + f] = acc + (bias ? bias[f] : 0.f);
     }
   } else {
-    for (int c = lane; c < C; c += 32) {
+    for (int c = lane; live && c < C; c += G) {
       float tot = 0.f;
       for (int h = 0; h < H; ++h) {
         float acc = 0.f;
-        int p = p0;
-        for (; p + 4 <= p1; p += 4) {
-          float a[4], x[4];
+        for (int p = p0; p < p1; p += kB) {
+          float a[kB], x[kB];
 #pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            a[b] = alpha[(int64_t)(p + b) * H + h];
-            x[b] = __ldg(xs + (int64_t)__ldg(src + p + b) * F + h * C + c);
+          for (int b = 0; b < kB; ++b) {
+            const bool ok = p + b < p1;
+            a[b] = ok ? alpha[(int64_t)(p + b) * H + h] : 0.f;
+            x[b] = ok ? __ldg(xs + (int64_t)__ldg(src + p + b) * F + h * C + c) : 0.f;
           }
 #pragma unroll
-          for (int b = 0; b < 4; ++b) acc = __fadd_rn(acc, __fmul_rn(a[b], x[b]));
+          for (int b = 0; b < kB; ++b)
+            if (p + b < p1) acc = __fadd_rn(acc, __fmul_rn(a[b], x[b]));
         }
-        for (; p < p1; ++p)
-          acc = __fadd_rn(acc, __fmul_rn(alpha[(int64_t)p * H + h], __ldg(xs + (int64_t)__ldg(src + p) * F + h * C + c)));
         tot = __fadd_rn(tot, acc);
       }
       out[row * C + c] = __fdiv_rn(tot, (float)H) + (bias ? bias[c] : 0.f);
@@ -255,23 +298,26 @@ __global__ void __launch_bounds__(kThreads) gat_bwd_dst_kernel(
   da_d[t] = acc;
 }
 
-// source pass: warp per source row over the CSC view
+// source pass: G lanes per source row over the CSC view
+template <int G>
 __global__ void __launch_bounds__(kThreads) gat_bwd_src_kernel(
     const int* __restrict__ ptr, const int* __restrict__ dst, const int* __restrict__ pos,
     const float* __restrict__ alpha, const float* __restrict__ dpre, const float* __restrict__ dout,
     const float* __restrict__ da_d, const float* __restrict__ att_src, const float* __restrict__ att_dst, int H,
     int C, int concat, float* __restrict__ dxs, float* da_s, int64_t n_rows) {
-  const int lane = threadIdx.x & 31;
-  const int64_t row = ((int64_t)blockIdx.x * kThreads + threadIdx.x) >> 5;
-  if (row >= n_rows) return;
-  const int q0 = ptr[row], q1 = ptr[row + 1];
+  const int lane = threadIdx.x % G;
+  int64_t row = ((int64_t)blockIdx.x * kThreads + threadIdx.x) / G;
+  const bool live = row < n_rows;
+  if (!live) row = 0;
+  const int q0 = live ? ptr[row] : 0, q1 = live ? ptr[row + 1] : 0;
   const int F = H * C;
   constexpr int kHMax = 8;
   float das[kHMax];
 #pragma unroll
   for (int h = 0; h < kHMax; ++h) das[h] = 0.f;
   if (H <= kHMax) {  // one lane per entry, warp-reduced: no serial walk over the row
-    for (int base = q0; base < q1; base += 32) {
+#pragma unroll 4
+    for (int base = q0; base < q1; base += G) {
       const int q = base + lane;
       if (q < q1) {
         const int64_t pq = __ldg(pos + q);
@@ -284,11 +330,11 @@ __global__ void __launch_bounds__(kThreads) gat_bwd_src_kernel(
     for (int h = 0; h < kHMax; ++h)
       if (h < H) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) das[h] += __shfl_xor_sync(0xffffffffu, das[h], o);
-        if (lane == h) da_s[row * H + h] = das[h];
+        for (int o = G / 2; o > 0; o >>= 1) das[h] += __shfl_xor_sync(0xffffffffu, das[h], o);
+        if (lane == h % G && live) da_s[row * H + h] = das[h];
       }
   } else {
-    for (int h = lane; h < H; h += 32) {
+    for (int h = lane; live && h < H; h += G) {
       float acc = 0.f;
       for (int q = q0; q < q1; ++q) acc += __ldg(dpre + (int64_t)__ldg(pos + q) * H + h);
       da_s[row * H + h] = acc;
@@ -296,24 +342,64 @@ __global__ void __launch_bounds__(kThreads) gat_bwd_src_kernel(
   }
   __syncwarp();
   const float dscale = concat ? 1.f : 1.f / (float)H;
-  for (int f = lane; f < F; f += 32) {
-    const int h = f / C, c = f - h * C;
-    float acc = 0.f;
-    int q = q0;
-    for (; q + 4 <= q1; q += 4) {
-      float d[4], a[4];
+  constexpr int kB = 8;  // entries in flight per batch (a hub row is walked by its lanes alone)
+  if (concat && F == 4 * G && (C & 3) == 0) {  // four contiguous features of one head per lane: 16-byte gathers
+    const int f0 = 4 * lane, h = f0 / C;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = q0; q < q1; q += kB) {
+      float a[kB];
+      float4 d[kB];
 #pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const int64_t dq = __ldg(dst + q + b);
-        d[b] = concat ? __ldg(dout + dq * F + f) : __ldg(dout + dq * C + c) * dscale;
-        a[b] = __ldg(alpha + (int64_t)__ldg(pos + q + b) * H + h);
+      for (int b = 0; b < kB; ++b) {
+        const bool ok = q + b < q1;
+        a[b] = ok ? __ldg(alpha + (int64_t)__ldg(pos + q + b) * H + h) : 0.f;
+        d[b] = ok ? __ldg(reinterpret_cast<const float4*>(dout + (int64_t)__ldg(dst + q + b) * F + f0))
+                  : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
-      for (int b = 0; b < 4; ++b) acc = fmaf(a[b], d[b], acc);
+      for (int b = 0; b < kB; ++b) {
+        if (q + b < q1) {
+          acc.x = fmaf(a[b], d[b].x, acc.x);
+          acc.y = fmaf(a[b], d[b].y, acc.y);
+          acc.z = fmaf(a[b], d[b].z, acc.z);
+          acc.w = fmaf(a[b], d[b].w, acc.w);
+        }
+      }
     }
-    for (; q < q1; ++q) {
-      const float d = concat ? dout[(int64_t)dst[q] * F + f] : dout[(int64_t)dst[q] * C + c] * dscale;
-      acc = fmaf(alpha[(int64_t)pos[q] * H + h], d, acc);
+    if (live) {
+      float das_h = 0.f;
+      if (H <= kHMax) {
+#pragma unroll
+        for (int k = 0; k < kHMax; ++k) das_h = k == h ? das[k] : das_h;
+      } else {
+        das_h = da_s[row * H + h];
+      }
+      const float dad = da_d[row * H + h];
+      float r[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        r[i] = fmaf(das_h, att_src[f0 + i], r[i]);
+        r[i] = fmaf(dad, att_dst[f0 + i], r[i]);
+        dxs[row * F + f0 + i] = r[i];
+      }
+    }
+    return;
+  }
+  for (int f = lane; live && f < F; f += G) {
+    const int h = f / C, c = f - h * C;
+    float acc = 0.f;
+    for (int q = q0; q < q1; q += kB) {
+      float d[kB], a[kB];
+#pragma unroll
+      for (int b = 0; b < kB; ++b) {
+        const bool ok = q + b < q1;
+        const int64_t dq = ok ? __ldg(dst + q + b) : 0;
+        d[b] = !ok ? 0.f : concat ? __ldg(dout + dq * F + f) : __ldg(dout + dq * C + c) * dscale;
+        a[b] = ok ? __ldg(alpha + (int64_t)__ldg(pos + q + b) * H + h) : 0.f;
+      }
+#pragma unroll
+      for (int b = 0; b < kB; ++b)
+        if (q + b < q1) acc = fmaf(a[b], d[b], acc);
     }
     float das_h = 0.f;
     if (H <= kHMax) {
@@ -350,7 +436,7 @@ extern "C" int egnn_gat_fwd(const int32_t* csr_ptr, const int32_t* csr_src, cons
   const char* fn = "egnn_gat_fwd";
   EGNN_REQUIRE(csr_ptr && csr_src && xs && a_s && a_d && alpha && out && H > 0 && C > 0, fn, "bad arguments");
   if (n_rows == 0) return 0;
-  gat_fwd_kernel<<<(unsigned)ceil_div(n_rows * 32, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+  gat_fwd_kernel<kGatLanes><<<(unsigned)ceil_div(n_rows * kGatLanes, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
       csr_ptr, csr_src, xs, a_s, a_d, negative_slope, H, C, concat, bias, alpha, out, n_rows);
   EGNN_LAUNCH_CHECK(fn);
   return 0;
@@ -378,7 +464,7 @@ extern "C" int egnn_gat_bwd_src(const int32_t* csc_ptr, const int32_t* csc_dst, 
                    da_s,
                fn, "null pointer");
   if (n_rows == 0) return 0;
-  gat_bwd_src_kernel<<<(unsigned)ceil_div(n_rows * 32, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+  gat_bwd_src_kernel<kGatLanes><<<(unsigned)ceil_div(n_rows * kGatLanes, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
       csc_ptr, csc_dst, csc_pos, alpha, dpre, dout, da_d, att_src, att_dst, H, C, concat, dxs, da_s, n_rows);
   EGNN_LAUNCH_CHECK(fn);
   return 0;
