@@ -210,6 +210,39 @@ class ShardedContext:
                 self.stats_reducer = P2PStatsReducer(shard.n_global, group, ar)
                 self.p2p = True
 
+    # ---- epoch tail over all shards -------------------------------------------------
+    def gather_rows(self, t: torch.Tensor, fill=0) -> torch.Tensor:
+        """Concatenation over the ranks of a per-row tensor `[n_local, ...]`, every rank's block padded with `fill`
+        to the largest shard (shards are whole timesteps, so their sizes differ): `[world * n_max, ...]`, identical
+        on every rank.  One all_gather; no host synchronisation."""
+        if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
+            return t
+        world = dist.get_world_size(self.group)
+        if not hasattr(self, "_n_max"):
+            sizes = torch.zeros(world, dtype=torch.int64, device=t.device)
+            sizes[dist.get_rank(self.group)] = t.size(0)
+            dist.all_reduce(sizes, group=self.group)
+            self._n_max = int(sizes.max().item())          # once per run
+        pad = torch.full((self._n_max,) + tuple(t.shape[1:]), fill, dtype=t.dtype, device=t.device)
+        pad[: t.size(0)] = t
+        out = torch.empty((world * self._n_max,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather(list(out.chunk(world)), pad, group=self.group)   # views of `out`: gloo and nccl alike
+        return out
+
+    def average_precision(self, y: torch.Tensor, mask: torch.Tensor, logits: torch.Tensor) -> torch.Tensor:
+        """GLOBAL validation PR-AUC (`pr_auc_illicit` over the whole graph's mask): every rank scores its own rows
+        (`egnn_average_precision` with `scores_out`), the per-row scores / labels / masks are all-gathered (padding
+        rows masked out) and the same device kernel ranks the union on every rank -> float64[4], identical
+        everywhere.  With one rank this is `metrics.average_precision`."""
+        from . import metrics
+        if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
+            return metrics.average_precision(y, mask, logits=logits)
+        scores = torch.empty(y.numel(), dtype=torch.float32, device=y.device)
+        metrics.average_precision(y, mask, logits=logits, scores_out=scores)
+        m8 = mask.to(torch.uint8)
+        return metrics.average_precision(self.gather_rows(y, -1), self.gather_rows(m8, 0),
+                                         scores=self.gather_rows(scores, 0.0))
+
     def attach(self, model):
         model.stats_reducer = self.stats_reducer
         model.row0 = self.shard.row0

@@ -57,9 +57,15 @@ def _worker(rank, world, port, out_path):
     ctx.reduce_grads(flat)
     lsum = loss.detach().clone()
     dist.all_reduce(lsum)
+    # --- epoch tail over all shards: per-row scores / labels / masks gathered with padding (ShardedContext.gather_rows)
+    score = torch.softmax(logits.detach(), 1)[:, 1].contiguous()
+    g_score = ctx.gather_rows(score, 0.0)
+    g_y = ctx.gather_rows(lg.y, -1)
+    g_mask = ctx.gather_rows(lg.val_mask.to(torch.uint8), 0)
     if rank == 0:
         torch.save({"row0": sh.row0, "n_local": sh.n_local, "n_train_total": ctx.n_train_total,
-                    "cw": ctx.class_weight, "stats": st, "grad": flat, "loss": lsum}, out_path)
+                    "cw": ctx.class_weight, "stats": st, "grad": flat, "loss": lsum,
+                    "g_score": g_score, "g_y": g_y, "g_mask": g_mask}, out_path)
     bounds = torch.tensor([sh.row0, sh.row0 + sh.n_local])
     got = [torch.zeros(2, dtype=torch.int64) for _ in range(world)]
     dist.all_gather(got, bounds)
@@ -99,6 +105,15 @@ def test_two_rank_shards_reproduce_the_single_process_step(tmp_path):
     flat = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
     assert abs(float(r["loss"]) - float(loss)) <= 1e-6 * abs(float(loss))
     assert (r["grad"] - flat).abs().max() <= 1e-5 * flat.abs().max()
+    # the gathered (padded, masked) rows carry exactly the whole graph's validation set: same PR-AUC as one process
+    from oracle import metrics_np as M
+    with torch.no_grad():
+        full_score = torch.softmax(model(gr.x, ei, None), 1)[:, 1].numpy()
+    vm = gr.val_mask.numpy()
+    want = M.average_precision((gr.y.numpy()[vm] == 1).astype(int), full_score[vm])
+    gm = r["g_mask"].numpy().astype(bool)
+    got = M.average_precision((r["g_y"].numpy()[gm] == 1).astype(int), r["g_score"].numpy()[gm])
+    assert got[1:] == want[1:] and abs(got[0] - want[0]) <= 1e-6
 
 
 @pytest.mark.parametrize("world", [1, 2, 3, 8])
