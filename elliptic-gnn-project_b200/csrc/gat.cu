@@ -35,6 +35,218 @@ __global__ void __launch_bounds__(kThreads) gat_scores_kernel(const float* __res
 
 __device__ __forceinline__ float leaky(float v, float slope) { return v > 0.f ? v : v * slope; }
 
+constexpr int kGatLongRow = 64;  // rows with more entries are processed by their whole warp (entry-parallel)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// One hub row, all 32 lanes of the warp (H <= 8).  Softmax sweeps take 32 entries at a time; the aggregation splits
+// the ENTRIES over the lanes (4 entry slots x 8 feature lanes with 16-byte gathers for the 4 x 8 layer, 32 entry
+// slots per feature otherwise) and combines the partial sums with shuffles, so a 481-entry row costs ~15 dependent
+// round trips instead of ~180.  The summation order differs from the short-row path; results agree to rounding.
+__device__ void gat_fwd_long_row(int64_t row, int p0, int p1, const int* __restrict__ src, const float* __restrict__ xs,
+                                 const float* __restrict__ a_s, const float* __restrict__ a_d, float slope, int H, int C,
+                                 int concat, const float* __restrict__ bias, float* alpha, float* __restrict__ out) {
+  constexpr int kHMax = 8;
+  const int wl = threadIdx.x & 31, F = H * C;
+  float ad[kHMax], mx[kHMax], den[kHMax];
+#pragma unroll
+  for (int h = 0; h < kHMax; ++h) {
+    ad[h] = h < H ? __ldg(a_d + row * H + h) : 0.f;
+    mx[h] = -INFINITY;
+    den[h] = 0.f;
+  }
+#pragma unroll 4
+  for (int base = p0; base < p1; base += 32) {
+    const int p = base + wl;
+    const bool valid = p < p1;
+    const int64_t sj = valid ? __ldg(src + p) : 0;
+#pragma unroll
+    for (int h = 0; h < kHMax; ++h)
+      if (h < H && valid) mx[h] = fmaxf(mx[h], leaky(__ldg(a_s + sj * H + h) + ad[h], slope));
+  }
+#pragma unroll
+  for (int h = 0; h < kHMax; ++h)
+    if (h < H)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], o));
+#pragma unroll 4
+  for (int base = p0; base < p1; base += 32) {
+    const int p = base + wl;
+    const bool valid = p < p1;
+    const int64_t sj = valid ? __ldg(src + p) : 0;
+#pragma unroll
+    for (int h = 0; h < kHMax; ++h)
+      if (h < H && valid) {
+        const float ex = expf(leaky(__ldg(a_s + sj * H + h) + ad[h], slope) - mx[h]);
+        den[h] += ex;
+        alpha[(int64_t)p * H + h] = ex;
+      }
+  }
+#pragma unroll
+  for (int h = 0; h < kHMax; ++h)
+    if (h < H) den[h] = warp_sum(den[h]) + 1e-16f;
+#pragma unroll 4
+  for (int base = p0; base < p1; base += 32) {
+    const int p = base + wl;
+    if (p < p1) {
+#pragma unroll
+      for (int h = 0; h < kHMax; ++h)
+        if (h < H) alpha[(int64_t)p * H + h] = __fdiv_rn(alpha[(int64_t)p * H + h], den[h]);
+    }
+  }
+  __syncwarp();
+  constexpr int kB = 8;
+  if (concat && F == 32 && (C & 3) == 0) {
+    const int fl = wl & 7, es = wl >> 3, f0 = 4 * fl, h = f0 / C;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = p0 + es; p < p1; p += 4 * kB) {
+      float a[kB];
+      float4 x[kB];
+#pragma unroll
+      for (int b = 0; b < kB; ++b) {
+        const int pp = p + 4 * b;
+        const bool ok = pp < p1;
+        a[b] = ok ? alpha[(int64_t)pp * H + h] : 0.f;
+        x[b] = ok ? __ldg(reinterpret_cast<const float4*>(xs + (int64_t)__ldg(src + pp) * F + f0))
+                  : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int b = 0; b < kB; ++b) {
+        acc.x = __fadd_rn(acc.x, __fmul_rn(a[b], x[b].x));
+        acc.y = __fadd_rn(acc.y, __fmul_rn(a[b], x[b].y));
+        acc.z = __fadd_rn(acc.z, __fmul_rn(a[b], x[b].z));
+        acc.w = __fadd_rn(acc.w, __fmul_rn(a[b], x[b].w));
+      }
+    }
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+      acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+      acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+      acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+    }
+    if (es == 0) {
+      float* o = out + row * F + f0;
+      o[0] = acc.x + (bias ? bias[f0] : 0.f);
+      o[1] = acc.y + (bias ? bias[f0 + 1] : 0.f);
+      o[2] = acc.z + (bias ? bias[f0 + 2] : 0.f);
+      o[3] = acc.w + (bias ? bias[f0 + 3] : 0.f);
+    }
+  } else {
+    const int n_out = concat ? F : C;
+    for (int oc = 0; oc < n_out; ++oc) {
+      const int h_lo = concat ? oc / C : 0, h_hi = concat ? h_lo + 1 : H;
+      float tot = 0.f;
+      for (int h = h_lo; h < h_hi; ++h) {
+        const int f = concat ? oc : h * C + oc;
+        float part = 0.f;
+#pragma unroll 4
+        for (int p = p0 + wl; p < p1; p += 32)
+          part = __fadd_rn(part, __fmul_rn(alpha[(int64_t)p * H + h], __ldg(xs + (int64_t)__ldg(src + p) * F + f)));
+        tot = __fadd_rn(tot, warp_sum(part));
+      }
+      if (wl == 0) out[row * n_out + oc] = (concat ? tot : __fdiv_rn(tot, (float)H)) + (bias ? bias[oc] : 0.f);
+    }
+  }
+}
+
+__device__ void gat_bwd_src_long_row(int64_t row, int q0, int q1, const int* __restrict__ dst, const int* __restrict__ pos,
+                                     const float* __restrict__ alpha, const float* __restrict__ dpre,
+                                     const float* __restrict__ dout, const float* __restrict__ da_d,
+                                     const float* __restrict__ att_src, const float* __restrict__ att_dst, int H, int C,
+                                     int concat, float* __restrict__ dxs, float* da_s) {
+  constexpr int kHMax = 8;
+  const int wl = threadIdx.x & 31, F = H * C;
+  float das[kHMax];
+#pragma unroll
+  for (int h = 0; h < kHMax; ++h) das[h] = 0.f;
+#pragma unroll 4
+  for (int base = q0; base < q1; base += 32) {
+    const int q = base + wl;
+    if (q < q1) {
+      const int64_t pq = __ldg(pos + q);
+#pragma unroll
+      for (int h = 0; h < kHMax; ++h)
+        if (h < H) das[h] += __ldg(dpre + pq * H + h);
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < kHMax; ++h)
+    if (h < H) {
+      das[h] = warp_sum(das[h]);
+      if (wl == h) da_s[row * H + h] = das[h];
+    }
+  const float dscale = concat ? 1.f : 1.f / (float)H;
+  constexpr int kB = 8;
+  if (concat && F == 32 && (C & 3) == 0) {
+    const int fl = wl & 7, es = wl >> 3, f0 = 4 * fl, h = f0 / C;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = q0 + es; q < q1; q += 4 * kB) {
+      float a[kB];
+      float4 d[kB];
+#pragma unroll
+      for (int b = 0; b < kB; ++b) {
+        const int qq = q + 4 * b;
+        const bool ok = qq < q1;
+        a[b] = ok ? __ldg(alpha + (int64_t)__ldg(pos + qq) * H + h) : 0.f;
+        d[b] = ok ? __ldg(reinterpret_cast<const float4*>(dout + (int64_t)__ldg(dst + qq) * F + f0))
+                  : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int b = 0; b < kB; ++b) {
+        acc.x = fmaf(a[b], d[b].x, acc.x);
+        acc.y = fmaf(a[b], d[b].y, acc.y);
+        acc.z = fmaf(a[b], d[b].z, acc.z);
+        acc.w = fmaf(a[b], d[b].w, acc.w);
+      }
+    }
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+      acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+      acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+      acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+    }
+    if (es == 0) {
+      float das_h = 0.f;
+#pragma unroll
+      for (int k = 0; k < kHMax; ++k) das_h = k == h ? das[k] : das_h;
+      const float dad = da_d[row * H + h];
+      float r[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        r[i] = fmaf(das_h, att_src[f0 + i], r[i]);
+        r[i] = fmaf(dad, att_dst[f0 + i], r[i]);
+        dxs[row * F + f0 + i] = r[i];
+      }
+    }
+  } else {
+    for (int f = 0; f < F; ++f) {
+      const int h = f / C, c = f - h * C;
+      float part = 0.f;
+#pragma unroll 4
+      for (int q = q0 + wl; q < q1; q += 32) {
+        const int64_t dq = __ldg(dst + q);
+        const float d = concat ? __ldg(dout + dq * F + f) : __ldg(dout + dq * C + c) * dscale;
+        part = fmaf(__ldg(alpha + (int64_t)__ldg(pos + q) * H + h), d, part);
+      }
+      part = warp_sum(part);
+      if (wl == 0) {
+        float das_h = 0.f;
+#pragma unroll
+        for (int k = 0; k < kHMax; ++k) das_h = k == h ? das[k] : das_h;
+        float acc = fmaf(das_h, att_src[f], part);
+        acc = fmaf(da_d[row * H + h], att_dst[f], acc);
+        dxs[row * F + f] = acc;
+      }
+    }
+  }
+}
+
 template <int G>
 __global__ void __launch_bounds__(kThreads) gat_fwd_kernel(const int* __restrict__ ptr, const int* __restrict__ src,
                                                            const float* __restrict__ xs,
@@ -48,9 +260,18 @@ __global__ void __launch_bounds__(kThreads) gat_fwd_kernel(const int* __restrict
   // each.  Rows past the end keep their lanes in the warp-wide shuffles with an empty range.
   const int lane = threadIdx.x % G;
   int64_t row = ((int64_t)blockIdx.x * kThreads + threadIdx.x) / G;
-  const bool live = row < n_rows;
-  if (!live) row = 0;
-  const int p0 = live ? ptr[row] : 0, p1 = live ? ptr[row + 1] : 0;
+  const bool in_range = row < n_rows;
+  if (!in_range) row = 0;
+  int p0 = in_range ? ptr[row] : 0, p1 = in_range ? ptr[row + 1] : 0;
+  // hub rows: the whole warp takes them one after the other, then the groups go on with their short rows
+  const bool is_long = G < 32 && H <= 8 && in_range && p1 - p0 > kGatLongRow;
+  for (unsigned lm = __ballot_sync(0xffffffffu, is_long && lane == 0); lm; lm &= lm - 1) {
+    const int sl = __ffs(lm) - 1;
+    gat_fwd_long_row(__shfl_sync(0xffffffffu, row, sl), __shfl_sync(0xffffffffu, p0, sl),
+                     __shfl_sync(0xffffffffu, p1, sl), src, xs, a_s, a_d, slope, H, C, concat, bias, alpha, out);
+  }
+  const bool live = in_range && !is_long;
+  if (!live) p0 = p1 = 0;
   const int F = H * C;
   // segment softmax with ONE LANE PER ENTRY (32 entries per sweep; the usual row is one sweep): all score
   // gathers of a row are issued together, max / sum are warp reductions, nothing walks the row serially
@@ -307,9 +528,18 @@ __global__ void __launch_bounds__(kThreads) gat_bwd_src_kernel(
     int C, int concat, float* __restrict__ dxs, float* da_s, int64_t n_rows) {
   const int lane = threadIdx.x % G;
   int64_t row = ((int64_t)blockIdx.x * kThreads + threadIdx.x) / G;
-  const bool live = row < n_rows;
-  if (!live) row = 0;
-  const int q0 = live ? ptr[row] : 0, q1 = live ? ptr[row + 1] : 0;
+  const bool in_range = row < n_rows;
+  if (!in_range) row = 0;
+  int q0 = in_range ? ptr[row] : 0, q1 = in_range ? ptr[row + 1] : 0;
+  const bool is_long = G < 32 && H <= 8 && in_range && q1 - q0 > kGatLongRow;
+  for (unsigned lm = __ballot_sync(0xffffffffu, is_long && lane == 0); lm; lm &= lm - 1) {
+    const int sl = __ffs(lm) - 1;
+    gat_bwd_src_long_row(__shfl_sync(0xffffffffu, row, sl), __shfl_sync(0xffffffffu, q0, sl),
+                         __shfl_sync(0xffffffffu, q1, sl), dst, pos, alpha, dpre, dout, da_d, att_src, att_dst, H, C,
+                         concat, dxs, da_s);
+  }
+  const bool live = in_range && !is_long;
+  if (!live) q0 = q1 = 0;
   const int F = H * C;
   constexpr int kHMax = 8;
   float das[kHMax];
