@@ -37,6 +37,7 @@ SIGNATURES = {
     "egnn_ap_workspace_bytes": (_sz, [_i64]),
     "egnn_average_precision": (_i32, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "egnn_early_stop_update": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp]),
+    "egnn_snapshot_if_improved": (_i32, [_vp, _vp, _vp, _i64, _vp]),
     "egnn_spmm_partition_tasks": (_i64, [_i64, _i64]),
     "egnn_spmm_partition": (_i32, [_vp, _i64, _vp, _i64, _vp]),
     "egnn_gemm_workspace_floats": (_sz, [_i64, _i64, _i64, _i32]),

@@ -182,6 +182,14 @@ __global__ void __launch_bounds__(kThreads) snapshot_kernel(const float4* __rest
   if (blockIdx.x == 0 && threadIdx.x < tail) dst_tail[threadIdx.x] = src_tail[threadIdx.x];
 }
 
+__global__ void __launch_bounds__(kThreads) snapshot_words_kernel(const uint32_t* __restrict__ src,
+                                                                  uint32_t* __restrict__ dst, int64_t n_words,
+                                                                  const double* __restrict__ state) {
+  if (state[4] == 0.0) return;
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n_words; i += stride) dst[i] = src[i];
+}
+
 }  // namespace
 }  // namespace egnn
 
@@ -251,5 +259,19 @@ extern "C" int egnn_early_stop_update(const double* ap, double* state, const flo
                                                            best_params + 4 * n4, tail, state);
     EGNN_LAUNCH_CHECK("snapshot_kernel");
   }
+  return 0;
+}
+
+extern "C" int egnn_snapshot_if_improved(const double* state, const void* src, void* dst, int64_t n_bytes, void* stream) {
+  const char* fn = "egnn_snapshot_if_improved";
+  EGNN_REQUIRE(state && src && dst && n_bytes >= 0, fn, "bad arguments");
+  EGNN_REQUIRE(n_bytes % 4 == 0 && (uintptr_t)src % 4 == 0 && (uintptr_t)dst % 4 == 0, fn, "4-byte aligned buffers only");
+  if (n_bytes == 0) return 0;
+  const int64_t n_words = n_bytes / 4;
+  int64_t blocks = ceil_div(n_words, kThreads);
+  if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
+  snapshot_words_kernel<<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint32_t*>(src), reinterpret_cast<uint32_t*>(dst), n_words, state);
+  EGNN_LAUNCH_CHECK(fn);
   return 0;
 }

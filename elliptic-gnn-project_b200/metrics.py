@@ -58,17 +58,27 @@ class EarlyStopper:
     parameter buffer (`train.FlatClipAdam.flat_param`) into `best_param`; nothing is read back.  `should_stop()`
     is the one host synchronisation (`bad >= patience`)."""
 
-    def __init__(self, patience: int = 20, flat_param: Optional[torch.Tensor] = None, device=None):
+    def __init__(self, patience: int = 20, flat_param: Optional[torch.Tensor] = None, device=None, extra=()):
+        """`extra`: further tensors of the state dict to snapshot with the parameters (BatchNorm running_mean /
+        running_var / num_batches_tracked live outside the flat parameter buffer)."""
         dev = flat_param.device if flat_param is not None else torch.device(device or "cuda")
         self.patience = int(patience)
         self.state = torch.tensor([-1.0, 0.0, 0.0, 0.0, 0.0], dtype=torch.float64, device=dev)
         self.flat_param = flat_param
         self.best_param = torch.empty_like(flat_param) if flat_param is not None else None
+        self.extra = [t for t in extra if t.numel() > 0]
+        for t in self.extra:
+            if not t.is_contiguous() or (t.numel() * t.element_size()) % 4:
+                raise ValueError("extra tensors must be contiguous with a 4-byte multiple size")
+        self.best_extra = [torch.empty_like(t) for t in self.extra]
 
     def update(self, ap: torch.Tensor) -> None:
         n = int(self.flat_param.numel()) if self.flat_param is not None else 0
-        check(lib().egnn_early_stop_update(ptr(ap), ptr(self.state), ptr(self.flat_param), ptr(self.best_param), n,
-                                           stream()))
+        L = lib()
+        check(L.egnn_early_stop_update(ptr(ap), ptr(self.state), ptr(self.flat_param), ptr(self.best_param), n,
+                                       stream()))
+        for t, b in zip(self.extra, self.best_extra):
+            check(L.egnn_snapshot_if_improved(ptr(self.state), ptr(t), ptr(b), t.numel() * t.element_size(), stream()))
 
     def should_stop(self) -> bool:
         return float(self.state[1].item()) >= self.patience
@@ -79,8 +89,11 @@ class EarlyStopper:
 
     def restore_best(self) -> None:
         """`model.load_state_dict(best_state)` (`src/train_gnn.py:416-417`) for the flat parameter buffer."""
-        if self.flat_param is not None and float(self.state[2].item()) > 0:
-            self.flat_param.copy_(self.best_param)
+        if float(self.state[2].item()) > 0:
+            if self.flat_param is not None:
+                self.flat_param.copy_(self.best_param)
+            for t, b in zip(self.extra, self.best_extra):
+                t.copy_(b)
 
 
 @torch.no_grad()
@@ -91,3 +104,38 @@ def eval_pr_auc(model, x, edge_index, timestep, y, mask, out: Optional[torch.Ten
     model.eval()
     logits = model(x, edge_index, timestep if model_uses_time_embed(model) else None)
     return average_precision(y, mask, logits=logits.float().contiguous(), out=out)
+
+
+def fit(model, x, edge_index, timestep, y, train_mask, val_mask, *, lr: float, weight_decay: float,
+        grad_clip: float = 1.0, amp: bool = False, max_epochs: int = 200, patience: int = 20, poll_every: int = 10,
+        capture: bool = True, log=None) -> dict:
+    """The reference's full-batch training loop (`/root/reference/src/train_gnn.py:375-417`) with the epoch tail on
+    the device: per epoch one (captured) train step, one fp32 eval forward, the validation PR-AUC and the
+    early-stopping update -- no host synchronisation.  The host looks at the device state every `poll_every`
+    epochs (`if bad >= patience: break`, `:411`); because the best parameters are snapshotted on the device at the
+    epoch they occur, the restored model is the reference's `best_state` even when the loop overshoots the stopping
+    epoch by up to `poll_every - 1` steps.  Returns {best_val, best_epoch, epochs, loss}."""
+    from .train import TrainStep
+    step = TrainStep(model, x, edge_index, timestep, y, train_mask, lr=lr, weight_decay=weight_decay,
+                     grad_clip=grad_clip, amp=amp)
+    step.run()
+    if capture:
+        step.capture(warmup=1)
+    buffers = [b for b in model.buffers() if b.is_cuda and b.numel() > 0]
+    stopper = EarlyStopper(patience=patience, flat_param=step.opt.flat_param, extra=buffers)
+    ap = torch.empty(4, dtype=torch.float64, device=x.device)
+    epochs = 0
+    for epoch in range(1, max_epochs + 1):
+        loss = step.run()
+        eval_pr_auc(model, x, edge_index, timestep, y, val_mask, out=ap)
+        stopper.update(ap)
+        epochs = epoch
+        if epoch % poll_every == 0 or epoch == max_epochs:
+            st = stopper.state.tolist()                     # the one host synchronisation per `poll_every` epochs
+            if log is not None:
+                log(epoch, float(loss), float(ap[0]), st[0])
+            if st[1] >= patience:
+                break
+    st = stopper.state.tolist()
+    stopper.restore_best()
+    return {"best_val": st[0], "best_epoch": int(st[2]), "epochs": epochs, "loss": float(step.loss)}

@@ -349,6 +349,10 @@ int egnn_average_precision(const float* logits, int64_t ld_logits, const float* 
  * 16-byte aligned, may be NULL together). */
 int egnn_early_stop_update(const double* ap, double* state, const float* params, float* best_params,
                            int64_t n_params, void* stream);
+/* The rest of `best_state` (BatchNorm running statistics and counters, any tensor outside the flat parameter
+ * buffer): dst <- src when the LAST egnn_early_stop_update improved the best value (state[4] != 0).  Buffers are
+ * 4-byte aligned, n_bytes a multiple of 4. */
+int egnn_snapshot_if_improved(const double* state, const void* src, void* dst, int64_t n_bytes, void* stream);
 
 #ifdef __cplusplus
 }

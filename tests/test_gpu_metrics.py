@@ -84,3 +84,48 @@ def test_early_stopper_matches_reference_bookkeeping(egnn):
     assert es.should_stop() and es.best == 0.31
     es.restore_best()
     assert torch.equal(flat, snap)
+
+
+def test_fit_loop_matches_host_side_early_stopping(egnn):
+    """metrics.fit (device-side epoch tail, polled every 4 epochs) against the reference's loop shape
+    (src/train_gnn.py:380-417) run on the host with the oracle metric: same best epoch, same best value to 1e-9,
+    and the restored parameters / BatchNorm buffers are the ones of the best epoch."""
+    from egnn_b200 import metrics, synthetic
+    from egnn_b200.train import TrainStep, eval_probs
+    cfg = dict(hidden_dim=32, layers=3, dropout=0.0, time_embed_dim=2, time_embed_type="sin", max_timestep=49)
+    gr = synthetic.make_elliptic_like(n_nodes=5000, n_edges=6000, n_timesteps=10, seed=4, hub_degree=80,
+                                      t_train_end=6, t_val_end=8)
+    ei = torch.cat([gr.edge_index, gr.edge_index.flip(0)], dim=1).cuda()
+    x, t, y = gr.x.cuda(), gr.timestep.cuda(), gr.y.cuda()
+    tm, vm = gr.train_mask.cuda(), gr.val_mask.cuda()
+    kw = dict(lr=3e-2, weight_decay=0.0, grad_clip=1.0, amp=False)
+    patience, max_epochs = 3, 24
+
+    torch.manual_seed(0)
+    ref_model = egnn.build_model("sage_resbn", 166, cfg).cuda()
+    step = TrainStep(ref_model, x, ei, t, y, tm, **kw)
+    step.run()                                            # metrics.fit runs one eager step before its loop, too
+    es, best_state, stop_epoch = M.EarlyStop(), None, None
+    yv = (gr.y.numpy()[gr.val_mask.numpy()] == 1).astype(int)
+    for epoch in range(1, max_epochs + 1):
+        step.run()
+        probs, _ = eval_probs(ref_model, x, ei, t)
+        ap = M.average_precision(yv, probs.cpu().numpy()[gr.val_mask.numpy()])[0]
+        if es.update(ap):
+            best_state = {k: v.detach().clone() for k, v in ref_model.state_dict().items()}
+        if es.bad >= patience:
+            stop_epoch = epoch
+            break
+    if stop_epoch is None:
+        stop_epoch = max_epochs          # never triggered: both loops run to the end
+
+    torch.manual_seed(0)
+    model = egnn.build_model("sage_resbn", 166, cfg).cuda()
+    res = metrics.fit(model, x, ei, t, y, tm, vm, max_epochs=max_epochs, patience=patience, poll_every=4,
+                      capture=False, **kw)
+    assert res["best_epoch"] == es.best_epoch
+    assert res["best_val"] == pytest.approx(es.best, rel=1e-6)   # device softmax vs torch.softmax: last-ulp scores
+    assert stop_epoch <= res["epochs"] < stop_epoch + 4 and res["epochs"] <= max_epochs   # bounded overshoot
+    got = model.state_dict()
+    for k, v in best_state.items():
+        assert torch.equal(got[k], v), k
