@@ -119,3 +119,18 @@ def test_ops_fail_loudly_without_the_extension(monkeypatch, egnn):
     monkeypatch.setattr(_lib, "LIB_PATH", os.path.join(ROOT, "does_not_exist", "libegnn_b200.so"))
     with pytest.raises(RuntimeError, match="must be built"):
         _lib.lib()
+
+
+def test_metrics_host_layer_rejects_cpu_tensors_and_bad_arguments():
+    """egnn_b200.metrics validates before touching the library: CPU tensors are an error (no fallback), exactly one
+    of logits / scores, float32 scores, int64 labels."""
+    import pytest
+    from egnn_b200 import metrics
+    y = torch.zeros(4, dtype=torch.int64)
+    s = torch.zeros(4)
+    with pytest.raises(RuntimeError):
+        metrics.average_precision(y, None, scores=s)
+    with pytest.raises(ValueError):
+        metrics.average_precision(y, None)
+    with pytest.raises(ValueError):
+        metrics.average_precision(y, None, scores=s, logits=torch.zeros(4, 2))
