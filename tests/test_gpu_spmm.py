@@ -156,3 +156,23 @@ def test_row_partition_matches_definition(egnn):
             got = part.cpu().numpy()
             assert got.shape[0] == g.n_tasks + 1 and got[0] == 0 and got[-1] == gr.num_nodes
             assert np.array_equal(got, want)
+
+
+def test_large_graph_groups_of_eight_tasks_bitexact(egnn):
+    """8x replicated graph (1.6 M rows): the streaming kernel hands out groups of 8 partition tasks here (more tasks
+    than two waves of lane groups), unlike on the base graph.  fp32 mean aggregation bit for bit against the oracle,
+    plus the size-independent checks."""
+    from egnn_b200 import ops, _lib, synthetic
+    gr = synthetic.replicate(synthetic.make_elliptic_like(), 8)
+    n = gr.num_nodes
+    ei = torch.cat([gr.edge_index, gr.edge_index.flip(0)], dim=1)
+    g = egnn.build_graph(ei.cuda(), n)
+    assert g.n_tasks // 8 > 4 * 148 * 16 * 2          # the large-matrix branch of the launcher (4 CTAs x 16 groups)
+    x = _feat(n, 64, seed=7)
+    got = ops.spmm(g, "csr", _lib.SPMM_MEAN, x.cuda(), torch.float32).cpu()
+    ref = O.scatter_mean(x.index_select(0, ei[0]), ei[1], n)
+    assert torch.equal(got, ref)
+    ones = torch.ones(n, 64, device="cuda")
+    s = ops.spmm(g, "csc", _lib.SPMM_SUM, ones, torch.float32)
+    deg_out = (g.csc_ptr[1:] - g.csc_ptr[:-1]).float()
+    assert torch.equal(s[:, 0], deg_out) and float(s[:, 0].sum()) == float(g.n_edges)
