@@ -247,7 +247,7 @@ def run_ours(args):
     ev_logits = ev_logits.float().contiguous()
     val_mask = lg.val_mask.to(dev)
     stopper = dev_metrics.EarlyStopper(patience=20, flat_param=step.opt.flat_param)
-    ap_out = torch.empty(4, dtype=torch.float64, device=dev)
+    ap_out = torch.empty(8, dtype=torch.float64, device=dev)
     for _ in range(2):
         dev_metrics.average_precision(devb["y"], val_mask, logits=ev_logits, out=ap_out)
         stopper.update(ap_out)

@@ -4,7 +4,7 @@
 // boolean-mask indexing -> sklearn `average_precision_score` (src/utils/metrics.py:11-13) -> `if pr_val > best_val`
 // -> a CPU clone of the whole state dict.  Each of these is a device synchronisation that costs more than the
 // ~0.7 ms train step.  Here the same quantities are produced by kernels and stay on the device:
-//   egnn_average_precision : AP of the positive class (label == 1) over the selected rows, sklearn's definition
+//   egnn_average_precision : AP (and ROC-AUC, out[4]) of the positive class (label == 1) over the selected rows, sklearn's definition
 //       AP = sum over distinct thresholds k (descending score) of (R_k - R_{k-1}) * P_k,  R = tp / P_total,
 //       P_k = tp_k / (tp_k + fp_k)   (precision_recall_curve + step integral; ties share one threshold),
 //     computed as: descending order-preserving 32-bit keys -> stable LSD radix sort (radix.cuh, four 8-bit passes)
@@ -70,31 +70,38 @@ __global__ void __launch_bounds__(kFinThreads) ap_finish(const int* __restrict__
   __shared__ int s_tp[kFinThreads];       // positives in the chunk -> exclusive prefix
   __shared__ int s_end_tp[kFinThreads];   // cumulative positives at the chunk's last threshold (-1: chunk has none)
   __shared__ int s_groups[kFinThreads];
+  __shared__ int s_end_cnt[kFinThreads];  // entries up to and including the chunk's last threshold (-1: none)
   __shared__ double s_sum[kFinThreads];
   const int n_sel = counters[0], n_pos = counters[1];
   const int t = threadIdx.x;
   const int chunk = (n_sel + kFinThreads - 1) / kFinThreads;
   const int lo = min(t * chunk, n_sel), hi = min(lo + chunk, n_sel);
   // pass 1: positives per chunk, positives up to the chunk's last threshold
-  int tp = 0, tp_at_end = -1, groups = 0;
+  int tp = 0, tp_at_end = -1, cnt_at_end = -1, groups = 0;
   for (int i = lo; i < hi; ++i) {
     tp += y[perm[i]] == 1;
     if (i == n_sel - 1 || keys[i] != keys[i + 1]) {
       tp_at_end = tp;
+      cnt_at_end = i + 1;
       ++groups;
     }
   }
   s_tp[t] = tp;
   s_end_tp[t] = tp_at_end;
+  s_end_cnt[t] = cnt_at_end;
   s_groups[t] = groups;
   __syncthreads();
-  if (t == 0) {  // 1024 sequential steps: exclusive prefix of the counts, cumulative count at the previous threshold
-    int run = 0, prev_end = 0, g = 0;
+  if (t == 0) {  // 1024 sequential steps: exclusive prefix of the counts, cumulative counts at the previous threshold
+    int run = 0, prev_end = 0, prev_cnt = 0, g = 0;
     for (int q = 0; q < kFinThreads; ++q) {
-      const int c = s_tp[q], e = s_end_tp[q];
+      const int c = s_tp[q], e = s_end_tp[q], ec = s_end_cnt[q];
       s_tp[q] = run;
       s_end_tp[q] = prev_end;
-      if (e >= 0) prev_end = run + e;
+      s_end_cnt[q] = prev_cnt;
+      if (e >= 0) {
+        prev_end = run + e;
+        prev_cnt = ec;
+      }
       run += c;
       g += s_groups[q];
     }
@@ -102,9 +109,11 @@ __global__ void __launch_bounds__(kFinThreads) ap_finish(const int* __restrict__
   }
   __syncthreads();
   // pass 2: the per-threshold terms (R_k - R_{k-1}) * P_k in float64, like numpy's float64 arrays
-  double sum = 0.0;
-  int run = s_tp[t], prev = s_end_tp[t];
-  const double P = (double)n_pos;
+  // and, over the same thresholds, the ROC trapezoids (fpr_k - fpr_{k-1}) * (tpr_k + tpr_{k-1}) / 2
+  // (`roc_auc_illicit` = sklearn roc_auc_score, src/utils/metrics.py:15-16; collinear points do not change the area)
+  double sum = 0.0, roc = 0.0;
+  int run = s_tp[t], prev = s_end_tp[t], prev_cnt = s_end_cnt[t];
+  const double P = (double)n_pos, Nn = (double)(n_sel - n_pos);
   for (int i = lo; i < hi; ++i) {
     run += y[perm[i]] == 1;
     if (i == n_sel - 1 || keys[i] != keys[i + 1]) {
@@ -112,8 +121,13 @@ __global__ void __launch_bounds__(kFinThreads) ap_finish(const int* __restrict__
         const double recall = (double)run / P, recall_prev = (double)prev / P;
         const double precision = (double)run / (double)(i + 1);
         sum += (recall - recall_prev) * precision;
+        if (Nn > 0.0) {
+          const double fpr = (double)(i + 1 - run) / Nn, fpr_prev = (double)(prev_cnt - prev) / Nn;
+          roc += (fpr - fpr_prev) * (recall + recall_prev) * 0.5;
+        }
       }
       prev = run;
+      prev_cnt = i + 1;
     }
   }
   s_sum[t] = sum;
@@ -122,11 +136,22 @@ __global__ void __launch_bounds__(kFinThreads) ap_finish(const int* __restrict__
     if (t < w) s_sum[t] += s_sum[t + w];
     __syncthreads();
   }
+  const double ap_total = s_sum[0];
+  __syncthreads();
+  s_sum[t] = roc;
+  __syncthreads();
+  for (int w = kFinThreads / 2; w > 0; w >>= 1) {
+    if (t < w) s_sum[t] += s_sum[t + w];
+    __syncthreads();
+  }
   if (t == 0) {
-    out[0] = n_pos > 0 ? fmax(0.0, s_sum[0]) : 0.0;  // sklearn: no positive class -> 0.0 (recall defined as 1)
+    out[0] = n_pos > 0 ? fmax(0.0, ap_total) : 0.0;  // sklearn: no positive class -> 0.0 (recall defined as 1)
     out[1] = (double)n_sel;
     out[2] = (double)n_pos;
     out[3] = (double)s_groups[0];
+    // ROC-AUC is undefined with a single class (sklearn raises): NaN
+    out[4] = (n_pos > 0 && n_sel > n_pos) ? s_sum[0] : __longlong_as_double(0x7ff8000000000000LL);
+    out[5] = out[6] = out[7] = 0.0;
   }
 }
 

@@ -18,8 +18,8 @@ from ._lib import check, lib, ptr, stream
 def average_precision(y: torch.Tensor, mask: Optional[torch.Tensor] = None, *, logits: Optional[torch.Tensor] = None,
                       scores: Optional[torch.Tensor] = None, scores_out: Optional[torch.Tensor] = None,
                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """PR-AUC of the class `y == 1` over the rows selected by `mask` -> float64[4] ON THE DEVICE:
-    `[AP, selected rows, positives, distinct thresholds]`.  Give `logits` ([N, 2] fp32; the score is
+    """PR-AUC of the class `y == 1` over the rows selected by `mask` -> float64[8] ON THE DEVICE:
+    `[AP, selected rows, positives, distinct thresholds, ROC-AUC, 0, 0, 0]`.  Give `logits` ([N, 2] fp32; the score is
     `softmax(logits, 1)[:, 1]` as in `eval_split`) or `scores` ([N] fp32)."""
     if (logits is None) == (scores is None):
         raise ValueError("give exactly one of logits / scores")
@@ -40,7 +40,9 @@ def average_precision(y: torch.Tensor, mask: Optional[torch.Tensor] = None, *, l
         if mask.numel() != n or mask.dtype not in (torch.bool, torch.uint8) or not mask.is_contiguous():
             raise ValueError("mask must be a contiguous bool / uint8 [N] tensor")
     if out is None:
-        out = torch.empty(4, dtype=torch.float64, device=src.device)
+        out = torch.empty(8, dtype=torch.float64, device=src.device)
+    elif out.dtype != torch.float64 or out.numel() < 8 or not out.is_contiguous() or not out.is_cuda:
+        raise ValueError("out must be a contiguous float64 CUDA tensor with at least 8 elements")
     L = lib()
     ws_bytes = L.egnn_ap_workspace_bytes(n)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=src.device)
@@ -123,7 +125,7 @@ def fit(model, x, edge_index, timestep, y, train_mask, val_mask, *, lr: float, w
         step.capture(warmup=1)
     buffers = [b for b in model.buffers() if b.is_cuda and b.numel() > 0]
     stopper = EarlyStopper(patience=patience, flat_param=step.opt.flat_param, extra=buffers)
-    ap = torch.empty(4, dtype=torch.float64, device=x.device)
+    ap = torch.empty(8, dtype=torch.float64, device=x.device)
     epochs = 0
     for epoch in range(1, max_epochs + 1):
         loss = step.run()

@@ -334,8 +334,10 @@ int egnn_clip_adam_step(float* param, const float* grad, float* exp_avg, float* 
  * Exactly one of `logits` (float [n_rows, >=2], leading dimension ld_logits; score = softmax(row)[1]) or `scores`
  * (float [n_rows]) is given; y int64 [n_rows] (positive class: y == 1, as the caller's `(y_val == 1).astype(int)`,
  * src/train_gnn.py:391); mask uint8/bool [n_rows] or NULL (all rows).  scores_out (float [n_rows] or NULL) receives
- * the scores.  out double[4] (device) = {AP, selected rows, positives, distinct thresholds}; no selected row or no
- * positive -> AP = 0.0 (the reference's `y_val.size == 0` guard / sklearn's no-positive convention).
+ * the scores.  out double[8] (device) = {AP, selected rows, positives, distinct thresholds, ROC-AUC, 0, 0, 0}; no
+ * selected row or no positive -> AP = 0.0 (the reference's `y_val.size == 0` guard / sklearn's no-positive
+ * convention).  ROC-AUC = trapezoid area over the same thresholds (`roc_auc_illicit` = sklearn `roc_auc_score`,
+ * src/utils/metrics.py:15-16, final metrics src/train_gnn.py:449-470); NaN when only one class is selected.
  * Counts are exact integers; AP is a fixed-order float64 sum (deterministic). */
 size_t egnn_ap_workspace_bytes(int64_t n_rows);
 int egnn_average_precision(const float* logits, int64_t ld_logits, const float* scores, const int64_t* y,

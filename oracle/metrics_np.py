@@ -45,6 +45,21 @@ def average_precision(y_true: np.ndarray, y_score: np.ndarray):
     return ap, int(y_true.size), n_pos, int(thr.size)
 
 
+def roc_auc(y_true: np.ndarray, y_score: np.ndarray) -> float:
+    """`roc_auc_illicit` (`/root/reference/src/utils/metrics.py:15-16`) = sklearn `roc_auc_score` for a binary target:
+    trapezoid area under (fpr, tpr) over the distinct thresholds, starting at (0, 0).  NaN when only one class is
+    present (sklearn raises ValueError there)."""
+    y_true = np.asarray(y_true)
+    if y_true.size == 0:
+        return float("nan")
+    fps, tps, _ = binary_clf_curve(y_true, y_score)
+    if tps[-1] == 0 or fps[-1] == 0:
+        return float("nan")
+    fpr = np.r_[0.0, fps / fps[-1]]
+    tpr = np.r_[0.0, tps / tps[-1]]
+    return float(np.sum(np.diff(fpr) * (tpr[1:] + tpr[:-1]) * 0.5))
+
+
 def softmax_pos(logits: np.ndarray) -> np.ndarray:
     """softmax(logits, 1)[:, 1] in float32 (`eval_split`, `src/train_gnn.py:254`)."""
     l = np.asarray(logits, dtype=np.float32)

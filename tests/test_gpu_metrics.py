@@ -30,21 +30,25 @@ def test_average_precision_matches_oracle(egnn, n, quant):
     ap, cnt, pos, thr = M.average_precision((y[mask] == 1).astype(int), s[mask])
     assert (int(out[1]), int(out[2]), int(out[3])) == (cnt, pos, thr)
     assert out[0] == pytest.approx(ap, rel=TOL, abs=1e-15)
+    roc = M.roc_auc((y[mask] == 1).astype(int), s[mask])
+    assert (np.isnan(roc) and np.isnan(out[4])) or out[4] == pytest.approx(roc, rel=TOL)
     # determinism: bitwise identical on a second run
     out2 = metrics.average_precision(torch.from_numpy(y).cuda(), torch.from_numpy(mask).cuda(),
                                      scores=torch.from_numpy(s).cuda()).cpu().numpy()
-    assert np.array_equal(out, out2)
+    assert np.array_equal(out, out2, equal_nan=True)
 
 
 def test_degenerate_selections(egnn):
     from egnn_b200 import metrics
     y = torch.tensor([1, 0, 0, 1, 0], device="cuda")
     same = torch.full((5,), 0.5, device="cuda")
-    assert metrics.average_precision(y, None, scores=same).cpu().tolist() == [pytest.approx(0.4), 5.0, 2.0, 1.0]
+    r = metrics.average_precision(y, None, scores=same).cpu().tolist()
+    assert r[:4] == [pytest.approx(0.4), 5.0, 2.0, 1.0] and r[4] == pytest.approx(0.5)   # one threshold: chance level
     none = torch.zeros(5, dtype=torch.bool, device="cuda")
-    assert metrics.average_precision(y, none, scores=same).cpu().tolist() == [0.0, 0.0, 0.0, 0.0]
+    r = metrics.average_precision(y, none, scores=same).cpu().tolist()
+    assert r[:4] == [0.0, 0.0, 0.0, 0.0] and r[4] != r[4]                                # ROC-AUC undefined: NaN
     neg = torch.zeros(5, dtype=torch.int64, device="cuda")
-    assert metrics.average_precision(neg, None, scores=torch.arange(5, device="cuda").float()).cpu().tolist() == \
+    assert metrics.average_precision(neg, None, scores=torch.arange(5, device="cuda").float()).cpu().tolist()[:4] == \
         [0.0, 5.0, 0.0, 5.0]
     with pytest.raises(RuntimeError):
         metrics.average_precision(y.cpu(), None, scores=same.cpu())      # no CPU fallback

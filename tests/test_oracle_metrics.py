@@ -36,6 +36,7 @@ def test_golden_vectors_from_the_reference_function():
             y, s = _case(c["seed"], c["n"], c["pos_rate"], c["quant"])
         ap = M.average_precision(y, s)[0]
         assert ap == pytest.approx(c["ap"], rel=1e-13, abs=1e-15), c
+        assert M.roc_auc(y, s) == pytest.approx(c["roc"], rel=1e-13), c
 
 
 def test_against_sklearn_including_ties_and_degenerate_inputs():
@@ -51,6 +52,10 @@ def test_against_sklearn_including_ties_and_degenerate_inputs():
         ap, cnt, pos, thr = M.average_precision(y, s)
         assert ap == pytest.approx(float(sk.average_precision_score(y, s)), rel=1e-13)
         assert (cnt, pos, thr) == (n, int(y.sum()), np.unique(s).size)
+        if 0 < y.sum() < n:
+            assert M.roc_auc(y, s) == pytest.approx(float(sk.roc_auc_score(y, s)), rel=1e-13)
+        else:
+            assert np.isnan(M.roc_auc(y, s))
     # all scores equal: one threshold, AP = prevalence
     y = np.array([1, 0, 0, 1, 0])
     assert M.average_precision(y, np.full(5, 0.5, np.float32))[0] == pytest.approx(0.4)
