@@ -16,6 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libegnn_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
+ABI_VERSION = 2  # EGNN_ABI_VERSION of include/egnn_b200.h
 F32, BF16, F64 = 0, 1, 2
 G_SYMMETRIZE, G_SELF_LOOPS = 1, 2
 SPMM_SUM, SPMM_MEAN, SPMM_DIV_NBR, SPMM_WEIGHTED = 0, 1, 2, 3
@@ -32,11 +33,14 @@ SIGNATURES = {
     "egnn_counter_add": (_i32, [_vp, _i64, _vp]),
     "egnn_graph_workspace_bytes": (_sz, [_i64, _i64, _i32]),
     "egnn_graph_build": (_i32, [_vp, _i64, _i64, _i32, _i32] + [_vp] * 16 + [_vp, _sz, _vp]),
+    "egnn_buffers_differ": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "egnn_spmm": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _i64, _vp, _i32, _i64, _i64,
                          _i64, _vp, _i32, _i32, _vp, _i64, _vp]),
     "egnn_ap_workspace_bytes": (_sz, [_i64]),
     "egnn_average_precision": (_i32, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
-    "egnn_early_stop_update": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp]),
+    "egnn_ranking_metrics": (_i32, [_vp, _i64, _vp, _vp, _vp, _i64, _i64, _f64, _vp, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "egnn_temperature_fit": (_i32, [_vp, _i64, _vp, _vp, _i64, _i32, _vp, _vp]),
+    "egnn_early_stop_update": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _vp]),
     "egnn_snapshot_if_improved": (_i32, [_vp, _vp, _vp, _i64, _vp]),
     "egnn_spmm_partition_tasks": (_i64, [_i64, _i64]),
     "egnn_spmm_partition": (_i32, [_vp, _i64, _vp, _i64, _vp]),
@@ -46,6 +50,8 @@ SIGNATURES = {
     "egnn_pack_sage_weights": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp]),
     "egnn_cast": (_i32, [_vp, _i32, _i64, _vp, _i32, _i64, _i64, _i64, _vp]),
     "egnn_inject_time": (_i32, [_vp, _i64, _vp, _vp, _i64, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _vp]),
+    "egnn_embed_grad_workspace_bytes": (_sz, [_i64, _i64, _i64]),
+    "egnn_embed_grad": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _vp]),
     "egnn_colreduce_workspace_bytes": (_sz, [_i64]),
     "egnn_colreduce": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "egnn_bn_finalize": (_i32, [_vp, _vp, _f64, _i64, _f32, _f32, _vp, _vp, _vp, _vp, _vp]),
@@ -73,7 +79,7 @@ SIGNATURES = {
     "egnn_skinny_wgrad": (_i32, [_vp, _i32, _i64, _vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp]),
     "egnn_skinny_dgrad": (_i32, [_vp, _vp, _i32, _vp, _i32, _i64, _i64, _i64, _vp]),
     "egnn_p2p_allreduce_buffer_bytes": (_sz, [_i32, _i64, _i32]),
-    "egnn_p2p_allreduce": (_i32, [_vp, _vp, _i64, _i32, _i64, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "egnn_p2p_allreduce": (_i32, [_vp, _vp, _i64, _i32, _i64, _vp, _i32, _i32, _vp, _vp, _i64, _vp]),
     "egnn_masked_ce": (_i32, [_vp, _i32, _i64, _vp, _vp, _i64, _vp, _f64, _vp, _vp, _vp, _vp]),
     "egnn_adam_workspace_floats": (_sz, [_i64]),
     "egnn_clip_adam_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _vp, _vp,
@@ -104,7 +110,7 @@ def lib() -> C.CDLL:
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(_lib, name)  # AttributeError if the .so lacks a declared symbol
             fn.restype, fn.argtypes = res, args
-        if _lib.egnn_abi_version() != 1:
+        if _lib.egnn_abi_version() != ABI_VERSION:
             raise RuntimeError("libegnn_b200.so ABI version mismatch; rebuild it")
     return _lib
 

@@ -100,6 +100,56 @@ __global__ void __launch_bounds__(kThreads) inject_time_kernel(
   }
 }
 
+// Gradient of the learned time-embedding table (nn.Embedding backward, src/models/gnn.py:152,172-176):
+// dtab[r, d] = sum over nodes n with clamp(t[n]-1, 0, T-1) == r of dout[n, col0 + d].  torch's index_add_ uses float
+// atomics on CUDA; here block (r, chunk) scans its node chunk for row r with a fixed thread -> node assignment and a
+// fixed shared-memory tree, and embed_grad_final adds the chunk partials in chunk order: same bits on every run.
+constexpr int kEmbChunk = 8192;
+constexpr int kEmbCols = 8;
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) embed_grad_partial(const T* __restrict__ dout, int64_t ld, int col0, int D,
+                                                               const int64_t* __restrict__ t, int64_t Tn, int64_t n_rows,
+                                                               double* __restrict__ partial) {
+  __shared__ double s[kThreads];
+  const int r = blockIdx.x, chunk = blockIdx.y, nchunks = gridDim.y;
+  const int64_t lo = (int64_t)chunk * kEmbChunk, hi = min(lo + (int64_t)kEmbChunk, n_rows);
+  for (int d0 = 0; d0 < D; d0 += kEmbCols) {
+    double acc[kEmbCols];
+#pragma unroll
+    for (int k = 0; k < kEmbCols; ++k) acc[k] = 0.0;
+    for (int64_t n = lo + threadIdx.x; n < hi; n += kThreads) {
+      int64_t ti = t[n] - 1;
+      ti = ti < 0 ? 0 : (ti > Tn - 1 ? Tn - 1 : ti);
+      if (ti != r) continue;
+#pragma unroll
+      for (int k = 0; k < kEmbCols; ++k)
+        if (d0 + k < D) acc[k] += (double)to_f32(dout[n * ld + col0 + d0 + k]);
+    }
+    for (int k = 0; k < kEmbCols && d0 + k < D; ++k) {
+      s[threadIdx.x] = acc[k];
+      __syncthreads();
+      for (int w = kThreads / 2; w > 0; w >>= 1) {
+        if ((int)threadIdx.x < w) s[threadIdx.x] += s[threadIdx.x + w];
+        __syncthreads();
+      }
+      if (threadIdx.x == 0) partial[((int64_t)r * nchunks + chunk) * D + d0 + k] = s[0];
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void embed_grad_final(const double* __restrict__ partial, int nchunks, int D, int64_t Tn,
+                                 float* __restrict__ dtab) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Tn * D) return;
+  const int64_t r = i / D;
+  const int d = (int)(i - r * D);
+  double a = 0.0;
+  for (int c = 0; c < nchunks; ++c) a += partial[(r * nchunks + c) * D + d];
+  dtab[i] = (float)a;
+}
+
 // ---- fused BN / activation / dropout element math ------------------------------------------
 struct ActCtx {
   const float *mean, *rstd, *gamma, *beta;
@@ -1030,6 +1080,31 @@ extern "C" int egnn_inject_time(const float* x, int64_t ld_x, const int64_t* t, 
   inject_time_kernel<<<grid, kThreads, 0, st>>>(x, ld_x, t, table, T, (int)D, out_f32,
                                                 (__nv_bfloat16*)out_bf16, ld_out, ld_out_bf16, n_rows,
                                                 (int)n_feat);
+  EGNN_LAUNCH_CHECK(fn);
+  return 0;
+}
+
+extern "C" size_t egnn_embed_grad_workspace_bytes(int64_t n_rows, int64_t T, int64_t D) {
+  return (size_t)T * (size_t)ceil_div(n_rows > 0 ? n_rows : 1, kEmbChunk) * (size_t)D * sizeof(double);
+}
+
+extern "C" int egnn_embed_grad(const void* dout, int dtype, int64_t ld, int64_t col0, int64_t D, const int64_t* t,
+                               int64_t T, int64_t n_rows, float* dtab, void* workspace, void* stream) {
+  const char* fn = "egnn_embed_grad";
+  EGNN_REQUIRE(dout && t && dtab && workspace, fn, "null pointer");
+  EGNN_REQUIRE(T > 0 && T <= 65535 && D > 0 && col0 >= 0 && ld >= col0 + D && n_rows >= 0, fn, "bad shape");
+  EGNN_REQUIRE(dtype == EGNN_F32 || dtype == EGNN_BF16, fn, "dtype must be EGNN_F32 or EGNN_BF16");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nchunks = (int)ceil_div(n_rows > 0 ? n_rows : 1, kEmbChunk);
+  double* partial = reinterpret_cast<double*>(workspace);
+  dim3 grid((unsigned)T, (unsigned)nchunks);
+  if (dtype == EGNN_F32)
+    embed_grad_partial<float><<<grid, kThreads, 0, st>>>((const float*)dout, ld, (int)col0, (int)D, t, T, n_rows, partial);
+  else
+    embed_grad_partial<__nv_bfloat16><<<grid, kThreads, 0, st>>>((const __nv_bfloat16*)dout, ld, (int)col0, (int)D, t, T,
+                                                               n_rows, partial);
+  EGNN_LAUNCH_CHECK(fn);
+  embed_grad_final<<<(unsigned)ceil_div(T * D, 128), 128, 0, st>>>(partial, nchunks, (int)D, T, dtab);
   EGNN_LAUNCH_CHECK(fn);
   return 0;
 }

@@ -270,10 +270,47 @@ int radix_sort_perm(const int* keys, const int* n_ptr, int64_t cap, int bits, Wo
   return 0;
 }
 
+// byte-wise comparison of two device buffers (train.HostFeed: rebuild the sorted views only when the edge list a
+// caller submits really differs from the one they were built from)
+__global__ void __launch_bounds__(kThreads) buffers_differ_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b,
+                                                                  int64_t n16, const uint8_t* __restrict__ ta,
+                                                                  const uint8_t* __restrict__ tb, int tail,
+                                                                  int* __restrict__ flag) {
+  bool diff = false;
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n16; i += stride) {
+    const uint4 u = a[i], v = b[i];
+    diff |= (u.x != v.x) | (u.y != v.y) | (u.z != v.z) | (u.w != v.w);
+  }
+  if (blockIdx.x == 0 && (int)threadIdx.x < tail) diff |= ta[threadIdx.x] != tb[threadIdx.x];
+  if (__syncthreads_or(diff) && threadIdx.x == 0) *flag = 1;
+}
+
+__global__ void clear_flag_kernel(int* flag) { *flag = 0; }
+
 }  // namespace
 }  // namespace egnn
 
 using namespace egnn;
+
+extern "C" int egnn_buffers_differ(const void* a, const void* b, int64_t n_bytes, int* flag, void* stream) {
+  const char* fn = "egnn_buffers_differ";
+  EGNN_REQUIRE(a && b && flag && n_bytes >= 0, fn, "bad arguments");
+  EGNN_REQUIRE((uintptr_t)a % 16 == 0 && (uintptr_t)b % 16 == 0, fn, "buffers must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  clear_flag_kernel<<<1, 1, 0, st>>>(flag);
+  EGNN_LAUNCH_CHECK(fn);
+  if (n_bytes == 0) return 0;
+  const int64_t n16 = n_bytes / 16;
+  const int tail = (int)(n_bytes - 16 * n16);
+  int64_t blocks = ceil_div(n16 > 0 ? n16 : 1, (int64_t)kThreads * 4);
+  if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+  buffers_differ_kernel<<<(unsigned)blocks, kThreads, 0, st>>>(
+      reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b), n16,
+      reinterpret_cast<const uint8_t*>(a) + 16 * n16, reinterpret_cast<const uint8_t*>(b) + 16 * n16, tail, flag);
+  EGNN_LAUNCH_CHECK(fn);
+  return 0;
+}
 
 extern "C" size_t egnn_graph_workspace_bytes(int64_t n_nodes, int64_t n_edges_in, int flags) {
   int64_t E_log = (flags & EGNN_G_SYMMETRIZE) ? 2 * n_edges_in : n_edges_in;

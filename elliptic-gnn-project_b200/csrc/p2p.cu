@@ -35,12 +35,27 @@ __host__ __device__ inline size_t flag_offset(int world, int64_t n_max, size_t e
 }
 
 // CTA c owns elements [c*kP2PChunk, ...) and its own flag row, so chunks complete independently
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
 template <typename T>
-__global__ void __launch_bounds__(kP2PThreads) p2p_allreduce_kernel(const T* __restrict__ in, T* out, int64_t n,
+__device__ __forceinline__ T poison();
+template <>
+__device__ __forceinline__ float poison<float>() { return __int_as_float(0x7fc00000); }
+template <>
+__device__ __forceinline__ double poison<double>() { return __longlong_as_double(0x7ff8000000000000LL); }
+
+// `in` may alias `out` (in-place call): no __restrict__ on either
+template <typename T>
+__global__ void __launch_bounds__(kP2PThreads) p2p_allreduce_kernel(const T* in, T* out, int64_t n,
                                                                     int64_t n_max, void* const* __restrict__ peer_bufs,
                                                                     int rank, int world,
                                                                     const unsigned long long* __restrict__ epoch,
-                                                                    int* __restrict__ error_flag) {
+                                                                    int* __restrict__ error_flag,
+                                                                    unsigned long long timeout_ns) {
   __shared__ int s_fail;
   if (threadIdx.x == 0) s_fail = 0;
   const unsigned long long e = *epoch + 1ull;   // advanced by p2p_epoch_advance after the whole grid
@@ -63,9 +78,9 @@ __global__ void __launch_bounds__(kP2PThreads) p2p_allreduce_kernel(const T* __r
     st_release_sys(pf + ((size_t)par * kP2PMaxChunks + blockIdx.x) * kP2PMaxWorld + rank, e);
     const unsigned long long* mine =
         reinterpret_cast<const unsigned long long*>(reinterpret_cast<const char*>(peer_bufs[rank]) + foff);
-    const long long t0 = clock64();
+    const unsigned long long t0 = global_ns();
     while (ld_acquire_sys(mine + ((size_t)par * kP2PMaxChunks + blockIdx.x) * kP2PMaxWorld + threadIdx.x) < e) {
-      if (clock64() - t0 > 4000000000ll) {  // ~2 s: a peer never arrived; fail loudly instead of hanging the GPU
+      if (global_ns() - t0 > timeout_ns) {  // a peer never arrived; fail loudly instead of hanging the GPU
         s_fail = 1;
         break;
       }
@@ -73,7 +88,10 @@ __global__ void __launch_bounds__(kP2PThreads) p2p_allreduce_kernel(const T* __r
   }
   __syncthreads();
   if (s_fail) {
+    // sticky and loud: the error flag stays set (the host checks it at every synchronisation point) and the result
+    // is NaN, so a loss / parameter computed from an un-reduced vector can never look valid
     if (threadIdx.x == 0 && error_flag) *error_flag = 1;
+    for (int i = threadIdx.x; i < cnt; i += kP2PThreads) out[i0 + i] = poison<T>();
     return;
   }
   // 4. sum the slots in rank order (identical on every rank)
@@ -99,21 +117,22 @@ extern "C" size_t egnn_p2p_allreduce_buffer_bytes(int world, int64_t n_max, int 
 
 extern "C" int egnn_p2p_allreduce(const void* in, void* out, int64_t n, int dtype, int64_t n_max,
                                   void* const* peer_bufs_dev, int rank, int world, int64_t* epoch, int* error_flag,
-                                  void* stream) {
+                                  int64_t timeout_ms, void* stream) {
   const char* fn = "egnn_p2p_allreduce";
   EGNN_REQUIRE(in && out && peer_bufs_dev && epoch, fn, "null pointer");
   EGNN_REQUIRE(dtype == EGNN_F32 || dtype == EGNN_F64, fn, "dtype must be EGNN_F32 or EGNN_F64");
   EGNN_REQUIRE(n > 0 && n <= n_max && n_max <= (int64_t)kP2PChunk * kP2PMaxChunks, fn, "n out of range");
   EGNN_REQUIRE(world >= 1 && world <= kP2PMaxWorld && rank >= 0 && rank < world, fn, "bad rank / world");
   cudaStream_t st = (cudaStream_t)stream;
+  const unsigned long long tmo = (unsigned long long)(timeout_ms > 0 ? timeout_ms : 2000) * 1000000ull;
   const unsigned grid = (unsigned)ceil_div(n, kP2PChunk);
   unsigned long long* ep = reinterpret_cast<unsigned long long*>(epoch);
   if (dtype == EGNN_F64)
     p2p_allreduce_kernel<double><<<grid, kP2PThreads, 0, st>>>((const double*)in, (double*)out, n, n_max,
-                                                               peer_bufs_dev, rank, world, ep, error_flag);
+                                                               peer_bufs_dev, rank, world, ep, error_flag, tmo);
   else
     p2p_allreduce_kernel<float><<<grid, kP2PThreads, 0, st>>>((const float*)in, (float*)out, n, n_max, peer_bufs_dev,
-                                                              rank, world, ep, error_flag);
+                                                              rank, world, ep, error_flag, tmo);
   EGNN_LAUNCH_CHECK(fn);
   p2p_epoch_advance<<<1, 1, 0, st>>>(ep);
   EGNN_LAUNCH_CHECK(fn);

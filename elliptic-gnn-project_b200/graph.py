@@ -33,8 +33,8 @@ class Graph:
     csc_pos: torch.Tensor          # int32[cap]  position in CSR order
     csr_long: torch.Tensor         # int32[cap/64+1]
     csc_long: torch.Tensor
-    csr_order: torch.Tensor        # int32[N] destination rows by descending in-degree (SpMM schedule)
-    csc_order: torch.Tensor        # int32[N] source rows by descending out-degree
+    csr_order: Optional[torch.Tensor] = None   # int32[N] rows by descending degree: only the per-row fall-back
+    csc_order: Optional[torch.Tensor] = None   # kernel (spmm_lean) reads it; built on request (`want_order`)
     csr_part: Optional[torch.Tensor] = None  # int32[n_tasks+1] cost-balanced row partition (streaming SpMM)
     csc_part: Optional[torch.Tensor] = None
     n_tasks: int = 0
@@ -63,7 +63,7 @@ def symmetrize(edge_index: torch.Tensor) -> torch.Tensor:
 
 def build_graph(edge_index: torch.Tensor, num_nodes: int, symmetrize: bool = False,
                 self_loops: bool = False, want_norm: bool = False, keep_edge_list: bool = False,
-                validate: bool = True, out: Optional[Graph] = None) -> Graph:
+                validate: bool = True, out: Optional[Graph] = None, want_order: bool = False) -> Graph:
     """Build the sorted views.  `out` re-uses the buffers of a previously built Graph of the same
     shape (so a captured CUDA graph that reads them sees the new structure)."""
     if edge_index.dim() != 2 or edge_index.size(0) != 2:
@@ -87,7 +87,8 @@ def build_graph(edge_index: torch.Tensor, num_nodes: int, symmetrize: bool = Fal
         csr_ptr=torch.empty(N + 1, **i32), csr_src=torch.empty(cap, **i32), csr_eid=torch.empty(cap, **i32),
         csc_ptr=torch.empty(N + 1, **i32), csc_dst=torch.empty(cap, **i32), csc_pos=torch.empty(cap, **i32),
         csr_long=torch.empty(cap // 64 + 1, **i32), csc_long=torch.empty(cap // 64 + 1, **i32),
-        csr_order=torch.empty(N, **i32), csc_order=torch.empty(N, **i32),
+        csr_order=torch.empty(N, **i32) if want_order else None,
+        csc_order=torch.empty(N, **i32) if want_order else None,
         ei2=torch.empty(2, cap, dtype=torch.int64, device=dev) if keep_edge_list else None,
         dis=torch.empty(N, dtype=torch.float32, device=dev) if norm else None,
         w_edge=torch.empty(cap, dtype=torch.float32, device=dev) if (norm and keep_edge_list) else None,
@@ -139,6 +140,15 @@ class GraphCache:
         self._d[key] = (edge_index, g)
         return g
 
+    def put(self, edge_index: torch.Tensor, num_nodes: int, self_loops: bool, g: Graph) -> None:
+        """Register an already built graph for `edge_index` in its CURRENT state (train.HostFeed rebuilds into
+        fixed buffers after an in-place `copy_`, which bumps `_version`)."""
+        key = (edge_index.data_ptr(), tuple(edge_index.shape), tuple(edge_index.stride()),
+               edge_index._version, int(num_nodes), bool(self_loops))
+        for k in [k for k, v in self._d.items() if v[1] is g and k != key]:
+            del self._d[k]
+        self._d[key] = (edge_index, g)
+
     def clear(self):
         self._d.clear()
 
@@ -148,3 +158,7 @@ _GLOBAL_CACHE = GraphCache()
 
 def cached_graph(edge_index: torch.Tensor, num_nodes: int, self_loops: bool = False) -> Graph:
     return _GLOBAL_CACHE.get(edge_index, num_nodes, self_loops)
+
+
+def register_graph(edge_index: torch.Tensor, num_nodes: int, g: Graph, self_loops: bool = False) -> None:
+    _GLOBAL_CACHE.put(edge_index, num_nodes, self_loops, g)

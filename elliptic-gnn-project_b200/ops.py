@@ -208,17 +208,19 @@ def dropout_mask(n_rows: int, n_feat: int, p: float, seed: int, layer: int, row0
 
 # Column sums of a gradient matrix produced as a by-product of the kernel that wrote it (the
 # BatchNorm backward), handed to the consumer (the conv's bias gradient) without another pass
-# over the matrix.  Keyed by the matrix' storage pointer; consumed once.
-_COLSUM_SIDE: dict = {}
-
-
+# over the matrix.  The sums ride on the gradient tensor OBJECT itself (autograd hands the very
+# tensor a backward returned to the next node when it is that node's only gradient); a tensor
+# that autograd re-created (accumulated gradients, hooks) simply lacks the attribute and the
+# consumer recomputes the sums -- no global state, nothing keyed on recyclable addresses.
 def _publish_colsum(t: torch.Tensor, s: torch.Tensor):
-    _COLSUM_SIDE.clear()
-    _COLSUM_SIDE[(t.data_ptr(), tuple(t.shape), t.dtype)] = s
+    t._egnn_colsum = (t._version, s)
 
 
 def _take_colsum(t: torch.Tensor) -> Optional[torch.Tensor]:
-    return _COLSUM_SIDE.pop((t.data_ptr(), tuple(t.shape), t.dtype), None)
+    side = getattr(t, "_egnn_colsum", None)
+    if side is None or side[0] != t._version or side[1].numel() != t.size(-1):
+        return None
+    return side[1]
 
 
 # --------------------------------------------------------------------------- SAGEConv ----
@@ -715,31 +717,36 @@ class InjectTimeFn(torch.autograd.Function):
                     else torch.empty((N, width), dtype=torch.bfloat16, device=x.device))
         check(lib().egnn_inject_time(ptr(x), _ld(x), ptr(t.contiguous()), ptr(tb), T, D, ptr(out), ptr(twin), width,
                                      _ld(twin) if twin is not None else 0, N, F, stream()))
-        InjectTimeFn.last_twin = twin
         ctx.dims = (F, D, T)
         ctx.save_for_backward(t)
-        return out
+        if twin is None:
+            twin = out.new_empty(0)
+        ctx.mark_non_differentiable(twin)
+        return out, twin
 
     @staticmethod
-    def backward(ctx, dout):
+    def backward(ctx, dout, _dtwin=None):
         (t,) = ctx.saved_tensors
         F, D, T = ctx.dims
         dx = dout[:, :F] if ctx.needs_input_grad[0] else None
         dtab = None
         if ctx.needs_input_grad[2]:
-            # learned nn.Embedding (not used by the BASELINE configs): rows are few (T <= 49)
-            idx = torch.clamp(t.long() - 1, 0, T - 1)
-            dtab = torch.zeros((T, D), dtype=torch.float32, device=dout.device)
-            dtab.index_add_(0, idx, dout[:, F:F + D].float())
+            # learned nn.Embedding (not used by the BASELINE configs): deterministic segmented sum over the T rows
+            dout = _rows(dout)
+            L = lib()
+            dtab = torch.empty((T, D), dtype=torch.float32, device=dout.device)
+            ws = torch.empty(L.egnn_embed_grad_workspace_bytes(dout.size(0), T, D), dtype=torch.uint8,
+                             device=dout.device)
+            check(L.egnn_embed_grad(ptr(dout), dt(dout), _ld(dout), F, D, ptr(t.contiguous()), T, dout.size(0),
+                                    ptr(dtab), ptr(ws), stream()))
         return dx, None, dtab, None, None
 
 
 def inject_time(x, t, table, width: int):
     want_twin = amp_bf16()
-    out = InjectTimeFn.apply(x, t, table, width, want_twin)
+    out, twin = InjectTimeFn.apply(x, t, table, width, want_twin)
     if want_twin:
-        out._egnn_twin = InjectTimeFn.last_twin
-        InjectTimeFn.last_twin = None
+        out._egnn_twin = twin
     return out
 
 

@@ -136,6 +136,7 @@ class P2PAllReduce:
         self.peer_ptrs = int(self.hdl.buffer_ptrs_dev)
         self.epoch = torch.zeros(1, dtype=torch.int64, device=device)
         self.err = torch.zeros(1, dtype=torch.int32, device=device)
+        self.timeout_ms = int(os.environ.get("EGNN_P2P_TIMEOUT_MS", "2000"))
         torch.cuda.synchronize(device)   # flags are zero; the caller's consensus all-reduce orders this before any push
 
     @staticmethod
@@ -163,12 +164,16 @@ class P2PAllReduce:
     def __call__(self, t: torch.Tensor) -> torch.Tensor:
         from ._lib import check, lib, stream
         check(lib().egnn_p2p_allreduce(t.data_ptr(), t.data_ptr(), t.numel(), self.code, self.n_max, self.peer_ptrs,
-                                       self.rank, self.world, self.epoch.data_ptr(), self.err.data_ptr(), stream()))
+                                       self.rank, self.world, self.epoch.data_ptr(), self.err.data_ptr(),
+                                       self.timeout_ms, stream()))
         return t
 
     def check(self):
+        """Host synchronisation point: raise if any call since the start timed out waiting for a peer (the kernel
+        has already poisoned its output with NaN; the flag is sticky)."""
         if int(self.err.item()):
-            raise RuntimeError("egnn_p2p_allreduce: a peer did not arrive (timeout inside the kernel)")
+            raise RuntimeError(f"egnn_p2p_allreduce: a peer did not arrive within {self.timeout_ms} ms "
+                               "(the affected result was set to NaN)")
 
 
 class P2PStatsReducer(StatsReducer):
@@ -242,6 +247,15 @@ class ShardedContext:
         m8 = mask.to(torch.uint8)
         return metrics.average_precision(self.gather_rows(y, -1), self.gather_rows(m8, 0),
                                          scores=self.gather_rows(scores, 0.0))
+
+    def check(self):
+        """Call wherever the host synchronises anyway (loss read-back, early-stopping poll): raises when a
+        peer-memory all-reduce of this context timed out (`P2PAllReduce.check`)."""
+        ar = getattr(self.stats_reducer, "ar", None)
+        if ar is not None:
+            ar.check()
+        if self._grad_ar is not None:
+            self._grad_ar.check()
 
     def attach(self, model):
         model.stats_reducer = self.stats_reducer

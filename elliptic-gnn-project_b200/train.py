@@ -99,8 +99,13 @@ class TrainStep:
     def __init__(self, model: nn.Module, x, edge_index, timestep, y, train_mask, *, lr: float,
                  weight_decay: float, grad_clip: float = 1.0, amp: bool = False,
                  cw: Optional[torch.Tensor] = None, n_train_total: Optional[int] = None,
-                 grad_reducer=None):
+                 grad_reducer=None, health_check=None):
+        """`train_mask` and `y` are read ONCE here (train-row indices, class weights, loss normaliser are static per
+        run in the reference too: `src/train_gnn.py:301-312,362-363`); a caller that changes them builds a new
+        TrainStep.  `health_check`: callable run at host synchronisation points (`loss_value()`), e.g.
+        `ShardedContext.check` (raises when a peer-memory all-reduce timed out)."""
         self.model, self.amp = model, amp
+        self.health_check = health_check
         self.x, self.edge_index, self.timestep, self.y = x, edge_index, timestep, y
         self.train_idx = torch.nonzero(train_mask, as_tuple=False).view(-1).contiguous()  # once per run
         self.cw = (cw if cw is not None else class_weight(y[train_mask])).to(x.device)
@@ -132,7 +137,31 @@ class TrainStep:
             self._body()
         return self.loss
 
-    def capture(self, warmup: int = 3):
+    def loss_value(self) -> float:
+        """Loss of the last step on the host (one synchronisation) after the health check."""
+        v = float(self.loss.item())
+        if self.health_check is not None:
+            self.health_check()
+        return v
+
+    def _mutable_state(self):
+        """Everything a step mutates: parameters, Adam moments and step count, BatchNorm buffers, dropout offset."""
+        o = self.opt
+        ts = [o.flat_param, o.exp_avg, o.exp_avg_sq, o.step_count, o.grad_norm, self.loss]
+        ts += [b for b in self.model.buffers() if b.is_cuda]
+        drop = getattr(self.model, "_drop", None)
+        if drop is not None:
+            ts.append(drop.offset)
+        return ts
+
+    def capture(self, warmup: int = 3, preserve_state: bool = False):
+        """Record the step into a CUDA graph after `warmup` eager steps.  The warm-up steps are real optimizer
+        steps; `preserve_state=True` puts parameters, Adam state, BatchNorm buffers and the dropout offset back to
+        their values before the warm-up, so that the first replay IS step 1 of the run (the reference trains exactly
+        `max_epochs` steps from the initial weights, `src/train_gnn.py:380-413`)."""
+        if preserve_state and getattr(self.model, "dropout", 0) > 0 and hasattr(self.model, "dropout_state"):
+            self.model.dropout_state(self.x.device)   # materialise the stream so its offset is part of the snapshot
+        saved = [t.clone() for t in self._mutable_state()] if preserve_state else None
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -144,6 +173,9 @@ class TrainStep:
         with torch.cuda.graph(g):
             self._body()
         self.graph = g
+        if saved is not None:
+            for t, v in zip(self._mutable_state(), saved):
+                t.copy_(v)
         return self
 
 
@@ -161,8 +193,8 @@ class HostFeed:
     """
 
     def __init__(self, step: TrainStep, host: dict, device_bufs: dict, num_nodes: int, graph):
-        from .graph import build_graph
-        self._build = build_graph
+        from .graph import build_graph, register_graph
+        self._build, self._register = build_graph, register_graph
         self.step, self.host, self.dst, self.n, self.graph = step, host, device_bufs, int(num_nodes), graph
         for k, v in host.items():
             if not v.is_pinned():
@@ -175,6 +207,9 @@ class HostFeed:
         self.ev_loss = [torch.cuda.Event(), torch.cuda.Event()]
         self.i = 0
         self._consumed_once = False
+        self.ei_flag = torch.zeros(1, dtype=torch.int32, device=next(iter(device_bufs.values())).device)
+        self.ei_flag_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.rebuilds = 0
         self.h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
 
     def submit(self) -> None:
@@ -187,25 +222,36 @@ class HostFeed:
         with torch.cuda.stream(cs):
             for k in sorted(self.host, key=lambda k: k != "ei"):   # edge_index first: its rebuild can start early
                 self.stage[k].copy_(self.host[k], non_blocking=True)
+                if k == "ei":   # did the edge list change?  (dst["ei"] is stable here: ev_free orders us after run())
+                    a, b = self.stage["ei"], self.dst["ei"]
+                    check(lib().egnn_buffers_differ(ptr(a), ptr(b), a.numel() * a.element_size(), ptr(self.ei_flag),
+                                                    cs.cuda_stream))
+                    self.ei_flag_host.copy_(self.ei_flag, non_blocking=True)
             self.ev_ready.record(cs)
 
     def run(self):
         """One step on the submitted inputs; returns the loss of the PREVIOUS step (None on the first call)."""
         main = torch.cuda.current_stream()
         main.wait_event(self.ev_ready)
+        ei_changed = False
         if "ei" in self.dst:
+            self.ev_ready.synchronize()        # the copy of THIS step's inputs has landed (it overlapped the last step)
+            ei_changed = bool(int(self.ei_flag_host[0]))
+        if ei_changed:
+            self.rebuilds += 1
             self.dst["ei"].copy_(self.stage["ei"], non_blocking=True)
             self.ev_ei.record(main)
             with torch.cuda.stream(self.side):
                 self.side.wait_event(self.ev_ei)
                 self._build(self.dst["ei"], self.n, validate=False, out=self.graph)
                 self.ev_graph.record(self.side)
+            self._register(self.dst["ei"], self.n, self.graph)   # eager steps look the graph up by tensor version
         for k in self.host:
             if k != "ei":
                 self.dst[k].copy_(self.stage[k], non_blocking=True)
         self.ev_free.record(main)
         self._consumed_once = True
-        if "ei" in self.dst:
+        if ei_changed:
             main.wait_event(self.ev_graph)
         self.step.run()
         slot = self.i & 1

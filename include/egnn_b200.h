@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define EGNN_ABI_VERSION 1
+#define EGNN_ABI_VERSION 2
 
 enum { EGNN_F32 = 0, EGNN_BF16 = 1, EGNN_F64 = 2 /* egnn_p2p_allreduce only */ };
 
@@ -88,6 +88,11 @@ int egnn_graph_build(const int64_t* ei, int64_t n_edges_in, int64_t n_nodes, int
                      int32_t* csr_long, int32_t* csc_long, int32_t* csr_order, int32_t* csc_order,
                      int64_t* ei2, float* dis, float* w_edge, float* w_csr, float* w_csc,
                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* *flag = 1 when the two device buffers differ in any byte, else 0 (both 16-byte aligned).  train.HostFeed uses it
+ * to rebuild the sorted views only when a submitted edge_index differs from the one they were built from (the
+ * reference builds nothing per step: `data.to(device)` once, src/train_gnn.py:350). */
+int egnn_buffers_differ(const void* a, const void* b, int64_t n_bytes, int* flag, void* stream);
 
 /* ---------------------------------------------------------------- K2/K3: SpMM --------- */
 /* Deterministic segmented gather-reduce over a sorted view (CSR for forward, CSC for the
@@ -200,6 +205,14 @@ int egnn_inject_time(const float* x, int64_t ld_x, const int64_t* t, const float
                      int64_t T, int64_t D, float* out_f32, void* out_bf16, int64_t ld_out,
                      int64_t ld_out_bf16, int64_t n_rows, int64_t n_feat, void* stream);
 
+/* Gradient of the learned time-embedding table (`nn.Embedding(max_timestep, dim)` backward, src/models/gnn.py:152,
+ * 172-176): dtab[r, d] = sum over rows n with clamp(t[n]-1, 0, T-1) == r of dout[n, col0 + d]  (float [T, D]).
+ * Deterministic (fixed-order float64 partial sums; torch's index_add_ uses float atomics on CUDA).
+ * workspace: egnn_embed_grad_workspace_bytes(n_rows, T, D). */
+size_t egnn_embed_grad_workspace_bytes(int64_t n_rows, int64_t T, int64_t D);
+int egnn_embed_grad(const void* dout, int dtype, int64_t ld, int64_t col0, int64_t D, const int64_t* t, int64_t T,
+                    int64_t n_rows, float* dtab, void* workspace, void* stream);
+
 /* column reductions over rows: sums[c] = sum_r a[r,c] (and sumsq[c] = sum_r a[r,c]^2 when
  * sumsq != NULL), deterministic two-level tree, fp64 combine.  Used for bias gradients and
  * BatchNorm batch statistics (nn.BatchNorm1d, src/models/gnn.py:134,189).
@@ -300,11 +313,13 @@ int egnn_gat_att_grad(const float* xs, const float* da_s, const float* da_d, int
  * peer_bufs_dev: DEVICE array of `world` base pointers, entry r = rank r's buffer of
  * egnn_p2p_allreduce_buffer_bytes(world, n_max, dtype) bytes, zero-initialised, mapped into this process (the
  * Python layer gets them from torch.distributed._symmetric_memory).  epoch: device int64, local, starts at 0
- * (CUDA-graph replayable).  error_flag (optional, device int): set to 1 if a peer did not arrive within ~2 s.
+ * (CUDA-graph replayable).  A peer that does not arrive within timeout_ms (<= 0: 2000; measured with %globaltimer)
+ * makes the call fail LOUDLY: error_flag (optional, device int) is set to 1 and stays set, and the affected chunk of
+ * `out` is filled with NaN, so nothing computed from the un-reduced vector can pass for a result.
  * in == out is allowed.  Every rank must make the same sequence of calls on a given buffer. */
 size_t egnn_p2p_allreduce_buffer_bytes(int world, int64_t n_max, int dtype);
 int egnn_p2p_allreduce(const void* in, void* out, int64_t n, int dtype, int64_t n_max, void* const* peer_bufs_dev,
-                       int rank, int world, int64_t* epoch, int* error_flag, void* stream);
+                       int rank, int world, int64_t* epoch, int* error_flag, int64_t timeout_ms, void* stream);
 
 /* ---------------------------------------------------------------- step tail ----------- */
 /* Masked weighted cross-entropy over precomputed train-row indices:
@@ -344,13 +359,39 @@ int egnn_average_precision(const float* logits, int64_t ld_logits, const float* 
                            const uint8_t* mask, int64_t n_rows, float* scores_out, double* out,
                            void* workspace, size_t workspace_bytes, void* stream);
 
+/* Final metrics of the reference's run tail (src/train_gnn.py:449-470) from the same sorted run:
+ * out double[16]: [0..7] as egnn_average_precision, then
+ *   [8]  max F1 over the precision-recall curve, [9] its threshold   (pick_threshold_max_f1, src/utils/metrics.py:22-27;
+ *        ties -> the lowest threshold, as np.nanargmax over sklearn's ascending thresholds)
+ *   [10] precision among the top_k scores, [15] = min(top_k, selected rows)   (precision_at_k, :39-41)
+ *   [11] max recall with precision >= target_precision                        (recall_at_precision, :43-48)
+ *   [12] lowest threshold with precision >= target_precision, 1.0 if none     (pick_threshold_for_precision, :29-37)
+ *   [13] F1 of the prediction `score >= thr`, thr = *threshold_dev (a DEVICE double, e.g. &out_val[9] of a previous
+ *        call on the validation rows) or this call's own [9] when threshold_dev is NULL   (f1_at_threshold, :18-20)
+ *   [14] expected calibration error over ece_bins (<= 32) equal-width bins    (expected_calibration_error, :50-66)
+ * Counts are exact integers; float64 everywhere the reference's numpy code is float64.  Same workspace as
+ * egnn_average_precision. */
+int egnn_ranking_metrics(const float* logits, int64_t ld_logits, const float* scores, const int64_t* y,
+                         const uint8_t* mask, int64_t n_rows, int64_t top_k, double target_precision,
+                         const double* threshold_dev, int ece_bins, float* scores_out, double* out,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* Temperature scaling (TemperatureScaler.fit, src/utils/calibrate.py:8-30; call site src/train_gnn.py:424-429): the T
+ * minimising CrossEntropyLoss(logits / T, y) over the rows with mask != 0 and y in {0, 1}.  The reference runs LBFGS
+ * on T from 1.0; here one CTA runs a damped Newton iteration on 1/T (the objective is convex in it) with float64
+ * fixed-order sums.  out double[5] (device): {T, mean NLL at T = 1, mean NLL at T, iterations, rows used}. */
+int egnn_temperature_fit(const float* logits, int64_t ld_logits, const int64_t* y, const uint8_t* mask,
+                         int64_t n_rows, int max_iter, double* out, void* stream);
+
 /* Early-stopping bookkeeping without a host round trip (src/train_gnn.py:392-402: `if pr_val > best_val` ->
  * best_state = CPU clone of the state dict; else bad += 1).  state double[5] (device) = {best value, epochs since
  * the best, epoch of the best (1-based), epochs seen, improved flag}; initialise to {-1, 0, 0, 0, 0} (best_val = -1.0,
  * src/train_gnn.py:375).  When the value improves, params[0..n_params) is copied to best_params (both float,
- * 16-byte aligned, may be NULL together). */
+ * 16-byte aligned, may be NULL together).  patience > 0: once state[1] >= patience (`if bad >= patience: break`,
+ * src/train_gnn.py:411) the call is a no-op (improved flag cleared), so epochs run past the stopping point before
+ * the host polls cannot change best value or snapshot; patience <= 0: never frozen. */
 int egnn_early_stop_update(const double* ap, double* state, const float* params, float* best_params,
-                           int64_t n_params, void* stream);
+                           int64_t n_params, int64_t patience, void* stream);
 /* The rest of `best_state` (BatchNorm running statistics and counters, any tensor outside the flat parameter
  * buffer): dst <- src when the LAST egnn_early_stop_update improved the best value (state[4] != 0).  Buffers are
  * 4-byte aligned, n_bytes a multiple of 4. */

@@ -1,4 +1,4 @@
-"""NumPy oracle for the epoch-tail metric  --  TEST INFRASTRUCTURE ONLY.
+"""NumPy oracle for the epoch-tail and final metrics  --  TEST INFRASTRUCTURE ONLY.
 
 Restates `pr_auc_illicit` (`/root/reference/src/utils/metrics.py:11-13`), i.e. scikit-learn's
 `average_precision_score` for a binary target (third-party, unpinned in the reference's `environment.yml:9`;
@@ -6,6 +6,11 @@ algorithm as published in `sklearn/metrics/_ranking.py`: `_binary_clf_curve` -> 
 `-sum(diff(recall) * precision[:-1])`).  PARITY PINNED: checked in tests/test_oracle_metrics.py against
 (a) scikit-learn itself (installed here and on the GPU box) and (b) golden vectors produced by importing the
 reference's own `src/utils/metrics.py` in this container (`tests/golden/make_metrics_golden.py`).
+
+The final-metrics functions (`pick_threshold_max_f1`, `pick_threshold_for_precision`, `f1_at_threshold`,
+`precision_at_k`, `recall_at_precision`, `expected_calibration_error`, `/root/reference/src/utils/metrics.py:18-66`) and
+the temperature-scaling objective (`/root/reference/src/utils/calibrate.py:8-30`) are pinned the same way: golden vectors
+from the reference's own functions / `TemperatureScaler.fit` (`tests/golden/make_metrics_golden.py`).
 
 Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import this module.
 """
@@ -58,6 +63,103 @@ def roc_auc(y_true: np.ndarray, y_score: np.ndarray) -> float:
     fpr = np.r_[0.0, fps / fps[-1]]
     tpr = np.r_[0.0, tps / tps[-1]]
     return float(np.sum(np.diff(fpr) * (tpr[1:] + tpr[:-1]) * 0.5))
+
+
+def precision_recall_curve(y_true: np.ndarray, y_score: np.ndarray):
+    """sklearn `precision_recall_curve` (no `drop_intermediate`): precision, recall over ASCENDING thresholds with the
+    final (1, 0) point appended; recall is 1 everywhere when there is no positive."""
+    fps, tps, thr = binary_clf_curve(y_true, y_score)
+    ps = tps + fps
+    precision = np.zeros_like(tps)
+    np.divide(tps, ps, out=precision, where=(ps != 0))
+    recall = np.ones_like(tps) if tps[-1] == 0 else tps / tps[-1]
+    return np.hstack((precision[::-1], 1.0)), np.hstack((recall[::-1], 0.0)), thr[::-1]
+
+
+def pick_threshold_max_f1(y_true: np.ndarray, y_score: np.ndarray):
+    """`/root/reference/src/utils/metrics.py:22-27` -> (threshold, f1)."""
+    precision, recall, thresholds = precision_recall_curve(y_true, y_score)
+    thresholds = np.append(thresholds, 1.0)
+    f1s = 2 * precision * recall / (precision + recall + 1e-12)
+    i = int(np.nanargmax(f1s))
+    return float(thresholds[i]), float(f1s[i])
+
+
+def pick_threshold_for_precision(y_true: np.ndarray, y_score: np.ndarray, target_p: float) -> float:
+    """`/root/reference/src/utils/metrics.py:29-37`."""
+    precision, recall, thresholds = precision_recall_curve(y_true, y_score)
+    cand = np.append(thresholds, 1.0)
+    mask = precision >= target_p
+    if not np.any(mask):
+        return pick_threshold_max_f1(y_true, y_score)[0]
+    return float(cand[int(np.argmax(mask))])
+
+
+def f1_at_threshold(y_true: np.ndarray, y_score: np.ndarray, thr: float) -> float:
+    """`/root/reference/src/utils/metrics.py:18-20` (sklearn `f1_score`, binary): 2 tp / (2 tp + fp + fn), 0 if undefined."""
+    y_true = np.asarray(y_true).astype(np.int64)
+    pred = (np.asarray(y_score) >= thr).astype(np.int64)
+    tp = int((pred & y_true).sum())
+    den = int(pred.sum()) + int(y_true.sum())
+    return 2.0 * tp / den if den > 0 else 0.0
+
+
+def precision_at_k(y_true: np.ndarray, y_score: np.ndarray, k: int) -> float:
+    """`/root/reference/src/utils/metrics.py:39-41` (ties at the k-th score are broken by a STABLE descending sort
+    here; the reference's `np.argsort(-s)` leaves them unspecified)."""
+    idx = np.argsort(-np.asarray(y_score), kind="stable")[:k]
+    return float(np.mean(np.asarray(y_true)[idx]))
+
+
+def recall_at_precision(y_true: np.ndarray, y_score: np.ndarray, target_p: float) -> float:
+    """`/root/reference/src/utils/metrics.py:43-48`."""
+    precision, recall, _ = precision_recall_curve(y_true, y_score)
+    mask = precision >= target_p
+    return float(np.max(recall[mask])) if np.any(mask) else 0.0
+
+
+def expected_calibration_error(y_true: np.ndarray, y_prob: np.ndarray, bins: int = 15) -> float:
+    """`/root/reference/src/utils/metrics.py:50-66`."""
+    y_true = np.asarray(y_true).astype(int)
+    y_prob = np.asarray(y_prob)
+    edges = np.linspace(0.0, 1.0, bins + 1)
+    ece = 0.0
+    for i in range(bins):
+        lo, hi = edges[i], edges[i + 1]
+        m = (y_prob >= lo) & ((y_prob < hi) if i < bins - 1 else (y_prob <= hi))
+        if not np.any(m):
+            continue
+        ece += m.mean() * abs(y_true[m].mean() - y_prob[m].mean())
+    return float(ece)
+
+
+def temperature_nll(logits: np.ndarray, y: np.ndarray, T: float) -> float:
+    """mean CrossEntropyLoss(logits / T, y) in float64 (the objective of `src/utils/calibrate.py:17-27`)."""
+    z = np.asarray(logits, dtype=np.float64) / T
+    m = z.max(axis=1, keepdims=True)
+    lse = (m + np.log(np.exp(z - m).sum(axis=1, keepdims=True)))[:, 0]
+    return float(np.mean(lse - z[np.arange(len(y)), np.asarray(y).astype(int)]))
+
+
+def fit_temperature(logits: np.ndarray, y: np.ndarray) -> float:
+    """The minimiser the reference's LBFGS converges to: argmin_T temperature_nll(logits, y, T), by golden-section
+    search on beta = 1/T (the objective is convex in beta)."""
+    lo, hi = 1e-4, 1e3
+    phi = (np.sqrt(5.0) - 1.0) / 2.0
+    f = lambda b: temperature_nll(logits, y, 1.0 / b)
+    a, b = lo, hi
+    c, d = b - phi * (b - a), a + phi * (b - a)
+    fc, fd = f(c), f(d)
+    for _ in range(200):
+        if fc < fd:
+            b, d, fd = d, c, fc
+            c = b - phi * (b - a)
+            fc = f(c)
+        else:
+            a, c, fc = c, d, fd
+            d = a + phi * (b - a)
+            fd = f(d)
+    return 2.0 / (a + b)
 
 
 def softmax_pos(logits: np.ndarray) -> np.ndarray:

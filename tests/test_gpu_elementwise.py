@@ -142,13 +142,13 @@ def test_inject_time_bitexact(egnn):
     ref = net._inject_time(x, t)
     table = sinusoid_table(T, 2)
     assert torch.equal(table, O.sinusoid_table(T, 2))
-    got = ops.InjectTimeFn.apply(x.cuda(), t.cuda(), table.cuda(), 168).cpu()
+    got = ops.InjectTimeFn.apply(x.cuda(), t.cuda(), table.cuda(), 168)[0].cpu()
     assert torch.equal(got, ref)
     # scalar-time append of train_gnn.py:315-317 through the same kernel (F -> F+1, padded to 168)
     tt = torch.randint(1, 50, (n,))
     tn = (tt.float() / float(tt.max())).unsqueeze(1)
     tab = (torch.arange(1, T + 1).float() / float(tt.max())).unsqueeze(1)
-    got = ops.InjectTimeFn.apply(x.cuda(), tt.cuda(), tab.cuda(), 168).cpu()
+    got = ops.InjectTimeFn.apply(x.cuda(), tt.cuda(), tab.cuda(), 168)[0].cpu()
     assert torch.equal(got[:, :167], torch.cat([x, tn], dim=1)) and (got[:, 167] == 0).all()
 
 
@@ -169,6 +169,51 @@ def test_p2p_allreduce_single_rank_protocol(egnn):
             x = torch.randn(n, dtype=dtype, device="cuda")
             want = x.clone()
             _lib.check(L.egnn_p2p_allreduce(x.data_ptr(), x.data_ptr(), n, code, n_max, ptrs.data_ptr(), 0, 1,
-                                            epoch.data_ptr(), err.data_ptr(), _lib.stream()))
+                                            epoch.data_ptr(), err.data_ptr(), 0, _lib.stream()))
             assert torch.equal(x, want)
         assert int(epoch.item()) == 5 and int(err.item()) == 0
+
+
+def test_p2p_allreduce_missing_peer_fails_loudly(egnn):
+    """a peer that never arrives must not yield a silently un-reduced vector.  World of 2 simulated on one
+    GPU (two buffers, rank 1 never runs): after the (shortened) timeout the error flag is set and stays set, the
+    output is NaN, and P2PAllReduce.check()-style polling of the flag raises."""
+    from egnn_b200 import _lib
+    L = _lib.lib()
+    n_max = n = 128
+    nbytes = L.egnn_p2p_allreduce_buffer_bytes(2, n_max, _lib.F64)
+    bufs = [torch.zeros((nbytes + 7) // 8, dtype=torch.int64, device="cuda") for _ in range(2)]
+    ptrs = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device="cuda")
+    epoch = torch.zeros(1, dtype=torch.int64, device="cuda")
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    x = torch.randn(n, dtype=torch.float64, device="cuda")
+    _lib.check(L.egnn_p2p_allreduce(x.data_ptr(), x.data_ptr(), n, _lib.F64, n_max, ptrs.data_ptr(), 0, 2,
+                                    epoch.data_ptr(), err.data_ptr(), 20, _lib.stream()))
+    torch.cuda.synchronize()
+    assert int(err.item()) == 1
+    assert torch.isnan(x).all()
+
+
+def test_learned_time_embedding_backward_is_deterministic(egnn):
+    """`time_embed_type: learned` (src/models/gnn.py:152,172-176): the table gradient is a fixed-order segmented
+    sum (egnn_embed_grad), equal to the oracle's index_add within fp32 and bitwise reproducible."""
+    from egnn_b200 import ops
+    n, f, T, D = 20000, 166, 49, 6
+    torch.manual_seed(4)
+    x = torch.randn(n, f)
+    t = torch.randint(-1, 55, (n,))
+    table = torch.randn(T, D)
+    w = torch.randn(n, 176)
+    ref_tab = table.clone().requires_grad_(True)
+    idx = torch.clamp(t - 1, 0, T - 1)
+    ref = torch.cat([x, ref_tab[idx]], dim=1)
+    (ref * w[:, :f + D]).sum().backward()
+    grads = []
+    for _ in range(2):
+        tab = table.cuda().requires_grad_(True)
+        out, _ = ops.InjectTimeFn.apply(x.cuda(), t.cuda(), tab, 176, False)
+        assert torch.equal(out[:, :f + D].cpu(), ref.detach()) and (out[:, f + D:] == 0).all()
+        (out * w.cuda()).sum().backward()
+        grads.append(tab.grad.clone())
+    assert torch.equal(grads[0], grads[1])
+    assert_close(grads[0], ref_tab.grad, REL_FP32, "d time_emb.weight")

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 def _check(egnn, ei_cpu, n, symmetrize, self_loops):
     g = egnn.build_graph(ei_cpu.cuda(), n, symmetrize=symmetrize, self_loops=self_loops, want_norm=True,
-                         keep_edge_list=True)
+                         keep_edge_list=True, want_order=True)
     ei = ei_cpu.numpy()
     ref = G.symmetrize(ei) if symmetrize else ei
     if self_loops:

@@ -44,6 +44,7 @@ def test_feed_reproduces_resident_steps(egnn, capture):
             got.append(prev)
     got.append(feed.drain())
     assert got == ref
+    assert feed.rebuilds == 0          # unchanged edge list: the sorted views are never rebuilt
 
 
 def test_feed_picks_up_new_host_contents(egnn):
@@ -62,6 +63,8 @@ def test_feed_picks_up_new_host_contents(egnn):
     feed.run()
     feed.drain()
     assert torch.equal(dev["x"].cpu(), host["x"]) and torch.equal(dev["ei"].cpu(), host["ei"])
+    assert feed.rebuilds == 1          # the permuted edge list was detected on the device, the first submit was not
+    assert egnn.cached_graph(dev["ei"], gr.num_nodes) is g   # eager steps find the rebuilt graph (no second build)
     fresh = egnn.build_graph(dev["ei"], gr.num_nodes)
     assert torch.equal(g.csr_src[: g.n_edges], fresh.csr_src[: fresh.n_edges])
     assert torch.equal(g.csr_part, fresh.csr_part)

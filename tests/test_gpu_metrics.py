@@ -90,10 +90,34 @@ def test_early_stopper_matches_reference_bookkeeping(egnn):
     assert torch.equal(flat, snap)
 
 
-def test_fit_loop_matches_host_side_early_stopping(egnn):
-    """metrics.fit (device-side epoch tail, polled every 4 epochs) against the reference's loop shape
-    (src/train_gnn.py:380-417) run on the host with the oracle metric: same best epoch, same best value to 1e-9,
-    and the restored parameters / BatchNorm buffers are the ones of the best epoch."""
+def test_early_stopper_freezes_at_patience(egnn):
+    """a value that improves AFTER `bad >= patience` (epochs the host runs before it polls) must not move
+    the best value or overwrite the snapshot -- the reference has left its loop by then (src/train_gnn.py:411)."""
+    from egnn_b200 import metrics
+    flat = torch.zeros(64, dtype=torch.float32, device="cuda")
+    es = metrics.EarlyStopper(patience=2, flat_param=flat)
+    seq = [0.5, 0.4, 0.3, 0.9, 0.95, 0.1]           # reference: best 0.5 at epoch 1, breaks after epoch 3
+    for v in seq:
+        flat += 1.0
+        es.update(torch.tensor([v, 0, 0, 0], dtype=torch.float64, device="cuda"))
+    st = es.state.cpu().tolist()
+    assert st[:4] == [0.5, 2.0, 1.0, 3.0] and st[4] == 0.0
+    assert torch.equal(es.best_param, torch.full((64,), 1.0, device="cuda"))
+    es.restore_best()
+    assert torch.equal(flat, torch.full((64,), 1.0, device="cuda"))
+    # patience <= 0: never frozen (plain bookkeeping)
+    es = metrics.EarlyStopper(patience=0, flat_param=flat)
+    for v in seq:
+        es.update(torch.tensor([v, 0, 0, 0], dtype=torch.float64, device="cuda"))
+    assert es.state.cpu().tolist()[:4] == [0.95, 1.0, 5.0, 6.0]
+
+
+@pytest.mark.parametrize("capture", [False, True])
+def test_fit_loop_matches_host_side_early_stopping(egnn, capture):
+    """metrics.fit (device-side epoch tail, polled every 4 epochs; eager and CUDA-graph captured) against the
+    reference's loop shape (src/train_gnn.py:380-417) run on the host with the oracle metric, both starting from the
+    SAME initial weights with epoch 1 = the first optimizer step: same best epoch, same stopping epoch, same best
+    value, and the restored parameters / BatchNorm buffers are bitwise the ones of the best epoch."""
     from egnn_b200 import metrics, synthetic
     from egnn_b200.train import TrainStep, eval_probs
     cfg = dict(hidden_dim=32, layers=3, dropout=0.0, time_embed_dim=2, time_embed_type="sin", max_timestep=49)
@@ -108,7 +132,6 @@ def test_fit_loop_matches_host_side_early_stopping(egnn):
     torch.manual_seed(0)
     ref_model = egnn.build_model("sage_resbn", 166, cfg).cuda()
     step = TrainStep(ref_model, x, ei, t, y, tm, **kw)
-    step.run()                                            # metrics.fit runs one eager step before its loop, too
     es, best_state, stop_epoch = M.EarlyStop(), None, None
     yv = (gr.y.numpy()[gr.val_mask.numpy()] == 1).astype(int)
     for epoch in range(1, max_epochs + 1):
@@ -126,10 +149,110 @@ def test_fit_loop_matches_host_side_early_stopping(egnn):
     torch.manual_seed(0)
     model = egnn.build_model("sage_resbn", 166, cfg).cuda()
     res = metrics.fit(model, x, ei, t, y, tm, vm, max_epochs=max_epochs, patience=patience, poll_every=4,
-                      capture=False, **kw)
+                      capture=capture, **kw)
     assert res["best_epoch"] == es.best_epoch
+    assert res["stop_epoch"] == stop_epoch
     assert res["best_val"] == pytest.approx(es.best, rel=1e-6)   # device softmax vs torch.softmax: last-ulp scores
     assert stop_epoch <= res["epochs"] < stop_epoch + 4 and res["epochs"] <= max_epochs   # bounded overshoot
     got = model.state_dict()
     for k, v in best_state.items():
         assert torch.equal(got[k], v), k
+
+
+@pytest.mark.parametrize("n,quant", [(1, 0), (9, 2), (1000, 0), (2049, 8), (46564, 0), (203769, 64), (203769, 0)])
+def test_ranking_metrics_match_oracle(egnn, n, quant):
+    """every number of the reference's run tail (src/train_gnn.py:449-470; src/utils/metrics.py:18-66)
+    from one device sort, against the oracle that is pinned to the reference's own functions."""
+    from egnn_b200 import metrics
+    y, s, mask = _inputs(n, seed=3 * n + quant, quant=quant)
+    yb, sb = (y[mask] == 1).astype(int), s[mask]
+    k = 100
+    thr_in = torch.tensor([0.37], dtype=torch.float64, device="cuda")
+    yc, mc, sc = torch.from_numpy(y).cuda(), torch.from_numpy(mask).cuda(), torch.from_numpy(s).cuda()
+    out = metrics.ranking_metrics(yc, mc, scores=sc, top_k=k, target_precision=0.2, threshold=thr_in).cpu().numpy()
+    out_self = metrics.ranking_metrics(yc, mc, scores=sc, top_k=k, target_precision=0.2).cpu().numpy()
+    if yb.size == 0:
+        assert out[1] == 0 and out[8] == 0.0
+        return
+    ap = M.average_precision(yb, sb)
+    assert out[0] == pytest.approx(ap[0], rel=TOL, abs=1e-15) and (int(out[1]), int(out[2])) == ap[1:3]
+    thr, f1 = M.pick_threshold_max_f1(yb, sb)
+    if yb.sum() > 0:
+        assert out[9] == thr and out[8] == pytest.approx(f1, rel=1e-12)
+        assert out[11] == pytest.approx(M.recall_at_precision(yb, sb, 0.2), rel=1e-12)
+        assert out[12] == M.pick_threshold_for_precision(yb, sb, 0.2)
+        assert out_self[13] == pytest.approx(M.f1_at_threshold(yb, sb, thr), rel=1e-12)
+    assert out[13] == pytest.approx(M.f1_at_threshold(yb, sb, 0.37), rel=1e-12, abs=1e-15)
+    assert int(out[15]) == min(k, yb.size)
+    if not quant:   # ties at the k-th score are unspecified in the reference (unstable argsort)
+        assert out[10] == pytest.approx(M.precision_at_k(yb, sb, k), rel=1e-12, abs=1e-15)
+    assert out[14] == pytest.approx(M.expected_calibration_error(yb, sb), rel=1e-6, abs=1e-9)   # fp32 bin means there
+
+
+def test_temperature_fit_matches_reference_scaler(egnn):
+    """egnn_temperature_fit against golden T values from the reference's own TemperatureScaler.fit
+    (tests/golden/make_metrics_golden.py) and the oracle minimiser."""
+    import json
+    import os
+    from egnn_b200 import metrics
+    from test_oracle_metrics import _temp_case
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "metrics_golden.json")))
+    for c in g["temperature"]:
+        logits, yy = _temp_case(c["seed"], c["n"], c["scale"])
+        out = metrics.fit_temperature(logits.cuda(), yy.cuda()).cpu().tolist()
+        T_or = M.fit_temperature(logits.numpy(), yy.numpy())
+        assert out[0] == pytest.approx(T_or, rel=1e-6), c
+        assert out[2] == pytest.approx(M.temperature_nll(logits.numpy(), yy.numpy(), T_or), rel=1e-9)
+        assert out[1] == pytest.approx(M.temperature_nll(logits.numpy(), yy.numpy(), 1.0), rel=1e-9)
+        assert int(out[4]) == c["n"] and out[3] < 50
+        if not c["reference_diverged"]:
+            assert out[0] == pytest.approx(c["T"], rel=2e-3), c      # the reference's fp32 LBFGS stops ~1e-3 short
+    # masked rows and unlabelled rows (-1) are ignored
+    logits, yy = _temp_case(0, 4000, 3.0)
+    y2 = yy.clone()
+    y2[::3] = -1
+    m = torch.rand(4000, generator=torch.Generator().manual_seed(1)) < 0.7
+    sel = (m & (y2 >= 0)).numpy()
+    out = metrics.fit_temperature(logits.cuda(), y2.cuda(), m.cuda()).cpu().tolist()
+    assert int(out[4]) == int(sel.sum())
+    assert out[0] == pytest.approx(M.fit_temperature(logits.numpy()[sel], y2.numpy()[sel]), rel=1e-6)
+
+
+def test_final_metrics_matches_the_reference_run_tail(egnn):
+    """metrics.final_metrics (device) against the reference's run tail restated with the oracle functions
+    (src/train_gnn.py:420-480): temperature on val, threshold on val, metrics on test."""
+    from egnn_b200 import metrics, synthetic
+    from egnn_b200.train import TrainStep, eval_probs
+    cfg = dict(hidden_dim=32, layers=3, dropout=0.0, time_embed_dim=2, time_embed_type="sin", max_timestep=49)
+    gr = synthetic.make_elliptic_like(n_nodes=20000, n_edges=23000, n_timesteps=12, seed=6, hub_degree=80,
+                                      t_train_end=7, t_val_end=9, label_signal=1.0)
+    ei = torch.cat([gr.edge_index, gr.edge_index.flip(0)], dim=1).cuda()
+    x, t, y = gr.x.cuda(), gr.timestep.cuda(), gr.y.cuda()
+    torch.manual_seed(0)
+    model = egnn.build_model("sage_resbn", 166, cfg).cuda()
+    step = TrainStep(model, x, ei, t, y, gr.train_mask.cuda(), lr=1e-2, weight_decay=0.0, amp=False)
+    for _ in range(15):
+        step.run()
+    vm, tm = gr.val_mask.numpy(), gr.test_mask.numpy()
+    for calib in (False, True):
+        got = metrics.final_metrics(model, x, ei, t, y, gr.val_mask.cuda(), gr.test_mask.cuda(),
+                                    calibrate_temperature=calib, top_k=50)
+        _, logits = eval_probs(model, x, ei, t)
+        logits = logits.float().cpu()
+        yn = gr.y.numpy()
+        if calib:
+            T = M.fit_temperature(logits.numpy()[vm], yn[vm])
+            assert got["temperature"] == pytest.approx(T, rel=1e-6)
+            logits = logits / torch.tensor(got["temperature"], dtype=torch.float32)
+        probs = torch.softmax(logits, dim=1)[:, 1].numpy()
+        yv, pv, yt, pt = (yn[vm] == 1).astype(int), probs[vm], (yn[tm] == 1).astype(int), probs[tm]
+        thr, _ = M.pick_threshold_max_f1(yv, pv)
+        # device softmax vs torch.softmax differ in the last ulp of a score: compare at 1e-6
+        assert got["threshold"] == pytest.approx(thr, rel=1e-6)
+        assert got["pr_auc_illicit"] == pytest.approx(M.average_precision(yt, pt)[0], rel=1e-6)
+        assert got["roc_auc"] == pytest.approx(M.roc_auc(yt, pt), rel=1e-6)
+        assert got["f1_illicit_at_thr"] == pytest.approx(M.f1_at_threshold(yt, pt, thr), abs=2e-3)
+        assert got["precision_at_k"] == pytest.approx(M.precision_at_k(yt, pt, 50), abs=0.021)
+        assert got["recall_at_precision"] == pytest.approx(M.recall_at_precision(yt, pt, 0.90), abs=2e-3)
+        assert got["ece"] == pytest.approx(M.expected_calibration_error(yt, pt), abs=1e-5)
+        assert got["n_test"] == int(tm.sum()) and got["pr_auc_illicit"] > 0.15

@@ -1,0 +1,92 @@
+"""Trajectory parity (`north_star`: "bf16-amp within a stated tolerance with identical PR-AUC/F1 to
+3 decimals").  rec_k8 (SAGE-ResBN, BatchNorm, residual, sin-2 time embedding, dropout 0.2, lr 5e-4) is trained for 30
+epochs on the FULL-SIZE synthetic graph by the CUDA path (CUDA-graph replays) and by the CPU oracle from the same
+initial weights; every epoch the oracle is fed the very Philox keep-masks the CUDA step drew
+(`egnn_dropout_mask`), so the two trajectories differ by arithmetic only.  The graph carries a planted label signal
+(`synthetic.make_elliptic_like(label_signal=1)`): validation PR-AUC climbs from chance (0.10) to ~0.4, so agreement to
+3 decimals is a statement about the models, not about ties between unordered scores.
+
+Checked every 5 epochs on the validation rows, both sides through the SAME metric code (oracle/metrics_np.py, pinned
+to the reference's `pr_auc_illicit` / `pick_threshold_max_f1`, src/utils/metrics.py:11-27) on fp32 eval forwards
+(`eval_split` is never under autocast, src/train_gnn.py:248-257):
+  |PR-AUC_cuda - PR-AUC_oracle| < 5e-4 and |maxF1_cuda - maxF1_oracle| < 5e-4  (equal to 3 decimals), fp32 AND bf16;
+  training loss: fp32 rel 1e-4 after 30 Adam steps (Adam's g/sqrt(v) amplifies the 1e-5 per-step difference of
+  near-zero gradient elements), bf16 rel 2e-2.
+The device metric kernel (`egnn_ranking_metrics`) is checked on the same logits against the same oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import metrics_np as M
+from oracle import pyg_restated as O
+from util import assert_close
+
+pytestmark = pytest.mark.gpu
+
+CFG = dict(arch="sage_resbn", hidden_dim=64, layers=3, dropout=0.2, time_embed_dim=2, time_embed_type="sin",
+           max_timestep=49)          # /root/reference/configs/rec_k8.yaml
+LR, WD, EPOCHS, SEED = 5.0e-4, 5.0e-5, 30, 42
+
+
+@pytest.fixture(scope="module")
+def planted_graph():
+    from egnn_b200 import synthetic
+    return synthetic.make_elliptic_like(train_window_k=8, label_signal=1.0)
+
+
+@pytest.mark.parametrize("amp", [False, True], ids=["fp32", "bf16"])
+def test_rec_k8_30_epoch_trajectory(egnn, planted_graph, amp):
+    from egnn_b200 import metrics, ops
+    from egnn_b200.train import TrainStep, eval_probs
+    gr = planted_graph
+    n = gr.num_nodes
+    ei = torch.cat([gr.edge_index, gr.edge_index.flip(0)], dim=1)
+    torch.manual_seed(0)
+    ours = egnn.build_model(CFG["arch"], 166, CFG)
+    ref = O.build_model(CFG["arch"], 166, CFG)
+    ref.load_state_dict(ours.state_dict())
+    ours = ours.cuda()
+    ours.set_dropout_seed(SEED)
+    cw = O.class_weight(gr.y[gr.train_mask])
+    xc, eic, tc, yc = gr.x.cuda(), ei.cuda(), gr.timestep.cuda(), gr.y.cuda()
+    step = TrainStep(ours, xc, eic, tc, yc, gr.train_mask.cuda(), lr=LR, weight_decay=WD, grad_clip=1.0, amp=amp, cw=cw)
+    step.capture(warmup=2, preserve_state=True)      # epoch 1 = the first optimizer step from the initial weights
+    opt_ref = torch.optim.Adam(ref.parameters(), lr=LR, weight_decay=WD)
+    vm = gr.val_mask.numpy()
+    yv = (gr.y.numpy()[vm] == 1).astype(int)
+    vmc = gr.val_mask.cuda()
+    rows = []
+    for epoch in range(1, EPOCHS + 1):
+        loss_o = float(step.run())
+        masks = [ops.dropout_mask(n, CFG["hidden_dim"], CFG["dropout"], SEED, li, seed_off=ours._drop.offset).cpu()
+                 for li in range(CFG["layers"] - 1)]
+        loss_r, _ = O.train_step(ref, gr.x, ei, gr.timestep, gr.y, gr.train_mask, cw, opt_ref, 1.0,
+                                 amp_dtype=torch.bfloat16 if amp else None, dropout_masks=masks)
+        if epoch % 5 and epoch != 1:
+            continue
+        p_o, logits_o = eval_probs(ours, xc, eic, tc)
+        p_r, _ = O.eval_probs(ref, gr.x, ei, gr.timestep)
+        so, sr = p_o.cpu().numpy()[vm], p_r.numpy()[vm]
+        ap_o, ap_r = M.average_precision(yv, so)[0], M.average_precision(yv, sr)[0]
+        f1_o, f1_r = M.pick_threshold_max_f1(yv, so)[1], M.pick_threshold_max_f1(yv, sr)[1]
+        dev = metrics.ranking_metrics(yc, vmc, logits=logits_o.float().contiguous()).cpu().tolist()
+        rows.append((epoch, loss_o, loss_r, ap_o, ap_r, f1_o, f1_r))
+        print(f"[trajectory {'bf16' if amp else 'fp32'}] epoch {epoch:2d} loss {loss_o:.6f} / {loss_r:.6f}  "
+              f"val PR-AUC {ap_o:.5f} / {ap_r:.5f}  max-F1 {f1_o:.5f} / {f1_r:.5f}")
+        assert dev[0] == pytest.approx(ap_o, rel=1e-6) and dev[8] == pytest.approx(f1_o, rel=1e-6)
+        assert abs(ap_o - ap_r) < 5e-4, (epoch, ap_o, ap_r)
+        assert abs(f1_o - f1_r) < 5e-4, (epoch, f1_o, f1_r)
+        assert abs(loss_o - loss_r) <= (2e-2 if amp else 1e-4) * abs(loss_r), (epoch, loss_o, loss_r)
+    assert rows[-1][0] == EPOCHS and rows[-1][3] > 0.30       # the models did learn the planted signal
+    import json
+    import os
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "r02")
+    if os.path.isdir(out_dir):                                 # evidence for profiles/ (the GPU box merges gpurun_out/ back)
+        json.dump({"precision": "bf16" if amp else "fp32", "columns": ["epoch", "loss_cuda", "loss_oracle",
+                   "val_pr_auc_cuda", "val_pr_auc_oracle", "val_max_f1_cuda", "val_max_f1_oracle"], "rows": rows},
+                  open(os.path.join(out_dir, f"trajectory_{'bf16' if amp else 'fp32'}.json"), "w"), indent=1)
+    if not amp:
+        for b, br in zip(ours.bns, ref.bns):
+            assert int(b.num_batches_tracked) == int(br.num_batches_tracked) == EPOCHS
+            assert_close(b.running_mean, br.running_mean, 1e-3, "running_mean after 30 epochs")
+            assert_close(b.running_var, br.running_var, 1e-3, "running_var after 30 epochs")

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol(egnn):
     lib = _lib.lib()
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.egnn_abi_version() == 1
+    assert lib.egnn_abi_version() == 2
     assert lib.egnn_launch_count() >= 0
 
 

@@ -39,6 +39,53 @@ def test_golden_vectors_from_the_reference_function():
         assert M.roc_auc(y, s) == pytest.approx(c["roc"], rel=1e-13), c
 
 
+def test_final_metrics_golden_from_the_reference_functions():
+    """pick_threshold_max_f1 / pick_threshold_for_precision / f1_at_threshold / precision_at_k / recall_at_precision /
+    expected_calibration_error (`/root/reference/src/utils/metrics.py:18-66`), recorded from the reference itself."""
+    g = json.load(open(os.path.join(HERE, "golden", "metrics_golden.json")))
+    n_checked = 0
+    for c in g["cases"]:
+        if c.get("reference_test"):
+            continue
+        y, s = _case(c["seed"], c["n"], c["pos_rate"], c["quant"])
+        thr, f1 = M.pick_threshold_max_f1(y, s)
+        assert thr == c["thr_max_f1"] and f1 == pytest.approx(c["max_f1"], rel=1e-13), c
+        assert M.pick_threshold_for_precision(y, s, 0.5) == c["thr_p50"], c
+        assert M.f1_at_threshold(y, s, thr) == pytest.approx(c["f1_at_thr"], rel=1e-13), c
+        assert M.f1_at_threshold(y, s, 0.45) == pytest.approx(c["f1_at_045"], rel=1e-13), c
+        if c["p_at_k"] is not None:
+            assert M.precision_at_k(y, s, c["k"]) == pytest.approx(c["p_at_k"], rel=1e-13), c
+        assert M.recall_at_precision(y, s, 0.5) == pytest.approx(c["rec_at_p50"], rel=1e-13), c
+        assert M.recall_at_precision(y, s, 0.9) == pytest.approx(c["rec_at_p90"], rel=1e-13), c
+        assert M.expected_calibration_error(y, s) == pytest.approx(c["ece"], rel=1e-12), c
+        n_checked += 1
+    assert n_checked >= 8
+
+
+def _temp_case(seed, n, scale):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    yy = (torch.rand(n, generator=g) < 0.15).long()
+    margin = torch.randn(n, generator=g) + 1.2 * (2 * yy.float() - 1)
+    logits = torch.stack([-0.5 * margin, 0.5 * margin], dim=1) * scale
+    return logits, yy
+
+
+def test_temperature_oracle_against_the_reference_scaler():
+    """`TemperatureScaler.fit` (`/root/reference/src/utils/calibrate.py:8-30`) is LBFGS in fp32 and stops within ~1e-3
+    of the minimiser; the oracle's minimiser must reach an NLL at least as low and a T within 2e-3 relative.  Where
+    the reference's LBFGS diverges (T < 0, recorded) only the objective is compared."""
+    g = json.load(open(os.path.join(HERE, "golden", "metrics_golden.json")))
+    assert len(g["temperature"]) >= 5
+    for c in g["temperature"]:
+        logits, yy = _temp_case(c["seed"], c["n"], c["scale"])
+        T = M.fit_temperature(logits.numpy(), yy.numpy())
+        nll = M.temperature_nll(logits.numpy(), yy.numpy(), T)
+        assert nll <= M.temperature_nll(logits.numpy(), yy.numpy(), c["T"]) + 1e-12
+        if not c["reference_diverged"]:
+            assert T == pytest.approx(c["T"], rel=2e-3), c
+
+
 def test_against_sklearn_including_ties_and_degenerate_inputs():
     sk = pytest.importorskip("sklearn.metrics")
     rng = np.random.default_rng(11)
