@@ -111,6 +111,227 @@ def spmm_bytes(n, f, e, in_es, out_es):
     return n * f * in_es + n * f * out_es + 4 * e + 4 * (n + 1)
 
 
+# BASELINE.json configs other than the headline one (reference configs/*.yaml); timed at N=1 and reported in `configs`
+OTHER_CONFIGS = {
+    "gcn": dict(arch="gcn", hidden_dim=128, layers=3, dropout=0.5, lr=1e-3, weight_decay=5e-4, k=10, sym=False, amp=False,
+                what="configs/gcn.yaml: GCN 167->128->128->2, self-loop graph E'=438124, fp32 (config 1 is the CPU run)"),
+    "sage": dict(arch="sage", hidden_dim=128, layers=2, dropout=0.5, lr=1e-3, weight_decay=5e-4, k=10, sym=True, amp=False,
+                 what="configs/sage.yaml + symmetrize_edges: SAGE 167->128->2, fp32"),
+    "gat": dict(arch="gat", hidden_dim=32, layers=2, heads=4, dropout=0.5, lr=1e-3, weight_decay=5e-4, k=10, sym=False,
+                amp=True, what="configs/gat.yaml: GAT 167->(4x8)->2, self-loop graph, bf16 autocast (attention fp32)"),
+    "sage_l3": dict(arch="sage", hidden_dim=128, layers=3, dropout=0.4, lr=1e-3, weight_decay=5e-4, k=18, sym=True,
+                    amp=True, what="configs/sage_l3_k18.yaml: SAGE 167->128->128->2 on the base graph (x1), bf16 autocast"),
+}
+
+
+def _timed(fn, n, barrier=None):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if barrier:
+        barrier()
+    else:
+        torch.cuda.synchronize()
+    a.record()
+    for _ in range(n):
+        fn()
+    b.record()
+    if barrier:
+        barrier()
+    else:
+        torch.cuda.synchronize()
+    return a.elapsed_time(b) / n
+
+
+def run_other_configs(dev, steps, peak):
+    """Step time of BASELINE configs 1, 2, 4 and 5 (x1) at N=1: CUDA-graph train step on the same synthetic graph, plus
+    the config's own dominant aggregation launch against the HBM roofline and, for gcn.yaml (defined as the CPU run),
+    the oracle's CPU step beside it."""
+    import egnn_b200 as E
+    from egnn_b200 import _lib, ops, synthetic
+    from egnn_b200.train import TrainStep
+    out = []
+    for name, cfg in OTHER_CONFIGS.items():
+        gr = synthetic.make_elliptic_like(train_window_k=cfg["k"])
+        x = torch.cat([gr.x, (gr.timestep.float() / gr.timestep.max().float()).unsqueeze(1)], dim=1)  # use_time_scalar
+        ei = torch.cat([gr.edge_index, gr.edge_index.flip(0)], 1) if cfg["sym"] else gr.edge_index
+        torch.manual_seed(42)
+        model = E.build_model(cfg["arch"], x.size(1), cfg).to(dev)
+        model.set_dropout_seed(42, dev)
+        step = TrainStep(model, x.to(dev), ei.to(dev), gr.timestep.to(dev), gr.y.to(dev), gr.train_mask.to(dev),
+                         lr=cfg["lr"], weight_decay=cfg["weight_decay"], grad_clip=1.0, amp=cfg["amp"])
+        step.run()
+        torch.cuda.synchronize()
+        n0 = _lib.launch_count()
+        step.run()
+        torch.cuda.synchronize()
+        launches = _lib.launch_count() - n0
+        step.capture(warmup=2)
+        for _ in range(3):
+            step.run()
+        ms = _timed(step.run, steps)
+        self_loops = cfg["arch"] in ("gcn", "gat")
+        e_used = ei.size(1)
+        ent = {"name": name, "workload": cfg["what"], "dtype": "bf16" if cfg["amp"] else "f32",
+               "ms_per_step": round(ms, 4), "gedges_per_s": round(e_used / (ms * 1e-3) / 1e9, 4), "edges": int(e_used),
+               "gpu_launches_per_step": int(launches), "loss": round(float(step.loss), 6)}
+        # the config's widest aggregation launch, alone, rotating inputs (algorithmic bytes as in SURVEY 8d)
+        g = E.cached_graph(step.edge_index, gr.num_nodes, self_loops=self_loops)
+        N = gr.num_nodes
+        if cfg["arch"] == "gcn":
+            F, idt, odt, mode, es_in, es_out, extra = 128, torch.float32, torch.float32, _lib.SPMM_WEIGHTED, 4, 4, 4
+            e_k, label = N + gr.edge_index.size(1), "weighted (gcn_norm) F=128 fp32"
+        elif cfg["arch"] == "gat":
+            F = None
+        elif name == "sage":
+            F, idt, odt, mode, es_in, es_out, extra = 168, torch.float32, torch.float32, _lib.SPMM_MEAN, 4, 4, 0
+            e_k, label = e_used, "mean F=168 (167 padded) fp32"
+        else:
+            F, idt, odt, mode, es_in, es_out, extra = 128, torch.bfloat16, torch.bfloat16, _lib.SPMM_MEAN, 2, 2, 0
+            e_k, label = e_used, "mean F=128 bf16"
+        if F is not None:
+            n_rot = 6 if es_in == 4 else 8
+            ins = [torch.randn(N, F, device=dev).to(idt) for _ in range(n_rot)]
+            o = torch.empty(N, F, dtype=odt, device=dev)
+            it = iter(range(10 ** 9))
+            fn = lambda: ops.spmm(g, "csr", mode, ins[next(it) % n_rot], odt, out=o)
+            for _ in range(n_rot):
+                fn()
+            t = _timed(fn, 20)
+            b = spmm_bytes(N, F, e_k, es_in, es_out) + extra * e_k
+            ent["spmm"] = {"kernel": label, "us": round(t * 1e3, 2), "algorithmic_bytes": int(b),
+                           "frac": round(b / t / 1e6 / peak, 4)}
+            del ins, o
+        if name == "gcn":
+            from oracle import pyg_restated as O
+            torch.set_num_threads(os.cpu_count() or 1)
+            torch.manual_seed(42)
+            ref = O.build_model(cfg["arch"], x.size(1), cfg)
+            opt = torch.optim.Adam(ref.parameters(), lr=cfg["lr"], weight_decay=cfg["weight_decay"])
+            cw = O.class_weight(gr.y[gr.train_mask])
+            ts = []
+            for _ in range(2):
+                t0 = time.perf_counter()
+                O.train_step(ref, x, ei, gr.timestep, gr.y, gr.train_mask, cw, opt, 1.0)
+                ts.append(time.perf_counter() - t0)
+            ent["cpu_ms_per_step"] = round(min(ts) * 1e3, 1)
+            ent["cpu_cores"] = torch.get_num_threads()
+        out.append(ent)
+        del step, model, x, ei, g
+        E.graph._GLOBAL_CACHE.clear()
+        torch.cuda.empty_cache()
+    return out
+
+
+def run_sage_l3_x64(dev, rank, world, steps, barrier, replicas=64):
+    """BASELINE config 5 / north_star 'replicated scale-up': 3-layer SAGE (configs/sage_l3_k18.yaml) on 64 block-diagonal
+    replicas of the Elliptic-shaped graph (N = 13 041 216, E' = 29 997 440), STRONG scaling: the 64 x 49 (replica, timestep)
+    blocks are split over the ranks as contiguous replica ranges (zero halo), the flat weight gradient is all-reduced.
+    Replica features are drawn on the device from per-replica seeds, so the global graph is the same for every N."""
+    import torch.distributed as dist
+    import egnn_b200 as E
+    from egnn_b200 import synthetic
+    from egnn_b200.shard import Shard, ShardedContext
+    from egnn_b200.train import TrainStep
+    cfg = dict(arch="sage", hidden_dim=128, layers=3, dropout=0.4, lr=1e-3, weight_decay=5e-4)
+    if replicas % world:
+        return {"skipped": f"{replicas} replicas do not divide over {world} ranks"}
+    base = synthetic.make_elliptic_like(train_window_k=18)
+    n1, kk = base.num_nodes, replicas // world
+    r0 = rank * kk
+    x = torch.empty((kk * n1, 168), dtype=torch.float32, device=dev)     # 167 = 166 + scalar time, padded to 16-byte rows
+    tcol = (base.timestep.float() / base.timestep.max().float()).to(dev)
+    for j in range(kk):
+        r = r0 + j
+        blk = x[j * n1:(j + 1) * n1]
+        if r == 0:
+            blk[:, :166] = base.x.to(dev)
+        else:
+            gen = torch.Generator(device=dev).manual_seed(42 + r)
+            blk[:, :166] = synthetic._features(n1, 166, gen)
+        blk[:, 166] = tcol
+        blk[:, 167] = 0.0
+    x = x[:, :167]                                                          # a strided view: rows stay 16-byte aligned
+    eb = base.edge_index.to(dev)
+    ei = torch.cat([eb + j * n1 for j in range(kk)], dim=1)
+    ei_sym = torch.cat([ei, ei.flip(0)], 1).contiguous()
+    rep = lambda t: t.repeat(kk)
+    local_g = synthetic.EllipticGraph(x=x[:0].cpu(), edge_index=ei[:, :0].cpu(), y=rep(base.y), timestep=rep(base.timestep),
+                                      train_mask=rep(base.train_mask), val_mask=rep(base.val_mask),
+                                      test_mask=rep(base.test_mask))
+    sh = Shard(rank=rank, world=world, row0=r0 * n1, n_local=kk * n1, n_global=replicas * n1, graph=local_g)
+    ctx = ShardedContext(sh, dev)
+    torch.manual_seed(42)
+    model = ctx.attach(E.build_model(cfg["arch"], 167, cfg).to(dev))
+    model.set_dropout_seed(42, dev)
+    if world > 1:
+        for p in model.parameters():
+            dist.broadcast(p.data, 0)
+    step = TrainStep(model, x, ei_sym, local_g.timestep.to(dev), local_g.y.to(dev), local_g.train_mask.to(dev),
+                     lr=cfg["lr"], weight_decay=cfg["weight_decay"], grad_clip=1.0, amp=True, cw=ctx.class_weight,
+                     n_train_total=ctx.n_train_total, grad_reducer=ctx.reduce_grads if world > 1 else None,
+                     health_check=ctx.check)
+    del ei, eb
+    step.run()
+    torch.cuda.synchronize()
+    step.capture(warmup=2)
+    for _ in range(2):
+        step.run()
+    ms = _timed(step.run, steps, barrier)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    loss = step.loss.detach().clone().double()
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(loss)
+    step.loss_value()
+    e_total = 2 * base.edge_index.size(1) * replicas
+    ms = float(t)
+    res = {"workload": "sage_l3_k18 (3-layer SAGE 167->128->128->2, bf16 autocast) on the 64x replicated graph",
+           "scaling": "strong", "n_gpus": world, "replicas": replicas, "nodes_total": replicas * n1,
+           "edges_total": int(e_total), "ms_per_step": round(ms, 4), "gedges_per_s": round(e_total / (ms * 1e-3) / 1e9, 4),
+           "steps": steps, "loss_sum_over_ranks": round(float(loss), 6),
+           "peak_mem_gib": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1),
+           "collectives": "peer-memory all-reduce kernel" if ctx.p2p else ("nccl" if world > 1 else "none")}
+    del step, model, x, ei_sym
+    E.graph._GLOBAL_CACHE.clear()
+    torch.cuda.empty_cache()
+    return res
+
+
+def step1_parity(init_state, masks, host_gr, ei_host, loss_bf16_gpu, gnorm_bf16_gpu, loss_fp32_gpu, gnorm_fp32_gpu):
+    """the first train step of THIS run (GPU, from the initial weights, its own Philox dropout masks)
+    against the CPU oracle on the same graph, same weights, same masks -- fp32 and bf16-autocast."""
+    from oracle import pyg_restated as O
+    res = {}
+    cw = O.class_weight(host_gr.y[host_gr.train_mask])
+    for tag, amp_dtype in (("fp32", None), ("bf16", torch.bfloat16)):
+        ref = O.build_model(CFG["arch"], host_gr.x.size(1), CFG)
+        ref.load_state_dict(init_state)
+        ref.train()
+        if amp_dtype is not None:
+            with torch.autocast(device_type="cpu", dtype=amp_dtype):
+                logits = ref(host_gr.x, ei_host, host_gr.timestep, dropout_masks=masks)
+                loss = O.masked_weighted_ce(logits.float(), host_gr.y, host_gr.train_mask, cw)
+        else:
+            logits = ref(host_gr.x, ei_host, host_gr.timestep, dropout_masks=masks)
+            loss = O.masked_weighted_ce(logits, host_gr.y, host_gr.train_mask, cw)
+        loss.backward()
+        gn = float(torch.nn.utils.clip_grad_norm_(ref.parameters(), CFG["grad_clip"]))
+        res[f"cpu_{tag}"] = {"loss": float(loss), "grad_norm": gn}
+    rel = lambda a, b: abs(a - b) / abs(b)
+    c32, c16 = res["cpu_fp32"], res["cpu_bf16"]
+    return {"what": "step 1 from the initial weights, same graph / weights / dropout masks: GPU vs CPU oracle",
+            "gpu_fp32_loss": loss_fp32_gpu, "gpu_bf16_loss": loss_bf16_gpu, "cpu_fp32_loss": c32["loss"],
+            "cpu_bf16_loss": c16["loss"], "loss_rel_fp32": rel(loss_fp32_gpu, c32["loss"]),
+            "loss_rel_bf16_vs_cpu_bf16": rel(loss_bf16_gpu, c16["loss"]),
+            "loss_rel_bf16_vs_cpu_fp32": rel(loss_bf16_gpu, c32["loss"]),
+            "cpu_bf16_vs_cpu_fp32": rel(c16["loss"], c32["loss"]),
+            "grad_norm_rel_fp32": rel(gnorm_fp32_gpu, c32["grad_norm"]),
+            "grad_norm_rel_bf16_vs_cpu_fp32": rel(gnorm_bf16_gpu, c32["grad_norm"]),
+            "cpu_bf16_grad_norm_vs_cpu_fp32": rel(c16["grad_norm"], c32["grad_norm"]),
+            "tolerance": {"fp32": 1e-5, "bf16": 4e-2},
+            "ok": bool(rel(loss_fp32_gpu, c32["loss"]) <= 1e-5 and rel(loss_bf16_gpu, c32["loss"]) <= 4e-2
+                       and rel(gnorm_fp32_gpu, c32["grad_norm"]) <= 1e-4)}
+
+
 # ------------------------------------------------------------------------------- ours -------
 def run_ours(args):
     import torch.distributed as dist
@@ -157,9 +378,26 @@ def run_ours(args):
     step = TrainStep(model, devb["x"], devb["ei"], devb["t"], devb["y"], devb["m"], lr=CFG["lr"],
                      weight_decay=CFG["weight_decay"], grad_clip=CFG["grad_clip"], amp=amp,
                      cw=ctx.class_weight, n_train_total=ctx.n_train_total,
-                     grad_reducer=ctx.reduce_grads if world > 1 else None)
+                     grad_reducer=ctx.reduce_grads if world > 1 else None, health_check=ctx.check)
+    parity_in = None
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        # step 1 of a throw-away fp32 twin and of the timed bf16 model, both from the same initial weights and the
+        # same dropout stream: losses / gradient norms for the GPU-vs-CPU parity block of the result line
+        import copy
+        init_state = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+        twin = copy.deepcopy(model)
+        twin.set_dropout_seed(42, dev)
+        st32 = TrainStep(twin, devb["x"], devb["ei"], devb["t"], devb["y"], devb["m"], lr=CFG["lr"],
+                         weight_decay=CFG["weight_decay"], grad_clip=CFG["grad_clip"], amp=False, cw=ctx.class_weight)
+        l32 = float(st32.run())
+        gn32 = float(st32.opt.grad_norm)
+        del st32, twin
     step.run()                      # first call builds and caches the CSR/CSC structure
     torch.cuda.synchronize()
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        masks = [ops.dropout_mask(lg.num_nodes, CFG["hidden_dim"], CFG["dropout"], 42, li, seed_off=model._drop.offset).cpu()
+                 for li in range(CFG["layers"] - 1)]
+        parity_in = (init_state, masks, float(step.loss), float(step.opt.grad_norm), l32, gn32)
     n0 = _lib.launch_count()
     step.run()
     torch.cuda.synchronize()
@@ -197,6 +435,7 @@ def run_ours(args):
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
+    ctx.check()       # a peer-memory all-reduce that timed out inside the timed region fails the run loudly
     # ---- end-to-end: host buffers in, loss out, every step ------------------------------------
     g_static = E.cached_graph(devb["ei"], lg.num_nodes)
     h2d = sum(v.numel() * v.element_size() for v in host.values())
@@ -227,6 +466,7 @@ def run_ours(args):
     barrier()
     assert len(e2e_losses) == e2e_steps
     ms_e2e = ev0.elapsed_time(ev1)
+    ctx.check()
     clocks = sampler.stop()
     # ---- eval_split forward (src/train_gnn.py:248-257): fp32, never under autocast, BatchNorm on running stats;
     # the reference's epoch = train step + this forward (eval_fwd_ms, ref_epoch_ms)
@@ -261,6 +501,7 @@ def run_ours(args):
     ms_tail = ev0.elapsed_time(ev1) / 5
     val_ap = [float(v) for v in ap_out.tolist()]
     model.train()
+    final_loss = float(step.loss)
     t = torch.tensor([ms, ms_e2e, ms_eval, ms_tail], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -308,8 +549,27 @@ def run_ours(args):
              "GBps": round(b64 / t64b / 1e6, 1)},
         ]
 
+    # ---- the other BASELINE configs (N=1) and the 64x strong-scaling workload (every N) --------------------------
+    rebuilds = feed.rebuilds
+    del feed, step, model, host, devb, g_static
+    E.graph._GLOBAL_CACHE.clear()
+    torch.cuda.empty_cache()
+    other = None
+    if world == 1 and rank == 0 and not args.skip_configs:
+        other = run_other_configs(dev, max(10, min(args.steps, 30)), peak)
+    x64 = None
+    if not args.skip_x64:
+        try:
+            x64 = run_sage_l3_x64(dev, rank, world, max(5, min(args.steps, 10)), barrier)
+        except Exception as ex:   # never lose the headline line to the secondary workload
+            x64 = {"failed": f"{type(ex).__name__}: {ex}"}
     if rank == 0:
         cpu = cpu_baseline_sample(budget_s=20.0) if (world == 1 and not args.no_cpu_baseline) else None
+        parity = None
+        if parity_in is not None:
+            gr_h = host_graph(1)
+            parity = step1_parity(parity_in[0], parity_in[1], gr_h,
+                                  torch.cat([gr_h.edge_index, gr_h.edge_index.flip(0)], dim=1), *parity_in[2:])
         line = {
             "metric": METRIC, "value": round(e_total / (ms_step * 1e-3) / 1e9, 4), "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4),
@@ -329,13 +589,15 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": round(e_total / (ms_e2e_step * 1e-3) / 1e9, 4), "unit": UNIT,
                     "ms_per_step": round(ms_e2e_step, 4), "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                    "steps": e2e_steps,
+                    "steps": e2e_steps, "graph_rebuilds": rebuilds,
                     "includes": "every step: pinned-host x/edge_index/timestep/y/mask -> device (staged on a copy stream, "
-                                "overlapping the previous step), CSR/CSC + row-partition rebuild, step, loss -> host"},
+                                "overlapping the previous step), byte-wise device comparison of the submitted edge_index "
+                                "with the one the CSR/CSC views were built from (rebuild only when it differs), step, "
+                                "loss -> host"},
             "gpu_launches": int(launches_per_step * args.steps),
             "gpu_launches_per_step": int(launches_per_step),
             "roofline": roof, "kernels": kernels, "cpu_baseline": cpu,
-            "loss": round(float(step.loss), 6),
+            "loss": round(final_loss, 6), "parity": parity, "configs": other, "sage_l3_x64": x64,
         }
         if stdout_fd is not None:
             sys.stdout.flush()
@@ -453,6 +715,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--eager", action="store_true", help="do not capture a CUDA graph (profiling runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU baseline leg (profiling runs)")
+    ap.add_argument("--skip-configs", action="store_true", help="skip the other BASELINE configs (profiling runs)")
+    ap.add_argument("--skip-x64", action="store_true", help="skip the 64x strong-scaling workload (profiling runs)")
     ap.add_argument("--max-seconds", type=float, default=840.0, help="watchdog: hard-exit if the run hangs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

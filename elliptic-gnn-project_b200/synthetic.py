@@ -153,10 +153,13 @@ def make_elliptic_like(n_nodes: int = N_NODES, n_edges: int = N_EDGES, n_feats: 
 
 
 def _features(n: int, f: int, g: torch.Generator) -> torch.Tensor:
-    x = torch.randn(n, f, generator=g)
+    """Drawn on the generator's device (CPU for everything the oracle sees; bench.py draws the replicas of the 64x
+    scale-up directly on the GPU)."""
+    dev = g.device
+    x = torch.randn(n, f, generator=g, device=dev)
     n_heavy = max(1, f // 20)  # ~5 % heavy-tailed columns (standardised features with outliers)
-    cols = torch.randperm(f, generator=g)[:n_heavy]
-    x[:, cols] = x[:, cols] * torch.exp(0.75 * torch.randn(n, n_heavy, generator=g))
+    cols = torch.randperm(f, generator=g, device=dev)[:n_heavy]
+    x[:, cols] = x[:, cols] * torch.exp(0.75 * torch.randn(n, n_heavy, generator=g, device=dev))
     return x
 
 
