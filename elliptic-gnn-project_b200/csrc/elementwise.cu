@@ -867,6 +867,48 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, const double
   }
 }
 
+// BatchNorm statistics from the per-(CTA, sub-partition) partial rows the layer GEMM's epilogue wrote
+// (egnn_linear_tc colstats): fixed-order float64 sum over the parts; FINALIZE also turns them into mean / rstd and
+// updates the running buffers (single-GPU: one launch between the GEMM and the BatchNorm apply).
+template <bool FINALIZE>
+__global__ void colstats_parts_kernel(const float* __restrict__ parts, int n_parts, int F, double* __restrict__ sums,
+                                      double count, float eps, float momentum, float* __restrict__ mean,
+                                      float* __restrict__ rstd, float* __restrict__ rmean, float* __restrict__ rvar,
+                                      int64_t* __restrict__ num_batches) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (FINALIZE && num_batches && c == 0) *num_batches += 1;   // bn.num_batches_tracked (one thread of one block)
+  if (c >= F) return;
+  double s0 = 0.0, s1 = 0.0, q0 = 0.0, q1 = 0.0;
+  int p = 0;
+  for (; p + 1 < n_parts; p += 2) {   // two independent chains (loads in flight), combined in a fixed order
+    s0 += (double)parts[(size_t)p * 2 * F + c];
+    q0 += (double)parts[(size_t)p * 2 * F + F + c];
+    s1 += (double)parts[(size_t)(p + 1) * 2 * F + c];
+    q1 += (double)parts[(size_t)(p + 1) * 2 * F + F + c];
+  }
+  if (p < n_parts) {
+    s0 += (double)parts[(size_t)p * 2 * F + c];
+    q0 += (double)parts[(size_t)p * 2 * F + F + c];
+  }
+  const double s = s0 + s1, q = q0 + q1;
+  if (sums) {
+    sums[c] = s;
+    sums[F + c] = q;
+  }
+  if (FINALIZE) {
+    const double m = s / count;
+    double var = q / count - m * m;
+    if (var < 0) var = 0;
+    mean[c] = (float)m;
+    rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (rmean) rmean[c] = (1.f - momentum) * rmean[c] + momentum * (float)m;
+    if (rvar) {
+      const double unb = count > 1 ? var * count / (count - 1) : var;
+      rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)unb;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kThreads) dropout_mask_kernel(uint8_t* __restrict__ mask,
                                                                 int64_t n_rows, int F, uint32_t thr,
                                                                 uint64_t seed, const int64_t* seed_off,
@@ -1034,7 +1076,7 @@ extern "C" int egnn_cast(const void* in, int in_dtype, int64_t ld_in, void* out,
 __global__ void __launch_bounds__(kThreads) pack_sage_weights_kernel(
     const float* __restrict__ w_l, const float* __restrict__ w_r, const float* __restrict__ w_res,
     const float* __restrict__ b_l, int No, int Nr, int K, int Kp, __nv_bfloat16* __restrict__ out,
-    float* __restrict__ bias_out) {
+    float* __restrict__ bias_out, __nv_bfloat16* __restrict__ out_t) {
   const int i = blockIdx.x * kThreads + threadIdx.x;
   const int W = 2 * Kp;
   if (i < No + Nr && bias_out) bias_out[i] = (i < No && b_l) ? b_l[i] : 0.f;
@@ -1047,17 +1089,20 @@ __global__ void __launch_bounds__(kThreads) pack_sage_weights_kernel(
     else if (half) v = w_res[(r - No) * K + k];
   }
   out[i] = __float2bfloat16_rn(v);
+  // [W_l | W_r]^T  ([2*Kp, No]): the contraction-contiguous B operand of the concatenated dgrad GEMM
+  if (out_t && r < No) out_t[(size_t)c * No + r] = __float2bfloat16_rn(v);
 }
 
 extern "C" int egnn_pack_sage_weights(const float* w_l, const float* w_r, const float* w_res, const float* b_l,
                                       int64_t n_out, int64_t n_res, int64_t K, int64_t K_padded, void* out_bf16,
-                                      float* bias_out, void* stream) {
+                                      float* bias_out, void* out_t_bf16, void* stream) {
   const char* fn = "egnn_pack_sage_weights";
   EGNN_REQUIRE(w_l && w_r && out_bf16 && (n_res == 0 || w_res), fn, "null pointer");
   EGNN_REQUIRE(n_out > 0 && K > 0 && K_padded >= K && (n_out + n_res) * 2 * K_padded < (1 << 30), fn, "bad shape");
   const int64_t total = (n_out + n_res) * 2 * K_padded;
   pack_sage_weights_kernel<<<(unsigned)ceil_div(total, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
-      w_l, w_r, w_res, b_l, (int)n_out, (int)n_res, (int)K, (int)K_padded, (__nv_bfloat16*)out_bf16, bias_out);
+      w_l, w_r, w_res, b_l, (int)n_out, (int)n_res, (int)K, (int)K_padded, (__nv_bfloat16*)out_bf16, bias_out,
+      (__nv_bfloat16*)out_t_bf16);
   EGNN_LAUNCH_CHECK(fn);
   return 0;
 }
@@ -1158,6 +1203,39 @@ extern "C" int egnn_bn_finalize(const double* sums, const double* sumsq, double 
   EGNN_REQUIRE(sums && sumsq && mean && rstd && count > 0, fn, "bad arguments");
   bn_finalize_kernel<<<(unsigned)ceil_div(n_feat, 128), 128, 0, (cudaStream_t)stream>>>(
       sums, sumsq, count, (int)n_feat, eps, momentum, mean, rstd, running_mean, running_var);
+  EGNN_LAUNCH_CHECK(fn);
+  return 0;
+}
+
+__global__ void f64_to_f32_kernel(const double* __restrict__ in, float* __restrict__ out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (float)in[i];
+}
+extern "C" int egnn_f64_to_f32(const double* in, float* out, int64_t n, void* stream) {
+  EGNN_REQUIRE(in && out && n >= 0, "egnn_f64_to_f32", "bad arguments");
+  if (n == 0) return 0;
+  f64_to_f32_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(in, out, n);
+  EGNN_LAUNCH_CHECK("egnn_f64_to_f32");
+  return 0;
+}
+
+extern "C" int egnn_colstats_reduce(const float* parts, int64_t n_parts, int64_t n_feat, double* sums, void* stream) {
+  const char* fn = "egnn_colstats_reduce";
+  EGNN_REQUIRE(parts && sums && n_parts > 0 && n_feat > 0, fn, "bad arguments");
+  colstats_parts_kernel<false><<<(unsigned)ceil_div(n_feat, 64), 64, 0, (cudaStream_t)stream>>>(
+      parts, (int)n_parts, (int)n_feat, sums, 1.0, 0.f, 0.f, nullptr, nullptr, nullptr, nullptr, nullptr);
+  EGNN_LAUNCH_CHECK(fn);
+  return 0;
+}
+
+extern "C" int egnn_bn_finalize_parts(const float* parts, int64_t n_parts, int64_t n_feat, double count, float eps,
+                                      float momentum, float* mean, float* rstd, float* running_mean,
+                                      float* running_var, int64_t* num_batches_tracked, void* stream) {
+  const char* fn = "egnn_bn_finalize_parts";
+  EGNN_REQUIRE(parts && mean && rstd && n_parts > 0 && n_feat > 0 && count > 0, fn, "bad arguments");
+  colstats_parts_kernel<true><<<(unsigned)ceil_div(n_feat, 64), 64, 0, (cudaStream_t)stream>>>(
+      parts, (int)n_parts, (int)n_feat, nullptr, count, eps, momentum, mean, rstd, running_mean, running_var,
+      num_batches_tracked);
   EGNN_LAUNCH_CHECK(fn);
   return 0;
 }

@@ -386,7 +386,12 @@ int run(GemmParams& P, cudaStream_t st) {
 
 int gemm_tcgen05_dispatch(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int c_dtype,
                           int64_t ld_c, int64_t M, int64_t N, int64_t K, const float* bias, int accumulate,
-                          const int32_t* row_div_ptr, int64_t row_div_cols, cudaStream_t st);  // gemm_tcgen05.cu
+                          const int32_t* row_div_ptr, int64_t row_div_cols, cudaStream_t st, const void* addend = nullptr,
+                          int64_t ld_add = 0, int64_t add_col0 = 0, float* stats = nullptr,
+                          int64_t stats_cols = 0);  // gemm_tcgen05.cu
+bool gemm_tcgen05_epilogue_supported(bool bias, bool row_div, bool accumulate, bool addend, bool stats, int64_t stats_cols,
+                                     int64_t add_col0);
+int64_t gemm_tcgen05_stats_parts(int64_t M);
 bool gemm_tcgen05_supported(int64_t lda, int64_t ldb, int64_t ld_c, int64_t M, int64_t N, int64_t K,
                             const void* A, const void* B, const void* C);
 size_t wgrad_tcgen05_workspace_floats(int64_t N_out, int64_t K_in);
@@ -397,6 +402,29 @@ int wgrad_tcgen05_dispatch(const void* G, int64_t ldg, const void* X, int64_t ld
 }  // namespace egnn
 
 using namespace egnn;
+
+// C[M,N] = A[M,K] . W[N,K]^T on the tcgen05 kernel with the fused layer epilogues (bf16 operands, both K-major).
+extern "C" int64_t egnn_linear_stats_parts(int64_t M) { return gemm_tcgen05_stats_parts(M); }
+
+extern "C" int egnn_linear_tc(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int c_dtype, int64_t ld_c,
+                              int64_t M, int64_t N, int64_t K, const float* bias, const int32_t* row_div_ptr,
+                              int64_t row_div_cols, int accumulate, const void* addend, int64_t ld_addend,
+                              int64_t addend_col0, float* colstats, int64_t colstats_cols, void* stream) {
+  const char* fn = "egnn_linear_tc";
+  EGNN_REQUIRE(A && W && C, fn, "null pointer");
+  EGNN_REQUIRE(M >= 0 && N > 0 && K > 0 && ld_c >= N, fn, "bad shape");
+  EGNN_REQUIRE(c_dtype == EGNN_F32 || c_dtype == EGNN_BF16, fn, "bad output dtype");
+  EGNN_REQUIRE(!addend || (ld_addend >= N - addend_col0 && addend_col0 >= 0 && addend_col0 < N), fn, "bad addend range");
+  EGNN_REQUIRE(!colstats || (colstats_cols > 0 && colstats_cols <= N), fn, "bad colstats_cols");
+  if (M == 0) return 0;
+  if (!gemm_tcgen05_supported(lda, ldw, ld_c, M, N, K, A, W, C))
+    return fail(fn, "shape / alignment outside the tcgen05 kernel (K <= 512, 8 <= N <= 256, 16-byte rows)");
+  if (!gemm_tcgen05_epilogue_supported(bias != nullptr, row_div_ptr != nullptr, accumulate != 0, addend != nullptr,
+                                       colstats != nullptr, colstats_cols, addend_col0))
+    return fail(fn, "epilogue combination not compiled in");
+  return gemm_tcgen05_dispatch(A, lda, W, ldw, C, c_dtype, ld_c, M, N, K, bias, accumulate, row_div_ptr, row_div_cols,
+                               (cudaStream_t)stream, addend, ld_addend, addend_col0, colstats, colstats_cols);
+}
 
 extern "C" size_t egnn_gemm_workspace_floats(int64_t M, int64_t N, int64_t K, int split_k) {
   (void)K;

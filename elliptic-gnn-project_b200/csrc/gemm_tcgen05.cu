@@ -140,14 +140,33 @@ struct Epilogue {
   int64_t ld_c;
   int c_dtype, accumulate;
   int row_div_cols;  // only columns [0, row_div_cols) are divided (<= 0: all)
+  // optional second addend: C[m, add_col0 + j] += addend[m, j] (same dtype as C; add_col0 a multiple of 16) -- the
+  // identity-residual gradient joining the root half of the concatenated SAGE dgrad
+  const void* addend;
+  int64_t ld_add;
+  int add_col0;
+  // optional BatchNorm statistics of the STORED values of columns [0, stats_cols), stats_cols <= 64:
+  // stats[(cta*4 + q)*2*stats_cols + {0: sum, 1: sum of squares}*stats_cols + c], rows of TMEM sub-partition q
+  float* stats;
+  int stats_cols;
 };
 
-// Epilogue of gemm_tn_kernel for one warp: FLAGS bit 0 = +bias, bit 1 = /row count, bit 2 = += C.
+// Epilogue of gemm_tn_kernel for one warp: FLAGS bit 0 = +bias, bit 1 = /row count, bit 2 = += C, bit 3 = second
+// addend, bit 4 = column statistics.
 template <typename TC, int FLAGS>
 __device__ __forceinline__ void epilogue_loop(const Epilogue& ep, const float* s_bias, uint64_t* t_full,
                                               uint64_t* t_empty, uint32_t tmem_base, int Npad, int M, int N,
                                               int n_tiles, int q, int half, int lane) {
   constexpr bool kBias = FLAGS & 1, kDiv = (FLAGS & 2) != 0, kAcc = (FLAGS & 4) != 0;
+  constexpr bool kAdd2 = (FLAGS & 8) != 0, kStats = (FLAGS & 16) != 0;
+  float st_sum[kStats ? 2 : 1][16], st_sq[kStats ? 2 : 1][16];   // this warp's <= 2 chunks of the statistics columns
+  if (kStats) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { st_sum[kStats ? h : 0][j] = 0.f; st_sq[kStats ? h : 0][j] = 0.f; }
+  }
+  const TC* __restrict__ Abase = reinterpret_cast<const TC*>(ep.addend);
   const int div_cols = ep.row_div_cols > 0 ? ep.row_div_cols : N;
   TC* __restrict__ Cbase = reinterpret_cast<TC*>(ep.C);
   const bool vec_ok = (ep.ld_c % 8 == 0) && ((uintptr_t)ep.C % 16 == 0);
@@ -179,6 +198,38 @@ __device__ __forceinline__ void epilogue_loop(const Epilogue& ep, const float* s
           // bf16 result: x * rn(1/deg) differs from the IEEE quotient by < 1 ulp(fp32), invisible after
           // rounding to 8 mantissa bits; fp32 result keeps the exact division (parity with CPU torch)
           if (c0 + j < div_cols) v[j] = sizeof(TC) == 2 ? v[j] * rinv : __fdiv_rn(v[j], rdiv);
+        }
+      }
+      if (kAdd2 && c0 >= ep.add_col0) {
+        const TC* a = Abase + row * ep.ld_add + (c0 - ep.add_col0);
+        if (nv == 16 && ep.ld_add % 8 == 0 && ((uintptr_t)ep.addend % 16 == 0)) {
+          if (sizeof(TC) == 4) {
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              const float4 o = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a) + 4 * h);
+              v[4 * h] += o.x; v[4 * h + 1] += o.y; v[4 * h + 2] += o.z; v[4 * h + 3] += o.w;
+            }
+          } else {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const F8 o = ld8(reinterpret_cast<const __nv_bfloat16*>(a) + 8 * h);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[8 * h + j] += o.v[j];
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < nv) v[j] += to_f32(a[j]);
+        }
+      }
+      if (kStats && c0 < ep.stats_cols) {   // statistics of the values as stored (rounded to the output dtype)
+        const int h = c0 >> 5;               // chunks half*16 + 32*h of this warp
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float r = (kAcc || c0 + j >= ep.stats_cols) ? 0.f : to_f32(from_f32<TC>(v[j]));
+          if (h == 0) { st_sum[0][j] += r; st_sq[0][j] = fmaf(r, r, st_sq[0][j]); }
+          else { st_sum[kStats ? 1 : 0][j] += r; st_sq[kStats ? 1 : 0][j] = fmaf(r, r, st_sq[kStats ? 1 : 0][j]); }
         }
       }
       if (nv == 16 && vec_ok) {
@@ -223,6 +274,28 @@ __device__ __forceinline__ void epilogue_loop(const Epilogue& ep, const float* s
     tcgen05_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&t_empty[buf]);
+  }
+  if (kStats) {
+    // fixed butterfly over the 32 rows of this warp, then one partial row per (CTA, TMEM sub-partition): the
+    // assignment of tiles to CTAs is static, so the partials (and their fixed-order sum) are reproducible
+    float* out = ep.stats + ((size_t)blockIdx.x * 4 + q) * 2 * ep.stats_cols;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c0 = half * 16 + 32 * h;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float a = st_sum[kStats ? h : 0][j], b = st_sq[kStats ? h : 0][j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          a += __shfl_xor_sync(0xffffffffu, a, o);
+          b += __shfl_xor_sync(0xffffffffu, b, o);
+        }
+        if (lane == 0 && c0 + j < ep.stats_cols) {
+          out[c0 + j] = a;
+          out[ep.stats_cols + c0 + j] = b;
+        }
+      }
+    }
   }
 }
 
@@ -321,7 +394,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // 8 epilogue warps: warp w reads TMEM lanes 32*(w&3).. (its sub-partition) and every second
     // 16-column chunk, so each scheduler has two epilogue warps to interleave
     const int q = warp & 3, half = (warp - 4) >> 2;
-    const int flags = (ep.bias ? 1 : 0) | (ep.row_div_ptr ? 2 : 0) | (ep.accumulate ? 4 : 0);
+    // the combinations the layers use are compiled in: plain 0-7, +second addend (with / without row division), and
+    // +statistics with bias (the SAGE layer GEMM feeding BatchNorm)
+    const int flags = (ep.bias ? 1 : 0) | (ep.row_div_ptr ? 2 : 0) | (ep.accumulate ? 4 : 0) | (ep.addend ? 8 : 0) |
+                      (ep.stats ? 16 : 0);
 #define EGNN_EPI_CASE(F)                                                                                      \
   case F:                                                                                                     \
     if (ep.c_dtype == EGNN_F32)                                                                               \
@@ -333,6 +409,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     switch (flags) {
       EGNN_EPI_CASE(0) EGNN_EPI_CASE(1) EGNN_EPI_CASE(2) EGNN_EPI_CASE(3)
       EGNN_EPI_CASE(4) EGNN_EPI_CASE(5) EGNN_EPI_CASE(6) EGNN_EPI_CASE(7)
+      EGNN_EPI_CASE(8) EGNN_EPI_CASE(10) EGNN_EPI_CASE(16) EGNN_EPI_CASE(17)
     }
 #undef EGNN_EPI_CASE
   }
@@ -532,9 +609,25 @@ bool gemm_tcgen05_supported(int64_t lda, int64_t ldb, int64_t ld_c, int64_t M, i
   return smem <= kMaxDynSmemTN && 2 * Npad <= 512;
 }
 
+// which (bias, row_div, accumulate, addend, stats) combinations gemm_tn_kernel has an epilogue for
+bool gemm_tcgen05_epilogue_supported(bool bias, bool row_div, bool accumulate, bool addend, bool stats, int64_t stats_cols,
+                                     int64_t add_col0) {
+  const int flags = (bias ? 1 : 0) | (row_div ? 2 : 0) | (accumulate ? 4 : 0) | (addend ? 8 : 0) | (stats ? 16 : 0);
+  if (flags < 8) return true;
+  if (addend && add_col0 % 16 != 0) return false;
+  if (stats && (stats_cols < 1 || stats_cols > 64)) return false;
+  return flags == 8 || flags == 10 || flags == 16 || flags == 17;
+}
+
+int64_t gemm_tcgen05_stats_parts(int64_t M) {
+  const int64_t n_tiles = (M + BM - 1) / BM;
+  return 4 * (n_tiles < kNumSMs ? n_tiles : kNumSMs);
+}
+
 int gemm_tcgen05_dispatch(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int c_dtype,
                           int64_t ld_c, int64_t M, int64_t N, int64_t K, const float* bias, int accumulate,
-                          const int32_t* row_div_ptr, int64_t row_div_cols, cudaStream_t st) {
+                          const int32_t* row_div_ptr, int64_t row_div_cols, cudaStream_t st, const void* addend,
+                          int64_t ld_add, int64_t add_col0, float* stats, int64_t stats_cols) {
   const char* fn = "egnn_gemm(tcgen05)";
   const int Npad = (int)((N + 15) / 16 * 16);
   const int KC = (int)((K + BK - 1) / BK);
@@ -549,7 +642,8 @@ int gemm_tcgen05_dispatch(const void* A, int64_t lda, const void* B, int64_t ldb
   }
   int n_tiles = (int)((M + BM - 1) / BM);
   int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
-  Epilogue ep{C, bias, row_div_ptr, ld_c, c_dtype, accumulate, (int)row_div_cols};
+  Epilogue ep{C, bias, row_div_ptr, ld_c, c_dtype, accumulate, (int)row_div_cols, addend, ld_add, (int)add_col0,
+              stats, (int)stats_cols};
   gemm_tn_kernel<kStagesTN><<<grid, kThreadsTN, smem, st>>>(tmA, tmW, (int)M, (int)N, Npad, (int)K, ep);
   EGNN_LAUNCH_CHECK(fn);
   return 0;

@@ -1,0 +1,406 @@
+"""The SAGE-ResBN step as ONE explicit kernel sequence (forward and backward), bf16 autocast.
+
+`/root/reference/src/models/gnn.py:182-194` composes, per hidden layer, PyG SAGEConv -> BatchNorm1d -> ReLU -> dropout
+-> `+ res_proj(h_in)`, and autograd replays it backwards op by op.  `ops.py` maps each of those ops to one
+`torch.autograd.Function`; this module is the same arithmetic with the op boundaries removed, so that work can move
+across them:
+
+  * the layer GEMM  [mean_j h_j | h] . [[W_l, W_r], [0, W_res]]^T  (tcgen05, `egnn_linear_tc`) also produces the
+    BatchNorm batch statistics of its own output in its epilogue (no separate pass over z);
+  * the gradient of the identity residual joins the root half of the concatenated dgrad GEMM in that GEMM's epilogue
+    (no `dx + dres` pass);
+  * the layer-0 input `h0 = [x | sin | cos]` (fp32 for the aggregation, bf16 for the GEMM) is a pure function of
+    (x, timestep) and is memoised per input version (`StaticInputs`), like the sorted graph views are per
+    `edge_index`; `static_inputs(False)` switches the memo off (inputs rewritten in place under a captured graph);
+  * gradients are produced in a known order and written straight into caller-provided buffers (`train.TrainStep`
+    hands in views of its flat gradient buffer), with no autograd bookkeeping kernels.
+
+`SageResBNFn` wraps the pair as a `torch.autograd.Function` for drop-in use (`loss.backward()`), `train.TrainStep`
+calls `forward` / `backward` directly.  Only shapes the tcgen05 kernels take are served (bf16 autocast, widths a
+multiple of 8, hidden <= 64 for the in-epilogue statistics); everything else keeps the per-op path of `ops.py`.
+"""
+from __future__ import annotations
+
+import contextlib
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib, ops
+from ._lib import ACT_RELU, check, dt, lib, ptr, stream
+from .graph import Graph
+
+_STATIC = True
+
+
+@contextlib.contextmanager
+def static_inputs(enabled: bool):
+    """Inside: whether layer-0 input layouts may be memoised per (tensor, version)."""
+    global _STATIC
+    old, _STATIC = _STATIC, bool(enabled)
+    try:
+        yield
+    finally:
+        _STATIC = old
+
+
+class StaticInputs:
+    """Memo of the layer-0 input layout, keyed on storage pointer / shape / in-place version of `x` and `t` and on the
+    time table's contents version (a learned table changes every step and is never memoised)."""
+
+    def __init__(self, max_entries: int = 4):
+        self._d: Dict[tuple, tuple] = {}
+        self.max_entries = max_entries
+        self.hits = self.misses = 0
+
+    @staticmethod
+    def _key(x, t, table, width):
+        k = (x.data_ptr(), tuple(x.shape), tuple(x.stride()), x._version, int(width))
+        if t is not None:
+            k += (t.data_ptr(), t._version, table.data_ptr(), table._version, tuple(table.shape))
+        return k
+
+    def get(self, x, t, table, width, build):
+        if not _STATIC or (table is not None and table.requires_grad):
+            return build()
+        key = self._key(x, t, table, width)
+        hit = self._d.get(key)
+        if hit is not None:
+            self.hits += 1
+            return hit[0]
+        self.misses += 1
+        val = build()
+        if len(self._d) >= self.max_entries:
+            self._d.pop(next(iter(self._d)))
+        self._d[key] = (val, x, t, table)       # keep the key tensors alive: their addresses cannot be recycled
+        return val
+
+    def clear(self):
+        self._d.clear()
+
+
+STATIC_INPUTS = StaticInputs()
+
+
+def supported(net, x: torch.Tensor, bf16: bool) -> bool:
+    """Shapes / modes the explicit path serves."""
+    if not bf16 or not x.is_cuda or x.dtype != torch.float32 or x.dim() != 2:
+        return False
+    H = net.convs[0].out_channels
+    if H % 16 or H > 128 or net.in_dim > 248:        # 2H and 2K columns per GEMM: N <= 256, K <= 512
+        return False
+    if any(c.out_channels != H for c in net.convs[:-1]) or net.convs[-1].out_channels not in (1, 2, 4):
+        return False
+    if net.time_emb is not None and (net.in_dim + 7) // 8 * 8 > 128:
+        return False                                  # learned table: the layer-0 dgrad [N, 2K] must fit one GEMM
+    return True
+
+
+class _Layer:
+    __slots__ = ("cat", "wcat", "wt", "z", "res_is_input", "has_proj", "mean", "rstd", "kb", "K", "No", "Nr", "p_eff",
+                 "y")
+
+
+class Saved:
+    """What the backward needs from the forward."""
+    __slots__ = ("layers", "g", "t", "x_cols", "h_last", "wout", "C", "seed", "soff", "n_total", "reducer", "row0",
+                 "use_bn", "D", "T")
+
+
+def _bn_stats_to_mean_rstd(parts, n_parts, F, n_total, bn, reducer, dev):
+    L = lib()
+    mean = torch.empty(F, dtype=torch.float32, device=dev)
+    rstd = torch.empty(F, dtype=torch.float32, device=dev)
+    track = bn.track_running_stats and bn.running_mean is not None
+    if reducer is None:
+        check(L.egnn_bn_finalize_parts(ptr(parts), n_parts, F, float(n_total), float(bn.eps), float(bn.momentum),
+                                       ptr(mean), ptr(rstd), ptr(bn.running_mean), ptr(bn.running_var),
+                                       ptr(bn.num_batches_tracked) if track else None, stream()))
+    else:
+        if track:
+            check(L.egnn_counter_add(ptr(bn.num_batches_tracked), 1, stream()))
+        st = torch.empty((2, F), dtype=torch.float64, device=dev)
+        check(L.egnn_colstats_reduce(ptr(parts), n_parts, F, ptr(st), stream()))
+        reducer.reduce_(st)
+        check(L.egnn_bn_finalize(st[0].data_ptr(), st[1].data_ptr(), float(n_total), F, float(bn.eps),
+                                 float(bn.momentum), ptr(mean), ptr(rstd), ptr(bn.running_mean), ptr(bn.running_var),
+                                 stream()))
+    return mean, rstd
+
+
+def _linear_tc(A, W, out, bias=None, row_div=None, row_div_cols=0, addend=None, add_col0=0, stats=None, stats_cols=0):
+    M, K = A.shape
+    N = W.size(0)
+    check(lib().egnn_linear_tc(ptr(A), A.stride(0), ptr(W), W.stride(0), ptr(out), dt(out), out.stride(0), M, N, K,
+                               ptr(bias), ptr(row_div), int(row_div_cols), 0, ptr(addend),
+                               addend.stride(0) if addend is not None else 0, int(add_col0), ptr(stats),
+                               int(stats_cols), stream()))
+    return out
+
+
+def forward(net, x: torch.Tensor, g: Graph, t: Optional[torch.Tensor], training: bool, need_grad: bool):
+    """logits [N, C] fp32 and (when `need_grad`) the Saved state.  bf16 activations, fp32 statistics / logits."""
+    L = lib()
+    dev = x.device
+    N = x.size(0)
+    cd = torch.bfloat16
+    H = net.convs[0].out_channels
+    n_hidden = len(net.convs) - 1
+    reducer = net.stats_reducer
+    n_total = float(reducer.n_total) if (reducer is not None and reducer.n_total) else float(N)
+    drop = None
+    if training and net.dropout > 0:
+        drop = net.dropout_state(dev)
+        drop.advance()
+    sv = Saved() if need_grad else None
+
+    # ---- layer-0 input: h0 = [x | time features | 0-pad], fp32 (aggregation input) + bf16 inside [agg | h0]
+    K0 = net.in_dim
+    K0p = (K0 + 7) // 8 * 8
+    use_t = net.time_embed_dim > 0 and t is not None
+    table = (net.time_emb.weight if net.time_embed_type == "learned" else net._sin_table) if use_t else None
+    if not use_t and x.size(1) != K0:
+        raise ValueError(f"expected x of shape [N, {K0}], got {tuple(x.shape)}")
+    x = ops._rows(x)
+
+    def build_h0():
+        h32 = torch.empty((N, K0p), dtype=torch.float32, device=dev)
+        cat0 = torch.empty((N, 2 * K0p), dtype=cd, device=dev)
+        tb = table.detach().contiguous().float() if table is not None else None
+        check(L.egnn_inject_time(ptr(x), ops._ld(x), ptr(t.contiguous()) if use_t else None, ptr(tb),
+                                 tb.size(0) if tb is not None else 0, tb.size(1) if tb is not None else 0, ptr(h32),
+                                 ptr(cat0[:, K0p:]), K0p, 2 * K0p, N, x.size(1), stream()))
+        return h32, cat0
+
+    h32, cat = STATIC_INPUTS.get(x, t if use_t else None, table, K0p, build_h0)
+    ops.spmm(g, "csr", _lib.SPMM_MEAN, h32, cd, out=cat[:, :K0p])
+
+    layers: List[_Layer] = []
+    K, Kraw = K0p, K0
+    h_in = cat[:, K0p:]
+    for li in range(n_hidden):
+        conv = net.convs[li]
+        # the reference adds `res_projs[li](h_in)` whatever `residual` says (src/models/gnn.py:192; the flag is stored
+        # but never read), and so does this path
+        proj = net.res_projs[li]
+        has_proj = not isinstance(proj, torch.nn.Identity)
+        Nr = H if has_proj else 0
+        wcat = torch.empty((H + Nr, 2 * K), dtype=cd, device=dev)
+        bias = torch.empty(H + Nr, dtype=torch.float32, device=dev)
+        want_wt = need_grad and (li > 0 or net.time_emb is not None)
+        wt = torch.empty((2 * K, H), dtype=cd, device=dev) if want_wt else None
+        check(L.egnn_pack_sage_weights(ptr(conv.lin_l.weight), ptr(conv.lin_r.weight),
+                                       ptr(proj.weight) if has_proj else None, ptr(conv.lin_l.bias), H, Nr, Kraw, K,
+                                       ptr(wcat), ptr(bias), ptr(wt), stream()))
+        zc = torch.empty((N, H + Nr), dtype=cd, device=dev)
+        bn = net.bns[li] if net.use_bn else None
+        stats_in_gemm = bn is not None and training and H <= 64
+        parts = n_parts = None
+        if stats_in_gemm:
+            n_parts = int(L.egnn_linear_stats_parts(N))
+            parts = torch.empty((n_parts, 2, H), dtype=torch.float32, device=dev)
+        _linear_tc(cat, wcat, zc, bias=bias, stats=parts, stats_cols=H if stats_in_gemm else 0)
+        z = zc[:, :H]
+        res = zc[:, H:] if has_proj else h_in
+        mean = rstd = None
+        if bn is not None:
+            if training:
+                if stats_in_gemm:
+                    mean, rstd = _bn_stats_to_mean_rstd(parts, n_parts, H, n_total, bn, reducer, dev)
+                else:
+                    if bn.track_running_stats:
+                        check(L.egnn_counter_add(ptr(bn.num_batches_tracked), 1, stream()))
+                    st = ops.colsum(z, want_sq=True)
+                    if reducer is not None:
+                        reducer.reduce_(st)
+                    mean = torch.empty(H, dtype=torch.float32, device=dev)
+                    rstd = torch.empty(H, dtype=torch.float32, device=dev)
+                    check(L.egnn_bn_finalize(st[0].data_ptr(), st[1].data_ptr(), n_total, H, float(bn.eps),
+                                             float(bn.momentum), ptr(mean), ptr(rstd), ptr(bn.running_mean),
+                                             ptr(bn.running_var), stream()))
+            else:
+                mean, rstd = bn.running_mean, torch.rsqrt(bn.running_var + bn.eps)
+        p_eff = float(net.dropout) if (training and net.dropout > 0) else 0.0
+        last = li == n_hidden - 1
+        nxt = torch.empty((N, 2 * H), dtype=cd, device=dev)     # [agg | y]: the next SAGEConv aggregates in place
+        y = nxt[:, H:]
+        kb = torch.empty((N, H // 4), dtype=torch.uint8, device=dev) if need_grad else None
+        check(L.egnn_bn_act_dropout_res_fwd(ptr(z), ptr(res), ptr(y), dt(z), z.stride(0), N, H, ptr(mean), ptr(rstd),
+                                            ptr(bn.weight) if bn is not None else None,
+                                            ptr(bn.bias) if bn is not None else None, ACT_RELU, p_eff,
+                                            drop.seed if drop is not None else 0,
+                                            ptr(drop.offset) if drop is not None else None, li, net.row0,
+                                            res.stride(0) if res is not None else 0, y.stride(0), ptr(kb), stream()))
+        if need_grad:
+            ly = _Layer()
+            ly.cat, ly.wcat, ly.wt, ly.z, ly.mean, ly.rstd, ly.kb = cat, wcat, wt, z, mean, rstd, kb
+            ly.has_proj, ly.res_is_input = has_proj, not has_proj
+            ly.K, ly.No, ly.Nr, ly.p_eff, ly.y = K, H, Nr, p_eff, y
+            layers.append(ly)
+        if not last:
+            ops.spmm(g, "csr", _lib.SPMM_MEAN, y, cd, out=nxt[:, :H])
+        cat, K, Kraw, h_in = nxt, H, H, y
+
+    # ---- logits layer, project first: p = h [W_l; W_r]^T, out_i = mean_j p_j[:C] + b + p_i[C:]
+    out_conv = net.convs[-1]
+    C = out_conv.out_channels
+    wout = torch.cat([out_conv.lin_l.weight.detach(), out_conv.lin_r.weight.detach()], dim=0).float().contiguous()
+    p = torch.empty((N, 2 * C), dtype=torch.float32, device=dev)
+    check(L.egnn_skinny_project(ptr(h_in), dt(h_in), h_in.stride(0), N, H, ptr(wout), 2 * C, ptr(p), stream()))
+    logits = torch.empty((N, C), dtype=torch.float32, device=dev)
+    tmp = torch.empty((g.cap, C), dtype=torch.float32, device=dev)
+    check(L.egnn_sage_out_fwd(ptr(g.csr_ptr), ptr(g.csr_src), ptr(p), ptr(out_conv.lin_l.bias), C, ptr(logits), N,
+                              ptr(tmp), g.cap, stream()))
+    if need_grad:
+        sv.layers, sv.g, sv.t, sv.x_cols = layers, g, (t if use_t else None), x.size(1)
+        sv.h_last, sv.wout, sv.C = h_in, wout, C
+        sv.seed, sv.soff = (drop.seed if drop is not None else 0), (drop.offset if drop is not None else None)
+        sv.n_total, sv.reducer, sv.row0, sv.use_bn = n_total, reducer, net.row0, net.use_bn
+        sv.D = net.time_embed_dim if (use_t and net.time_embed_type == "learned") else 0
+        sv.T = net.max_timestep
+    return logits, sv
+
+
+def param_order(net) -> List[torch.nn.Parameter]:
+    """The parameters `backward` produces gradients for, in the order it returns them."""
+    ps: List[torch.nn.Parameter] = []
+    n_hidden = len(net.convs) - 1
+    for li in range(n_hidden):
+        c = net.convs[li]
+        ps += [c.lin_l.weight, c.lin_l.bias, c.lin_r.weight]
+        if net.use_bn:
+            ps += [net.bns[li].weight, net.bns[li].bias]
+        if not isinstance(net.res_projs[li], torch.nn.Identity):
+            ps.append(net.res_projs[li].weight)
+    c = net.convs[-1]
+    ps += [c.lin_l.weight, c.lin_l.bias, c.lin_r.weight]
+    if net.time_emb is not None:
+        ps.append(net.time_emb.weight)
+    return ps
+
+
+def backward(net, sv: Saved, dlogits: torch.Tensor, out: Optional[List[torch.Tensor]] = None) -> List[torch.Tensor]:
+    """Gradients of every parameter in `param_order(net)`; written into `out[i]` (fp32, the parameter's shape) when
+    given.  `dlogits` fp32 [N, C]."""
+    L = lib()
+    g = sv.g
+    dev = dlogits.device
+    N = dlogits.size(0)
+    cd = torch.bfloat16
+    H = sv.layers[0].No
+    C = sv.C
+    order = param_order(net)
+    grads: Dict[int, torch.Tensor] = {}
+
+    def emit(param, value):
+        """value: fp32 tensor (1-D, or 2-D with unit column stride) holding the gradient of `param`."""
+        i = next(k for k, q in enumerate(order) if q is param)
+        if out is None:
+            grads[i] = value
+            return
+        dst = out[i]
+        v2 = value if value.dim() == 2 else value.reshape(1, -1)
+        d2 = dst.reshape(v2.shape) if dst.dim() != 2 else dst
+        check(L.egnn_cast(ptr(v2), dt(v2), v2.stride(0) if v2.size(0) > 1 else v2.size(1), ptr(d2), dt(d2),
+                          d2.stride(0) if d2.size(0) > 1 else d2.size(1), v2.size(0), v2.size(1), stream()))
+        grads[i] = dst
+
+    # ---- logits layer
+    oc = net.convs[-1]
+    dlogits = ops._rows(dlogits).contiguous()
+    dp = torch.empty((N, 2 * C), dtype=torch.float32, device=dev)
+    tmp = torch.empty((g.cap, C), dtype=torch.float32, device=dev)
+    check(L.egnn_sage_out_bwd(ptr(g.csc_ptr), ptr(g.csc_dst), ptr(g.csr_ptr), ptr(dlogits), dt(dlogits), C, ptr(dp), N,
+                              ptr(tmp), g.cap, stream()))
+    h = sv.h_last
+    dw = torch.empty((2 * C, H), dtype=torch.float32, device=dev)
+    dsum = torch.empty(2 * C, dtype=torch.float32, device=dev)
+    ws = torch.empty(L.egnn_skinny_wgrad_workspace_floats(N, H, 2 * C), dtype=torch.float32, device=dev)
+    check(L.egnn_skinny_wgrad(ptr(h), dt(h), h.stride(0), ptr(dp), 2 * C, N, H, ptr(dw), ptr(dsum), ptr(ws), stream()))
+    emit(oc.lin_l.weight, dw[:C])
+    emit(oc.lin_l.bias, dsum[C:])
+    emit(oc.lin_r.weight, dw[C:])
+    dy = torch.empty((N, H), dtype=cd, device=dev)
+    check(L.egnn_skinny_dgrad(ptr(dp), ptr(sv.wout), 2 * C, ptr(dy), dt(dy), H, N, H, stream()))
+
+    # ---- hidden layers, last to first
+    dh0 = None
+    for li in range(len(sv.layers) - 1, -1, -1):
+        ly = sv.layers[li]
+        conv = net.convs[li]
+        bn = net.bns[li] if sv.use_bn else None
+        z, K = ly.z, ly.K
+        dz = torch.empty((N, H), dtype=cd, device=dev)
+        dzsum = torch.empty(H, dtype=torch.float32, device=dev)
+        ws2 = torch.empty(L.egnn_colreduce_workspace_bytes(H) + 64 * H, dtype=torch.uint8, device=dev)
+        if bn is not None:
+            sg = torch.empty((2, H), dtype=torch.float64, device=dev)
+            wsr = torch.empty(L.egnn_colreduce_workspace_bytes(H), dtype=torch.uint8, device=dev)
+            check(L.egnn_bn_act_dropout_bwd_reduce(ptr(dy), ptr(z), dt(z), H, N, H, ptr(ly.mean), ptr(ly.rstd),
+                                                   ptr(bn.weight), ptr(bn.bias), ACT_RELU, ly.p_eff, sv.seed,
+                                                   ptr(sv.soff), li, sv.row0, sg[0].data_ptr(), sg[1].data_ptr(),
+                                                   ptr(wsr), z.stride(0), ptr(ly.kb), stream()))
+            if sv.reducer is not None:
+                sv.reducer.reduce_(sg)
+            check(L.egnn_bn_act_dropout_bwd_apply(ptr(dy), ptr(z), ptr(dz), dt(z), H, N, H, ptr(ly.mean), ptr(ly.rstd),
+                                                  ptr(bn.weight), ptr(bn.bias), ACT_RELU, ly.p_eff, sv.seed,
+                                                  ptr(sv.soff), li, sv.row0, sg[0].data_ptr(), sg[1].data_ptr(),
+                                                  sv.n_total, ptr(dzsum), ptr(ws2), z.stride(0), ptr(ly.kb), stream()))
+            sgf = torch.empty((2, H), dtype=torch.float32, device=dev)
+            check(L.egnn_f64_to_f32(ptr(sg), ptr(sgf), 2 * H, stream()))
+            emit(bn.bias, sgf[0])
+            emit(bn.weight, sgf[1])
+        else:
+            check(L.egnn_bn_act_dropout_bwd_apply(ptr(dy), ptr(z), ptr(dz), dt(z), H, N, H, None, None, None, None,
+                                                  ACT_RELU, ly.p_eff, sv.seed, ptr(sv.soff), li, sv.row0, None, None,
+                                                  1.0, ptr(dzsum), ptr(ws2), z.stride(0), ptr(ly.kb), stream()))
+        emit(conv.lin_l.bias, dzsum)
+        # weight gradients: dz^T [m | h]  (and dres^T h for a projected residual; dres = dy)
+        cat = ly.cat
+        Kraw = conv.in_channels
+        if 2 * K <= 384:
+            dwc = ops.linear_wgrad(dz, cat)
+            dwl, dwr = dwc[:, :K], dwc[:, K:]
+        else:
+            dwl, dwr = ops.linear_wgrad(dz, cat[:, :K]), ops.linear_wgrad(dz, cat[:, K:])
+        emit(conv.lin_l.weight, dwl[:, :Kraw])
+        emit(conv.lin_r.weight, dwr[:, :Kraw])
+        if ly.has_proj:
+            emit(net.res_projs[li].weight, ops.linear_wgrad(dy, cat[:, K:])[:, :Kraw])
+        need_dh = li > 0 or sv.D > 0
+        if not need_dh:
+            break
+        # [dm / in-degree | dx_root (+ dy of an identity residual)] = dz . [W_l | W_r]; dh = dx_root + A^T (dm / deg)
+        o2 = torch.empty((N, 2 * K), dtype=cd, device=dev)      # ly.wt = [W_l | W_r]^T, packed by the forward
+        _linear_tc(dz, ly.wt, o2, row_div=g.csr_ptr, row_div_cols=K, addend=dy if ly.res_is_input else None,
+                   add_col0=K)
+        if ly.has_proj:
+            ops.linear_dgrad(dy, ly.wcat[H:, K:], out=o2[:, K:], accumulate=True)
+        dh = ops.spmm(g, "csc", _lib.SPMM_SUM, o2[:, :K], cd, addend=o2[:, K:])
+        if li == 0:
+            dh0 = dh
+        dy = dh
+    if sv.D > 0:
+        dtab = torch.empty((sv.T, sv.D), dtype=torch.float32, device=dev)
+        wse = torch.empty(L.egnn_embed_grad_workspace_bytes(N, sv.T, sv.D), dtype=torch.uint8, device=dev)
+        check(L.egnn_embed_grad(ptr(dh0), dt(dh0), dh0.stride(0), sv.x_cols, sv.D, ptr(sv.t.contiguous()), sv.T, N,
+                                ptr(dtab), ptr(wse), stream()))
+        emit(net.time_emb.weight, dtab)
+    return [grads[i] for i in range(len(order))]
+
+
+class SageResBNFn(torch.autograd.Function):
+    """Drop-in autograd wrapper: logits = SageResBNFn.apply(net, x, g, t, *param_order(net))."""
+
+    @staticmethod
+    def forward(ctx, net, x, g, t, *params):
+        need = any(ctx.needs_input_grad[4:])
+        logits, sv = forward(net, x, g, t, net.training, need)
+        ctx.net, ctx.sv = net, sv
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        grads = backward(ctx.net, ctx.sv, dlogits.float())
+        ctx.sv = None
+        return (None, None, None, None) + tuple(grads)

@@ -11,9 +11,9 @@ from typing import Optional, Union
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import fused, ops
 from ._lib import ACT_ELU, ACT_RELU
-from .graph import Graph
+from .graph import Graph, cached_graph
 from .nn import GATConv, GCNConv, SAGEConv
 
 
@@ -177,6 +177,10 @@ class SAGEResBNNet(nn.Module, _DropoutMixin):
         return ops.inject_time(x, t_idx, table, self.in_dim)
 
     def forward(self, x, edge_index: Union[torch.Tensor, Graph], t_idx: Optional[torch.Tensor] = None):
+        if fused.supported(self, x, ops.amp_bf16()):
+            # bf16 autocast: the whole net as one explicit kernel sequence (fused.py), same arithmetic as below
+            g = edge_index if isinstance(edge_index, Graph) else cached_graph(edge_index, x.size(0))
+            return fused.SageResBNFn.apply(self, x, g, t_idx, *fused.param_order(self))
         x = self._inject_time(x, t_idx)
         h = x
         drop = None

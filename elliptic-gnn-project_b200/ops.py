@@ -260,7 +260,7 @@ class SageConvFn(torch.autograd.Function):
             check(lib().egnn_pack_sage_weights(ptr(w_l.contiguous()), ptr(w_r.contiguous()),
                                                ptr(w_res.contiguous()) if w_res is not None else None,
                                                ptr(b_l.contiguous()) if b_l is not None else None, No, Nr, K0, K,
-                                               ptr(wcat), ptr(bias), stream()))
+                                               ptr(wcat), ptr(bias), None, stream()))
             zc = linear_fwd(cat, wcat, bias=bias, out_dtype=cd)
             ctx.cat_path = True
             ctx.save_for_backward(cat, wcat)

@@ -11,8 +11,8 @@ from typing import Optional
 import torch
 import torch.nn as nn
 
-from . import ops
-from ._lib import check, lib, ptr, stream
+from . import fused, ops
+from ._lib import check, dt, lib, ptr, stream
 
 
 def class_weight(train_y: torch.Tensor) -> torch.Tensor:
@@ -99,12 +99,19 @@ class TrainStep:
     def __init__(self, model: nn.Module, x, edge_index, timestep, y, train_mask, *, lr: float,
                  weight_decay: float, grad_clip: float = 1.0, amp: bool = False,
                  cw: Optional[torch.Tensor] = None, n_train_total: Optional[int] = None,
-                 grad_reducer=None, health_check=None):
+                 grad_reducer=None, health_check=None, static_inputs: bool = True):
         """`train_mask` and `y` are read ONCE here (train-row indices, class weights, loss normaliser are static per
         run in the reference too: `src/train_gnn.py:301-312,362-363`); a caller that changes them builds a new
         TrainStep.  `health_check`: callable run at host synchronisation points (`loss_value()`), e.g.
-        `ShardedContext.check` (raises when a peer-memory all-reduce timed out)."""
+        `ShardedContext.check` (raises when a peer-memory all-reduce timed out).  `static_inputs` (default): `x`,
+        `timestep` and `edge_index` are not rewritten in place between steps -- the reference moves the graph to the
+        device once (`src/train_gnn.py:350`) -- so layouts derived from them (sorted graph views, the layer-0 input
+        `[x | time features]`) are memoised per tensor version and a captured CUDA graph may bake them in.
+        `capture_dynamic()` / `run(dynamic=True)` is the variant that re-derives them every step (`HostFeed`)."""
         self.model, self.amp = model, amp
+        self.static_inputs = bool(static_inputs)
+        self.graph_dynamic: Optional[torch.cuda.CUDAGraph] = None
+        self._keepalive = []
         self.health_check = health_check
         self.x, self.edge_index, self.timestep, self.y = x, edge_index, timestep, y
         self.train_idx = torch.nonzero(train_mask, as_tuple=False).view(-1).contiguous()  # once per run
@@ -112,29 +119,66 @@ class TrainStep:
         self.n_train_total = float(n_train_total if n_train_total is not None else self.train_idx.numel())
         self.opt = FlatClipAdam(model.parameters(), lr=lr, weight_decay=weight_decay, max_norm=grad_clip)
         self.grad_reducer = grad_reducer
-        self.loss = torch.zeros((), dtype=torch.float32, device=x.device)
+        self.loss = torch.zeros(1, dtype=torch.float32, device=x.device).squeeze(0)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self._fused_views = None
 
-    def _body(self):
+    def _fused_ok(self) -> bool:
+        from .models import SAGEResBNNet
+        m = self.model
+        return (isinstance(m, SAGEResBNNet) and type(m).forward is SAGEResBNNet.forward
+                and fused.supported(m, self.x, self.amp) and all(p.requires_grad for p in m.parameters())
+                and len(self.opt.params) == len(fused.param_order(m)))
+
+    def _body_fused(self):
+        """SAGE-ResBN, bf16: forward, loss, backward as one explicit kernel sequence (fused.py) -- no autograd graph,
+        gradients written straight into the flat buffer clip + Adam read."""
+        from .graph import Graph, cached_graph
         m = self.model
         m.train()
-        self.opt.zero_grad()
+        L = lib()
+        g = self.edge_index if isinstance(self.edge_index, Graph) else cached_graph(self.edge_index, self.x.size(0))
         t = self.timestep if model_uses_time_embed(m) else None
-        with torch.autocast(device_type="cuda", dtype=torch.bfloat16, enabled=self.amp):
-            logits = m(self.x, self.edge_index, t)
-        loss = ops.masked_weighted_ce(logits, self.y, self.train_idx, self.cw, self.n_train_total)
-        loss.backward()
-        self.opt.gather_grads()
+        logits, sv = fused.forward(m, self.x, g, t, True, True)
+        n = logits.size(0)
+        dlog = torch.empty_like(logits)
+        ws = torch.empty(L.egnn_ce_workspace_floats(self.train_idx.numel()), dtype=torch.float32, device=logits.device)
+        check(L.egnn_masked_ce(ptr(logits), dt(logits), n, ptr(self.y), ptr(self.train_idx), self.train_idx.numel(),
+                               ptr(self.cw), float(self.n_train_total), ptr(self.loss), ptr(dlog), ptr(ws), stream()))
+        if self._fused_views is None:
+            by_id = {id(p): v for p, v in zip(self.opt.params, self.opt.views)}
+            self._fused_views = [by_id[id(p)] for p in fused.param_order(m)]
+            for p, v in zip(self.opt.params, self.opt.views):
+                p.grad = v
+        fused.backward(m, sv, dlog, out=self._fused_views)
+
+    def _body(self, dynamic: bool = False):
+        m = self.model
+        with fused.static_inputs(self.static_inputs and not dynamic):
+            if self._fused_ok():
+                self._body_fused()
+            else:
+                m.train()
+                self.opt.zero_grad()
+                t = self.timestep if model_uses_time_embed(m) else None
+                with torch.autocast(device_type="cuda", dtype=torch.bfloat16, enabled=self.amp):
+                    logits = m(self.x, self.edge_index, t)
+                loss = ops.masked_weighted_ce(logits, self.y, self.train_idx, self.cw, self.n_train_total)
+                loss.backward()
+                self.opt.gather_grads()
+                self.loss.copy_(loss.detach())
         if self.grad_reducer is not None:
             self.grad_reducer(self.opt.flat_grad)
         self.opt.step()
-        self.loss.copy_(loss.detach())
 
-    def run(self) -> torch.Tensor:
-        if self.graph is not None:
-            self.graph.replay()
+    def run(self, dynamic: bool = False) -> torch.Tensor:
+        """One step.  `dynamic=True`: the variant that assumes `x` / `timestep` were rewritten in place since the last
+        step (no memoised input layouts; its own CUDA graph after `capture_dynamic()`)."""
+        graph = self.graph_dynamic if dynamic else self.graph
+        if graph is not None:
+            graph.replay()
         else:
-            self._body()
+            self._body(dynamic)
         return self.loss
 
     def loss_value(self) -> float:
@@ -154,7 +198,12 @@ class TrainStep:
             ts.append(drop.offset)
         return ts
 
-    def capture(self, warmup: int = 3, preserve_state: bool = False):
+    def capture_dynamic(self, warmup: int = 2):
+        """CUDA graph of the dynamic-input variant (`run(dynamic=True)`); the optimizer / BatchNorm / dropout state is
+        left as it was."""
+        return self.capture(warmup=warmup, preserve_state=True, dynamic=True)
+
+    def capture(self, warmup: int = 3, preserve_state: bool = False, dynamic: bool = False):
         """Record the step into a CUDA graph after `warmup` eager steps.  The warm-up steps are real optimizer
         steps; `preserve_state=True` puts parameters, Adam state, BatchNorm buffers and the dropout offset back to
         their values before the warm-up, so that the first replay IS step 1 of the run (the reference trains exactly
@@ -166,13 +215,19 @@ class TrainStep:
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(warmup):
-                self._body()
+                self._body(dynamic)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self._body()
-        self.graph = g
+            self._body(dynamic)
+        if dynamic:
+            self.graph_dynamic = g
+        else:
+            self.graph = g
+        # tensors the graph reads but did not allocate (memoised input layouts, sorted graph views) must outlive it
+        from .graph import _GLOBAL_CACHE
+        self._keepalive.append((list(fused.STATIC_INPUTS._d.values()), list(_GLOBAL_CACHE._d.values())))
         if saved is not None:
             for t, v in zip(self._mutable_state(), saved):
                 t.copy_(v)
@@ -196,6 +251,8 @@ class HostFeed:
         from .graph import build_graph, register_graph
         self._build, self._register = build_graph, register_graph
         self.step, self.host, self.dst, self.n, self.graph = step, host, device_bufs, int(num_nodes), graph
+        if step.graph is not None and step.graph_dynamic is None:
+            step.capture_dynamic()      # the inputs change under the step: its graph must re-derive their layouts
         for k, v in host.items():
             if not v.is_pinned():
                 raise ValueError(f"host tensor '{k}' must be pinned")
@@ -253,7 +310,7 @@ class HostFeed:
         self._consumed_once = True
         if ei_changed:
             main.wait_event(self.ev_graph)
-        self.step.run()
+        self.step.run(dynamic=True)
         slot = self.i & 1
         self.loss_host[slot].copy_(self.step.loss, non_blocking=True)
         self.ev_loss[slot].record(main)

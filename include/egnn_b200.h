@@ -150,6 +150,31 @@ int egnn_gemm(const void* A, int a_dtype, int64_t a_sm, int64_t a_sk, const void
               int64_t N, int64_t K, const float* bias, const int32_t* row_div_ptr, int64_t row_div_cols,
               int accumulate, int split_k, float* workspace, int impl, void* stream);
 
+/* The layer GEMM of the fused SAGE / SAGE-ResBN step: C[M,N] = A[M,K] . W[N,K]^T on the tcgen05 kernel (bf16 A and W,
+ * both contiguous along K, 16-byte rows; K <= 512, 8 <= N <= 256; C fp32 or bf16) with the epilogues the layers need:
+ *   bias [N], row_div_ptr / row_div_cols and accumulate as in egnn_gemm;
+ *   addend (same dtype as C, leading dimension ld_addend): C[m, addend_col0 + j] += addend[m, j] for the columns from
+ *     addend_col0 (a multiple of 16) on -- the identity-residual gradient `+ h_in` of src/models/gnn.py:192 joining the
+ *     root half of the concatenated dgrad [dm/deg | dx_root];
+ *   colstats (float [egnn_linear_stats_parts(M), 2, colstats_cols], colstats_cols <= 64): per-(CTA, TMEM sub-partition)
+ *     partial column sums and sums of squares of the values AS STORED in columns [0, colstats_cols) -- the batch
+ *     statistics of nn.BatchNorm1d over all rows (src/models/gnn.py:134,189) without another pass over the layer
+ *     output.  egnn_colstats_reduce sums the parts in a fixed order (float64 [2, F]; the multi-GPU path all-reduces
+ *     that vector), egnn_bn_finalize_parts does the same and finalises mean / rstd / running buffers in one launch.
+ * Compiled epilogue combinations: everything egnn_gemm accepts; addend (+ row_div); colstats (+ bias).  Any other
+ * shape or combination is an error (the callers then use egnn_gemm + egnn_colreduce). */
+int64_t egnn_linear_stats_parts(int64_t M);
+int egnn_linear_tc(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int c_dtype, int64_t ld_c,
+                   int64_t M, int64_t N, int64_t K, const float* bias, const int32_t* row_div_ptr,
+                   int64_t row_div_cols, int accumulate, const void* addend, int64_t ld_addend,
+                   int64_t addend_col0, float* colstats, int64_t colstats_cols, void* stream);
+int egnn_colstats_reduce(const float* parts, int64_t n_parts, int64_t n_feat, double* sums, void* stream);
+int egnn_bn_finalize_parts(const float* parts, int64_t n_parts, int64_t n_feat, double count, float eps,
+                           float momentum, float* mean, float* rstd, float* running_mean, float* running_var,
+                           int64_t* num_batches_tracked /* optional device counter, += 1 */, void* stream);
+/* out[i] = (float)in[i]: the float64 statistics / reductions handed to fp32 parameter gradients */
+int egnn_f64_to_f32(const double* in, float* out, int64_t n, void* stream);
+
 /* ---------------------------------------------------------------- narrow-output SAGEConv -- */
 /* The `hidden -> num_classes` SAGEConv of every SAGE net (src/models/gnn.py:44,128: PyG
  * SAGEConv(hidden, 2), A.2) evaluated project-first -- aggregation and projection commute:
@@ -190,7 +215,8 @@ int egnn_skinny_dgrad(const float* dp, const float* W, int P, void* dh, int dtyp
  * (src/models/gnn.py:125-128,141-144). */
 int egnn_pack_sage_weights(const float* w_l, const float* w_r, const float* w_res, const float* b_l,
                            int64_t n_out, int64_t n_res, int64_t K, int64_t K_padded, void* out_bf16,
-                           float* bias_out, void* stream);
+                           float* bias_out, void* out_t_bf16 /* optional [2*K_padded, n_out] = [W_l | W_r]^T */,
+                           void* stream);
 
 /* cast / copy with optional column padding: out[r, 0:F] = in[r, 0:F], out[r, F:ld_out] = 0 */
 int egnn_cast(const void* in, int in_dtype, int64_t ld_in, void* out, int out_dtype,
