@@ -167,12 +167,10 @@ struct ActCtx {
 __device__ __forceinline__ void act_eval(const ActCtx& C, int64_t r, int c, int F, F4 z, F4& y,
                                          F4& dfac, F4& xhat) {
   float zz[4] = {z.x, z.y, z.z, z.w}, yy[4], dd[4], xh[4];
-  uint32_t words[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+  uint32_t keep = 0xfu;
   if (C.drop) {
     const uint64_t seed = C.seed + (C.seed_off ? (uint64_t)*C.seed_off : 0ull);
-    Philox4 w = dropout_words(seed, C.layer, C.row0 + r, (uint32_t)(c >> 2));
-#pragma unroll
-    for (int k = 0; k < 4; ++k) words[k] = w.v[k];
+    keep = (dropout_keep8(seed, C.layer, C.row0 + r, (uint32_t)(c >> 3), C.thr) >> (c & 4)) & 0xfu;
   }
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -193,7 +191,7 @@ __device__ __forceinline__ void act_eval(const ActCtx& C, int64_t r, int c, int 
       da = u > 0.f ? 1.f : e + 1.f;
     }
     float ks = 1.f;
-    if (C.drop) ks = words[k] >= C.thr ? C.scale : 0.f;
+    if (C.drop) ks = (keep >> k) & 1u ? C.scale : 0.f;
     yy[k] = a * ks;
     dd[k] = da * ks;
   }
@@ -490,9 +488,7 @@ __device__ __forceinline__ void load_col4(const ActCtx& C, int c, Col4& k) {
 }
 // 4 keep bits of (row r, columns c..c+3) from Philox (same words as egnn_dropout_mask)
 __device__ __forceinline__ uint32_t keep_bits4(const ActCtx& C, uint64_t seed, int64_t r, int c) {
-  Philox4 w = dropout_words(seed, C.layer, C.row0 + r, (uint32_t)(c >> 2));
-  return (w.v[0] >= C.thr ? 1u : 0u) | (w.v[1] >= C.thr ? 2u : 0u) | (w.v[2] >= C.thr ? 4u : 0u) |
-         (w.v[3] >= C.thr ? 8u : 0u);
+  return (dropout_keep8(seed, C.layer, C.row0 + r, (uint32_t)(c >> 3), C.thr) >> (c & 4)) & 0xfu;
 }
 // u = bn(z); a = act(u); returns y = a*ks, dfac = act'(u)*ks, xhat.  bits: low nibble = dropout keep bits; with
 // STORED_GATE (backward, ReLU, bits saved by the forward) the high nibble holds the ReLU gates u > 0, so the
@@ -566,6 +562,124 @@ __global__ void __launch_bounds__(kThreads, 3) bn_act_fwd_lean(const T* __restri
           for (int i = 0; i < 4; ++i) y[i] += rv[i];
         }
         st4f(yout + r * ld_y + c, y);
+      }
+    }
+  }
+}
+
+// ---- 8 columns per thread: one Philox draw (all eight 16-bit lanes) per thread-row, 16-byte bf16 accesses, and --
+// optionally (PROJ) the logits-layer projection p[r, 0:4] = y[r, :] . Wp[0:4, :]^T of the NEXT SAGEConv
+// (`SAGEConv(hidden, 2)` evaluated project-first: [W_l ; W_r], src/models/gnn.py:128,193) as a by-product, so that
+// layer does not read the activation again.  The projection uses the activation AS STORED (rounded to T).
+// store 8 values, returning them as stored (rounded to the element type)
+__device__ __forceinline__ void st8r(float* p, float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *(reinterpret_cast<float4*>(p) + 1) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void st8r(__nv_bfloat16* p, float (&v)[8]) {
+  uint4 q;
+  q.x = pack_bf16x2(v[0], v[1]); q.y = pack_bf16x2(v[2], v[3]);
+  q.z = pack_bf16x2(v[4], v[5]); q.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = q;
+  v[0] = __uint_as_float(q.x << 16); v[1] = __uint_as_float(q.x & 0xffff0000u);
+  v[2] = __uint_as_float(q.y << 16); v[3] = __uint_as_float(q.y & 0xffff0000u);
+  v[4] = __uint_as_float(q.z << 16); v[5] = __uint_as_float(q.z & 0xffff0000u);
+  v[6] = __uint_as_float(q.w << 16); v[7] = __uint_as_float(q.w & 0xffff0000u);
+}
+
+constexpr int kRows8 = 4;   // rows in flight per thread
+constexpr int kProjP = 4;   // projected outputs (2 classes x [W_l ; W_r])
+
+template <typename T, bool BN, int ACT, bool PROJ>
+__global__ void __launch_bounds__(kThreads, 2) bn_act_fwd8(const T* __restrict__ z, const T* __restrict__ res,
+                                                          T* __restrict__ yout, int64_t ld, int64_t ld_res,
+                                                          int64_t ld_y, int64_t n_rows, int F, int cg_shift,
+                                                          int64_t rows_per_block, ActCtx C,
+                                                          uint8_t* __restrict__ keep_bits,
+                                                          const float* __restrict__ Wp, float* __restrict__ pout) {
+  const int CG = 1 << cg_shift, RL = kThreads >> cg_shift;   // CG = F / 8 lanes per row (<= 32: one warp)
+  const int cgi = threadIdx.x & (CG - 1), c = cgi * 8, rl = threadIdx.x >> cg_shift;
+  float mean[8], rstd[8], gamma[8], beta[8];
+  if (BN) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      mean[i] = C.mean[c + i]; rstd[i] = C.rstd[c + i]; gamma[i] = C.gamma[c + i]; beta[i] = C.beta[c + i];
+    }
+  }
+  float wp[PROJ ? kProjP : 1][8];
+  if (PROJ) {
+#pragma unroll
+    for (int p = 0; p < kProjP; ++p)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) wp[PROJ ? p : 0][i] = Wp[p * F + c + i];
+  }
+  const uint64_t seed = C.seed + (C.seed_off ? (uint64_t)*C.seed_off : 0ull);
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(n_rows, r0 + rows_per_block);
+  // uniform trip count over the block (rows_per_block is a multiple of RL * kRows8): every lane reaches the shuffles
+  for (int64_t rb = r0 + rl; rb < r0 + rows_per_block; rb += (int64_t)RL * kRows8) {
+    Raw8<T> zr[kRows8], rr[kRows8];
+#pragma unroll
+    for (int u = 0; u < kRows8; ++u) {
+      const int64_t r = rb + (int64_t)u * RL;
+      if (r < r1) {
+        zr[u].load(z + r * ld + c);
+        if (res) rr[u].load(res + r * ld_res + c);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kRows8; ++u) {
+      const int64_t r = rb + (int64_t)u * RL;
+      const bool valid = r < r1;
+      float y[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) y[i] = 0.f;
+      if (valid) {
+        float zv[8];
+        zr[u].unpack(zv);
+        const uint32_t bits = C.drop ? dropout_keep8(seed, C.layer, C.row0 + r, (uint32_t)cgi, C.thr) : 0xffu;
+        uint32_t gates = 0u;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float uu = zv[i];
+          if (BN) uu = ((zv[i] - mean[i]) * rstd[i]) * gamma[i] + beta[i];
+          float a = uu;
+          if (ACT == EGNN_ACT_RELU) {
+            const bool on = uu > 0.f;
+            gates |= (on ? 1u : 0u) << i;
+            a = on ? uu : 0.f;
+          } else if (ACT == EGNN_ACT_ELU) {
+            a = uu > 0.f ? uu : expm1f(uu);
+          }
+          y[i] = a * ((bits >> i) & 1u ? C.scale : 0.f);
+        }
+        if (keep_bits)   // one byte per 4 columns: low nibble = keep bits, high nibble = ReLU gates
+          *reinterpret_cast<uint16_t*>(keep_bits + r * (2 * CG) + 2 * cgi) =
+              (uint16_t)(((bits & 0xfu) | ((gates & 0xfu) << 4)) | ((((bits >> 4) & 0xfu) | (gates & 0xf0u)) << 8));
+        if (res) {
+          float rv[8];
+          rr[u].unpack(rv);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) y[i] += rv[i];
+        }
+        st8r(yout + r * ld_y + c, y);
+      }
+      if (PROJ) {
+        float sp[kProjP];
+#pragma unroll
+        for (int p = 0; p < kProjP; ++p) {
+          float a = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) a = fmaf(y[i], wp[PROJ ? p : 0][i], a);
+          sp[p] = a;
+        }
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {   // fixed butterfly over the CG lanes of the row
+          if (o < CG) {
+#pragma unroll
+            for (int p = 0; p < kProjP; ++p) sp[p] += __shfl_xor_sync(0xffffffffu, sp[p], o);
+          }
+        }
+        if (valid && cgi == 0) *reinterpret_cast<float4*>(pout + r * kProjP) = make_float4(sp[0], sp[1], sp[2], sp[3]);
       }
     }
   }
@@ -833,6 +947,26 @@ inline FastPlan lean_plan(int64_t n_rows, int64_t F, int dtype, std::initializer
   return p;
 }
 
+inline FastPlan plan8(int64_t n_rows, int64_t F, int dtype, std::initializer_list<int64_t> lds,
+                      std::initializer_list<const void*> ptrs) {
+  FastPlan p{false, 0, 0, 0};
+  if (F % 8 != 0 || F > 256) return p;
+  int cg = (int)(F / 8), sh = 0;
+  while ((1 << sh) < cg) ++sh;
+  if ((1 << sh) != cg) return p;
+  for (int64_t l : lds)
+    if (l % 8 != 0) return p;
+  (void)dtype;
+  for (const void* q : ptrs)
+    if (q && (uintptr_t)q % 16 != 0) return p;
+  const int RL = kThreads >> sh;
+  const int64_t unit = (int64_t)RL * kRows8;
+  int64_t rpb = ceil_div(ceil_div(n_rows > 0 ? n_rows : 1, (int64_t)kNumSMs * 2), unit) * unit;   // one wave, 2 blocks / SM
+  if (rpb < unit) rpb = unit;
+  p.ok = true; p.cg_shift = sh; p.rpb = rpb; p.nblk = (int)ceil_div(n_rows > 0 ? n_rows : 1, rpb);
+  return p;
+}
+
 // one block per column: fixed-order sum of nblk doubles
 __global__ void __launch_bounds__(kThreads) colsum_final(const double* __restrict__ partial, int nblk, int F,
                                                          float* __restrict__ out) {
@@ -867,30 +1001,40 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, const double
   }
 }
 
-// BatchNorm statistics from the per-(CTA, sub-partition) partial rows the layer GEMM's epilogue wrote
+// BatchNorm statistics from the per-CTA partial rows the layer GEMM's epilogue wrote
 // (egnn_linear_tc colstats): fixed-order float64 sum over the parts; FINALIZE also turns them into mean / rstd and
 // updates the running buffers (single-GPU: one launch between the GEMM and the BatchNorm apply).
+constexpr int kPartCols = 64;     // columns per block
+constexpr int kPartGroups = 16;   // part groups per block (threads = 64 x 16)
 template <bool FINALIZE>
-__global__ void colstats_parts_kernel(const float* __restrict__ parts, int n_parts, int F, double* __restrict__ sums,
-                                      double count, float eps, float momentum, float* __restrict__ mean,
-                                      float* __restrict__ rstd, float* __restrict__ rmean, float* __restrict__ rvar,
-                                      int64_t* __restrict__ num_batches) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (FINALIZE && num_batches && c == 0) *num_batches += 1;   // bn.num_batches_tracked (one thread of one block)
-  if (c >= F) return;
-  double s0 = 0.0, s1 = 0.0, q0 = 0.0, q1 = 0.0;
-  int p = 0;
-  for (; p + 1 < n_parts; p += 2) {   // two independent chains (loads in flight), combined in a fixed order
-    s0 += (double)parts[(size_t)p * 2 * F + c];
-    q0 += (double)parts[(size_t)p * 2 * F + F + c];
-    s1 += (double)parts[(size_t)(p + 1) * 2 * F + c];
-    q1 += (double)parts[(size_t)(p + 1) * 2 * F + F + c];
+__global__ void __launch_bounds__(kPartCols * kPartGroups)
+colstats_parts_kernel(const float* __restrict__ parts, int n_parts, int F, double* __restrict__ sums, double count,
+                      float eps, float momentum, float* __restrict__ mean, float* __restrict__ rstd,
+                      float* __restrict__ rmean, float* __restrict__ rvar, int64_t* __restrict__ num_batches) {
+  __shared__ double sm[2][kPartGroups][kPartCols];
+  const int cl = threadIdx.x & (kPartCols - 1), gq = threadIdx.x / kPartCols;
+  const int c = blockIdx.x * kPartCols + cl;
+  if (FINALIZE && num_batches && blockIdx.x == 0 && threadIdx.x == 0) *num_batches += 1;   // bn.num_batches_tracked
+  double s = 0.0, q = 0.0;
+  if (c < F) {
+    // group gq sums parts gq, gq + 16, ... in that order: every (group, column) chain is fixed, and so is the
+    // order in which the 16 group totals are combined below
+    for (int p = gq; p < n_parts; p += kPartGroups) {
+      s += (double)parts[(size_t)p * 2 * F + c];
+      q += (double)parts[(size_t)p * 2 * F + F + c];
+    }
   }
-  if (p < n_parts) {
-    s0 += (double)parts[(size_t)p * 2 * F + c];
-    q0 += (double)parts[(size_t)p * 2 * F + F + c];
+  sm[0][gq][cl] = s;
+  sm[1][gq][cl] = q;
+  __syncthreads();
+  if (gq != 0 || c >= F) return;
+  s = 0.0;
+  q = 0.0;
+#pragma unroll
+  for (int k = 0; k < kPartGroups; ++k) {
+    s += sm[0][k][cl];
+    q += sm[1][k][cl];
   }
-  const double s = s0 + s1, q = q0 + q1;
   if (sums) {
     sums[c] = s;
     sums[F + c] = q;
@@ -913,15 +1057,15 @@ __global__ void __launch_bounds__(kThreads) dropout_mask_kernel(uint8_t* __restr
                                                                 int64_t n_rows, int F, uint32_t thr,
                                                                 uint64_t seed, const int64_t* seed_off,
                                                                 uint32_t layer, int64_t row0) {
-  const int F4n = (F + 3) >> 2;
+  const int F8n = (F + 7) >> 3;
   int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  if (i >= n_rows * F4n) return;
-  int64_t r = i / F4n;
-  int cb = (int)(i - r * F4n);
-  Philox4 w = dropout_words(seed + (seed_off ? (uint64_t)*seed_off : 0ull), layer, row0 + r, (uint32_t)cb);
+  if (i >= n_rows * F8n) return;
+  int64_t r = i / F8n;
+  int cb = (int)(i - r * F8n);
+  const uint32_t keep = dropout_keep8(seed + (seed_off ? (uint64_t)*seed_off : 0ull), layer, row0 + r, (uint32_t)cb, thr);
 #pragma unroll
-  for (int k = 0; k < 4; ++k)
-    if (cb * 4 + k < F) mask[r * F + cb * 4 + k] = w.v[k] >= thr ? 1 : 0;
+  for (int k = 0; k < 8; ++k)
+    if (cb * 8 + k < F) mask[r * F + cb * 8 + k] = (keep >> k) & 1u;
 }
 
 // ---- masked weighted cross-entropy (2 classes) --------------------------------------------------
@@ -1222,7 +1366,7 @@ extern "C" int egnn_f64_to_f32(const double* in, float* out, int64_t n, void* st
 extern "C" int egnn_colstats_reduce(const float* parts, int64_t n_parts, int64_t n_feat, double* sums, void* stream) {
   const char* fn = "egnn_colstats_reduce";
   EGNN_REQUIRE(parts && sums && n_parts > 0 && n_feat > 0, fn, "bad arguments");
-  colstats_parts_kernel<false><<<(unsigned)ceil_div(n_feat, 64), 64, 0, (cudaStream_t)stream>>>(
+  colstats_parts_kernel<false><<<(unsigned)ceil_div(n_feat, kPartCols), kPartCols * kPartGroups, 0, (cudaStream_t)stream>>>(
       parts, (int)n_parts, (int)n_feat, sums, 1.0, 0.f, 0.f, nullptr, nullptr, nullptr, nullptr, nullptr);
   EGNN_LAUNCH_CHECK(fn);
   return 0;
@@ -1233,7 +1377,7 @@ extern "C" int egnn_bn_finalize_parts(const float* parts, int64_t n_parts, int64
                                       float* running_var, int64_t* num_batches_tracked, void* stream) {
   const char* fn = "egnn_bn_finalize_parts";
   EGNN_REQUIRE(parts && mean && rstd && n_parts > 0 && n_feat > 0 && count > 0, fn, "bad arguments");
-  colstats_parts_kernel<true><<<(unsigned)ceil_div(n_feat, 64), 64, 0, (cudaStream_t)stream>>>(
+  colstats_parts_kernel<true><<<(unsigned)ceil_div(n_feat, kPartCols), kPartCols * kPartGroups, 0, (cudaStream_t)stream>>>(
       parts, (int)n_parts, (int)n_feat, nullptr, count, eps, momentum, mean, rstd, running_mean, running_var,
       num_batches_tracked);
   EGNN_LAUNCH_CHECK(fn);
@@ -1247,7 +1391,7 @@ static ActCtx make_ctx(const float* mean, const float* rstd, const float* gamma,
   C.act = act;
   C.drop = p > 0.f;
   C.scale = p > 0.f ? (float)(1.0 / (1.0 - (double)p)) : 1.f;
-  C.thr = dropout_threshold(p);
+  C.thr = dropout_threshold16(p);
   C.seed = seed; C.seed_off = seed_off; C.layer = layer; C.row0 = row0;
   return C;
 }
@@ -1257,7 +1401,7 @@ extern "C" int egnn_bn_act_dropout_res_fwd(const void* z, const void* res, void*
                                            const float* rstd, const float* gamma, const float* beta,
                                            int act, float p, uint64_t seed, const int64_t* seed_off, uint32_t layer,
                                            int64_t row0, int64_t ld_res, int64_t ld_y, uint8_t* keep_bits,
-                                           void* stream) {
+                                           const float* proj_w, float* proj_out, void* stream) {
   const char* fn = "egnn_bn_act_dropout_res_fwd";
   if (ld_y <= 0) ld_y = ld;
   if (ld_res <= 0) ld_res = ld;
@@ -1265,9 +1409,37 @@ extern "C" int egnn_bn_act_dropout_res_fwd(const void* z, const void* res, void*
   EGNN_REQUIRE(z && y, fn, "null pointer");
   EGNN_REQUIRE(!mean || (rstd && gamma && beta), fn, "incomplete BatchNorm arguments");
   EGNN_REQUIRE(p >= 0.f && p < 1.f, fn, "dropout p must be in [0,1)");
+  EGNN_REQUIRE((proj_w == nullptr) == (proj_out == nullptr), fn, "proj_w / proj_out must be given together");
   if (n_rows == 0) return 0;
   ActCtx C = make_ctx(mean, rstd, gamma, beta, act, p, seed, seed_off, layer, row0);
   cudaStream_t st = (cudaStream_t)stream;
+  FastPlan f8 = plan8(n_rows, n_feat, dtype, {ld, res ? ld_res : 8, ld_y}, {z, res, y});
+  EGNN_REQUIRE(!proj_w || (f8.ok && act == EGNN_ACT_RELU && (uintptr_t)proj_out % 16 == 0), fn,
+               "the fused projection needs the 8-column path (F/8 a power of two <= 32, 16-byte rows) and ReLU");
+  if (f8.ok) {
+#define EGNN_FWD8(TT, BNF, ACTF, PJ)                                                                              \
+  bn_act_fwd8<TT, BNF, ACTF, PJ><<<f8.nblk, kThreads, 0, st>>>((const TT*)z, (const TT*)res, (TT*)y, ld, ld_res, ld_y, \
+                                                               n_rows, (int)n_feat, f8.cg_shift, f8.rpb, C, keep_bits, \
+                                                               proj_w, proj_out)
+#define EGNN_FWD8_ACT(TT, BNF)                                               \
+  do {                                                                       \
+    if (proj_w) EGNN_FWD8(TT, BNF, EGNN_ACT_RELU, true);                     \
+    else if (act == EGNN_ACT_RELU) EGNN_FWD8(TT, BNF, EGNN_ACT_RELU, false); \
+    else if (act == EGNN_ACT_ELU) EGNN_FWD8(TT, BNF, EGNN_ACT_ELU, false);   \
+    else EGNN_FWD8(TT, BNF, EGNN_ACT_NONE, false);                           \
+  } while (0)
+    if (dtype == EGNN_F32) {
+      if (mean) EGNN_FWD8_ACT(float, true);
+      else EGNN_FWD8_ACT(float, false);
+    } else {
+      if (mean) EGNN_FWD8_ACT(__nv_bfloat16, true);
+      else EGNN_FWD8_ACT(__nv_bfloat16, false);
+    }
+#undef EGNN_FWD8_ACT
+#undef EGNN_FWD8
+    EGNN_LAUNCH_CHECK(fn);
+    return 0;
+  }
   FastPlan fp = lean_plan(n_rows, n_feat, dtype, {ld, res ? ld_res : 4, ld_y}, {z, res, y});
   if (fp.ok) {
     EGNN_LEAN_DISPATCH(bn_act_fwd_lean, fp.nblk, (const TT*)z, (const TT*)res, (TT*)y, ld, ld_res, ld_y, n_rows,
@@ -1378,9 +1550,9 @@ extern "C" int egnn_dropout_mask(uint8_t* mask, int64_t n_rows, int64_t n_feat, 
   const char* fn = "egnn_dropout_mask";
   EGNN_REQUIRE(mask && n_feat > 0, fn, "bad arguments");
   if (n_rows == 0) return 0;
-  unsigned grid = (unsigned)ceil_div(n_rows * ceil_div(n_feat, 4), kThreads);
+  unsigned grid = (unsigned)ceil_div(n_rows * ceil_div(n_feat, 8), kThreads);
   dropout_mask_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(mask, n_rows, (int)n_feat,
-                                                                   dropout_threshold(p), seed, seed_off, layer, row0);
+                                                                   dropout_threshold16(p), seed, seed_off, layer, row0);
   EGNN_LAUNCH_CHECK(fn);
   return 0;
 }

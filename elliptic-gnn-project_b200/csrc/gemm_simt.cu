@@ -398,7 +398,8 @@ size_t wgrad_tcgen05_workspace_floats(int64_t N_out, int64_t K_in);
 bool wgrad_tcgen05_supported(const void* G, int64_t ldg, const void* X, int64_t ldx, int64_t M_rows, int64_t N_out,
                              int64_t K_in);
 int wgrad_tcgen05_dispatch(const void* G, int64_t ldg, const void* X, int64_t ldx, float* dW, int64_t M_rows,
-                           int64_t N_out, int64_t K_in, int accumulate, float* workspace, cudaStream_t st);
+                           int64_t N_out, int64_t K_in, int accumulate, float* workspace, cudaStream_t st,
+                           float* dst1 = nullptr, int64_t split = 0, int64_t valid = 0);
 }  // namespace egnn
 
 using namespace egnn;
@@ -424,6 +425,23 @@ extern "C" int egnn_linear_tc(const void* A, int64_t lda, const void* W, int64_t
     return fail(fn, "epilogue combination not compiled in");
   return gemm_tcgen05_dispatch(A, lda, W, ldw, C, c_dtype, ld_c, M, N, K, bias, accumulate, row_div_ptr, row_div_cols,
                                (cudaStream_t)stream, addend, ld_addend, addend_col0, colstats, colstats_cols);
+}
+
+// dW[N_out, K_in] = G[M, N_out]^T . X[M, K_in] on the tcgen05 wgrad kernel, the result written as two dense parameter
+// gradients (see wgrad_reduce_split_kernel)
+extern "C" size_t egnn_wgrad_tc_workspace_floats(int64_t N_out, int64_t K_in) {
+  return wgrad_tcgen05_workspace_floats(N_out, K_in);
+}
+extern "C" int egnn_wgrad_tc(const void* G, int64_t ldg, const void* X, int64_t ldx, int64_t M, int64_t N_out,
+                             int64_t K_in, float* dst0, float* dst1, int64_t split_col, int64_t valid_cols,
+                             float* workspace, void* stream) {
+  const char* fn = "egnn_wgrad_tc";
+  EGNN_REQUIRE(G && X && dst0 && workspace, fn, "null pointer");
+  EGNN_REQUIRE(M > 0 && split_col > 0 && split_col <= K_in && valid_cols > 0 && valid_cols <= split_col, fn, "bad split");
+  if (!wgrad_tcgen05_supported(G, ldg, X, ldx, M, N_out, K_in))
+    return fail(fn, "shape / alignment outside the tcgen05 wgrad kernel (N_out <= 256, K_in <= 384, 16-byte rows)");
+  return wgrad_tcgen05_dispatch(G, ldg, X, ldx, dst0, M, N_out, K_in, 0, workspace, (cudaStream_t)stream, dst1, split_col,
+                                valid_cols);
 }
 
 extern "C" size_t egnn_gemm_workspace_floats(int64_t M, int64_t N, int64_t K, int split_k) {

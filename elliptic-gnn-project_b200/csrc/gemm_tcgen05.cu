@@ -146,7 +146,7 @@ struct Epilogue {
   int64_t ld_add;
   int add_col0;
   // optional BatchNorm statistics of the STORED values of columns [0, stats_cols), stats_cols <= 64:
-  // stats[(cta*4 + q)*2*stats_cols + {0: sum, 1: sum of squares}*stats_cols + c], rows of TMEM sub-partition q
+  // stats[(cta*2 + {0: sum, 1: sum of squares})*stats_cols + c]: one partial row per CTA
   float* stats;
   int stats_cols;
 };
@@ -167,6 +167,12 @@ __device__ __forceinline__ void epilogue_loop(const Epilogue& ep, const float* s
       for (int j = 0; j < 16; ++j) { st_sum[kStats ? h : 0][j] = 0.f; st_sq[kStats ? h : 0][j] = 0.f; }
   }
   const TC* __restrict__ Abase = reinterpret_cast<const TC*>(ep.addend);
+  // the second addend of a tile is requested BEFORE the wait for its accumulator (its address depends on the tile
+  // index only), so the loads overlap the MMAs instead of sitting on the epilogue's critical path: 2 chunks per warp
+  constexpr int kPreVec = sizeof(TC) == 2 ? 2 : 4;   // 16-byte vectors per 16-column chunk
+  uint4 pre[kAdd2 ? 2 : 1][kPreVec];
+  const bool pre_ok = kAdd2 && (N - ep.add_col0 <= 64) && (ep.add_col0 % 32 == 0) && (N % 16 == 0) &&
+                      (ep.ld_add % 8 == 0) && ((uintptr_t)ep.addend % 16 == 0);
   const int div_cols = ep.row_div_cols > 0 ? ep.row_div_cols : N;
   TC* __restrict__ Cbase = reinterpret_cast<TC*>(ep.C);
   const bool vec_ok = (ep.ld_c % 8 == 0) && ((uintptr_t)ep.C % 16 == 0);
@@ -174,10 +180,21 @@ __device__ __forceinline__ void epilogue_loop(const Epilogue& ep, const float* s
   for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
     const int buf = it & 1;
     const uint32_t use = (uint32_t)(it >> 1);
-    mbar_wait(&t_full[buf], use & 1);
-    tcgen05_fence_after();
     const int64_t row = (int64_t)t * BM + q * 32 + lane;
     const bool row_ok = row < M;
+    if (kAdd2 && pre_ok && row_ok) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int cc = half * 16 + 32 * i;   // column inside the addend
+        if (ep.add_col0 + cc < N) {
+          const uint4* src = reinterpret_cast<const uint4*>(Abase + row * ep.ld_add + cc);
+#pragma unroll
+          for (int u = 0; u < kPreVec; ++u) pre[kAdd2 ? i : 0][u] = __ldg(src + u);
+        }
+      }
+    }
+    mbar_wait(&t_full[buf], use & 1);
+    tcgen05_fence_after();
     float rdiv = 1.f, rinv = 1.f;
     if (kDiv && row_ok) {
       int d = ep.row_div_ptr[row + 1] - ep.row_div_ptr[row];
@@ -200,7 +217,22 @@ __device__ __forceinline__ void epilogue_loop(const Epilogue& ep, const float* s
           if (c0 + j < div_cols) v[j] = sizeof(TC) == 2 ? v[j] * rinv : __fdiv_rn(v[j], rdiv);
         }
       }
-      if (kAdd2 && c0 >= ep.add_col0) {
+      if (kAdd2 && c0 >= ep.add_col0 && pre_ok) {
+        const bool second = (c0 - ep.add_col0) >= 32;
+#pragma unroll
+        for (int u = 0; u < kPreVec; ++u) {
+          const uint4 w = second ? pre[kAdd2 ? 1 : 0][u] : pre[0][u];
+          if (sizeof(TC) == 4) {
+            v[4 * u] += __uint_as_float(w.x); v[4 * u + 1] += __uint_as_float(w.y);
+            v[4 * u + 2] += __uint_as_float(w.z); v[4 * u + 3] += __uint_as_float(w.w);
+          } else {
+            v[8 * u] += __uint_as_float(w.x << 16); v[8 * u + 1] += __uint_as_float(w.x & 0xffff0000u);
+            v[8 * u + 2] += __uint_as_float(w.y << 16); v[8 * u + 3] += __uint_as_float(w.y & 0xffff0000u);
+            v[8 * u + 4] += __uint_as_float(w.z << 16); v[8 * u + 5] += __uint_as_float(w.z & 0xffff0000u);
+            v[8 * u + 6] += __uint_as_float(w.w << 16); v[8 * u + 7] += __uint_as_float(w.w & 0xffff0000u);
+          }
+        }
+      } else if (kAdd2 && c0 >= ep.add_col0) {
         const TC* a = Abase + row * ep.ld_add + (c0 - ep.add_col0);
         if (nv == 16 && ep.ld_add % 8 == 0 && ((uintptr_t)ep.addend % 16 == 0)) {
           if (sizeof(TC) == 4) {
@@ -276,9 +308,10 @@ __device__ __forceinline__ void epilogue_loop(const Epilogue& ep, const float* s
     if (lane == 0) mbar_arrive(&t_empty[buf]);
   }
   if (kStats) {
-    // fixed butterfly over the 32 rows of this warp, then one partial row per (CTA, TMEM sub-partition): the
-    // assignment of tiles to CTAs is static, so the partials (and their fixed-order sum) are reproducible
-    float* out = ep.stats + ((size_t)blockIdx.x * 4 + q) * 2 * ep.stats_cols;
+    // fixed butterfly over the 32 rows of this warp, the four sub-partitions combined in order through shared
+    // memory, then ONE partial row per CTA: the assignment of tiles to CTAs is static, so the partials (and their
+    // fixed-order sum in colstats_parts_kernel) are reproducible
+    __shared__ float s_st[4][2][64];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int c0 = half * 16 + 32 * h;
@@ -290,11 +323,19 @@ __device__ __forceinline__ void epilogue_loop(const Epilogue& ep, const float* s
           a += __shfl_xor_sync(0xffffffffu, a, o);
           b += __shfl_xor_sync(0xffffffffu, b, o);
         }
-        if (lane == 0 && c0 + j < ep.stats_cols) {
-          out[c0 + j] = a;
-          out[ep.stats_cols + c0 + j] = b;
+        if (lane == 0) {
+          s_st[q][0][c0 + j] = a;
+          s_st[q][1][c0 + j] = b;
         }
       }
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 epilogue warps only
+    const int tid = (half * 4 + q) * 32 + lane;      // 0..255
+    if (tid < 128) {
+      const int which = tid >> 6, c = tid & 63;
+      if (c < ep.stats_cols)
+        ep.stats[((size_t)blockIdx.x * 2 + which) * ep.stats_cols + c] =
+            ((s_st[0][which][c] + s_st[1][which][c]) + s_st[2][which][c]) + s_st[3][which][c];
     }
   }
 }
@@ -559,6 +600,40 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
   }
 }
 
+// the same reduction writing the [N_out, K_in] result as two parameter gradients: columns [0, split) -> dst0, columns
+// [split, K_in) -> dst1 (may be null), each [N_out, valid] dense with the zero-padding columns >= valid dropped --
+// dW_l / dW_r of a SAGE layer straight into the flat gradient buffer, no slicing copies
+__global__ void __launch_bounds__(256) wgrad_reduce_split_kernel(const float* __restrict__ partial, int n_part,
+                                                                 int N_out, int K_in, float* __restrict__ dst0,
+                                                                 float* __restrict__ dst1, int split, int valid) {
+  __shared__ float sm[4][64];
+  const int el = threadIdx.x & 63, q = threadIdx.x >> 6;
+  const int64_t n_elem = (int64_t)N_out * K_in;
+  const int64_t i = (int64_t)blockIdx.x * 64 + el;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (i < n_elem) {
+    int p = q;
+    for (; p + 12 < n_part; p += 16) {
+      s0 += partial[(size_t)p * n_elem + i];
+      s1 += partial[(size_t)(p + 4) * n_elem + i];
+      s2 += partial[(size_t)(p + 8) * n_elem + i];
+      s3 += partial[(size_t)(p + 12) * n_elem + i];
+    }
+    for (; p < n_part; p += 4) s0 += partial[(size_t)p * n_elem + i];
+  }
+  sm[q][el] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (q == 0 && i < n_elem) {
+    const float s = (sm[0][el] + sm[1][el]) + (sm[2][el] + sm[3][el]);
+    const int n = (int)(i / K_in), k = (int)(i - (int64_t)n * K_in);
+    if (k < split) {
+      if (k < valid) dst0[(size_t)n * valid + k] = s;
+    } else if (dst1 && k - split < valid) {
+      dst1[(size_t)n * valid + (k - split)] = s;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ host side ---------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -591,7 +666,7 @@ bool make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int6
 }
 
 constexpr int kStagesTN = 6;
-constexpr size_t kMaxDynSmemTN = 227 * 1024;
+constexpr size_t kMaxDynSmemTN = 218 * 1024;   // + 8 KB of static shared memory (epilogue statistics, 4 variants)
 constexpr int kStagesWG = 4;
 
 }  // namespace
@@ -621,7 +696,7 @@ bool gemm_tcgen05_epilogue_supported(bool bias, bool row_div, bool accumulate, b
 
 int64_t gemm_tcgen05_stats_parts(int64_t M) {
   const int64_t n_tiles = (M + BM - 1) / BM;
-  return 4 * (n_tiles < kNumSMs ? n_tiles : kNumSMs);
+  return n_tiles < kNumSMs ? n_tiles : kNumSMs;
 }
 
 int gemm_tcgen05_dispatch(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int c_dtype,
@@ -664,7 +739,8 @@ bool wgrad_tcgen05_supported(const void* G, int64_t ldg, const void* X, int64_t 
 
 // dW[N_out, K_in] (fp32, ld = K_in) (+)= G[M,N_out]^T X[M,K_in]; workspace >= wgrad_tcgen05_workspace_floats
 int wgrad_tcgen05_dispatch(const void* G, int64_t ldg, const void* X, int64_t ldx, float* dW, int64_t M_rows,
-                           int64_t N_out, int64_t K_in, int accumulate, float* workspace, cudaStream_t st) {
+                           int64_t N_out, int64_t K_in, int accumulate, float* workspace, cudaStream_t st,
+                           float* dst1, int64_t split, int64_t valid) {
   const char* fn = "egnn_gemm(tcgen05 wgrad)";
   const int Nopad = (int)((N_out + 15) / 16 * 16);
   const int MT = (int)((K_in + 127) / 128);
@@ -693,7 +769,11 @@ int wgrad_tcgen05_dispatch(const void* G, int64_t ldg, const void* X, int64_t ld
     gemm_wgrad_kernel<2><<<grid, kThreads, smem, st>>>(tmX, tmG, (int)M_rows, (int)N_out, Nopad, (int)K_in, workspace);
   EGNN_LAUNCH_CHECK(fn);
   int64_t n_elem = N_out * K_in;
-  wgrad_reduce_kernel<<<(unsigned)ceil_div(n_elem, 64), 256, 0, st>>>(workspace, grid, n_elem, dW, accumulate);
+  if (valid > 0)
+    wgrad_reduce_split_kernel<<<(unsigned)ceil_div(n_elem, 64), 256, 0, st>>>(workspace, grid, (int)N_out, (int)K_in, dW,
+                                                                             dst1, (int)split, (int)valid);
+  else
+    wgrad_reduce_kernel<<<(unsigned)ceil_div(n_elem, 64), 256, 0, st>>>(workspace, grid, n_elem, dW, accumulate);
   EGNN_LAUNCH_CHECK(fn);
   return 0;
 }

@@ -175,6 +175,14 @@ def forward(net, x: torch.Tensor, g: Graph, t: Optional[torch.Tensor], training:
     h32, cat = STATIC_INPUTS.get(x, t if use_t else None, table, K0p, build_h0)
     ops.spmm(g, "csr", _lib.SPMM_MEAN, h32, cd, out=cat[:, :K0p])
 
+    # logits layer operand [W_l ; W_r] (fp32, [2C, H])
+    out_conv = net.convs[-1]
+    C_out = out_conv.out_channels
+    wout = torch.empty((2 * C_out, H), dtype=torch.float32, device=dev)
+    check(L.egnn_cast(ptr(out_conv.lin_l.weight), _lib.F32, H, ptr(wout), _lib.F32, H, C_out, H, stream()))
+    check(L.egnn_cast(ptr(out_conv.lin_r.weight), _lib.F32, H, ptr(wout[C_out:]), _lib.F32, H, C_out, H, stream()))
+    p_out = None
+
     layers: List[_Layer] = []
     K, Kraw = K0p, K0
     h_in = cat[:, K0p:]
@@ -225,12 +233,17 @@ def forward(net, x: torch.Tensor, g: Graph, t: Optional[torch.Tensor], training:
         nxt = torch.empty((N, 2 * H), dtype=cd, device=dev)     # [agg | y]: the next SAGEConv aggregates in place
         y = nxt[:, H:]
         kb = torch.empty((N, H // 4), dtype=torch.uint8, device=dev) if need_grad else None
+        # the last hidden layer also emits p = y [W_l ; W_r]^T of the logits layer (project-first), from the same pass
+        fold = last and C_out == 2 and H <= 256 and (H // 8) & (H // 8 - 1) == 0
+        if fold:
+            p_out = torch.empty((N, 2 * C_out), dtype=torch.float32, device=dev)
         check(L.egnn_bn_act_dropout_res_fwd(ptr(z), ptr(res), ptr(y), dt(z), z.stride(0), N, H, ptr(mean), ptr(rstd),
                                             ptr(bn.weight) if bn is not None else None,
                                             ptr(bn.bias) if bn is not None else None, ACT_RELU, p_eff,
                                             drop.seed if drop is not None else 0,
                                             ptr(drop.offset) if drop is not None else None, li, net.row0,
-                                            res.stride(0) if res is not None else 0, y.stride(0), ptr(kb), stream()))
+                                            res.stride(0) if res is not None else 0, y.stride(0), ptr(kb),
+                                            ptr(wout) if fold else None, ptr(p_out) if fold else None, stream()))
         if need_grad:
             ly = _Layer()
             ly.cat, ly.wcat, ly.wt, ly.z, ly.mean, ly.rstd, ly.kb = cat, wcat, wt, z, mean, rstd, kb
@@ -242,11 +255,11 @@ def forward(net, x: torch.Tensor, g: Graph, t: Optional[torch.Tensor], training:
         cat, K, Kraw, h_in = nxt, H, H, y
 
     # ---- logits layer, project first: p = h [W_l; W_r]^T, out_i = mean_j p_j[:C] + b + p_i[C:]
-    out_conv = net.convs[-1]
-    C = out_conv.out_channels
-    wout = torch.cat([out_conv.lin_l.weight.detach(), out_conv.lin_r.weight.detach()], dim=0).float().contiguous()
-    p = torch.empty((N, 2 * C), dtype=torch.float32, device=dev)
-    check(L.egnn_skinny_project(ptr(h_in), dt(h_in), h_in.stride(0), N, H, ptr(wout), 2 * C, ptr(p), stream()))
+    C = C_out
+    p = p_out
+    if p is None:
+        p = torch.empty((N, 2 * C), dtype=torch.float32, device=dev)
+        check(L.egnn_skinny_project(ptr(h_in), dt(h_in), h_in.stride(0), N, H, ptr(wout), 2 * C, ptr(p), stream()))
     logits = torch.empty((N, C), dtype=torch.float32, device=dev)
     tmp = torch.empty((g.cap, C), dtype=torch.float32, device=dev)
     check(L.egnn_sage_out_fwd(ptr(g.csr_ptr), ptr(g.csr_src), ptr(p), ptr(out_conv.lin_l.bias), C, ptr(logits), N,
@@ -280,8 +293,9 @@ def param_order(net) -> List[torch.nn.Parameter]:
 
 
 def backward(net, sv: Saved, dlogits: torch.Tensor, out: Optional[List[torch.Tensor]] = None) -> List[torch.Tensor]:
-    """Gradients of every parameter in `param_order(net)`; written into `out[i]` (fp32, the parameter's shape) when
-    given.  `dlogits` fp32 [N, C]."""
+    """Gradients of every parameter in `param_order(net)`, fp32; the kernels write them straight into `out[i]`
+    (contiguous, the parameter's shape -- `train.TrainStep` passes views of its flat gradient buffer) when given.
+    `dlogits` fp32 [N, C]."""
     L = lib()
     g = sv.g
     dev = dlogits.device
@@ -290,36 +304,42 @@ def backward(net, sv: Saved, dlogits: torch.Tensor, out: Optional[List[torch.Ten
     H = sv.layers[0].No
     C = sv.C
     order = param_order(net)
-    grads: Dict[int, torch.Tensor] = {}
+    if out is None:
+        out = [torch.empty(p.shape, dtype=torch.float32, device=dev) for p in order]
+    index = {id(p): k for k, p in enumerate(order)}
+    dst = lambda param: out[index[id(param)]]
+    f32 = dict(dtype=torch.float32, device=dev)
 
-    def emit(param, value):
-        """value: fp32 tensor (1-D, or 2-D with unit column stride) holding the gradient of `param`."""
-        i = next(k for k, q in enumerate(order) if q is param)
-        if out is None:
-            grads[i] = value
-            return
-        dst = out[i]
+    def copy_into(param, value):
+        """small strided fp32 block -> the parameter's gradient buffer"""
+        d = dst(param)
         v2 = value if value.dim() == 2 else value.reshape(1, -1)
-        d2 = dst.reshape(v2.shape) if dst.dim() != 2 else dst
+        d2 = d if d.dim() == 2 else d.reshape(1, -1)
         check(L.egnn_cast(ptr(v2), dt(v2), v2.stride(0) if v2.size(0) > 1 else v2.size(1), ptr(d2), dt(d2),
                           d2.stride(0) if d2.size(0) > 1 else d2.size(1), v2.size(0), v2.size(1), stream()))
-        grads[i] = dst
+
+    def wgrad(G, X, K, Kraw, d0, d1):
+        """[d0 | d1] = G^T X split at column K, zero-padding columns >= Kraw dropped"""
+        No, Kin = G.size(1), X.size(1)
+        ws = torch.empty(L.egnn_wgrad_tc_workspace_floats(No, Kin), **f32)
+        check(L.egnn_wgrad_tc(ptr(G), G.stride(0), ptr(X), X.stride(0), N, No, Kin, ptr(d0), ptr(d1), K, Kraw, ptr(ws),
+                              stream()))
 
     # ---- logits layer
     oc = net.convs[-1]
     dlogits = ops._rows(dlogits).contiguous()
-    dp = torch.empty((N, 2 * C), dtype=torch.float32, device=dev)
-    tmp = torch.empty((g.cap, C), dtype=torch.float32, device=dev)
+    dp = torch.empty((N, 2 * C), **f32)
+    tmp = torch.empty((g.cap, C), **f32)
     check(L.egnn_sage_out_bwd(ptr(g.csc_ptr), ptr(g.csc_dst), ptr(g.csr_ptr), ptr(dlogits), dt(dlogits), C, ptr(dp), N,
                               ptr(tmp), g.cap, stream()))
     h = sv.h_last
-    dw = torch.empty((2 * C, H), dtype=torch.float32, device=dev)
-    dsum = torch.empty(2 * C, dtype=torch.float32, device=dev)
-    ws = torch.empty(L.egnn_skinny_wgrad_workspace_floats(N, H, 2 * C), dtype=torch.float32, device=dev)
+    dw = torch.empty((2 * C, H), **f32)
+    dsum = torch.empty(2 * C, **f32)
+    ws = torch.empty(L.egnn_skinny_wgrad_workspace_floats(N, H, 2 * C), **f32)
     check(L.egnn_skinny_wgrad(ptr(h), dt(h), h.stride(0), ptr(dp), 2 * C, N, H, ptr(dw), ptr(dsum), ptr(ws), stream()))
-    emit(oc.lin_l.weight, dw[:C])
-    emit(oc.lin_l.bias, dsum[C:])
-    emit(oc.lin_r.weight, dw[C:])
+    copy_into(oc.lin_l.weight, dw[:C])
+    copy_into(oc.lin_l.bias, dsum[C:])
+    copy_into(oc.lin_r.weight, dw[C:])
     dy = torch.empty((N, H), dtype=cd, device=dev)
     check(L.egnn_skinny_dgrad(ptr(dp), ptr(sv.wout), 2 * C, ptr(dy), dt(dy), H, N, H, stream()))
 
@@ -331,7 +351,7 @@ def backward(net, sv: Saved, dlogits: torch.Tensor, out: Optional[List[torch.Ten
         bn = net.bns[li] if sv.use_bn else None
         z, K = ly.z, ly.K
         dz = torch.empty((N, H), dtype=cd, device=dev)
-        dzsum = torch.empty(H, dtype=torch.float32, device=dev)
+        dzsum = dst(conv.lin_l.bias)                    # column sums of dz = the conv bias gradient
         ws2 = torch.empty(L.egnn_colreduce_workspace_bytes(H) + 64 * H, dtype=torch.uint8, device=dev)
         if bn is not None:
             sg = torch.empty((2, H), dtype=torch.float64, device=dev)
@@ -346,27 +366,22 @@ def backward(net, sv: Saved, dlogits: torch.Tensor, out: Optional[List[torch.Ten
                                                   ptr(bn.weight), ptr(bn.bias), ACT_RELU, ly.p_eff, sv.seed,
                                                   ptr(sv.soff), li, sv.row0, sg[0].data_ptr(), sg[1].data_ptr(),
                                                   sv.n_total, ptr(dzsum), ptr(ws2), z.stride(0), ptr(ly.kb), stream()))
-            sgf = torch.empty((2, H), dtype=torch.float32, device=dev)
-            check(L.egnn_f64_to_f32(ptr(sg), ptr(sgf), 2 * H, stream()))
-            emit(bn.bias, sgf[0])
-            emit(bn.weight, sgf[1])
+            check(L.egnn_f64_to_f32(sg[0].data_ptr(), ptr(dst(bn.bias)), H, stream()))      # d beta  = sum g
+            check(L.egnn_f64_to_f32(sg[1].data_ptr(), ptr(dst(bn.weight)), H, stream()))    # d gamma = sum g * xhat
         else:
             check(L.egnn_bn_act_dropout_bwd_apply(ptr(dy), ptr(z), ptr(dz), dt(z), H, N, H, None, None, None, None,
                                                   ACT_RELU, ly.p_eff, sv.seed, ptr(sv.soff), li, sv.row0, None, None,
                                                   1.0, ptr(dzsum), ptr(ws2), z.stride(0), ptr(ly.kb), stream()))
-        emit(conv.lin_l.bias, dzsum)
         # weight gradients: dz^T [m | h]  (and dres^T h for a projected residual; dres = dy)
         cat = ly.cat
         Kraw = conv.in_channels
         if 2 * K <= 384:
-            dwc = ops.linear_wgrad(dz, cat)
-            dwl, dwr = dwc[:, :K], dwc[:, K:]
+            wgrad(dz, cat, K, Kraw, dst(conv.lin_l.weight), dst(conv.lin_r.weight))
         else:
-            dwl, dwr = ops.linear_wgrad(dz, cat[:, :K]), ops.linear_wgrad(dz, cat[:, K:])
-        emit(conv.lin_l.weight, dwl[:, :Kraw])
-        emit(conv.lin_r.weight, dwr[:, :Kraw])
+            wgrad(dz, cat[:, :K], K, Kraw, dst(conv.lin_l.weight), None)
+            wgrad(dz, cat[:, K:], K, Kraw, dst(conv.lin_r.weight), None)
         if ly.has_proj:
-            emit(net.res_projs[li].weight, ops.linear_wgrad(dy, cat[:, K:])[:, :Kraw])
+            wgrad(dy, cat[:, K:], K, Kraw, dst(net.res_projs[li].weight), None)
         need_dh = li > 0 or sv.D > 0
         if not need_dh:
             break
@@ -381,12 +396,10 @@ def backward(net, sv: Saved, dlogits: torch.Tensor, out: Optional[List[torch.Ten
             dh0 = dh
         dy = dh
     if sv.D > 0:
-        dtab = torch.empty((sv.T, sv.D), dtype=torch.float32, device=dev)
         wse = torch.empty(L.egnn_embed_grad_workspace_bytes(N, sv.T, sv.D), dtype=torch.uint8, device=dev)
         check(L.egnn_embed_grad(ptr(dh0), dt(dh0), dh0.stride(0), sv.x_cols, sv.D, ptr(sv.t.contiguous()), sv.T, N,
-                                ptr(dtab), ptr(wse), stream()))
-        emit(net.time_emb.weight, dtab)
-    return [grads[i] for i in range(len(order))]
+                                ptr(dst(net.time_emb.weight)), ptr(wse), stream()))
+    return out
 
 
 class SageResBNFn(torch.autograd.Function):

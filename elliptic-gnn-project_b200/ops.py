@@ -644,7 +644,8 @@ class BnActDropResFn(torch.autograd.Function):
               if (strided_ok and training and z.requires_grad) else None)
         check(L.egnn_bn_act_dropout_res_fwd(ptr(z), ptr(res), ptr(y), dt(z), _ld(z), N, F, ptr(mean), ptr(rstd),
                                             ptr(gamma), ptr(beta), act, p_eff, seed, ptr(soff), layer, row0,
-                                            _ld(res) if res is not None else 0, _ld(y), ptr(kb), stream()))
+                                            _ld(res) if res is not None else 0, _ld(y), ptr(kb), None, None,
+                                            stream()))
         ctx.kb = kb
         ctx.cfg = (use_bn, act, p_eff, seed, layer, row0, n_total, reducer, res is not None)
         ctx.soff = soff

@@ -156,7 +156,7 @@ int egnn_gemm(const void* A, int a_dtype, int64_t a_sm, int64_t a_sk, const void
  *   addend (same dtype as C, leading dimension ld_addend): C[m, addend_col0 + j] += addend[m, j] for the columns from
  *     addend_col0 (a multiple of 16) on -- the identity-residual gradient `+ h_in` of src/models/gnn.py:192 joining the
  *     root half of the concatenated dgrad [dm/deg | dx_root];
- *   colstats (float [egnn_linear_stats_parts(M), 2, colstats_cols], colstats_cols <= 64): per-(CTA, TMEM sub-partition)
+ *   colstats (float [egnn_linear_stats_parts(M), 2, colstats_cols], colstats_cols <= 64): per-CTA
  *     partial column sums and sums of squares of the values AS STORED in columns [0, colstats_cols) -- the batch
  *     statistics of nn.BatchNorm1d over all rows (src/models/gnn.py:134,189) without another pass over the layer
  *     output.  egnn_colstats_reduce sums the parts in a fixed order (float64 [2, F]; the multi-GPU path all-reduces
@@ -168,6 +168,15 @@ int egnn_linear_tc(const void* A, int64_t lda, const void* W, int64_t ldw, void*
                    int64_t M, int64_t N, int64_t K, const float* bias, const int32_t* row_div_ptr,
                    int64_t row_div_cols, int accumulate, const void* addend, int64_t ld_addend,
                    int64_t addend_col0, float* colstats, int64_t colstats_cols, void* stream);
+/* Weight gradient of the concatenated SAGE GEMM on the tcgen05 wgrad kernel: dW[N_out, K_in] = G[M, N_out]^T . X[M, K_in]
+ * (bf16 operands, rows 16-byte aligned, N_out <= 256, K_in <= 384; deterministic per-CTA partials + fixed-order sum),
+ * written as TWO dense fp32 parameter gradients: columns [0, split_col) -> dst0, [split_col, K_in) -> dst1 (NULL: dropped),
+ * each [N_out, valid_cols] with the zero-padding columns >= valid_cols dropped -- d lin_l.weight / d lin_r.weight of
+ * `SAGEConv` (src/models/gnn.py:125-128) straight into their gradient buffers.
+ * workspace: egnn_wgrad_tc_workspace_floats(N_out, K_in) floats. */
+size_t egnn_wgrad_tc_workspace_floats(int64_t N_out, int64_t K_in);
+int egnn_wgrad_tc(const void* G, int64_t ldg, const void* X, int64_t ldx, int64_t M, int64_t N_out, int64_t K_in,
+                  float* dst0, float* dst1, int64_t split_col, int64_t valid_cols, float* workspace, void* stream);
 int egnn_colstats_reduce(const float* parts, int64_t n_parts, int64_t n_feat, double* sums, void* stream);
 int egnn_bn_finalize_parts(const float* parts, int64_t n_parts, int64_t n_feat, double count, float eps,
                            float momentum, float* mean, float* rstd, float* running_mean, float* running_var,
@@ -257,7 +266,8 @@ int egnn_bn_finalize(const double* sums, const double* sumsq, double count, int6
 
 /* y = dropout(act(bn(z))) + res      -- src/models/gnn.py:186-192 (SAGE-ResBN hidden layer)
  *   bn(z) = (z-mean)*rstd*gamma+beta when mean != NULL, else z (+ nothing)
- *   dropout keep-mask = Philox4x32-10(seed; row0+r, col, layer) >= p  (see egnn_dropout_mask),
+ *   dropout keep-mask = 16-bit lane (col % 8) of Philox4x32-10(seed; row0+r, col / 8, layer) >= floor(p * 2^16)
+ *   (see egnn_dropout_mask; all 128 bits of a draw are used),
  *   kept values scaled by 1/(1-p); p == 0 disables it.  seed_off (device int64, may be NULL)
  *   is added to seed at run time so a captured CUDA graph draws a new mask on every replay
  *   (advance it with egnn_counter_add inside the graph).
@@ -265,12 +275,17 @@ int egnn_bn_finalize(const double* sums, const double* sumsq, double count, int6
  *   ld_y (0 = ld): the output may be the right half of a wider [h_agg | h] buffer.
  *   keep_bits (optional, uint8 [n_rows, n_feat/4], n_feat % 4 == 0): receives the dropout keep bits drawn
  *   (bit i of byte (r, c/4) = column c+i kept, low nibble; bit 4+i = ReLU gate of column c+i when act = ReLU); passing them to the backward kernels skips the Philox
- *   recomputation there.  The bits ARE the Philox mask of egnn_dropout_mask. */
+ *   recomputation there.  The bits ARE the Philox mask of egnn_dropout_mask.
+ *   proj_w (optional, float [4, n_feat]) + proj_out (float [n_rows, 4], 16-byte aligned): also emit
+ *   proj_out[r, :] = y[r, :] . proj_w^T computed from y AS STORED -- the project-first evaluation of the logits layer
+ *   `SAGEConv(hidden, 2)` (src/models/gnn.py:128,193; proj_w = [lin_l.weight ; lin_r.weight]) riding on the pass that
+ *   produces its input (needs act = ReLU, n_feat / 8 a power of two <= 32 and 16-byte aligned rows). */
 int egnn_bn_act_dropout_res_fwd(const void* z, const void* res, void* y, int dtype, int64_t ld,
                                 int64_t n_rows, int64_t n_feat, const float* mean,
                                 const float* rstd, const float* gamma, const float* beta, int act,
                                 float p, uint64_t seed, const int64_t* seed_off, uint32_t layer,
-                                int64_t row0, int64_t ld_res, int64_t ld_y, uint8_t* keep_bits, void* stream);
+                                int64_t row0, int64_t ld_res, int64_t ld_y, uint8_t* keep_bits,
+                                const float* proj_w, float* proj_out, void* stream);
 
 /* backward stage 1: g = dy * keep/(1-p) * act'(.) ; sums[c] = sum g, sums_xhat[c] = sum g*xhat
  * (BatchNorm dbeta, dgamma).  stage 2: dz = gamma*rstd*(g - sum_g/n - xhat*sum_gx/n) (or g

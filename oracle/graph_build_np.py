@@ -82,19 +82,22 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
 
 
 def dropout_threshold(p: float) -> int:
-    """keep iff u32 >= thr;  thr = min(floor(p * 2^32), 2^32-1)."""
-    return int(min(int(np.floor(float(p) * 4294967296.0)), 4294967295))
+    """keep iff u16 lane >= thr;  thr = min(floor(p * 2^16), 2^16-1)."""
+    return int(min(int(np.floor(float(p) * 65536.0)), 65535))
 
 
 def dropout_keep_mask(seed: int, layer: int, row0: int, n: int, f: int, p: float) -> np.ndarray:
-    """uint8 [n, f]; element (r, c) uses Philox counter (row0+r lo, row0+r hi, c//4, layer),
-    key (seed lo, seed hi), lane c%4."""
+    """uint8 [n, f]; element (r, c) uses Philox counter (row0+r lo, row0+r hi, c//8, layer), key (seed lo, seed hi)
+    and the 16-bit lane c%8 of the four output words (even lane = low half, odd lane = high half of word (c%8)//2)."""
     rows = np.arange(row0, row0 + n, dtype=np.uint64)
-    nb = (f + 3) // 4
+    nb = (f + 7) // 8
     r_lo = np.repeat((rows & np.uint64(0xFFFFFFFF)).astype(np.uint32), nb)
     r_hi = np.repeat((rows >> np.uint64(32)).astype(np.uint32), nb)
     cb = np.tile(np.arange(nb, dtype=np.uint32), n)
     lay = np.full(n * nb, layer, dtype=np.uint32)
     o = philox4x32_10(r_lo, r_hi, cb, lay, seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
-    u = np.stack(o, axis=1).reshape(n, nb * 4)[:, :f]
+    lanes = []
+    for w in o:
+        lanes += [w & np.uint32(0xFFFF), w >> np.uint32(16)]
+    u = np.stack(lanes, axis=1).reshape(n, nb * 8)[:, :f]
     return (u >= np.uint32(dropout_threshold(p))).astype(np.uint8)

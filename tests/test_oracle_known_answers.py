@@ -162,7 +162,7 @@ def test_dropout_mask_statistics_and_shard_invariance():
     part = G.dropout_keep_mask(42, 0, 700, 300, 64, 0.2)
     assert np.array_equal(part, m[700:1000])
     assert not np.array_equal(G.dropout_keep_mask(42, 1, 0, 2000, 64, 0.2), m)
-    assert G.dropout_threshold(0.5) == 2**31 and G.dropout_threshold(0.0) == 0
+    assert G.dropout_threshold(0.5) == 2**15 and G.dropout_threshold(0.0) == 0
 
 
 # ---- golden fixtures recorded from the reference's own nets / train_epoch ---------------------
