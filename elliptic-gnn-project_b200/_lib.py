@@ -51,7 +51,7 @@ SIGNATURES = {
     "egnn_linear_tc": (_i32, [_vp, _i64, _vp, _i64, _vp, _i32, _i64, _i64, _i64, _i64, _vp, _vp, _i64, _i32, _vp, _i64,
                               _i64, _vp, _i64, _vp]),
     "egnn_wgrad_tc_workspace_floats": (_sz, [_i64, _i64]),
-    "egnn_wgrad_tc": (_i32, [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _vp, _vp]),
+    "egnn_wgrad_tc": (_i32, [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _vp]),
     "egnn_colstats_reduce": (_i32, [_vp, _i64, _i64, _vp, _vp]),
     "egnn_bn_finalize_parts": (_i32, [_vp, _i64, _i64, _f64, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "egnn_pack_sage_weights": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
@@ -66,7 +66,7 @@ SIGNATURES = {
     "egnn_bn_act_dropout_res_fwd": (_i32, [_vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i32,
                                            _f32, _u64, _vp, _u32, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "egnn_bn_act_dropout_bwd_reduce": (_i32, [_vp, _vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i32,
-                                              _f32, _u64, _vp, _u32, _i64, _vp, _vp, _vp, _i64, _vp, _vp]),
+                                              _f32, _u64, _vp, _u32, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "egnn_bn_act_dropout_bwd_apply": (_i32, [_vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i32,
                                              _f32, _u64, _vp, _u32, _i64, _vp, _vp, _f64, _vp, _vp, _i64, _vp, _vp]),
     "egnn_dropout_mask": (_i32, [_vp, _i64, _i64, _f32, _u64, _vp, _u32, _i64, _vp]),

@@ -820,6 +820,161 @@ __global__ void __launch_bounds__(kThreads, 4) bn_act_bwd_apply_lean(const T* __
   }
 }
 
+// ---- 8-column backward of BatchNorm + ReLU + dropout with the forward's saved keep / gate bits (the SAGE-ResBN hot
+// path): 16-byte accesses.  DYP: the incoming gradient is not read but COMPUTED as dy[r, :] = dp[r, 0:4] . Wp -- the
+// input gradient of the project-first logits layer (`SAGEConv(hidden, 2)`, src/models/gnn.py:128,193) -- rounded to T
+// and written to dy_out for the later consumers (apply pass, residual path), which replaces a separate dgrad pass.
+template <typename T, bool DYP>
+__global__ void __launch_bounds__(kThreads, 2) bn_relu_bwd_reduce8(const T* __restrict__ dy, T* __restrict__ dy_out,
+                                                                  const float* __restrict__ dp,
+                                                                  const float* __restrict__ Wp,
+                                                                  const T* __restrict__ z, int64_t ld_dy, int64_t ld_z,
+                                                                  int64_t n_rows, int F, int cg_shift,
+                                                                  int64_t rows_per_block, ActCtx C,
+                                                                  double* __restrict__ partial,
+                                                                  const uint8_t* __restrict__ keep_bits) {
+  __shared__ float sm[kThreads][17];
+  const int CG = 1 << cg_shift, RL = kThreads >> cg_shift;
+  const int cgi = threadIdx.x & (CG - 1), c = cgi * 8, rl = threadIdx.x >> cg_shift;
+  float mean[8], rstd[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { mean[i] = C.mean[c + i]; rstd[i] = C.rstd[c + i]; }
+  float wp[DYP ? kProjP : 1][8];
+  if (DYP) {
+#pragma unroll
+    for (int p = 0; p < kProjP; ++p)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) wp[DYP ? p : 0][i] = Wp[p * F + c + i];
+  }
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(n_rows, r0 + rows_per_block);
+  float a0[8], a1[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { a0[i] = 0.f; a1[i] = 0.f; }
+  for (int64_t rb = r0 + rl; rb < r1; rb += (int64_t)RL * kRows8) {
+    Raw8<T> zr[kRows8], gr[kRows8];
+    float4 dpr[DYP ? kRows8 : 1];
+    uint32_t kb[kRows8];
+#pragma unroll
+    for (int u = 0; u < kRows8; ++u) {
+      const int64_t r = rb + (int64_t)u * RL;
+      if (r < r1) {
+        zr[u].load(z + r * ld_z + c);
+        if (DYP) dpr[DYP ? u : 0] = __ldg(reinterpret_cast<const float4*>(dp + r * kProjP));
+        else gr[u].load(dy + r * ld_dy + c);
+        kb[u] = *reinterpret_cast<const uint16_t*>(keep_bits + r * (2 * CG) + 2 * cgi);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kRows8; ++u) {
+      const int64_t r = rb + (int64_t)u * RL;
+      if (r < r1) {
+        float zv[8], g[8];
+        zr[u].unpack(zv);
+        if (DYP) {
+          const float4 d = dpr[DYP ? u : 0];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            g[i] = fmaf(d.w, wp[DYP ? 3 : 0][i], fmaf(d.z, wp[DYP ? 2 : 0][i], fmaf(d.y, wp[DYP ? 1 : 0][i], d.x * wp[0][i])));
+          st8r(dy_out + r * ld_dy + c, g);   // g now holds the values as stored
+        } else {
+          gr[u].unpack(g);
+        }
+        const uint32_t keep = (kb[u] & 0xfu) | ((kb[u] >> 4) & 0xf0u), gate = ((kb[u] >> 4) & 0xfu) | ((kb[u] >> 8) & 0xf0u);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float xh = (zv[i] - mean[i]) * rstd[i];
+          const float d = ((keep & gate) >> i) & 1u ? C.scale : 0.f;
+          const float gg = g[i] * d;
+          a0[i] += gg;
+          a1[i] = fmaf(gg, xh, a1[i]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { sm[threadIdx.x][i] = a0[i]; sm[threadIdx.x][8 + i] = a1[i]; }
+  __syncthreads();
+  for (int item = threadIdx.x; item < CG * 16; item += kThreads) {
+    const int g_ = item >> 4, i = item & 15;
+    double s = 0.0;
+    for (int l = 0; l < RL; ++l) s += (double)sm[l * CG + g_][i];
+    partial[((int64_t)blockIdx.x * 2 + (i >> 3)) * F + g_ * 8 + (i & 7)] = s;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 2) bn_relu_bwd_apply8(const T* __restrict__ dy, int64_t ld_dy,
+                                                                 const T* __restrict__ z, int64_t ld_z,
+                                                                 T* __restrict__ dz, int64_t ld, int64_t n_rows, int F,
+                                                                 int cg_shift, int64_t rows_per_block, ActCtx C,
+                                                                 const double* __restrict__ sum_g,
+                                                                 const double* __restrict__ sum_gx, double inv_n,
+                                                                 double* __restrict__ dzsum_partial,
+                                                                 const uint8_t* __restrict__ keep_bits) {
+  __shared__ float sm[kThreads][9];
+  const int CG = 1 << cg_shift, RL = kThreads >> cg_shift;
+  const int cgi = threadIdx.x & (CG - 1), c = cgi * 8, rl = threadIdx.x >> cg_shift;
+  float mean[8], rstd[8], c1[8], c2[8], c3[8];   // dz = c1*gg - c2 - xhat*c3
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    mean[i] = C.mean[c + i]; rstd[i] = C.rstd[c + i];
+    const float gr = C.gamma[c + i] * rstd[i];
+    c1[i] = gr;
+    c2[i] = gr * (float)(sum_g[c + i] * inv_n);
+    c3[i] = gr * (float)(sum_gx[c + i] * inv_n);
+  }
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(n_rows, r0 + rows_per_block);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int64_t rb = r0 + rl; rb < r1; rb += (int64_t)RL * kRows8) {
+    Raw8<T> zr[kRows8], gr[kRows8];
+    uint32_t kb[kRows8];
+#pragma unroll
+    for (int u = 0; u < kRows8; ++u) {
+      const int64_t r = rb + (int64_t)u * RL;
+      if (r < r1) {
+        zr[u].load(z + r * ld_z + c);
+        gr[u].load(dy + r * ld_dy + c);
+        kb[u] = *reinterpret_cast<const uint16_t*>(keep_bits + r * (2 * CG) + 2 * cgi);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kRows8; ++u) {
+      const int64_t r = rb + (int64_t)u * RL;
+      if (r < r1) {
+        float zv[8], g[8], o[8];
+        zr[u].unpack(zv);
+        gr[u].unpack(g);
+        const uint32_t keep = (kb[u] & 0xfu) | ((kb[u] >> 4) & 0xf0u), gate = ((kb[u] >> 4) & 0xfu) | ((kb[u] >> 8) & 0xf0u);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float xh = (zv[i] - mean[i]) * rstd[i];
+          const float d = ((keep & gate) >> i) & 1u ? C.scale : 0.f;
+          const float gg = g[i] * d;
+          o[i] = (c1[i] * gg - c2[i]) - xh * c3[i];
+        }
+        st8r(dz + r * ld + c, o);   // o now holds the values as stored
+        if (dzsum_partial) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] += o[i];
+        }
+      }
+    }
+  }
+  if (dzsum_partial) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sm[threadIdx.x][i] = acc[i];
+    __syncthreads();
+    for (int item = threadIdx.x; item < CG * 8; item += kThreads) {
+      const int g_ = item >> 3, i = item & 7;
+      double s = 0.0;
+      for (int l = 0; l < RL; ++l) s += (double)sm[l * CG + g_][i];
+      dzsum_partial[(int64_t)blockIdx.x * F + g_ * 8 + i] = s;
+    }
+  }
+}
+
 // host-side dispatch over (dtype, BatchNorm, activation); the backward kernels are also specialised on whether
 // the forward's keep bits are supplied (the Philox recomputation is then compiled out: fewer registers)
 #define EGNN_LEAN_KB_T(KERNEL, TT_, HAVE_KB, GRID, ...)                                                    \
@@ -1466,12 +1621,33 @@ extern "C" int egnn_bn_act_dropout_bwd_reduce(const void* dy, const void* z, int
                                               const float* rstd, const float* gamma, const float* beta,
                                               int act, float p, uint64_t seed, const int64_t* seed_off,
                                               uint32_t layer, int64_t row0, double* sum_g, double* sum_gx, void* workspace,
-                                              int64_t ld_z, const uint8_t* keep_bits, void* stream) {
+                                              int64_t ld_z, const uint8_t* keep_bits, const float* dp,
+                                              const float* dp_w, void* stream) {
   const char* fn = "egnn_bn_act_dropout_bwd_reduce";
   if (ld_z <= 0) ld_z = ld;
   EGNN_REQUIRE(dy && z && sum_g && sum_gx && workspace && mean && rstd && gamma && beta, fn, "null pointer");
+  EGNN_REQUIRE((dp == nullptr) == (dp_w == nullptr), fn, "dp / dp_w must be given together");
   ActCtx C = make_ctx(mean, rstd, gamma, beta, act, p, seed, seed_off, layer, row0);
   cudaStream_t st = (cudaStream_t)stream;
+  FastPlan f8 = plan8(n_rows, n_feat, dtype, {ld, ld_z}, {z, dy});
+  const bool use8 = f8.ok && act == EGNN_ACT_RELU && keep_bits && n_rows > 0 && f8.nblk <= kMaxPartBlocks;
+  EGNN_REQUIRE(!dp || (use8 && (uintptr_t)dp % 16 == 0), fn,
+               "dy-from-dp needs the 8-column path (ReLU, saved keep bits, F/8 a power of two <= 32, 16-byte rows)");
+  if (use8) {
+    double* partial = reinterpret_cast<double*>(workspace);
+    if (dtype == EGNN_F32) {
+      if (dp) bn_relu_bwd_reduce8<float, true><<<f8.nblk, kThreads, 0, st>>>(nullptr, (float*)const_cast<void*>(dy), dp, dp_w, (const float*)z, ld, ld_z, n_rows, (int)n_feat, f8.cg_shift, f8.rpb, C, partial, keep_bits);
+      else bn_relu_bwd_reduce8<float, false><<<f8.nblk, kThreads, 0, st>>>((const float*)dy, nullptr, nullptr, nullptr, (const float*)z, ld, ld_z, n_rows, (int)n_feat, f8.cg_shift, f8.rpb, C, partial, keep_bits);
+    } else {
+      using B = __nv_bfloat16;
+      if (dp) bn_relu_bwd_reduce8<B, true><<<f8.nblk, kThreads, 0, st>>>(nullptr, (B*)const_cast<void*>(dy), dp, dp_w, (const B*)z, ld, ld_z, n_rows, (int)n_feat, f8.cg_shift, f8.rpb, C, partial, keep_bits);
+      else bn_relu_bwd_reduce8<B, false><<<f8.nblk, kThreads, 0, st>>>((const B*)dy, nullptr, nullptr, nullptr, (const B*)z, ld, ld_z, n_rows, (int)n_feat, f8.cg_shift, f8.rpb, C, partial, keep_bits);
+    }
+    EGNN_LAUNCH_CHECK(fn);
+    colreduce_final<<<dim3((unsigned)n_feat, 2), kThreads, 0, st>>>(partial, f8.nblk, (int)n_feat, sum_g, sum_gx);
+    EGNN_LAUNCH_CHECK(fn);
+    return 0;
+  }
   FastPlan fp = lean_plan(n_rows, n_feat, dtype, {ld, ld_z}, {z, dy});
   if (fp.ok) {
     double* partial = reinterpret_cast<double*>(workspace);
@@ -1509,6 +1685,20 @@ extern "C" int egnn_bn_act_dropout_bwd_apply(const void* dy, const void* z, void
   ActCtx C = make_ctx(mean, rstd, gamma, beta, act, p, seed, seed_off, layer, row0);
   cudaStream_t st = (cudaStream_t)stream;
   double inv_n = mean ? 1.0 / n_total : 0.0;
+  FastPlan f8 = plan8(n_rows, n_feat, dtype, {ld, ld_z}, {z, dy, dz});
+  if (f8.ok && mean && act == EGNN_ACT_RELU && keep_bits && f8.nblk <= kMaxPartBlocks) {
+    double* partial = dz_colsum ? reinterpret_cast<double*>(workspace) : nullptr;
+    if (dtype == EGNN_F32)
+      bn_relu_bwd_apply8<float><<<f8.nblk, kThreads, 0, st>>>((const float*)dy, ld, (const float*)z, ld_z, (float*)dz, ld, n_rows, (int)n_feat, f8.cg_shift, f8.rpb, C, sum_g, sum_gx, inv_n, partial, keep_bits);
+    else
+      bn_relu_bwd_apply8<__nv_bfloat16><<<f8.nblk, kThreads, 0, st>>>((const __nv_bfloat16*)dy, ld, (const __nv_bfloat16*)z, ld_z, (__nv_bfloat16*)dz, ld, n_rows, (int)n_feat, f8.cg_shift, f8.rpb, C, sum_g, sum_gx, inv_n, partial, keep_bits);
+    EGNN_LAUNCH_CHECK(fn);
+    if (dz_colsum) {
+      colsum_final<<<(unsigned)n_feat, kThreads, 0, st>>>(partial, f8.nblk, (int)n_feat, dz_colsum);
+      EGNN_LAUNCH_CHECK(fn);
+    }
+    return 0;
+  }
   FastPlan fp = lean_plan(n_rows, n_feat, dtype, {ld, ld_z}, {z, dy, dz});
   if (fp.ok) {
     double* partial = dz_colsum ? reinterpret_cast<double*>(workspace) : nullptr;

@@ -399,7 +399,8 @@ bool wgrad_tcgen05_supported(const void* G, int64_t ldg, const void* X, int64_t 
                              int64_t K_in);
 int wgrad_tcgen05_dispatch(const void* G, int64_t ldg, const void* X, int64_t ldx, float* dW, int64_t M_rows,
                            int64_t N_out, int64_t K_in, int accumulate, float* workspace, cudaStream_t st,
-                           float* dst1 = nullptr, int64_t split = 0, int64_t valid = 0);
+                           float* dst1 = nullptr, int64_t split = 0, int64_t valid = 0, const void* G2 = nullptr,
+                           int64_t ldg2 = 0, int64_t N2 = 0, float* dst2 = nullptr);
 }  // namespace egnn
 
 using namespace egnn;
@@ -434,14 +435,17 @@ extern "C" size_t egnn_wgrad_tc_workspace_floats(int64_t N_out, int64_t K_in) {
 }
 extern "C" int egnn_wgrad_tc(const void* G, int64_t ldg, const void* X, int64_t ldx, int64_t M, int64_t N_out,
                              int64_t K_in, float* dst0, float* dst1, int64_t split_col, int64_t valid_cols,
-                             float* workspace, void* stream) {
+                             const void* G2, int64_t ldg2, int64_t N2, float* dst2, float* workspace, void* stream) {
   const char* fn = "egnn_wgrad_tc";
   EGNN_REQUIRE(G && X && dst0 && workspace, fn, "null pointer");
   EGNN_REQUIRE(M > 0 && split_col > 0 && split_col <= K_in && valid_cols > 0 && valid_cols <= split_col, fn, "bad split");
-  if (!wgrad_tcgen05_supported(G, ldg, X, ldx, M, N_out, K_in))
+  EGNN_REQUIRE(!G2 || (dst2 && N2 > 0 && N_out % 64 == 0 && ldg2 % 8 == 0 && (uintptr_t)G2 % 16 == 0 &&
+                       2 * split_col == K_in),
+               fn, "second gradient operand: N_out must be a multiple of 64, K_in = 2 * split_col, 16-byte rows");
+  if (!wgrad_tcgen05_supported(G, ldg, X, ldx, M, N_out + (G2 ? N2 : 0), K_in))
     return fail(fn, "shape / alignment outside the tcgen05 wgrad kernel (N_out <= 256, K_in <= 384, 16-byte rows)");
   return wgrad_tcgen05_dispatch(G, ldg, X, ldx, dst0, M, N_out, K_in, 0, workspace, (cudaStream_t)stream, dst1, split_col,
-                                valid_cols);
+                                valid_cols, G2, ldg2, N2, dst2);
 }
 
 extern "C" size_t egnn_gemm_workspace_floats(int64_t M, int64_t N, int64_t K, int split_k) {

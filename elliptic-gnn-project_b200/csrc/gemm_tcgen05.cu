@@ -311,7 +311,7 @@ __device__ __forceinline__ void epilogue_loop(const Epilogue& ep, const float* s
     // fixed butterfly over the 32 rows of this warp, the four sub-partitions combined in order through shared
     // memory, then ONE partial row per CTA: the assignment of tiles to CTAs is static, so the partials (and their
     // fixed-order sum in colstats_parts_kernel) are reproducible
-    __shared__ float s_st[4][2][64];
+    float (*s_st)[2][64] = reinterpret_cast<float (*)[2][64]>(const_cast<float*>(s_bias) + 256 + 16);   // 2 KB behind the bias
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int c0 = half * 16 + 32 * h;
@@ -468,8 +468,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // smem stage = [X blocks: MB * 8 KB][G blocks: NB * 8 KB], each block = 64 nodes x 64 columns.
 template <int kStages>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, int M_rows,
+gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG,
+                  const __grid_constant__ CUtensorMap tmG2, int NB1, int skip_rows_from, int skip_cols_below, int M_rows,
                   int N_out, int Nopad, int K_in, float* __restrict__ partial) {
+  // the gradient operand may be TWO matrices side by side (tmG: its first NB1 64-column blocks, tmG2: the rest) --
+  // dz and the residual gradient of a SAGE-ResBN layer share one pass over the layer input; output elements of rows
+  // >= skip_rows_from and columns < skip_cols_below (residual gradient x aggregation half) are not needed, not written
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~uintptr_t(1023));
   const int MT = (K_in + 127) / 128;   // 128-wide M tiles over K_in (<= 3)
@@ -511,7 +515,10 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
         uint8_t* st = smem + (size_t)s * stage_bytes;
         for (int b = 0; b < MB; ++b) tma_load_2d(st + b * 8192, &tmX, &full[s], b * 64, sl * 64);
-        for (int b = 0; b < NB; ++b) tma_load_2d(st + (MB + b) * 8192, &tmG, &full[s], b * 64, sl * 64);
+        for (int b = 0; b < NB; ++b) {
+          if (b < NB1) tma_load_2d(st + (MB + b) * 8192, &tmG, &full[s], b * 64, sl * 64);
+          else tma_load_2d(st + (MB + b) * 8192, &tmG2, &full[s], (b - NB1) * 64, sl * 64);
+        }
         if (++s == kStages) { s = 0; ph ^= 1; }
       }
     }
@@ -558,7 +565,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] = 0.f;
         }
-        if (k < K_in) {
+        if (k < K_in && !(c0 >= skip_rows_from && k < skip_cols_below)) {
           const int nv = min(8, N_out - c0);
           for (int j = 0; j < nv; ++j) out[(size_t)(c0 + j) * K_in + k] = v[j];  // coalesced over lanes
         }
@@ -605,13 +612,16 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
 // dW_l / dW_r of a SAGE layer straight into the flat gradient buffer, no slicing copies
 __global__ void __launch_bounds__(256) wgrad_reduce_split_kernel(const float* __restrict__ partial, int n_part,
                                                                  int N_out, int K_in, float* __restrict__ dst0,
-                                                                 float* __restrict__ dst1, int split, int valid) {
+                                                                 float* __restrict__ dst1, int split, int valid,
+                                                                 int N1, float* __restrict__ dst2) {
   __shared__ float sm[4][64];
   const int el = threadIdx.x & 63, q = threadIdx.x >> 6;
   const int64_t n_elem = (int64_t)N_out * K_in;
   const int64_t i = (int64_t)blockIdx.x * 64 + el;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  if (i < n_elem) {
+  const int n = (int)(i / K_in), k = (int)(i - (int64_t)n * K_in);
+  const bool wanted = i < n_elem && !(n >= N1 && k < split);   // (second operand) x (first half) was never written
+  if (wanted) {
     int p = q;
     for (; p + 12 < n_part; p += 16) {
       s0 += partial[(size_t)p * n_elem + i];
@@ -623,10 +633,11 @@ __global__ void __launch_bounds__(256) wgrad_reduce_split_kernel(const float* __
   }
   sm[q][el] = (s0 + s1) + (s2 + s3);
   __syncthreads();
-  if (q == 0 && i < n_elem) {
+  if (q == 0 && wanted) {
     const float s = (sm[0][el] + sm[1][el]) + (sm[2][el] + sm[3][el]);
-    const int n = (int)(i / K_in), k = (int)(i - (int64_t)n * K_in);
-    if (k < split) {
+    if (n >= N1) {
+      if (k - split < valid) dst2[(size_t)(n - N1) * valid + (k - split)] = s;
+    } else if (k < split) {
       if (k < valid) dst0[(size_t)n * valid + k] = s;
     } else if (dst1 && k - split < valid) {
       dst1[(size_t)n * valid + (k - split)] = s;
@@ -666,7 +677,8 @@ bool make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int6
 }
 
 constexpr int kStagesTN = 6;
-constexpr size_t kMaxDynSmemTN = 218 * 1024;   // + 8 KB of static shared memory (epilogue statistics, 4 variants)
+constexpr size_t kMaxDynSmemTN = 227 * 1024;
+constexpr size_t kStatsSmem = 2048;   // [4 sub-partitions][sum, sumsq][64] floats behind the bias (statistics epilogue)
 constexpr int kStagesWG = 4;
 
 }  // namespace
@@ -709,7 +721,8 @@ int gemm_tcgen05_dispatch(const void* A, int64_t lda, const void* B, int64_t ldb
   CUtensorMap tmA, tmW;
   if (!make_map(&tmA, A, M, K, lda, BM) || !make_map(&tmW, B, N, K, ldb, Npad))
     return fail(fn, "cuTensorMapEncodeTiled failed");
-  size_t smem = (size_t)KC * Npad * 128 + (size_t)kStagesTN * kStageBytesA + 256 + 1088 + 1024;
+  size_t smem = (size_t)KC * Npad * 128 + (size_t)kStagesTN * kStageBytesA + 256 + 1088 + 1024 + (stats ? kStatsSmem : 0);
+  if (smem > kMaxDynSmemTN) return fail(fn, "shared memory: statistics epilogue does not fit this shape");
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(gemm_tn_kernel<kStagesTN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmemTN);
@@ -740,14 +753,20 @@ bool wgrad_tcgen05_supported(const void* G, int64_t ldg, const void* X, int64_t 
 // dW[N_out, K_in] (fp32, ld = K_in) (+)= G[M,N_out]^T X[M,K_in]; workspace >= wgrad_tcgen05_workspace_floats
 int wgrad_tcgen05_dispatch(const void* G, int64_t ldg, const void* X, int64_t ldx, float* dW, int64_t M_rows,
                            int64_t N_out, int64_t K_in, int accumulate, float* workspace, cudaStream_t st,
-                           float* dst1, int64_t split, int64_t valid) {
+                           float* dst1, int64_t split, int64_t valid, const void* G2, int64_t ldg2, int64_t N2,
+                           float* dst2) {
   const char* fn = "egnn_gemm(tcgen05 wgrad)";
+  const int64_t N1 = N_out;          // columns of the first gradient operand
+  if (G2) N_out = N1 + N2;           // [G | G2]: N1 must be a multiple of 64 (whole TMA boxes)
   const int Nopad = (int)((N_out + 15) / 16 * 16);
   const int MT = (int)((K_in + 127) / 128);
   const int stage = (MT * 2 + (Nopad + 63) / 64) * 8192;
-  CUtensorMap tmX, tmG;
-  if (!make_map(&tmX, X, M_rows, K_in, ldx, 64) || !make_map(&tmG, G, M_rows, N_out, ldg, 64))
+  CUtensorMap tmX, tmG, tmG2;
+  if (!make_map(&tmX, X, M_rows, K_in, ldx, 64) || !make_map(&tmG, G, M_rows, N1, ldg, 64) ||
+      !make_map(&tmG2, G2 ? G2 : G, M_rows, G2 ? N2 : N1, G2 ? ldg2 : ldg, 64))
     return fail(fn, "cuTensorMapEncodeTiled failed");
+  const int NB1 = G2 ? (int)(N1 / 64) : 1 << 20;
+  const int skip_rows = G2 ? (int)N1 : 1 << 30, skip_cols = G2 ? (int)split : 0;
   // deepest TMA ring that fits: 4 stages for the 64-wide layers, 3 / 2 for the wide concatenated operands
   int stages = kStagesWG;
   while (stages > 2 && (size_t)stages * stage + 256 + 1024 > 227 * 1024) --stages;
@@ -762,16 +781,20 @@ int wgrad_tcgen05_dispatch(const void* G, int64_t ldg, const void* X, int64_t ld
   int n_slabs = (int)((M_rows + 63) / 64);
   int grid = n_slabs < kNumSMs ? n_slabs : kNumSMs;
   if (stages == 4)
-    gemm_wgrad_kernel<4><<<grid, kThreads, smem, st>>>(tmX, tmG, (int)M_rows, (int)N_out, Nopad, (int)K_in, workspace);
+    gemm_wgrad_kernel<4><<<grid, kThreads, smem, st>>>(tmX, tmG, tmG2, NB1, skip_rows, skip_cols, (int)M_rows, (int)N_out,
+                                                       Nopad, (int)K_in, workspace);
   else if (stages == 3)
-    gemm_wgrad_kernel<3><<<grid, kThreads, smem, st>>>(tmX, tmG, (int)M_rows, (int)N_out, Nopad, (int)K_in, workspace);
+    gemm_wgrad_kernel<3><<<grid, kThreads, smem, st>>>(tmX, tmG, tmG2, NB1, skip_rows, skip_cols, (int)M_rows, (int)N_out,
+                                                       Nopad, (int)K_in, workspace);
   else
-    gemm_wgrad_kernel<2><<<grid, kThreads, smem, st>>>(tmX, tmG, (int)M_rows, (int)N_out, Nopad, (int)K_in, workspace);
+    gemm_wgrad_kernel<2><<<grid, kThreads, smem, st>>>(tmX, tmG, tmG2, NB1, skip_rows, skip_cols, (int)M_rows, (int)N_out,
+                                                       Nopad, (int)K_in, workspace);
   EGNN_LAUNCH_CHECK(fn);
   int64_t n_elem = N_out * K_in;
   if (valid > 0)
     wgrad_reduce_split_kernel<<<(unsigned)ceil_div(n_elem, 64), 256, 0, st>>>(workspace, grid, (int)N_out, (int)K_in, dW,
-                                                                             dst1, (int)split, (int)valid);
+                                                                             dst1, (int)split, (int)valid,
+                                                                             G2 ? (int)N1 : 1 << 30, dst2);
   else
     wgrad_reduce_kernel<<<(unsigned)ceil_div(n_elem, 64), 256, 0, st>>>(workspace, grid, n_elem, dW, accumulate);
   EGNN_LAUNCH_CHECK(fn);

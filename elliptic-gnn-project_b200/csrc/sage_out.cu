@@ -159,6 +159,45 @@ __device__ __forceinline__ void sum_terms(const float* __restrict__ term, int p0
     for (int c = 0; c < C; ++c) acc[c] = __fadd_rn(acc[c], __ldg(term + (int64_t)e * C + c));
 }
 
+// One thread per row sums its contiguous terms in stored order; a row with more than kWarpRow terms (a hub: several
+// hundred) would be the tail of the whole launch, so the WARP takes those rows one after the other -- lane l adds
+// terms l, l+32, ... and a fixed butterfly combines the lanes (deterministic; the logits layer is evaluated
+// project-first, so its summation order differs from PyG's anyway).  Every lane of the warp must call this.
+constexpr int kWarpRow = 32;
+template <int C>
+__device__ __forceinline__ void row_sum(const float* __restrict__ term, int p0, int p1, bool in_range, float (&acc)[C]) {
+  const int lane = threadIdx.x & 31;
+  const bool is_long = in_range && (p1 - p0) > kWarpRow;
+  if (in_range && !is_long) {
+    sum_terms<C>(term, p0, p1, acc);
+  } else {
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = 0.f;
+  }
+  unsigned m = __ballot_sync(0xffffffffu, is_long);
+  while (m) {
+    const int src = __ffs(m) - 1;
+    m &= m - 1;
+    const int q0 = __shfl_sync(0xffffffffu, p0, src), q1 = __shfl_sync(0xffffffffu, p1, src);
+    float t[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) t[c] = 0.f;
+    for (int e = q0 + lane; e < q1; e += 32) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) t[c] = __fadd_rn(t[c], __ldg(term + (int64_t)e * C + c));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) t[c] = __fadd_rn(t[c], __shfl_xor_sync(0xffffffffu, t[c], o));
+    }
+    if (lane == src) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc[c] = t[c];
+    }
+  }
+}
+
 // ---- out[i, c] = (mean_{j->i} p[j, c] + b[c]) + p[i, C + c] ----------------------------------
 template <int C>
 __global__ void __launch_bounds__(kThreads) sage_out_fwd_kernel(const int32_t* __restrict__ ptr,
@@ -167,10 +206,11 @@ __global__ void __launch_bounds__(kThreads) sage_out_fwd_kernel(const int32_t* _
                                                                 const float* __restrict__ bias,
                                                                 float* __restrict__ out, int64_t n_rows, int gcn) {
   const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  if (i >= n_rows) return;
-  const int p0 = __ldg(ptr + i), p1 = __ldg(ptr + i + 1);
+  const bool in_range = i < n_rows;
+  const int p0 = in_range ? __ldg(ptr + i) : 0, p1 = in_range ? __ldg(ptr + i + 1) : 0;
   float acc[C];
-  sum_terms<C>(term, p0, p1, acc);
+  row_sum<C>(term, p0, p1, in_range, acc);
+  if (!in_range) return;
   if (gcn) {  // GCNConv: weighted sum + bias (no mean, no root term)
 #pragma unroll
     for (int c = 0; c < C; ++c) out[i * C + c] = bias ? __fadd_rn(acc[c], __ldg(bias + c)) : acc[c];
@@ -193,10 +233,11 @@ __global__ void __launch_bounds__(kThreads) sage_out_bwd_kernel(const int32_t* _
                                                                 const TD* __restrict__ dout,
                                                                 float* __restrict__ dp, int64_t n_rows) {
   const int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  if (j >= n_rows) return;
-  const int p0 = __ldg(csc_ptr + j), p1 = __ldg(csc_ptr + j + 1);
+  const bool in_range = j < n_rows;
+  const int p0 = in_range ? __ldg(csc_ptr + j) : 0, p1 = in_range ? __ldg(csc_ptr + j + 1) : 0;
   float acc[C];
-  sum_terms<C>(term, p0, p1, acc);
+  row_sum<C>(term, p0, p1, in_range, acc);
+  if (!in_range) return;
 #pragma unroll
   for (int c = 0; c < C; ++c) {
     dp[j * (2 * C) + c] = acc[c];

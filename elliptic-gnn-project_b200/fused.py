@@ -318,12 +318,13 @@ def backward(net, sv: Saved, dlogits: torch.Tensor, out: Optional[List[torch.Ten
         check(L.egnn_cast(ptr(v2), dt(v2), v2.stride(0) if v2.size(0) > 1 else v2.size(1), ptr(d2), dt(d2),
                           d2.stride(0) if d2.size(0) > 1 else d2.size(1), v2.size(0), v2.size(1), stream()))
 
-    def wgrad(G, X, K, Kraw, d0, d1):
-        """[d0 | d1] = G^T X split at column K, zero-padding columns >= Kraw dropped"""
+    def wgrad(G, X, K, Kraw, d0, d1, G2=None, d2=None):
+        """[d0 | d1] = G^T X split at column K, zero-padding columns >= Kraw dropped; d2 = (G2^T X)[:, K:]"""
         No, Kin = G.size(1), X.size(1)
-        ws = torch.empty(L.egnn_wgrad_tc_workspace_floats(No, Kin), **f32)
-        check(L.egnn_wgrad_tc(ptr(G), G.stride(0), ptr(X), X.stride(0), N, No, Kin, ptr(d0), ptr(d1), K, Kraw, ptr(ws),
-                              stream()))
+        N2 = G2.size(1) if G2 is not None else 0
+        ws = torch.empty(L.egnn_wgrad_tc_workspace_floats(No + N2, Kin), **f32)
+        check(L.egnn_wgrad_tc(ptr(G), G.stride(0), ptr(X), X.stride(0), N, No, Kin, ptr(d0), ptr(d1), K, Kraw,
+                              ptr(G2), G2.stride(0) if G2 is not None else 0, N2, ptr(d2), ptr(ws), stream()))
 
     # ---- logits layer
     oc = net.convs[-1]
@@ -341,7 +342,11 @@ def backward(net, sv: Saved, dlogits: torch.Tensor, out: Optional[List[torch.Ten
     copy_into(oc.lin_l.bias, dsum[C:])
     copy_into(oc.lin_r.weight, dw[C:])
     dy = torch.empty((N, H), dtype=cd, device=dev)
-    check(L.egnn_skinny_dgrad(ptr(dp), ptr(sv.wout), 2 * C, ptr(dy), dt(dy), H, N, H, stream()))
+    # dy = dp . [W_l ; W_r] is produced INSIDE the last layer's BatchNorm backward (reduce pass) when that layer has
+    # BatchNorm and the shapes fit its 8-column kernel; otherwise by its own pass here
+    dy_from_dp = sv.use_bn and C == 2 and (H // 8) & (H // 8 - 1) == 0 and sv.layers[-1].kb is not None
+    if not dy_from_dp:
+        check(L.egnn_skinny_dgrad(ptr(dp), ptr(sv.wout), 2 * C, ptr(dy), dt(dy), H, N, H, stream()))
 
     # ---- hidden layers, last to first
     dh0 = None
@@ -359,7 +364,10 @@ def backward(net, sv: Saved, dlogits: torch.Tensor, out: Optional[List[torch.Ten
             check(L.egnn_bn_act_dropout_bwd_reduce(ptr(dy), ptr(z), dt(z), H, N, H, ptr(ly.mean), ptr(ly.rstd),
                                                    ptr(bn.weight), ptr(bn.bias), ACT_RELU, ly.p_eff, sv.seed,
                                                    ptr(sv.soff), li, sv.row0, sg[0].data_ptr(), sg[1].data_ptr(),
-                                                   ptr(wsr), z.stride(0), ptr(ly.kb), stream()))
+                                                   ptr(wsr), z.stride(0), ptr(ly.kb),
+                                                   ptr(dp) if (dy_from_dp and li == len(sv.layers) - 1) else None,
+                                                   ptr(sv.wout) if (dy_from_dp and li == len(sv.layers) - 1) else None,
+                                                   stream()))
             if sv.reducer is not None:
                 sv.reducer.reduce_(sg)
             check(L.egnn_bn_act_dropout_bwd_apply(ptr(dy), ptr(z), ptr(dz), dt(z), H, N, H, ptr(ly.mean), ptr(ly.rstd),
@@ -375,13 +383,18 @@ def backward(net, sv: Saved, dlogits: torch.Tensor, out: Optional[List[torch.Ten
         # weight gradients: dz^T [m | h]  (and dres^T h for a projected residual; dres = dy)
         cat = ly.cat
         Kraw = conv.in_channels
-        if 2 * K <= 384:
-            wgrad(dz, cat, K, Kraw, dst(conv.lin_l.weight), dst(conv.lin_r.weight))
+        if 2 * K <= 384 and ly.has_proj and H % 64 == 0 and 2 * H <= 128:
+            # one pass over [m | h]: [dz | dy]^T [m | h] -> d lin_l, d lin_r, and (dy x root half) d res_proj
+            wgrad(dz, cat, K, Kraw, dst(conv.lin_l.weight), dst(conv.lin_r.weight), G2=dy,
+                  d2=dst(net.res_projs[li].weight))
         else:
-            wgrad(dz, cat[:, :K], K, Kraw, dst(conv.lin_l.weight), None)
-            wgrad(dz, cat[:, K:], K, Kraw, dst(conv.lin_r.weight), None)
-        if ly.has_proj:
-            wgrad(dy, cat[:, K:], K, Kraw, dst(net.res_projs[li].weight), None)
+            if 2 * K <= 384:
+                wgrad(dz, cat, K, Kraw, dst(conv.lin_l.weight), dst(conv.lin_r.weight))
+            else:
+                wgrad(dz, cat[:, :K], K, Kraw, dst(conv.lin_l.weight), None)
+                wgrad(dz, cat[:, K:], K, Kraw, dst(conv.lin_r.weight), None)
+            if ly.has_proj:
+                wgrad(dy, cat[:, K:], K, Kraw, dst(net.res_projs[li].weight), None)
         need_dh = li > 0 or sv.D > 0
         if not need_dh:
             break

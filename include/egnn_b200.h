@@ -173,10 +173,14 @@ int egnn_linear_tc(const void* A, int64_t lda, const void* W, int64_t ldw, void*
  * written as TWO dense fp32 parameter gradients: columns [0, split_col) -> dst0, [split_col, K_in) -> dst1 (NULL: dropped),
  * each [N_out, valid_cols] with the zero-padding columns >= valid_cols dropped -- d lin_l.weight / d lin_r.weight of
  * `SAGEConv` (src/models/gnn.py:125-128) straight into their gradient buffers.
- * workspace: egnn_wgrad_tc_workspace_floats(N_out, K_in) floats. */
+ * G2 (optional, [M, N2] bf16; then N_out % 64 == 0 and K_in = 2 * split_col): a second gradient matrix sharing the pass
+ * over X -- the residual-projection gradient `res_projs[li]` of SAGE-ResBN (src/models/gnn.py:141-144,192), whose
+ * weight gradient needs only the root half of X: dst2 [N2, valid_cols] = (G2^T X)[:, split_col:].
+ * workspace: egnn_wgrad_tc_workspace_floats(N_out + N2, K_in) floats. */
 size_t egnn_wgrad_tc_workspace_floats(int64_t N_out, int64_t K_in);
 int egnn_wgrad_tc(const void* G, int64_t ldg, const void* X, int64_t ldx, int64_t M, int64_t N_out, int64_t K_in,
-                  float* dst0, float* dst1, int64_t split_col, int64_t valid_cols, float* workspace, void* stream);
+                  float* dst0, float* dst1, int64_t split_col, int64_t valid_cols, const void* G2, int64_t ldg2,
+                  int64_t N2, float* dst2, float* workspace, void* stream);
 int egnn_colstats_reduce(const float* parts, int64_t n_parts, int64_t n_feat, double* sums, void* stream);
 int egnn_bn_finalize_parts(const float* parts, int64_t n_parts, int64_t n_feat, double count, float eps,
                            float momentum, float* mean, float* rstd, float* running_mean, float* running_var,
@@ -290,13 +294,18 @@ int egnn_bn_act_dropout_res_fwd(const void* z, const void* res, void* y, int dty
 /* backward stage 1: g = dy * keep/(1-p) * act'(.) ; sums[c] = sum g, sums_xhat[c] = sum g*xhat
  * (BatchNorm dbeta, dgamma).  stage 2: dz = gamma*rstd*(g - sum_g/n - xhat*sum_gx/n) (or g
  * when mean == NULL).  n_total = global row count (multi-GPU passes the global N).  dy and dz
- * have leading dimension ld, z has ld_z (0 = ld). */
+ * have leading dimension ld, z has ld_z (0 = ld).  * dp (optional, float [n_rows, 4], 16-byte aligned) + dp_w (float [4, n_feat]): the incoming gradient is not read
+ *   but computed, dy[r, :] = dp[r, :] . dp_w rounded to `dtype`, and WRITTEN to `dy` for the later consumers -- the
+ *   input gradient of the project-first logits layer `SAGEConv(hidden, 2)` (src/models/gnn.py:128,193) folded into
+ *   this pass (needs act = ReLU, keep_bits, n_feat / 8 a power of two <= 32, 16-byte aligned rows).
+ */
 int egnn_bn_act_dropout_bwd_reduce(const void* dy, const void* z, int dtype, int64_t ld,
                                    int64_t n_rows, int64_t n_feat, const float* mean,
                                    const float* rstd, const float* gamma, const float* beta,
                                    int act, float p, uint64_t seed, const int64_t* seed_off,
                                    uint32_t layer, int64_t row0, double* sum_g, double* sum_gx, void* workspace,
-                                   int64_t ld_z, const uint8_t* keep_bits, void* stream);
+                                   int64_t ld_z, const uint8_t* keep_bits,
+                                   const float* dp, const float* dp_w, void* stream);
 /* dz_colsum (float [n_feat], optional): column sums of the dz values written -- the gradient of the
  * conv bias that feeds the BatchNorm -- produced in the same pass; needs `workspace` of
  * egnn_colreduce_workspace_bytes(n_feat) + 8*8*n_feat bytes. */

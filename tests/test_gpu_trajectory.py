@@ -6,12 +6,19 @@ initial weights; every epoch the oracle is fed the very Philox keep-masks the CU
 (`synthetic.make_elliptic_like(label_signal=1)`): validation PR-AUC climbs from chance (0.10) to ~0.4, so agreement to
 3 decimals is a statement about the models, not about ties between unordered scores.
 
-Checked every 5 epochs on the validation rows, both sides through the SAME metric code (oracle/metrics_np.py, pinned
+Checked every 5 epochs on the validation rows, all sides through the SAME metric code (oracle/metrics_np.py, pinned
 to the reference's `pr_auc_illicit` / `pick_threshold_max_f1`, src/utils/metrics.py:11-27) on fp32 eval forwards
 (`eval_split` is never under autocast, src/train_gnn.py:248-257):
-  |PR-AUC_cuda - PR-AUC_oracle| < 5e-4 and |maxF1_cuda - maxF1_oracle| < 5e-4  (equal to 3 decimals), fp32 AND bf16;
-  training loss: fp32 rel 1e-4 after 30 Adam steps (Adam's g/sqrt(v) amplifies the 1e-5 per-step difference of
-  near-zero gradient elements), bf16 rel 2e-2.
+
+  fp32: |PR-AUC_cuda - PR-AUC_oracle| < 5e-4 and |maxF1_cuda - maxF1_oracle| < 5e-4 (equal to 3 decimals; measured:
+        equal to 5), training loss rel 1e-4 after 30 Adam steps.
+  bf16: THREE trajectories -- CUDA bf16, CPU-oracle bf16 autocast, CPU-oracle fp32.  Two different bf16 evaluation
+        orders cannot agree to 3 decimals by construction: max-F1 moves in quanta of 2 / (predicted + actual
+        positives) ~ 1.2e-3 on these 8 747 validation rows, i.e. ONE validation node crossing the threshold already
+        changes the third decimal, and the CPU bf16 oracle itself sits 1-2e-3 from the fp32 oracle.  Stated tolerance:
+        the CUDA path is within 2.5e-3 (PR-AUC) / 4e-3 (max-F1, three quanta) of BOTH oracles, and no further from the
+        fp32 truth than twice the CPU bf16 oracle's own distance plus one quantum; training loss rel 2e-2.  The
+        number of checkpoints at which the CUDA path and the bf16 oracle DO agree to 3 decimals is recorded.
 The device metric kernel (`egnn_ranking_metrics`) is checked on the same logits against the same oracle."""
 import numpy as np
 import pytest
@@ -52,6 +59,11 @@ def test_rec_k8_30_epoch_trajectory(egnn, planted_graph, amp):
     step = TrainStep(ours, xc, eic, tc, yc, gr.train_mask.cuda(), lr=LR, weight_decay=WD, grad_clip=1.0, amp=amp, cw=cw)
     step.capture(warmup=2, preserve_state=True)      # epoch 1 = the first optimizer step from the initial weights
     opt_ref = torch.optim.Adam(ref.parameters(), lr=LR, weight_decay=WD)
+    ref32 = opt32 = None
+    if amp:       # the fp32 truth both bf16 trajectories are measured against
+        import copy
+        ref32 = copy.deepcopy(ref)
+        opt32 = torch.optim.Adam(ref32.parameters(), lr=LR, weight_decay=WD)
     vm = gr.val_mask.numpy()
     yv = (gr.y.numpy()[vm] == 1).astype(int)
     vmc = gr.val_mask.cuda()
@@ -62,6 +74,8 @@ def test_rec_k8_30_epoch_trajectory(egnn, planted_graph, amp):
                  for li in range(CFG["layers"] - 1)]
         loss_r, _ = O.train_step(ref, gr.x, ei, gr.timestep, gr.y, gr.train_mask, cw, opt_ref, 1.0,
                                  amp_dtype=torch.bfloat16 if amp else None, dropout_masks=masks)
+        if amp:
+            O.train_step(ref32, gr.x, ei, gr.timestep, gr.y, gr.train_mask, cw, opt32, 1.0, dropout_masks=masks)
         if epoch % 5 and epoch != 1:
             continue
         p_o, logits_o = eval_probs(ours, xc, eic, tc)
@@ -74,16 +88,32 @@ def test_rec_k8_30_epoch_trajectory(egnn, planted_graph, amp):
         print(f"[trajectory {'bf16' if amp else 'fp32'}] epoch {epoch:2d} loss {loss_o:.6f} / {loss_r:.6f}  "
               f"val PR-AUC {ap_o:.5f} / {ap_r:.5f}  max-F1 {f1_o:.5f} / {f1_r:.5f}")
         assert dev[0] == pytest.approx(ap_o, rel=1e-6) and dev[8] == pytest.approx(f1_o, rel=1e-6)
-        assert abs(ap_o - ap_r) < 5e-4, (epoch, ap_o, ap_r)
-        assert abs(f1_o - f1_r) < 5e-4, (epoch, f1_o, f1_r)
         assert abs(loss_o - loss_r) <= (2e-2 if amp else 1e-4) * abs(loss_r), (epoch, loss_o, loss_r)
+        if not amp:
+            assert abs(ap_o - ap_r) < 5e-4, (epoch, ap_o, ap_r)
+            assert abs(f1_o - f1_r) < 5e-4, (epoch, f1_o, f1_r)
+            continue
+        p_32, _ = O.eval_probs(ref32, gr.x, ei, gr.timestep)
+        s32 = p_32.numpy()[vm]
+        ap_32, f1_32 = M.average_precision(yv, s32)[0], M.pick_threshold_max_f1(yv, s32)[1]
+        quantum = 2.0 / (2 * int(yv.sum()))                  # one node across the threshold (predicted ~ actual positives)
+        print(f"                    fp32 oracle: val PR-AUC {ap_32:.5f}  max-F1 {f1_32:.5f}  (F1 quantum {quantum:.1e})")
+        rows[-1] = rows[-1] + (ap_32, f1_32)
+        assert abs(ap_o - ap_r) < 2.5e-3 and abs(ap_o - ap_32) < 2.5e-3, (epoch, ap_o, ap_r, ap_32)
+        assert abs(f1_o - f1_r) < 4e-3 and abs(f1_o - f1_32) < 4e-3, (epoch, f1_o, f1_r, f1_32)
+        assert abs(ap_o - ap_32) <= 2 * abs(ap_r - ap_32) + 5e-4, (epoch, ap_o, ap_r, ap_32)
+        assert abs(f1_o - f1_32) <= 2 * abs(f1_r - f1_32) + quantum, (epoch, f1_o, f1_r, f1_32)
     assert rows[-1][0] == EPOCHS and rows[-1][3] > 0.30       # the models did learn the planted signal
     import json
     import os
     out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "r02")
     if os.path.isdir(out_dir):                                 # evidence for profiles/ (the GPU box merges gpurun_out/ back)
         json.dump({"precision": "bf16" if amp else "fp32", "columns": ["epoch", "loss_cuda", "loss_oracle",
-                   "val_pr_auc_cuda", "val_pr_auc_oracle", "val_max_f1_cuda", "val_max_f1_oracle"], "rows": rows},
+                   "val_pr_auc_cuda", "val_pr_auc_oracle", "val_max_f1_cuda", "val_max_f1_oracle",
+                   "val_pr_auc_fp32_oracle (bf16 run)", "val_max_f1_fp32_oracle (bf16 run)"],
+                   "agree_to_3_decimals": sum(1 for r in rows if round(r[3], 3) == round(r[4], 3)
+                                              and round(r[5], 3) == round(r[6], 3)), "checkpoints": len(rows),
+                   "rows": rows},
                   open(os.path.join(out_dir, f"trajectory_{'bf16' if amp else 'fp32'}.json"), "w"), indent=1)
     if not amp:
         for b, br in zip(ours.bns, ref.bns):
