@@ -436,6 +436,20 @@ def run_ours(args):
     barrier()
     ms = ev0.elapsed_time(ev1)
     ctx.check()       # a peer-memory all-reduce that timed out inside the timed region fails the run loudly
+    # the same step WITHOUT the memoised layer-0 input layout ([x | sin | cos] fp32 + bf16 is re-derived from x and the
+    # timesteps inside every step, as the reference's `_inject_time` does): reported beside the headline number
+    ms_dyn = None
+    if graphed:
+        step.capture_dynamic()
+        for _ in range(3):
+            step.run(dynamic=True)
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            step.run(dynamic=True)
+        ev1.record()
+        barrier()
+        ms_dyn = ev0.elapsed_time(ev1) / args.steps
     # ---- end-to-end: host buffers in, loss out, every step ------------------------------------
     g_static = E.cached_graph(devb["ei"], lg.num_nodes)
     h2d = sum(v.numel() * v.element_size() for v in host.values())
@@ -502,10 +516,10 @@ def run_ours(args):
     val_ap = [float(v) for v in ap_out.tolist()]
     model.train()
     final_loss = float(step.loss)
-    t = torch.tensor([ms, ms_e2e, ms_eval, ms_tail], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, ms_e2e, ms_eval, ms_tail, ms_dyn or 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e, ms_eval, ms_tail = (float(v) for v in t.tolist())
+    ms, ms_e2e, ms_eval, ms_tail, ms_dyn = (float(v) for v in t.tolist())
     ms_step, ms_e2e_step = ms / args.steps, ms_e2e / e2e_steps
 
     # ---- roofline of the dominant sparse kernel (layer-0 mean SpMM, F=168, fp32 -> bf16), timed alone
@@ -573,7 +587,8 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": round(e_total / (ms_step * 1e-3) / 1e9, 4), "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4),
-            "epoch_ms": round(ms_step, 4), "eval_fwd_ms": round(ms_eval, 4),
+            "epoch_ms": round(ms_step, 4), "ms_per_step_inputs_rederived": round(ms_dyn, 4) if ms_dyn else None,
+            "eval_fwd_ms": round(ms_eval, 4),
             "ref_epoch_ms": round(ms_step + ms_eval, 4), "epoch_tail_ms": round(ms_tail, 4),
             "val_pr_auc": {"value": round(val_ap[0], 6), "rows": int(val_ap[1]), "positives": int(val_ap[2]),
                            "where": "device (egnn_average_precision + egnn_early_stop_update)"},
@@ -585,7 +600,13 @@ def run_ours(args):
                        "parallelism": f"timestep-sharded dp{world}", "cuda_graph": graphed,
                        "collectives": ("peer-memory all-reduce kernel (csrc/p2p.cu) for BatchNorm statistics and "
                                        "gradients" if ctx.p2p else ("nccl" if world > 1 else "none")),
-                       "l2": "inputs larger than L2 (x alone 135 MB; ~1 GB touched per step)"},
+                       "l2": "inputs larger than L2 (x alone 135 MB; ~0.9 GB touched per step)",
+                       "static_inputs": "x / timestep / edge_index are device-resident and unchanged between steps (the "
+                                        "reference moves the graph to the device once): the sorted graph views and the "
+                                        "layer-0 input layout [x | sin | cos] (fp32 + bf16) are memoised per tensor "
+                                        "version; ms_per_step_inputs_rederived is the same step with the layout "
+                                        "re-derived from x every step, and e2e (inputs re-copied every step) always "
+                                        "re-derives it"},
             "clocks": clocks,
             "e2e": {"value": round(e_total / (ms_e2e_step * 1e-3) / 1e9, 4), "unit": UNIT,
                     "ms_per_step": round(ms_e2e_step, 4), "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,

@@ -66,7 +66,8 @@ SIGNATURES = {
     "egnn_bn_act_dropout_res_fwd": (_i32, [_vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i32,
                                            _f32, _u64, _vp, _u32, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "egnn_bn_act_dropout_bwd_reduce": (_i32, [_vp, _vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i32,
-                                              _f32, _u64, _vp, _u32, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+                                              _f32, _u64, _vp, _u32, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp,
+                                              _vp]),
     "egnn_bn_act_dropout_bwd_apply": (_i32, [_vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i32,
                                              _f32, _u64, _vp, _u32, _i64, _vp, _vp, _f64, _vp, _vp, _i64, _vp, _vp]),
     "egnn_dropout_mask": (_i32, [_vp, _i64, _i64, _f32, _u64, _vp, _u32, _i64, _vp]),
@@ -85,6 +86,8 @@ SIGNATURES = {
     "egnn_gcn_out_bwd": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _i64, _vp, _i64, _vp]),
     "egnn_skinny_wgrad_workspace_floats": (_sz, [_i64, _i64, _i32]),
     "egnn_skinny_wgrad": (_i32, [_vp, _i32, _i64, _vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "egnn_skinny_wgrad_split": (_i32, [_vp, _i32, _i64, _vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "egnn_concat2_f32": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp]),
     "egnn_skinny_dgrad": (_i32, [_vp, _vp, _i32, _vp, _i32, _i64, _i64, _i64, _vp]),
     "egnn_p2p_allreduce_buffer_bytes": (_sz, [_i32, _i64, _i32]),
     "egnn_p2p_allreduce": (_i32, [_vp, _vp, _i64, _i32, _i64, _vp, _i32, _i32, _vp, _vp, _i64, _vp]),

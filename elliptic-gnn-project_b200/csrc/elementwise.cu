@@ -349,11 +349,13 @@ __global__ void __launch_bounds__(kThreads) colreduce_partial(Prod prod, int64_t
 // one block per (which, column): fixed-order strided sum + fixed tree
 __global__ void __launch_bounds__(kThreads) colreduce_final(const double* __restrict__ partial,
                                                             int nblk, int F, double* __restrict__ out0,
-                                                            double* __restrict__ out1) {
+                                                            double* __restrict__ out1, float* __restrict__ f0 = nullptr,
+                                                            float* __restrict__ f1 = nullptr) {
   __shared__ double sm[kThreads];
   const int Fp = ((F + 3) >> 2) << 2;
   const int col = blockIdx.x, which = blockIdx.y;
   double* out = which == 0 ? out0 : out1;
+  float* fout = which == 0 ? f0 : f1;   // optional fp32 copy (a parameter gradient: d beta / d gamma of BatchNorm)
   if (!out) return;
   double s = 0;
   for (int b = threadIdx.x; b < nblk; b += kThreads) s += partial[((int64_t)b * 2 + which) * Fp + col];
@@ -363,7 +365,10 @@ __global__ void __launch_bounds__(kThreads) colreduce_final(const double* __rest
     if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x == 0) out[col] = sm[0];
+  if (threadIdx.x == 0) {
+    out[col] = sm[0];
+    if (fout) fout[col] = (float)sm[0];
+  }
 }
 
 template <typename Prod>
@@ -1506,6 +1511,20 @@ extern "C" int egnn_bn_finalize(const double* sums, const double* sumsq, double 
   return 0;
 }
 
+__global__ void concat2_f32_kernel(const float* __restrict__ a, int64_t na, const float* __restrict__ b, int64_t nb,
+                                   float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < na) out[i] = a[i];
+  else if (i < na + nb) out[i] = b[i - na];
+}
+extern "C" int egnn_concat2_f32(const float* a, int64_t na, const float* b, int64_t nb, float* out, void* stream) {
+  EGNN_REQUIRE(a && b && out && na >= 0 && nb >= 0, "egnn_concat2_f32", "bad arguments");
+  if (na + nb == 0) return 0;
+  concat2_f32_kernel<<<(unsigned)ceil_div(na + nb, 256), 256, 0, (cudaStream_t)stream>>>(a, na, b, nb, out);
+  EGNN_LAUNCH_CHECK("egnn_concat2_f32");
+  return 0;
+}
+
 __global__ void f64_to_f32_kernel(const double* __restrict__ in, float* __restrict__ out, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = (float)in[i];
@@ -1622,7 +1641,7 @@ extern "C" int egnn_bn_act_dropout_bwd_reduce(const void* dy, const void* z, int
                                               int act, float p, uint64_t seed, const int64_t* seed_off,
                                               uint32_t layer, int64_t row0, double* sum_g, double* sum_gx, void* workspace,
                                               int64_t ld_z, const uint8_t* keep_bits, const float* dp,
-                                              const float* dp_w, void* stream) {
+                                              const float* dp_w, float* sum_g_f32, float* sum_gx_f32, void* stream) {
   const char* fn = "egnn_bn_act_dropout_bwd_reduce";
   if (ld_z <= 0) ld_z = ld;
   EGNN_REQUIRE(dy && z && sum_g && sum_gx && workspace && mean && rstd && gamma && beta, fn, "null pointer");
@@ -1644,10 +1663,12 @@ extern "C" int egnn_bn_act_dropout_bwd_reduce(const void* dy, const void* z, int
       else bn_relu_bwd_reduce8<B, false><<<f8.nblk, kThreads, 0, st>>>((const B*)dy, nullptr, nullptr, nullptr, (const B*)z, ld, ld_z, n_rows, (int)n_feat, f8.cg_shift, f8.rpb, C, partial, keep_bits);
     }
     EGNN_LAUNCH_CHECK(fn);
-    colreduce_final<<<dim3((unsigned)n_feat, 2), kThreads, 0, st>>>(partial, f8.nblk, (int)n_feat, sum_g, sum_gx);
+    colreduce_final<<<dim3((unsigned)n_feat, 2), kThreads, 0, st>>>(partial, f8.nblk, (int)n_feat, sum_g, sum_gx,
+                                                                    sum_g_f32, sum_gx_f32);
     EGNN_LAUNCH_CHECK(fn);
     return 0;
   }
+  EGNN_REQUIRE(!sum_g_f32 && !sum_gx_f32, fn, "fp32 copies of the sums need the 8-column path");
   FastPlan fp = lean_plan(n_rows, n_feat, dtype, {ld, ld_z}, {z, dy});
   if (fp.ok) {
     double* partial = reinterpret_cast<double*>(workspace);

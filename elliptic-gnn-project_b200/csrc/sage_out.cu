@@ -311,7 +311,9 @@ __global__ void __launch_bounds__(kThreads) skinny_wgrad_kernel(const T* __restr
 // accumulators keep the loads in flight), then a fixed-order combine over the 32 lanes.
 __global__ void __launch_bounds__(kThreads) skinny_wgrad_final(const float* __restrict__ partial, int nblk, int P,
                                                                int K, int Kp, float* __restrict__ dW,
-                                                               float* __restrict__ dsum) {
+                                                               float* __restrict__ dsum, int split = 1 << 30,
+                                                               float* __restrict__ dW_hi = nullptr,
+                                                               float* __restrict__ dsum_hi = nullptr) {
   __shared__ double sm[32][9];
   const int kl = threadIdx.x & 7, bl = threadIdx.x >> 3;
   const int k = blockIdx.x * 8 + kl, p = blockIdx.y;
@@ -336,7 +338,11 @@ __global__ void __launch_bounds__(kThreads) skinny_wgrad_final(const float* __re
     double t = 0;
 #pragma unroll
     for (int l = 0; l < 32; ++l) t += sm[l][kl];
-    if (k < K) dW[p * K + k] = (float)t;
+    // rows >= split go to their own destinations (d lin_r.weight / the bias gradient of the project-first logits layer)
+    if (p >= split) {
+      if (k < K) dW_hi[(p - split) * K + k] = (float)t;
+      else if (dsum_hi) dsum_hi[p - split] = (float)t;
+    } else if (k < K) dW[p * K + k] = (float)t;
     else if (dsum) dsum[p] = (float)t;
   }
 }
@@ -521,8 +527,25 @@ extern "C" size_t egnn_skinny_wgrad_workspace_floats(int64_t n_rows, int64_t K, 
   return (size_t)w.nblk * P * (w.Kp + 8);
 }
 
+static int skinny_wgrad_impl(const void* a, int dtype, int64_t ld, const float* dp, int P, int64_t n_rows, int64_t K,
+                             float* dW, float* dsum, float* workspace, int split, float* dW_hi, float* dsum_hi,
+                             void* stream);
+
 extern "C" int egnn_skinny_wgrad(const void* a, int dtype, int64_t ld, const float* dp, int P, int64_t n_rows,
                                  int64_t K, float* dW, float* dsum, float* workspace, void* stream) {
+  return skinny_wgrad_impl(a, dtype, ld, dp, P, n_rows, K, dW, dsum, workspace, 1 << 30, nullptr, nullptr, stream);
+}
+
+extern "C" int egnn_skinny_wgrad_split(const void* a, int dtype, int64_t ld, const float* dp, int P, int64_t n_rows,
+                                       int64_t K, float* dW_lo, float* dW_hi, float* dsum_hi, float* workspace,
+                                       void* stream) {
+  if (!dW_hi || P % 2) return fail("egnn_skinny_wgrad_split", "dW_hi missing or odd P");
+  return skinny_wgrad_impl(a, dtype, ld, dp, P, n_rows, K, dW_lo, nullptr, workspace, P / 2, dW_hi, dsum_hi, stream);
+}
+
+static int skinny_wgrad_impl(const void* a, int dtype, int64_t ld, const float* dp, int P, int64_t n_rows, int64_t K,
+                             float* dW, float* dsum, float* workspace, int split, float* dW_hi, float* dsum_hi,
+                             void* stream) {
   const char* fn = "egnn_skinny_wgrad";
   EGNN_REQUIRE(a && dp && dW && workspace, fn, "null pointer");
   EGNN_REQUIRE(K > 0 && K <= kMaxK && K % 8 == 0 && ld % 8 == 0, fn, "K and ld must be multiples of 8");
@@ -539,7 +562,7 @@ extern "C" int egnn_skinny_wgrad(const void* a, int dtype, int64_t ld, const flo
 #undef LAUNCH
   EGNN_LAUNCH_CHECK(fn);
   skinny_wgrad_final<<<dim3((unsigned)ceil_div(K + 1, 8), (unsigned)P), kThreads, 0, st>>>(
-      workspace, w.nblk, P, (int)K, w.Kp, dW, dsum);
+      workspace, w.nblk, P, (int)K, w.Kp, dW, dsum, split, dW_hi, dsum_hi);
   EGNN_LAUNCH_CHECK(fn);
   return 0;
 }

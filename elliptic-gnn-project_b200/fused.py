@@ -179,8 +179,8 @@ def forward(net, x: torch.Tensor, g: Graph, t: Optional[torch.Tensor], training:
     out_conv = net.convs[-1]
     C_out = out_conv.out_channels
     wout = torch.empty((2 * C_out, H), dtype=torch.float32, device=dev)
-    check(L.egnn_cast(ptr(out_conv.lin_l.weight), _lib.F32, H, ptr(wout), _lib.F32, H, C_out, H, stream()))
-    check(L.egnn_cast(ptr(out_conv.lin_r.weight), _lib.F32, H, ptr(wout[C_out:]), _lib.F32, H, C_out, H, stream()))
+    check(L.egnn_concat2_f32(ptr(out_conv.lin_l.weight), C_out * H, ptr(out_conv.lin_r.weight), C_out * H, ptr(wout),
+                             stream()))
     p_out = None
 
     layers: List[_Layer] = []
@@ -334,13 +334,9 @@ def backward(net, sv: Saved, dlogits: torch.Tensor, out: Optional[List[torch.Ten
     check(L.egnn_sage_out_bwd(ptr(g.csc_ptr), ptr(g.csc_dst), ptr(g.csr_ptr), ptr(dlogits), dt(dlogits), C, ptr(dp), N,
                               ptr(tmp), g.cap, stream()))
     h = sv.h_last
-    dw = torch.empty((2 * C, H), **f32)
-    dsum = torch.empty(2 * C, **f32)
     ws = torch.empty(L.egnn_skinny_wgrad_workspace_floats(N, H, 2 * C), **f32)
-    check(L.egnn_skinny_wgrad(ptr(h), dt(h), h.stride(0), ptr(dp), 2 * C, N, H, ptr(dw), ptr(dsum), ptr(ws), stream()))
-    copy_into(oc.lin_l.weight, dw[:C])
-    copy_into(oc.lin_l.bias, dsum[C:])
-    copy_into(oc.lin_r.weight, dw[C:])
+    check(L.egnn_skinny_wgrad_split(ptr(h), dt(h), h.stride(0), ptr(dp), 2 * C, N, H, ptr(dst(oc.lin_l.weight)),
+                                    ptr(dst(oc.lin_r.weight)), ptr(dst(oc.lin_l.bias)), ptr(ws), stream()))
     dy = torch.empty((N, H), dtype=cd, device=dev)
     # dy = dp . [W_l ; W_r] is produced INSIDE the last layer's BatchNorm backward (reduce pass) when that layer has
     # BatchNorm and the shapes fit its 8-column kernel; otherwise by its own pass here
@@ -359,6 +355,7 @@ def backward(net, sv: Saved, dlogits: torch.Tensor, out: Optional[List[torch.Ten
         dzsum = dst(conv.lin_l.bias)                    # column sums of dz = the conv bias gradient
         ws2 = torch.empty(L.egnn_colreduce_workspace_bytes(H) + 64 * H, dtype=torch.uint8, device=dev)
         if bn is not None:
+            fused_sums = ly.kb is not None and (H // 8) & (H // 8 - 1) == 0 and H <= 256   # the 8-column reduce kernel
             sg = torch.empty((2, H), dtype=torch.float64, device=dev)
             wsr = torch.empty(L.egnn_colreduce_workspace_bytes(H), dtype=torch.uint8, device=dev)
             check(L.egnn_bn_act_dropout_bwd_reduce(ptr(dy), ptr(z), dt(z), H, N, H, ptr(ly.mean), ptr(ly.rstd),
@@ -367,6 +364,8 @@ def backward(net, sv: Saved, dlogits: torch.Tensor, out: Optional[List[torch.Ten
                                                    ptr(wsr), z.stride(0), ptr(ly.kb),
                                                    ptr(dp) if (dy_from_dp and li == len(sv.layers) - 1) else None,
                                                    ptr(sv.wout) if (dy_from_dp and li == len(sv.layers) - 1) else None,
+                                                   ptr(dst(bn.bias)) if (fused_sums and sv.reducer is None) else None,
+                                                   ptr(dst(bn.weight)) if (fused_sums and sv.reducer is None) else None,
                                                    stream()))
             if sv.reducer is not None:
                 sv.reducer.reduce_(sg)
@@ -374,8 +373,9 @@ def backward(net, sv: Saved, dlogits: torch.Tensor, out: Optional[List[torch.Ten
                                                   ptr(bn.weight), ptr(bn.bias), ACT_RELU, ly.p_eff, sv.seed,
                                                   ptr(sv.soff), li, sv.row0, sg[0].data_ptr(), sg[1].data_ptr(),
                                                   sv.n_total, ptr(dzsum), ptr(ws2), z.stride(0), ptr(ly.kb), stream()))
-            check(L.egnn_f64_to_f32(sg[0].data_ptr(), ptr(dst(bn.bias)), H, stream()))      # d beta  = sum g
-            check(L.egnn_f64_to_f32(sg[1].data_ptr(), ptr(dst(bn.weight)), H, stream()))    # d gamma = sum g * xhat
+            if not (fused_sums and sv.reducer is None):   # (sharded: the sums are complete only after the all-reduce)
+                check(L.egnn_f64_to_f32(sg[0].data_ptr(), ptr(dst(bn.bias)), H, stream()))      # d beta  = sum g
+                check(L.egnn_f64_to_f32(sg[1].data_ptr(), ptr(dst(bn.weight)), H, stream()))    # d gamma = sum g * xhat
         else:
             check(L.egnn_bn_act_dropout_bwd_apply(ptr(dy), ptr(z), ptr(dz), dt(z), H, N, H, None, None, None, None,
                                                   ACT_RELU, ly.p_eff, sv.seed, ptr(sv.soff), li, sv.row0, None, None,

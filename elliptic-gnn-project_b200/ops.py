@@ -671,7 +671,7 @@ class BnActDropResFn(torch.autograd.Function):
             check(L.egnn_bn_act_dropout_bwd_reduce(ptr(dy), ptr(z), dt(z), F, N, F, ptr(mean), ptr(rstd),
                                                    ptr(gamma), ptr(beta), act, p_eff, seed, ptr(soff), layer,
                                                    row0, sg[0].data_ptr(), sg[1].data_ptr(), ptr(ws), _ld(z),
-                                                   ptr(ctx.kb), None, None, stream()))
+                                                   ptr(ctx.kb), None, None, None, None, stream()))
             if reducer is not None:
                 reducer.reduce_(sg)
             dzsum = torch.empty(F, dtype=torch.float32, device=z.device)

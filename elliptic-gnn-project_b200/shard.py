@@ -204,7 +204,9 @@ class ShardedContext:
         else:
             self.class_weight = torch.tensor([(pos + neg) / (2.0 * neg), (pos + neg) / (2.0 * pos)],
                                              dtype=torch.float32)
-        self.stats_reducer = StatsReducer(n_total=shard.n_global, group=group)
+        multi = dist.is_initialized() and dist.get_world_size(group) > 1
+        # one rank: no reducer at all, so the model takes its single-GPU fast path (statistics finalised in one launch)
+        self.stats_reducer = StatsReducer(n_total=shard.n_global, group=group) if multi else None
         self.p2p = False
         self._grad_ar = None
         self._grad_ar_tried = False

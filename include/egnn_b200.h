@@ -185,6 +185,8 @@ int egnn_colstats_reduce(const float* parts, int64_t n_parts, int64_t n_feat, do
 int egnn_bn_finalize_parts(const float* parts, int64_t n_parts, int64_t n_feat, double count, float eps,
                            float momentum, float* mean, float* rstd, float* running_mean, float* running_var,
                            int64_t* num_batches_tracked /* optional device counter, += 1 */, void* stream);
+/* out = [a | b] (fp32 vectors): [lin_l.weight ; lin_r.weight] of the logits layer, one launch */
+int egnn_concat2_f32(const float* a, int64_t na, const float* b, int64_t nb, float* out, void* stream);
 /* out[i] = (float)in[i]: the float64 statistics / reductions handed to fp32 parameter gradients */
 int egnn_f64_to_f32(const double* in, float* out, int64_t n, void* stream);
 
@@ -219,6 +221,11 @@ int egnn_gcn_out_bwd(const int32_t* csc_ptr, const int32_t* csc_dst, const float
 size_t egnn_skinny_wgrad_workspace_floats(int64_t n_rows, int64_t K, int P);
 int egnn_skinny_wgrad(const void* a, int dtype, int64_t ld, const float* dp, int P, int64_t n_rows,
                       int64_t K, float* dW, float* dsum, float* workspace, void* stream);
+/* egnn_skinny_wgrad with the result written as the parameter gradients of the project-first logits layer: rows
+ * [0, P/2) of dW -> dW_lo (d lin_l.weight), rows [P/2, P) -> dW_hi (d lin_r.weight), their dsum -> dsum_hi (the bias
+ * gradient sum_r dout[r, :], optional). */
+int egnn_skinny_wgrad_split(const void* a, int dtype, int64_t ld, const float* dp, int P, int64_t n_rows, int64_t K,
+                            float* dW_lo, float* dW_hi, float* dsum_hi, float* workspace, void* stream);
 int egnn_skinny_dgrad(const float* dp, const float* W, int P, void* dh, int dtype, int64_t ld,
                       int64_t n_rows, int64_t K, void* stream);
 
@@ -298,6 +305,8 @@ int egnn_bn_act_dropout_res_fwd(const void* z, const void* res, void* y, int dty
  *   but computed, dy[r, :] = dp[r, :] . dp_w rounded to `dtype`, and WRITTEN to `dy` for the later consumers -- the
  *   input gradient of the project-first logits layer `SAGEConv(hidden, 2)` (src/models/gnn.py:128,193) folded into
  *   this pass (needs act = ReLU, keep_bits, n_feat / 8 a power of two <= 32, 16-byte aligned rows).
+ * sum_g_f32 / sum_gx_f32 (optional, same path): fp32 copies of the two sums = d beta / d gamma of BatchNorm, written
+ *   where the caller keeps those parameter gradients.
  */
 int egnn_bn_act_dropout_bwd_reduce(const void* dy, const void* z, int dtype, int64_t ld,
                                    int64_t n_rows, int64_t n_feat, const float* mean,
@@ -305,7 +314,8 @@ int egnn_bn_act_dropout_bwd_reduce(const void* dy, const void* z, int dtype, int
                                    int act, float p, uint64_t seed, const int64_t* seed_off,
                                    uint32_t layer, int64_t row0, double* sum_g, double* sum_gx, void* workspace,
                                    int64_t ld_z, const uint8_t* keep_bits,
-                                   const float* dp, const float* dp_w, void* stream);
+                                   const float* dp, const float* dp_w, float* sum_g_f32, float* sum_gx_f32,
+                                   void* stream);
 /* dz_colsum (float [n_feat], optional): column sums of the dz values written -- the gradient of the
  * conv bias that feeds the BatchNorm -- produced in the same pass; needs `workspace` of
  * egnn_colreduce_workspace_bytes(n_feat) + 8*8*n_feat bytes. */
