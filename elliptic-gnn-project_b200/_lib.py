@@ -91,6 +91,10 @@ SIGNATURES = {
     "egnn_skinny_dgrad": (_i32, [_vp, _vp, _i32, _vp, _i32, _i64, _i64, _i64, _vp]),
     "egnn_p2p_allreduce_buffer_bytes": (_sz, [_i32, _i64, _i32]),
     "egnn_p2p_allreduce": (_i32, [_vp, _vp, _i64, _i32, _i64, _vp, _i32, _i32, _vp, _vp, _i64, _vp]),
+    "egnn_bn_stats_exchange": (_i32, [_vp, _i64, _i64, _f64, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _i32,
+                                      _vp, _vp, _i64, _vp]),
+    "egnn_bn_bwd_sums_exchange": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _i64, _vp]),
+    "egnn_bn_bwd_reduce_parts": (_i64, [_i64, _i64]),
     "egnn_masked_ce": (_i32, [_vp, _i32, _i64, _vp, _vp, _i64, _vp, _f64, _vp, _vp, _vp, _vp]),
     "egnn_adam_workspace_floats": (_sz, [_i64]),
     "egnn_clip_adam_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _vp, _vp,

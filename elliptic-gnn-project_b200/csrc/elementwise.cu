@@ -1635,6 +1635,11 @@ extern "C" int egnn_bn_act_dropout_res_fwd(const void* z, const void* res, void*
   return 0;
 }
 
+extern "C" int64_t egnn_bn_bwd_reduce_parts(int64_t n_rows, int64_t n_feat) {
+  FastPlan f8 = plan8(n_rows, n_feat, EGNN_BF16, {}, {});
+  return f8.ok ? f8.nblk : 0;
+}
+
 extern "C" int egnn_bn_act_dropout_bwd_reduce(const void* dy, const void* z, int dtype, int64_t ld,
                                               int64_t n_rows, int64_t n_feat, const float* mean,
                                               const float* rstd, const float* gamma, const float* beta,
@@ -1644,7 +1649,8 @@ extern "C" int egnn_bn_act_dropout_bwd_reduce(const void* dy, const void* z, int
                                               const float* dp_w, float* sum_g_f32, float* sum_gx_f32, void* stream) {
   const char* fn = "egnn_bn_act_dropout_bwd_reduce";
   if (ld_z <= 0) ld_z = ld;
-  EGNN_REQUIRE(dy && z && sum_g && sum_gx && workspace && mean && rstd && gamma && beta, fn, "null pointer");
+  EGNN_REQUIRE(dy && z && workspace && mean && rstd && gamma && beta, fn, "null pointer");
+  EGNN_REQUIRE((sum_g == nullptr) == (sum_gx == nullptr), fn, "sum_g / sum_gx must be given together");
   EGNN_REQUIRE((dp == nullptr) == (dp_w == nullptr), fn, "dp / dp_w must be given together");
   ActCtx C = make_ctx(mean, rstd, gamma, beta, act, p, seed, seed_off, layer, row0);
   cudaStream_t st = (cudaStream_t)stream;
@@ -1663,11 +1669,14 @@ extern "C" int egnn_bn_act_dropout_bwd_reduce(const void* dy, const void* z, int
       else bn_relu_bwd_reduce8<B, false><<<f8.nblk, kThreads, 0, st>>>((const B*)dy, nullptr, nullptr, nullptr, (const B*)z, ld, ld_z, n_rows, (int)n_feat, f8.cg_shift, f8.rpb, C, partial, keep_bits);
     }
     EGNN_LAUNCH_CHECK(fn);
-    colreduce_final<<<dim3((unsigned)n_feat, 2), kThreads, 0, st>>>(partial, f8.nblk, (int)n_feat, sum_g, sum_gx,
-                                                                    sum_g_f32, sum_gx_f32);
-    EGNN_LAUNCH_CHECK(fn);
+    if (sum_g) {   // NULL: the caller reduces the egnn_bn_bwd_reduce_parts(...) partial rows itself (fused exchange)
+      colreduce_final<<<dim3((unsigned)n_feat, 2), kThreads, 0, st>>>(partial, f8.nblk, (int)n_feat, sum_g, sum_gx,
+                                                                      sum_g_f32, sum_gx_f32);
+      EGNN_LAUNCH_CHECK(fn);
+    }
     return 0;
   }
+  EGNN_REQUIRE(sum_g, fn, "partials-only mode needs the 8-column path");
   EGNN_REQUIRE(!sum_g_f32 && !sum_gx_f32, fn, "fp32 copies of the sums need the 8-column path");
   FastPlan fp = lean_plan(n_rows, n_feat, dtype, {ld, ld_z}, {z, dy});
   if (fp.ok) {

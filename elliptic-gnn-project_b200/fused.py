@@ -116,6 +116,11 @@ def _bn_stats_to_mean_rstd(parts, n_parts, F, n_total, bn, reducer, dev):
         check(L.egnn_bn_finalize_parts(ptr(parts), n_parts, F, float(n_total), float(bn.eps), float(bn.momentum),
                                        ptr(mean), ptr(rstd), ptr(bn.running_mean), ptr(bn.running_var),
                                        ptr(bn.num_batches_tracked) if track else None, stream()))
+    elif getattr(reducer, "fused_args", None) is not None and reducer.fused_args(F) is not None:
+        # sharded, peer memory: reduce the parts + exchange + finalise in ONE single-block kernel
+        check(L.egnn_bn_stats_exchange(ptr(parts), n_parts, F, float(n_total), float(bn.eps), float(bn.momentum),
+                                       ptr(mean), ptr(rstd), ptr(bn.running_mean), ptr(bn.running_var),
+                                       ptr(bn.num_batches_tracked) if track else None, *reducer.fused_args(F), stream()))
     else:
         if track:
             check(L.egnn_counter_add(ptr(bn.num_batches_tracked), 1, stream()))
@@ -358,22 +363,30 @@ def backward(net, sv: Saved, dlogits: torch.Tensor, out: Optional[List[torch.Ten
             fused_sums = ly.kb is not None and (H // 8) & (H // 8 - 1) == 0 and H <= 256   # the 8-column reduce kernel
             sg = torch.empty((2, H), dtype=torch.float64, device=dev)
             wsr = torch.empty(L.egnn_colreduce_workspace_bytes(H), dtype=torch.uint8, device=dev)
+            xargs = None
+            if fused_sums and getattr(sv.reducer, "fused_args", None) is not None:
+                xargs = sv.reducer.fused_args(H)
             check(L.egnn_bn_act_dropout_bwd_reduce(ptr(dy), ptr(z), dt(z), H, N, H, ptr(ly.mean), ptr(ly.rstd),
                                                    ptr(bn.weight), ptr(bn.bias), ACT_RELU, ly.p_eff, sv.seed,
-                                                   ptr(sv.soff), li, sv.row0, sg[0].data_ptr(), sg[1].data_ptr(),
+                                                   ptr(sv.soff), li, sv.row0,
+                                                   sg[0].data_ptr() if xargs is None else None,
+                                                   sg[1].data_ptr() if xargs is None else None,
                                                    ptr(wsr), z.stride(0), ptr(ly.kb),
                                                    ptr(dp) if (dy_from_dp and li == len(sv.layers) - 1) else None,
                                                    ptr(sv.wout) if (dy_from_dp and li == len(sv.layers) - 1) else None,
                                                    ptr(dst(bn.bias)) if (fused_sums and sv.reducer is None) else None,
                                                    ptr(dst(bn.weight)) if (fused_sums and sv.reducer is None) else None,
                                                    stream()))
-            if sv.reducer is not None:
+            if xargs is not None:      # partial rows -> all ranks' [sum g | sum g*xhat] (+ d beta / d gamma) in one kernel
+                check(L.egnn_bn_bwd_sums_exchange(ptr(wsr), int(L.egnn_bn_bwd_reduce_parts(N, H)), H, ptr(sg),
+                                                  ptr(dst(bn.bias)), ptr(dst(bn.weight)), *xargs, stream()))
+            elif sv.reducer is not None:
                 sv.reducer.reduce_(sg)
             check(L.egnn_bn_act_dropout_bwd_apply(ptr(dy), ptr(z), ptr(dz), dt(z), H, N, H, ptr(ly.mean), ptr(ly.rstd),
                                                   ptr(bn.weight), ptr(bn.bias), ACT_RELU, ly.p_eff, sv.seed,
                                                   ptr(sv.soff), li, sv.row0, sg[0].data_ptr(), sg[1].data_ptr(),
                                                   sv.n_total, ptr(dzsum), ptr(ws2), z.stride(0), ptr(ly.kb), stream()))
-            if not (fused_sums and sv.reducer is None):   # (sharded: the sums are complete only after the all-reduce)
+            if not (fused_sums and sv.reducer is None) and xargs is None:   # (sharded: complete only after the all-reduce)
                 check(L.egnn_f64_to_f32(sg[0].data_ptr(), ptr(dst(bn.bias)), H, stream()))      # d beta  = sum g
                 check(L.egnn_f64_to_f32(sg[1].data_ptr(), ptr(dst(bn.weight)), H, stream()))    # d gamma = sum g * xhat
         else:

@@ -134,7 +134,7 @@ class P2PAllReduce:
         self.buf.zero_()
         self.hdl = symm_mem.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
         self.peer_ptrs = int(self.hdl.buffer_ptrs_dev)
-        self.epoch = torch.zeros(1, dtype=torch.int64, device=device)
+        self.epoch = torch.zeros(2, dtype=torch.int64, device=device)   # {calls completed, ticket of the running call}
         self.err = torch.zeros(1, dtype=torch.int32, device=device)
         self.timeout_ms = int(os.environ.get("EGNN_P2P_TIMEOUT_MS", "2000"))
         torch.cuda.synchronize(device)   # flags are zero; the caller's consensus all-reduce orders this before any push
@@ -177,11 +177,20 @@ class P2PAllReduce:
 
 
 class P2PStatsReducer(StatsReducer):
-    """BatchNorm-statistics all-reduce through the peer-memory kernel (NCCL for anything it does not cover)."""
+    """BatchNorm-statistics all-reduce through the peer-memory kernel (NCCL for anything it does not cover).
+    `fused_args()` hands the raw exchange arguments to the single-kernel reduce + exchange + finalise entry points
+    (`egnn_bn_stats_exchange`, `egnn_bn_bwd_sums_exchange`) used by `fused.py`."""
 
     def __init__(self, n_total: int, group, ar: "P2PAllReduce"):
         super().__init__(n_total=n_total, group=group)
         self.ar = ar
+
+    def fused_args(self, n_feat: int):
+        """(n_max, peer_ptrs, rank, world, epoch_ptr, err_ptr, timeout_ms) or None when 2 * n_feat does not fit."""
+        a = self.ar
+        if a.dtype != torch.float64 or 2 * n_feat > min(a.n_max, 1024):
+            return None
+        return (a.n_max, a.peer_ptrs, a.rank, a.world, a.epoch.data_ptr(), a.err.data_ptr(), a.timeout_ms)
 
     def reduce_(self, buf: torch.Tensor) -> torch.Tensor:
         return self.ar(buf) if self.ar.supports(buf) else super().reduce_(buf)

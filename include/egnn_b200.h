@@ -305,9 +305,12 @@ int egnn_bn_act_dropout_res_fwd(const void* z, const void* res, void* y, int dty
  *   but computed, dy[r, :] = dp[r, :] . dp_w rounded to `dtype`, and WRITTEN to `dy` for the later consumers -- the
  *   input gradient of the project-first logits layer `SAGEConv(hidden, 2)` (src/models/gnn.py:128,193) folded into
  *   this pass (needs act = ReLU, keep_bits, n_feat / 8 a power of two <= 32, 16-byte aligned rows).
+ * sum_g == sum_gx == NULL (same path): only the per-block partial rows are produced, workspace = double
+ *   [egnn_bn_bwd_reduce_parts(n_rows, n_feat), 2, n_feat]; egnn_bn_bwd_sums_exchange reduces and all-reduces them.
  * sum_g_f32 / sum_gx_f32 (optional, same path): fp32 copies of the two sums = d beta / d gamma of BatchNorm, written
  *   where the caller keeps those parameter gradients.
  */
+int64_t egnn_bn_bwd_reduce_parts(int64_t n_rows, int64_t n_feat);
 int egnn_bn_act_dropout_bwd_reduce(const void* dy, const void* z, int dtype, int64_t ld,
                                    int64_t n_rows, int64_t n_feat, const float* mean,
                                    const float* rstd, const float* gamma, const float* beta,
@@ -372,14 +375,32 @@ int egnn_gat_att_grad(const float* xs, const float* da_s, const float* da_d, int
  * the slots in rank order (bit-identical on every rank).  n <= n_max <= 131 072; dtype EGNN_F32 | EGNN_F64.
  * peer_bufs_dev: DEVICE array of `world` base pointers, entry r = rank r's buffer of
  * egnn_p2p_allreduce_buffer_bytes(world, n_max, dtype) bytes, zero-initialised, mapped into this process (the
- * Python layer gets them from torch.distributed._symmetric_memory).  epoch: device int64, local, starts at 0
- * (CUDA-graph replayable).  A peer that does not arrive within timeout_ms (<= 0: 2000; measured with %globaltimer)
+ * Python layer gets them from torch.distributed._symmetric_memory).  epoch: device int64[2], local, zeros at start
+ * ({calls completed, ticket counter}: the last block of a call advances the epoch; CUDA-graph replayable).  A peer that does not arrive within timeout_ms (<= 0: 2000; measured with %globaltimer)
  * makes the call fail LOUDLY: error_flag (optional, device int) is set to 1 and stays set, and the affected chunk of
  * `out` is filled with NaN, so nothing computed from the un-reduced vector can pass for a result.
  * in == out is allowed.  Every rank must make the same sequence of calls on a given buffer. */
 size_t egnn_p2p_allreduce_buffer_bytes(int world, int64_t n_max, int dtype);
 int egnn_p2p_allreduce(const void* in, void* out, int64_t n, int dtype, int64_t n_max, void* const* peer_bufs_dev,
                        int rank, int world, int64_t* epoch, int* error_flag, int64_t timeout_ms, void* stream);
+
+/* The BatchNorm exchanges of the timestep-sharded SAGE-ResBN step as ONE single-block kernel each, producer and consumer
+ * included (same buffers / flags / epoch protocol as egnn_p2p_allreduce on a float64 buffer with 2 * n_feat <= n_max):
+ *   egnn_bn_stats_exchange   : reduce the layer GEMM's statistics parts (egnn_linear_tc colstats) -> push [sum, sumsq] to
+ *                              every peer -> wait -> add the world's slots in rank order -> mean / rstd / running
+ *                              buffers / num_batches_tracked (`count` = GLOBAL row count).  Replaces
+ *                              egnn_colstats_reduce + egnn_p2p_allreduce + egnn_bn_finalize.
+ *   egnn_bn_bwd_sums_exchange: reduce the backward partial rows -> exchange -> sums double [2, n_feat] = [sum g, sum g*xhat]
+ *                              over ALL ranks (+ fp32 copies = d beta / d gamma).
+ * A peer that does not arrive: NaN results and the sticky error flag, as egnn_p2p_allreduce.
+ * `epoch` of all three entry points: device int64[2] = {calls completed, ticket of the running call}, both 0 at start. */
+int egnn_bn_stats_exchange(const float* parts, int64_t n_parts, int64_t n_feat, double count, float eps, float momentum,
+                           float* mean, float* rstd, float* running_mean, float* running_var,
+                           int64_t* num_batches_tracked, int64_t n_max, void* const* peer_bufs_dev, int rank, int world,
+                           int64_t* epoch, int* error_flag, int64_t timeout_ms, void* stream);
+int egnn_bn_bwd_sums_exchange(const double* partial, int64_t n_parts, int64_t n_feat, double* sums, float* sum_g_f32,
+                              float* sum_gx_f32, int64_t n_max, void* const* peer_bufs_dev, int rank, int world,
+                              int64_t* epoch, int* error_flag, int64_t timeout_ms, void* stream);
 
 /* ---------------------------------------------------------------- step tail ----------- */
 /* Masked weighted cross-entropy over precomputed train-row indices:

@@ -163,7 +163,7 @@ def test_p2p_allreduce_single_rank_protocol(egnn):
         nbytes = L.egnn_p2p_allreduce_buffer_bytes(1, n_max, code)
         buf = torch.zeros((nbytes + 7) // 8, dtype=torch.int64, device="cuda")
         ptrs = torch.tensor([buf.data_ptr()], dtype=torch.int64, device="cuda")
-        epoch = torch.zeros(1, dtype=torch.int64, device="cuda")
+        epoch = torch.zeros(2, dtype=torch.int64, device="cuda")    # {calls completed, ticket}
         err = torch.zeros(1, dtype=torch.int32, device="cuda")
         for it in range(5):
             x = torch.randn(n, dtype=dtype, device="cuda")
@@ -171,7 +171,7 @@ def test_p2p_allreduce_single_rank_protocol(egnn):
             _lib.check(L.egnn_p2p_allreduce(x.data_ptr(), x.data_ptr(), n, code, n_max, ptrs.data_ptr(), 0, 1,
                                             epoch.data_ptr(), err.data_ptr(), 0, _lib.stream()))
             assert torch.equal(x, want)
-        assert int(epoch.item()) == 5 and int(err.item()) == 0
+        assert epoch.tolist() == [5, 0] and int(err.item()) == 0
 
 
 def test_p2p_allreduce_missing_peer_fails_loudly(egnn):
@@ -184,7 +184,7 @@ def test_p2p_allreduce_missing_peer_fails_loudly(egnn):
     nbytes = L.egnn_p2p_allreduce_buffer_bytes(2, n_max, _lib.F64)
     bufs = [torch.zeros((nbytes + 7) // 8, dtype=torch.int64, device="cuda") for _ in range(2)]
     ptrs = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device="cuda")
-    epoch = torch.zeros(1, dtype=torch.int64, device="cuda")
+    epoch = torch.zeros(2, dtype=torch.int64, device="cuda")
     err = torch.zeros(1, dtype=torch.int32, device="cuda")
     x = torch.randn(n, dtype=torch.float64, device="cuda")
     _lib.check(L.egnn_p2p_allreduce(x.data_ptr(), x.data_ptr(), n, _lib.F64, n_max, ptrs.data_ptr(), 0, 2,
