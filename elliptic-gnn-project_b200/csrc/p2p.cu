@@ -226,14 +226,16 @@ __global__ void __launch_bounds__(kXThreads) bn_bwd_exchange_kernel(
   const unsigned long long e = *epoch + 1ull;
   __syncthreads();
   cta_reduce_parts<double>(partial, n_parts, F, vals, red);
-  const bool ok = cta_exchange_f64(vals, 2 * F, n_max, peer_bufs, rank, world, e, timeout_ns, &s_fail);
   const int j = threadIdx.x;
   if (j < 2 * F) {
-    const double v = ok ? vals[j] : poison<double>();
-    sums[j] = v;                                   // [sum g | sum g*xhat]
+    // d beta / d gamma: THIS rank's share -- the flat weight-gradient all-reduce adds the ranks' shares later, like
+    // every other parameter gradient (handing out the world-wide sums here would count them `world` times)
     float* f = j < F ? f0 : f1;
-    if (f) f[j < F ? j : j - F] = (float)v;        // d beta / d gamma
+    if (f) f[j < F ? j : j - F] = (float)vals[j];
   }
+  __syncthreads();
+  const bool ok = cta_exchange_f64(vals, 2 * F, n_max, peer_bufs, rank, world, e, timeout_ns, &s_fail);
+  if (j < 2 * F) sums[j] = ok ? vals[j] : poison<double>();   // [sum g | sum g*xhat] over all ranks
   if (threadIdx.x == 0) {
     if (!ok && error_flag) *error_flag = 1;
     epoch[0] = e;

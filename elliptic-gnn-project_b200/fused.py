@@ -381,12 +381,15 @@ def backward(net, sv: Saved, dlogits: torch.Tensor, out: Optional[List[torch.Ten
                 check(L.egnn_bn_bwd_sums_exchange(ptr(wsr), int(L.egnn_bn_bwd_reduce_parts(N, H)), H, ptr(sg),
                                                   ptr(dst(bn.bias)), ptr(dst(bn.weight)), *xargs, stream()))
             elif sv.reducer is not None:
+                # d beta / d gamma = THIS rank's share (the gradient all-reduce adds the shares), then the exchange
+                check(L.egnn_f64_to_f32(sg[0].data_ptr(), ptr(dst(bn.bias)), H, stream()))
+                check(L.egnn_f64_to_f32(sg[1].data_ptr(), ptr(dst(bn.weight)), H, stream()))
                 sv.reducer.reduce_(sg)
             check(L.egnn_bn_act_dropout_bwd_apply(ptr(dy), ptr(z), ptr(dz), dt(z), H, N, H, ptr(ly.mean), ptr(ly.rstd),
                                                   ptr(bn.weight), ptr(bn.bias), ACT_RELU, ly.p_eff, sv.seed,
                                                   ptr(sv.soff), li, sv.row0, sg[0].data_ptr(), sg[1].data_ptr(),
                                                   sv.n_total, ptr(dzsum), ptr(ws2), z.stride(0), ptr(ly.kb), stream()))
-            if not (fused_sums and sv.reducer is None) and xargs is None:   # (sharded: complete only after the all-reduce)
+            if not fused_sums and sv.reducer is None:
                 check(L.egnn_f64_to_f32(sg[0].data_ptr(), ptr(dst(bn.bias)), H, stream()))      # d beta  = sum g
                 check(L.egnn_f64_to_f32(sg[1].data_ptr(), ptr(dst(bn.weight)), H, stream()))    # d gamma = sum g * xhat
         else:

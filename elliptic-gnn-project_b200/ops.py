@@ -672,6 +672,9 @@ class BnActDropResFn(torch.autograd.Function):
                                                    ptr(gamma), ptr(beta), act, p_eff, seed, ptr(soff), layer,
                                                    row0, sg[0].data_ptr(), sg[1].data_ptr(), ptr(ws), _ld(z),
                                                    ptr(ctx.kb), None, None, None, None, stream()))
+            # d beta / d gamma: THIS rank's share (taken before the cross-rank sum the BatchNorm backward needs; the
+            # weight-gradient all-reduce adds the ranks' shares -- returning the global sums would count them twice)
+            sgf = sg.float()
             if reducer is not None:
                 reducer.reduce_(sg)
             dzsum = torch.empty(F, dtype=torch.float32, device=z.device)
@@ -681,7 +684,6 @@ class BnActDropResFn(torch.autograd.Function):
                                                   ptr(soff), layer, row0, sg[0].data_ptr(), sg[1].data_ptr(),
                                                   n_total, ptr(dzsum), ptr(ws2), _ld(z), ptr(ctx.kb), stream()))
             _publish_colsum(dz, dzsum)
-            sgf = sg.float()
             dbeta, dgamma = sgf[0], sgf[1]
         else:
             check(L.egnn_bn_act_dropout_bwd_apply(ptr(dy), ptr(z), ptr(dz), dt(z), F, N, F, None, None, None,

@@ -391,7 +391,8 @@ int egnn_p2p_allreduce(const void* in, void* out, int64_t n, int dtype, int64_t 
  *                              buffers / num_batches_tracked (`count` = GLOBAL row count).  Replaces
  *                              egnn_colstats_reduce + egnn_p2p_allreduce + egnn_bn_finalize.
  *   egnn_bn_bwd_sums_exchange: reduce the backward partial rows -> exchange -> sums double [2, n_feat] = [sum g, sum g*xhat]
- *                              over ALL ranks (+ fp32 copies = d beta / d gamma).
+ *                              over ALL ranks; the fp32 outputs receive THIS rank's share (d beta / d gamma before
+ *                              the weight-gradient all-reduce, which adds the ranks' shares like any other gradient).
  * A peer that does not arrive: NaN results and the sticky error flag, as egnn_p2p_allreduce.
  * `epoch` of all three entry points: device int64[2] = {calls completed, ticket of the running call}, both 0 at start. */
 int egnn_bn_stats_exchange(const float* parts, int64_t n_parts, int64_t n_feat, double count, float eps, float momentum,

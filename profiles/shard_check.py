@@ -74,22 +74,27 @@ for amp, graphed in ((False, False), (True, False), (True, True)):
                 g1_ref = st_1.opt.flat_grad.detach().clone()
             ref.append(float(st_1.loss))
         skip = zero_grad_names(m_1)
-        off, gd, pd = 0, 0.0, 0.0
+        off, gd, pd, gd_name = 0, 0.0, 0.0, ""
         gmax = float(g1_ref.abs().max())
         for (n, a), (_, b) in zip(m_sh.named_parameters(), m_1.named_parameters()):
             k = b.numel()
             ga, gb = g1[off:off + k], g1_ref[off:off + k]
             off += k
             if n in skip:
-                assert float(gb.abs().max()) < 1e-4 * gmax, (n, "expected an analytically zero gradient")
+                # rounding noise of a cancelling sum (bf16: the sum of ~2e5 rounded dz values)
+                assert float(gb.abs().max()) < (5e-2 if amp else 1e-4) * gmax, (n, "expected an analytically zero gradient",
+                                                                               float(gb.abs().max()), gmax)
                 continue
-            gd = max(gd, float((ga - gb).abs().max() / gb.abs().max().clamp_min(1e-30)))
-            pd = max(pd, float((a - b).abs().max() / b.abs().max().clamp_min(1e-12)))
+            d_g = float((ga - gb).abs().max() / gb.abs().max().clamp_min(1e-30))
+            d_p = float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+            if d_g > gd:
+                gd, gd_name = d_g, n
+            pd = max(pd, d_p)
         tol_l, tol_g, tol_p = (2e-2, 5e-2, 5e-2) if amp else (1e-5, 2e-4, 5e-4)
         good = all(abs(a - b) <= tol_l * abs(b) for a, b in zip(losses, ref)) and gd <= tol_g and pd <= tol_p
         ok &= good
         line = (f"{'bf16' if amp else 'fp32'}{' cuda-graph' if graphed else ''} world={world} p2p={ctx.p2p}: sharded losses "
-                f"{losses} | single-GPU {ref} | worst step-1 gradient rel diff {gd:.2e} | worst param rel diff after 3 "
+                f"{losses} | single-GPU {ref} | worst step-1 gradient rel diff {gd:.2e} ({gd_name}) | worst param rel diff after 3 "
                 f"steps {pd:.2e} (excluded analytically-zero: {sorted(skip)}) -> {'OK' if good else 'MISMATCH'}")
         lines.append(line)
         print(line, flush=True)
