@@ -31,6 +31,18 @@ from ._lib import ACT_RELU, check, dt, lib, ptr, stream
 from .graph import Graph
 
 _STATIC = True
+# weight-gradient GEMMs on a side stream: they depend on dz only, while the chain to the next layer (dgrad GEMM ->
+# transposed aggregation -> BatchNorm backward -> cross-rank exchange) is latency-bound on several GPUs -- the side
+# stream fills the exchange's waiting time.  "auto": when the step is sharded (a statistics reducer is attached).
+OVERLAP_WGRAD = "auto"
+_SIDE = {}
+
+
+def _side_stream(dev):
+    st = _SIDE.get(dev)
+    if st is None:
+        st = _SIDE[dev] = torch.cuda.Stream(device=dev)
+    return st
 
 
 @contextlib.contextmanager
@@ -331,6 +343,11 @@ def backward(net, sv: Saved, dlogits: torch.Tensor, out: Optional[List[torch.Ten
         check(L.egnn_wgrad_tc(ptr(G), G.stride(0), ptr(X), X.stride(0), N, No, Kin, ptr(d0), ptr(d1), K, Kraw,
                               ptr(G2), G2.stride(0) if G2 is not None else 0, N2, ptr(d2), ptr(ws), stream()))
 
+    overlap = (sv.reducer is not None) if OVERLAP_WGRAD == "auto" else bool(OVERLAP_WGRAD)
+    main_st = torch.cuda.current_stream(dev)
+    side_st = _side_stream(dev) if overlap else None
+    keep = []          # operands of side-stream kernels stay referenced until the streams join
+
     # ---- logits layer
     oc = net.convs[-1]
     dlogits = ops._rows(dlogits).contiguous()
@@ -339,9 +356,21 @@ def backward(net, sv: Saved, dlogits: torch.Tensor, out: Optional[List[torch.Ten
     check(L.egnn_sage_out_bwd(ptr(g.csc_ptr), ptr(g.csc_dst), ptr(g.csr_ptr), ptr(dlogits), dt(dlogits), C, ptr(dp), N,
                               ptr(tmp), g.cap, stream()))
     h = sv.h_last
-    ws = torch.empty(L.egnn_skinny_wgrad_workspace_floats(N, H, 2 * C), **f32)
-    check(L.egnn_skinny_wgrad_split(ptr(h), dt(h), h.stride(0), ptr(dp), 2 * C, N, H, ptr(dst(oc.lin_l.weight)),
-                                    ptr(dst(oc.lin_r.weight)), ptr(dst(oc.lin_l.bias)), ptr(ws), stream()))
+
+    def out_wgrad():
+        ws = torch.empty(L.egnn_skinny_wgrad_workspace_floats(N, H, 2 * C), **f32)
+        check(L.egnn_skinny_wgrad_split(ptr(h), dt(h), h.stride(0), ptr(dp), 2 * C, N, H, ptr(dst(oc.lin_l.weight)),
+                                        ptr(dst(oc.lin_r.weight)), ptr(dst(oc.lin_l.bias)), ptr(ws), stream()))
+
+    if overlap:
+        ev0 = torch.cuda.Event()
+        ev0.record(main_st)
+        keep.append((dp, h))
+        with torch.cuda.stream(side_st):
+            side_st.wait_event(ev0)
+            out_wgrad()
+    else:
+        out_wgrad()
     dy = torch.empty((N, H), dtype=cd, device=dev)
     # dy = dp . [W_l ; W_r] is produced INSIDE the last layer's BatchNorm backward (reduce pass) when that layer has
     # BatchNorm and the shapes fit its 8-column kernel; otherwise by its own pass here
@@ -399,18 +428,30 @@ def backward(net, sv: Saved, dlogits: torch.Tensor, out: Optional[List[torch.Ten
         # weight gradients: dz^T [m | h]  (and dres^T h for a projected residual; dres = dy)
         cat = ly.cat
         Kraw = conv.in_channels
-        if 2 * K <= 384 and ly.has_proj and H % 64 == 0 and 2 * H <= 128:
-            # one pass over [m | h]: [dz | dy]^T [m | h] -> d lin_l, d lin_r, and (dy x root half) d res_proj
-            wgrad(dz, cat, K, Kraw, dst(conv.lin_l.weight), dst(conv.lin_r.weight), G2=dy,
-                  d2=dst(net.res_projs[li].weight))
-        else:
-            if 2 * K <= 384:
-                wgrad(dz, cat, K, Kraw, dst(conv.lin_l.weight), dst(conv.lin_r.weight))
+
+        def layer_wgrads():
+            if 2 * K <= 384 and ly.has_proj and H % 64 == 0 and 2 * H <= 128:
+                # one pass over [m | h]: [dz | dy]^T [m | h] -> d lin_l, d lin_r, and (dy x root half) d res_proj
+                wgrad(dz, cat, K, Kraw, dst(conv.lin_l.weight), dst(conv.lin_r.weight), G2=dy,
+                      d2=dst(net.res_projs[li].weight))
             else:
-                wgrad(dz, cat[:, :K], K, Kraw, dst(conv.lin_l.weight), None)
-                wgrad(dz, cat[:, K:], K, Kraw, dst(conv.lin_r.weight), None)
-            if ly.has_proj:
-                wgrad(dy, cat[:, K:], K, Kraw, dst(net.res_projs[li].weight), None)
+                if 2 * K <= 384:
+                    wgrad(dz, cat, K, Kraw, dst(conv.lin_l.weight), dst(conv.lin_r.weight))
+                else:
+                    wgrad(dz, cat[:, :K], K, Kraw, dst(conv.lin_l.weight), None)
+                    wgrad(dz, cat[:, K:], K, Kraw, dst(conv.lin_r.weight), None)
+                if ly.has_proj:
+                    wgrad(dy, cat[:, K:], K, Kraw, dst(net.res_projs[li].weight), None)
+
+        if overlap and li > 0:
+            ev = torch.cuda.Event()
+            ev.record(main_st)
+            keep.append((dz, dy, cat))
+            with torch.cuda.stream(side_st):
+                side_st.wait_event(ev)
+                layer_wgrads()
+        else:
+            layer_wgrads()
         need_dh = li > 0 or sv.D > 0
         if not need_dh:
             break
@@ -424,6 +465,9 @@ def backward(net, sv: Saved, dlogits: torch.Tensor, out: Optional[List[torch.Ten
         if li == 0:
             dh0 = dh
         dy = dh
+    if overlap:
+        main_st.wait_stream(side_st)
+        keep.clear()
     if sv.D > 0:
         wse = torch.empty(L.egnn_embed_grad_workspace_bytes(N, sv.T, sv.D), dtype=torch.uint8, device=dev)
         check(L.egnn_embed_grad(ptr(dh0), dt(dh0), dh0.stride(0), sv.x_cols, sv.D, ptr(sv.t.contiguous()), sv.T, N,
