@@ -6,7 +6,8 @@ state-dict names, computed by hand-written sm_100a kernels behind a C-ABI shared
 (`include/egnn_b200.h`, `libegnn_b200.so`).  CUDA only; no CPU or PyTorch fallback.
 """
 from . import _lib  # noqa: F401
-from .graph import Graph, GraphCache, build_graph, cached_graph, symmetrize  # noqa: F401
+from .graph import (Graph, GraphCache, ablate_hubs, build_graph, cached_graph, drop_edges,  # noqa: F401
+                    register_graph, symmetrize)
 from .nn import GATConv, GCNConv, SAGEConv  # noqa: F401
 from .models import GATNet, GCNNet, SAGENet, SAGEResBNNet, build_model  # noqa: F401
 from . import metrics, ops, synthetic  # noqa: F401

@@ -33,6 +33,9 @@ SIGNATURES = {
     "egnn_counter_add": (_i32, [_vp, _i64, _vp]),
     "egnn_graph_workspace_bytes": (_sz, [_i64, _i64, _i32]),
     "egnn_graph_build": (_i32, [_vp, _i64, _i64, _i32, _i32] + [_vp] * 16 + [_vp, _sz, _vp]),
+    "egnn_hub_ablation_workspace_bytes": (_sz, [_i64, _i64]),
+    "egnn_hub_ablation": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "egnn_edge_gather": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _vp]),
     "egnn_buffers_differ": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "egnn_spmm": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _i64, _vp, _i32, _i64, _i64,
                          _i64, _vp, _i32, _i32, _vp, _i64, _vp]),

@@ -389,6 +389,17 @@ int gemm_tcgen05_dispatch(const void* A, int64_t lda, const void* B, int64_t ldb
                           const int32_t* row_div_ptr, int64_t row_div_cols, cudaStream_t st, const void* addend = nullptr,
                           int64_t ld_add = 0, int64_t add_col0 = 0, float* stats = nullptr,
                           int64_t stats_cols = 0);  // gemm_tcgen05.cu
+bool gemm_tf32x3_supported(int64_t lda, int64_t ldw, int64_t M, int64_t N, int64_t K, const void* A, const void* W);
+size_t gemm_tf32x3_workspace_floats(int64_t N, int64_t K);
+int gemm_tf32x3_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int c_dtype, int64_t ld_c,
+                         int64_t M, int64_t N, int64_t K, const float* bias, int accumulate,
+                         const int32_t* row_div_ptr, int64_t row_div_cols, float* workspace, cudaStream_t st,
+                         const void* addend = nullptr, int64_t ld_add = 0, int64_t add_col0 = 0, float* stats = nullptr,
+                         int64_t stats_cols = 0);
+bool wgrad_tf32x3_supported(const void* G, int64_t ldg, const void* X, int64_t ldx, int64_t M_rows, int64_t N_out,
+                            int64_t K_in);
+int wgrad_tf32x3_dispatch(const void* G, int64_t ldg, const void* X, int64_t ldx, float* dW, int64_t M_rows,
+                          int64_t N_out, int64_t K_in, int accumulate, float* workspace, cudaStream_t st);
 bool gemm_tcgen05_epilogue_supported(bool bias, bool row_div, bool accumulate, bool addend, bool stats, int64_t stats_cols,
                                      int64_t add_col0);
 int64_t gemm_tcgen05_stats_parts(int64_t M);
@@ -448,11 +459,14 @@ extern "C" int egnn_wgrad_tc(const void* G, int64_t ldg, const void* X, int64_t 
                                 valid_cols, G2, ldg2, N2, dst2);
 }
 
+constexpr int64_t kTf32MinRows = 1024;   // fp32 products with fewer rows stay on the FFMA kernel
+
 extern "C" size_t egnn_gemm_workspace_floats(int64_t M, int64_t N, int64_t K, int split_k) {
   (void)K;
   size_t need = split_k > 1 ? (size_t)split_k * (size_t)M * (size_t)N : 0;
   if (M <= 8) need = std::max(need, (size_t)(kNumSMs * 4 + 1) * (size_t)M * (size_t)N);  // skinny wgrad chunks
   if (M <= 256 && N <= 384) need = std::max(need, wgrad_tcgen05_workspace_floats(M, N));     // tcgen05 wgrad
+  if (M >= kTf32MinRows && N <= 256) need = std::max(need, gemm_tf32x3_workspace_floats(N, K));  // 3xTF32 weight split
   return need;
 }
 
@@ -477,6 +491,18 @@ extern "C" int egnn_gemm(const void* A, int a_dtype, int64_t a_sm, int64_t a_sk,
   const bool tc_wg = both_bf16 && a_sm == 1 && b_sn == 1 && c_dtype == EGNN_F32 && ld_c == N && !bias &&
                      !row_div_ptr && workspace && M >= 8 && K >= 1024 &&
                      wgrad_tcgen05_supported(A, a_sk, B, b_sk, K, M, N);
+  // fp32 operands, both contiguous along the contraction: 3xTF32 on the tensor cores (fp32-exact to ~1e-6)
+  const bool both_f32 = a_dtype == EGNN_F32 && b_dtype == EGNN_F32;
+  const bool tc_f32 = both_f32 && a_sk == 1 && b_sk == 1 && workspace && split_k <= 1 && M >= kTf32MinRows &&
+                      gemm_tf32x3_supported(a_sm, b_sn, M, N, K, A, B);
+  if (impl != 1 && tc_f32)
+    return gemm_tf32x3_dispatch(A, a_sm, B, b_sn, C, c_dtype, ld_c, M, N, K, bias, accumulate, row_div_ptr, row_div_cols,
+                                workspace, st);
+  // fp32 weight gradient (both operands contiguous along the non-contracted dimension, long reduction): 3xTF32
+  const bool tc_wg32 = both_f32 && a_sm == 1 && b_sn == 1 && c_dtype == EGNN_F32 && ld_c == N && !bias && !row_div_ptr &&
+                       workspace && M >= 8 && K >= kTf32MinRows && wgrad_tf32x3_supported(A, a_sk, B, b_sk, K, M, N);
+  if (impl != 1 && tc_wg32)
+    return wgrad_tf32x3_dispatch(A, a_sk, B, b_sk, (float*)C, K, M, N, accumulate, workspace, st);
   if (impl == 2 && !(tc_tn || tc_wg)) return fail(fn, "shape/dtype/layout not supported by the tcgen05 path");
   if (impl != 1 && tc_tn)
     return gemm_tcgen05_dispatch(A, a_sm, B, b_sn, C, c_dtype, ld_c, M, N, K, bias, accumulate, row_div_ptr, row_div_cols, st);

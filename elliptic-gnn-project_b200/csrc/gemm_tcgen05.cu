@@ -23,6 +23,8 @@
 //             bytes further; one MMA (K=16) advances the start address by 2048 B.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace egnn {
@@ -125,6 +127,18 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;  // version
   d |= (uint64_t)2 << 61;  // LayoutType::SWIZZLE_128B
+  return d;
+}
+// the same with LayoutType::SWIZZLE_128B_BASE32B (1): the only shared-memory layout the tensor core accepts for MN-major
+// 32-bit (tf32) operands -- 32-byte chunks of a 128-byte row are XOR-ed with the row index inside 4-row groups (TMA:
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B); SBO = distance between 4-row groups, LBO = distance between 128-byte column blocks
+__device__ __forceinline__ uint64_t make_desc_b32(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // version
+  d |= (uint64_t)1 << 61;  // LayoutType::SWIZZLE_128B_BASE32B
   return d;
 }
 // instruction descriptor: D=f32, A=B=bf16, M=128, N=n
@@ -463,6 +477,214 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+// ------------------------------------------------------------------ fp32 operands: 3xTF32 ---
+// The exact-fp32 path (every `eval_split` forward, src/train_gnn.py:248-257, and the fp32 configs) needs rel 1e-5:
+// plain TF32 (10-bit mantissa) is not enough, FFMA leaves the tensor cores idle.  3xTF32: a = a_hi + a_lo with
+// a_hi = rna_tf32(a), and  a.w ~= a_lo.w_hi + a_hi.w_lo + a_hi.w_hi  accumulated in fp32 in TMEM (the dropped
+// a_lo.w_lo term and the truncation of the lo parts are ~2^-22 relative).  W_hi / W_lo are split once per call by a
+// small kernel; the A tile arrives by TMA as fp32 and two converter warps split it IN SHARED MEMORY (hi written back
+// in place, lo into a second tile at the same swizzled offsets), then hand the stage to the MMA warp.
+constexpr int BK32 = 32;   // fp32 elements per 128-byte swizzled row
+
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int n, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void tcgen05_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ float rna_tf32(float a) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(a));
+  return __uint_as_float(r);
+}
+// hi / lo split of `n16` 16-byte vectors by `nthreads` threads: hi in place, lo at the same offset of `lo`
+// (batches of 8 independent loads: the in-place stores would otherwise serialise every iteration on its own load)
+__device__ __forceinline__ void split_tile_tf32(uint8_t* hi, uint8_t* lo, int n16, int tid, int nthreads) {
+  constexpr int kBatch = 8;
+  for (int i0 = tid; i0 < n16; i0 += nthreads * kBatch) {
+    float4 v[kBatch];
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const int i = i0 + u * nthreads;
+      if (i < n16) v[u] = *reinterpret_cast<const float4*>(hi + (size_t)i * 16);
+    }
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const int i = i0 + u * nthreads;
+      if (i < n16) {
+        const float4 h = make_float4(rna_tf32(v[u].x), rna_tf32(v[u].y), rna_tf32(v[u].z), rna_tf32(v[u].w));
+        *reinterpret_cast<float4*>(hi + (size_t)i * 16) = h;
+        // lo rounded to tf32 here (the tensor core would TRUNCATE it: a biased 2^-21 error instead of a 2^-22 rounding)
+        *reinterpret_cast<float4*>(lo + (size_t)i * 16) =
+            make_float4(rna_tf32(v[u].x - h.x), rna_tf32(v[u].y - h.y), rna_tf32(v[u].z - h.z), rna_tf32(v[u].w - h.w));
+      }
+    }
+  }
+}
+
+__global__ void split_tf32_kernel(const float* __restrict__ w, int64_t n, float* __restrict__ hi, float* __restrict__ lo) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = w[i], h = rna_tf32(v);
+  hi[i] = h;
+  lo[i] = rna_tf32(v - h);
+}
+
+// smem map (dynamic, 1024-aligned): stages of [A 16 KB][A_lo 16 KB][W_hi chunk Npad*128][W_lo chunk Npad*128], then
+// barriers / TMEM slot / bias / statistics scratch as in gemm_tn_kernel
+// kConvWarps: 2 (warps 2-3; 384 threads, every epilogue compiled in) or 6 (warps 2-3 and 12-15; 512 threads, i.e. 128
+// registers per thread: the statistics epilogues, which need more, are left out of that variant)
+template <int kStages, int kConvWarps>
+__global__ void __launch_bounds__(kThreadsTN + (kConvWarps - 2) * 32, 1)
+gemm_tn_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWhi,
+                      const __grid_constant__ CUtensorMap tmWlo, int M, int N, int Npad, int K, Epilogue ep, int dbg) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~uintptr_t(1023));
+  const int KC = (K + BK32 - 1) / BK32;
+  const int w_chunk_bytes = Npad * 128;
+  const int stage_bytes = 2 * kStageBytesA + 2 * w_chunk_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * stage_bytes);
+  uint64_t* full = bars;                     // [kStages]  TMA landed
+  uint64_t* conv = bars + kStages;           // [kStages]  A split into hi / lo
+  uint64_t* empty = bars + 2 * kStages;      // [kStages]  MMAs retired
+  uint64_t* t_full = bars + 3 * kStages;     // [2]
+  uint64_t* t_empty = t_full + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = (M + BM - 1) / BM;
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
+  for (int i = threadIdx.x; i < 256 + 16; i += blockDim.x) s_bias[i] = (ep.bias && i < N) ? ep.bias[i] : 0.f;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < 2 * Npad) tmem_cols <<= 1;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&conv[s], kConvWarps); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&t_full[b], 1); mbar_init(&t_empty[b], kEpiWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        for (int kc = 0; kc < KC; ++kc) {
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* st = smem + (size_t)s * stage_bytes;
+          mbar_expect_tx(&full[s], (uint32_t)(kStageBytesA + 2 * w_chunk_bytes));
+          tma_load_2d(st, &tmA, &full[s], kc * BK32, t * BM);
+          tma_load_2d(st + 2 * kStageBytesA, &tmWhi, &full[s], kc * BK32, 0);
+          tma_load_2d(st + 2 * kStageBytesA + w_chunk_bytes, &tmWlo, &full[s], kc * BK32, 0);
+          if (++s == kStages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 2 || warp == 3 || warp >= 12) {
+    // converters: kConvWarps warps split the A tile of every stage
+    const int tid = (warp >= 12 ? warp - 10 : warp - 2) * 32 + lane;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      for (int kc = 0; kc < KC; ++kc) {
+        mbar_wait(&full[s], ph);
+        uint8_t* st = smem + (size_t)s * stage_bytes;
+        if (!(dbg & 1)) split_tile_tf32(st, st + kStageBytesA, kStageBytesA / 16, tid, kConvWarps * 32);
+        fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&conv[s]);
+        if (++s == kStages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc_tf32(Npad, 0, 0);
+    int s = 0;
+    uint32_t ph = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1);
+      mbar_wait(&t_empty[buf], (use & 1) ^ 1);
+      tcgen05_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * Npad);
+      for (int kc = 0; kc < KC; ++kc) {
+        mbar_wait(&conv[s], ph);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const int k_left = K - kc * BK32;
+          const int n_k = k_left >= BK32 ? BK32 / 8 : (k_left + 7) / 8;
+          const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint32_t a_lo = a_hi + kStageBytesA;
+          const uint32_t w_hi = a_hi + 2 * kStageBytesA;
+          const uint32_t w_lo = w_hi + w_chunk_bytes;
+          for (int k4 = 0; k4 < n_k; ++k4) {
+            const uint64_t ah = make_desc(a_hi + k4 * 32, 16, 1024), al = make_desc(a_lo + k4 * 32, 16, 1024);
+            const uint64_t wh = make_desc(w_hi + k4 * 32, 16, 1024), wl = make_desc(w_lo + k4 * 32, 16, 1024);
+            if (dbg & 2) {
+              tcgen05_mma_tf32(d_tmem, ah, wh, idesc, (kc | k4) != 0);
+              continue;
+            }
+            tcgen05_mma_tf32(d_tmem, al, wh, idesc, (kc | k4) != 0);   // small terms first
+            tcgen05_mma_tf32(d_tmem, ah, wl, idesc, 1u);
+            tcgen05_mma_tf32(d_tmem, ah, wh, idesc, 1u);
+          }
+          tcgen05_commit(&empty[s]);
+          if (kc == KC - 1) tcgen05_commit(&t_full[buf]);
+        }
+        __syncwarp();
+        if (++s == kStages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp >= 4 && warp < 12) {
+    const int q = warp & 3, half = (warp - 4) >> 2;
+    const int flags = (ep.bias ? 1 : 0) | (ep.row_div_ptr ? 2 : 0) | (ep.accumulate ? 4 : 0) | (ep.addend ? 8 : 0) |
+                      (ep.stats ? 16 : 0);
+#define EGNN_EPI_CASE(F)                                                                                      \
+  case F:                                                                                                     \
+    if (ep.c_dtype == EGNN_F32)                                                                               \
+      epilogue_loop<float, F>(ep, s_bias, t_full, t_empty, tmem_base, Npad, M, N, n_tiles, q, half, lane);    \
+    else                                                                                                      \
+      epilogue_loop<__nv_bfloat16, F>(ep, s_bias, t_full, t_empty, tmem_base, Npad, M, N, n_tiles, q, half,   \
+                                      lane);                                                                  \
+    break;
+    switch (flags) {
+      EGNN_EPI_CASE(0) EGNN_EPI_CASE(1) EGNN_EPI_CASE(2) EGNN_EPI_CASE(3)
+      EGNN_EPI_CASE(4) EGNN_EPI_CASE(5) EGNN_EPI_CASE(6) EGNN_EPI_CASE(7)
+      EGNN_EPI_CASE(8) EGNN_EPI_CASE(10)
+      default:
+        if constexpr (kConvWarps == 2) {
+          switch (flags) { EGNN_EPI_CASE(16) EGNN_EPI_CASE(17) }
+        }
+    }
+#undef EGNN_EPI_CASE
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
+  }
+}
+
 // ------------------------------------------------------------------ wgrad ------------------
 // dW^T tile: UMMA M axis = K_in (up to three 128-wide M tiles), N axis = N_out.
 // smem stage = [X blocks: MB * 8 KB][G blocks: NB * 8 KB], each block = 64 nodes x 64 columns.
@@ -580,6 +802,161 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   }
 }
 
+// ---- fp32 weight gradient: 3xTF32 -------------------------------------------------------------------------------
+// dW[N_out, K_in] = G[M, N_out]^T . X[M, K_in] with fp32 operands.  Both operands are MN-major (32 fp32 = 128 bytes of one
+// node's row per swizzled shared-memory row); a stage holds a slab of 16 nodes: X blocks (K_in / 32 x 2 KB), G blocks
+// (N_out / 32 x 2 KB) and, behind them, the lo parts written by the converter warps.  Per slab: 2 K-steps (8 nodes) x
+// (X_lo G_hi + X_hi G_lo + X_hi G_hi) per 128-wide M tile over K_in.  Per-CTA partial in TMEM, fixed-order reduction.
+constexpr int kSlab32 = 16;              // nodes per stage
+constexpr int kBlk32 = kSlab32 * 128;    // bytes of one 32-column block of a slab
+constexpr int kThreadsWG32 = 384;        // warp 0 TMA, 1 MMA, 2-3 + 8-11 converters, 4-7 epilogue
+
+template <int kStages>
+__global__ void __launch_bounds__(kThreadsWG32, 1)
+gemm_wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, int M_rows,
+                         int N_out, int Nopad, int K_in, int P, float* __restrict__ partial) {
+  // P phases per CTA, one partial each: the tensor core adds into its fp32 accumulator with truncation, so the error of
+  // a long accumulation chain grows linearly (1e-5 after ~500 steps); every phase keeps the chain short (~130 steps)
+  // and the phases are then combined with IEEE adds by wgrad_reduce_kernel.
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~uintptr_t(1023));
+  const int MT = (K_in + 127) / 128;     // 128-wide M tiles over K_in (<= 3)
+  const int XB = MT * 4;                 // 32-column X blocks per stage
+  const int GB = (Nopad + 31) / 32;      // 32-column G blocks per stage
+  const int half_bytes = (XB + GB) * kBlk32;   // hi part of a stage; the lo part follows
+  const int stage_bytes = 2 * half_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* conv = bars + kStages;
+  uint64_t* empty = bars + 2 * kStages;
+  uint64_t* done = bars + 3 * kStages;      // MMA -> epilogue: a phase's accumulator is complete
+  uint64_t* drained = done + 1;             // epilogue -> MMA: the accumulator has been read
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(drained + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_slabs = (M_rows + kSlab32 - 1) / kSlab32;
+  const int n_my = (int)blockIdx.x < n_slabs ? (n_slabs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < MT * Nopad) tmem_cols <<= 1;
+  constexpr int kConvWarps = 6;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&conv[s], kConvWarps); mbar_init(&empty[s], 1); }
+    mbar_init(done, 1);
+    mbar_init(drained, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < n_my; ++it) {
+        const int sl = blockIdx.x + it * gridDim.x;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full[s], (uint32_t)half_bytes);
+        uint8_t* st = smem + (size_t)s * stage_bytes;
+        for (int b = 0; b < XB; ++b) tma_load_2d(st + b * kBlk32, &tmX, &full[s], b * 32, sl * kSlab32);
+        for (int b = 0; b < GB; ++b) tma_load_2d(st + (XB + b) * kBlk32, &tmG, &full[s], b * 32, sl * kSlab32);
+        if (++s == kStages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 2 || warp == 3 || warp >= 8) {
+    const int tid = (warp >= 8 ? warp - 6 : warp - 2) * 32 + lane;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < n_my; ++it) {
+      mbar_wait(&full[s], ph);
+      uint8_t* st = smem + (size_t)s * stage_bytes;
+      split_tile_tf32(st, st + half_bytes, half_bytes / 16, tid, kConvWarps * 32);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&conv[s]);
+      if (++s == kStages) { s = 0; ph ^= 1; }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc_tf32(Nopad, 1, 1);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int p = 0; p < P; ++p) {
+      const int it0 = (int)((int64_t)n_my * p / P), it1 = (int)((int64_t)n_my * (p + 1) / P);
+      if (p > 0) {
+        mbar_wait(drained, (uint32_t)((p - 1) & 1));
+        tcgen05_fence_after();
+      }
+      bool first = true;
+      for (int it = it0; it < it1; ++it) {
+        mbar_wait(&conv[s], ph);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint32_t hi = smem_u32(smem + (size_t)s * stage_bytes), lo = hi + half_bytes;
+          for (int mt = 0; mt < MT; ++mt) {
+            for (int k2 = 0; k2 < kSlab32 / 8; ++k2) {
+              // operand descriptors: 8 nodes = two 4-row (512-byte) swizzle groups; the next 32 columns are kBlk32 bytes further
+              const uint32_t xo = mt * 4 * kBlk32 + k2 * 1024, go = XB * kBlk32 + k2 * 1024;
+              const uint64_t xh = make_desc_b32(hi + xo, kBlk32, 512), xl = make_desc_b32(lo + xo, kBlk32, 512);
+              const uint64_t gh = make_desc_b32(hi + go, kBlk32, 512), gl = make_desc_b32(lo + go, kBlk32, 512);
+              const uint32_t d = tmem_base + (uint32_t)(mt * Nopad);
+              tcgen05_mma_tf32(d, xl, gh, idesc, (!first || k2 != 0) ? 1u : 0u);
+              tcgen05_mma_tf32(d, xh, gl, idesc, 1u);
+              tcgen05_mma_tf32(d, xh, gh, idesc, 1u);
+            }
+          }
+          tcgen05_commit(&empty[s]);
+        }
+        __syncwarp();
+        first = false;
+        if (++s == kStages) { s = 0; ph ^= 1; }
+      }
+      if (elect_one()) tcgen05_commit(done);
+      __syncwarp();
+    }
+  } else if (warp >= 4 && warp < 8) {
+    const int q = warp & 3;
+    for (int p = 0; p < P; ++p) {
+      const int it0 = (int)((int64_t)n_my * p / P), it1 = (int)((int64_t)n_my * (p + 1) / P);
+      const bool has_work = it1 > it0;
+      float* out = partial + ((size_t)blockIdx.x * P + p) * N_out * K_in;
+      mbar_wait(done, (uint32_t)(p & 1));
+      tcgen05_fence_after();
+      for (int mt = 0; mt < MT; ++mt) {
+        const int k = mt * 128 + q * 32 + lane;
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * Nopad);
+        for (int c0 = 0; c0 < N_out; c0 += 8) {
+          float v[8];
+          if (has_work) {
+            tmem_ld8(t_addr + c0, v);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = 0.f;
+          }
+          if (k < K_in) {
+            const int nv = min(8, N_out - c0);
+            for (int j = 0; j < nv; ++j) out[(size_t)(c0 + j) * K_in + k] = v[j];
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(drained);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
+  }
+}
+
 // block = 64 output elements x 4 partial lanes; lane q sums partials q, q+4, ... with four independent
 // accumulators (loads in flight), then the four lanes are combined in a fixed order: deterministic
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int n_part,
@@ -676,6 +1053,21 @@ bool make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int6
   return r == CUDA_SUCCESS;
 }
 
+// fp32 [rows, cols] row-major, box = 32 cols (128 bytes) x box_rows
+bool make_map_f32(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                  CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 constexpr int kStagesTN = 6;
 constexpr size_t kMaxDynSmemTN = 227 * 1024;
 constexpr size_t kStatsSmem = 2048;   // [4 sub-partitions][sum, sumsq][64] floats behind the bias (statistics epilogue)
@@ -737,7 +1129,149 @@ int gemm_tcgen05_dispatch(const void* A, int64_t lda, const void* B, int64_t ldb
   return 0;
 }
 
-size_t wgrad_tcgen05_workspace_floats(int64_t N_out, int64_t K_in) { return (size_t)kNumSMs * N_out * K_in; }
+// ---- fp32 operands (3xTF32) ----------------------------------------------------------------------------------------
+static int tf32_stages(int Npad, bool stats) {
+  const size_t stage = 2 * (size_t)kStageBytesA + 2 * (size_t)Npad * 128;
+  const size_t fixed = 256 + 1088 + 1024 + (stats ? kStatsSmem : 0) + 64;
+  int st = 4;
+  while (st > 1 && st * stage + fixed > kMaxDynSmemTN) --st;
+  return st;
+}
+
+bool gemm_tf32x3_supported(int64_t lda, int64_t ldw, int64_t M, int64_t N, int64_t K, const void* A, const void* W) {
+  if (M < 1 || N < 8 || N > 256 || K < 8 || K > 4096) return false;
+  if (lda % 4 || ldw % 4 || K % 4) return false;                  // TMA: 16-byte global strides
+  if (((uintptr_t)A | (uintptr_t)W) & 15) return false;
+  if (M >= (int64_t)1 << 31) return false;
+  const int Npad = (int)((N + 15) / 16 * 16);
+  return tf32_stages(Npad, true) >= 2 && 2 * Npad <= 512;
+}
+
+size_t gemm_tf32x3_workspace_floats(int64_t N, int64_t K) { return 2 * (size_t)N * (size_t)K + 64; }
+
+// C[M,N] = A[M,K] . W[N,K]^T, fp32 operands, fp32 accumulate; workspace >= gemm_tf32x3_workspace_floats(N, K) floats
+int gemm_tf32x3_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int c_dtype, int64_t ld_c,
+                         int64_t M, int64_t N, int64_t K, const float* bias, int accumulate,
+                         const int32_t* row_div_ptr, int64_t row_div_cols, float* workspace, cudaStream_t st,
+                         const void* addend, int64_t ld_add, int64_t add_col0, float* stats, int64_t stats_cols) {
+  const char* fn = "egnn_gemm(tcgen05 3xTF32)";
+  const int Npad = (int)((N + 15) / 16 * 16);
+  // dense [N, K] hi / lo copies of the weight (16-byte aligned halves of the workspace)
+  float* whi = reinterpret_cast<float*>(((uintptr_t)workspace + 15) & ~uintptr_t(15));
+  float* wlo = whi + ((N * K + 3) / 4) * 4;
+  if (ldw == K) {
+    split_tf32_kernel<<<(unsigned)ceil_div(N * K, 256), 256, 0, st>>>((const float*)W, N * K, whi, wlo);
+    EGNN_LAUNCH_CHECK(fn);
+  } else {
+    for (int64_t r = 0; r < N; ++r) {   // strided weight: row by row (rare; the layers pass dense weights)
+      split_tf32_kernel<<<(unsigned)ceil_div(K, 256), 256, 0, st>>>((const float*)W + r * ldw, K, whi + r * K, wlo + r * K);
+      EGNN_LAUNCH_CHECK(fn);
+    }
+  }
+  CUtensorMap tmA, tmWhi, tmWlo;
+  if (!make_map_f32(&tmA, A, M, K, lda, BM) || !make_map_f32(&tmWhi, whi, N, K, K, Npad) ||
+      !make_map_f32(&tmWlo, wlo, N, K, K, Npad))
+    return fail(fn, "cuTensorMapEncodeTiled failed");
+  const int stages = tf32_stages(Npad, stats != nullptr);
+  if (stages < 2) return fail(fn, "shared memory: shape does not fit");
+  const size_t stage = 2 * (size_t)kStageBytesA + 2 * (size_t)Npad * 128;
+  const size_t smem = stages * stage + 256 + 1088 + 1024 + (stats ? kStatsSmem : 0) + 64;
+  static bool attr_set = false;
+  if (!attr_set) {
+#define EGNN_TF32_ATTR(S, C) \
+  cudaFuncSetAttribute(gemm_tn_tf32x3_kernel<S, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmemTN)
+    EGNN_TF32_ATTR(4, 2); EGNN_TF32_ATTR(3, 2); EGNN_TF32_ATTR(2, 2);
+    EGNN_TF32_ATTR(4, 6); EGNN_TF32_ATTR(3, 6); EGNN_TF32_ATTR(2, 6);
+#undef EGNN_TF32_ATTR
+    attr_set = true;
+  }
+  const int n_tiles = (int)((M + BM - 1) / BM);
+  const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
+  Epilogue ep{C, bias, row_div_ptr, ld_c, c_dtype, accumulate, (int)row_div_cols, addend, ld_add, (int)add_col0,
+              stats, (int)stats_cols};
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("EGNN_TF32_DEBUG"); dbg = e ? atoi(e) : 0; }
+#define EGNN_TF32_LAUNCH(S, C)                                                                                  \
+  gemm_tn_tf32x3_kernel<S, C><<<grid, kThreadsTN + (C - 2) * 32, smem, st>>>(tmA, tmWhi, tmWlo, (int)M, (int)N, Npad, \
+                                                                             (int)K, ep, dbg)
+  if (stats) {   // statistics epilogue: the 384-thread variant
+    if (stages == 4) EGNN_TF32_LAUNCH(4, 2); else if (stages == 3) EGNN_TF32_LAUNCH(3, 2); else EGNN_TF32_LAUNCH(2, 2);
+  } else {
+    if (stages == 4) EGNN_TF32_LAUNCH(4, 6); else if (stages == 3) EGNN_TF32_LAUNCH(3, 6); else EGNN_TF32_LAUNCH(2, 6);
+  }
+#undef EGNN_TF32_LAUNCH
+  EGNN_LAUNCH_CHECK(fn);
+  return 0;
+}
+
+// phases (= partials) per CTA of the fp32 wgrad: accumulation chains of at most ~352 rows (132 tensor-core adds)
+constexpr int kMaxPhases32 = 8;
+static int wgrad32_phases(int64_t M_rows) {
+  const int64_t rows_per_cta = (M_rows + kNumSMs - 1) / kNumSMs;
+  int64_t P = (rows_per_cta + 351) / 352;
+  return (int)(P < 1 ? 1 : (P > kMaxPhases32 ? kMaxPhases32 : P));
+}
+
+static int wgrad32_stages(int XB, int GB) {
+  const size_t stage = 2 * (size_t)(XB + GB) * kBlk32;
+  int st = 6;
+  while (st > 1 && st * stage + 256 + 1024 > 227 * 1024) --st;
+  return st;
+}
+
+bool wgrad_tf32x3_supported(const void* G, int64_t ldg, const void* X, int64_t ldx, int64_t M_rows, int64_t N_out,
+                            int64_t K_in) {
+  if (N_out < 8 || N_out > 256 || K_in < 8 || K_in > 384 || M_rows < 1 || M_rows >= (int64_t)1 << 31) return false;
+  if (ldg % 4 || ldx % 4 || N_out % 4 || K_in % 4) return false;
+  if (((uintptr_t)G | (uintptr_t)X) & 15) return false;
+  const int Nopad = (int)((N_out + 15) / 16 * 16);
+  const int MT = (int)((K_in + 127) / 128);
+  return wgrad32_stages(MT * 4, (Nopad + 31) / 32) >= 2 && MT * Nopad <= 512;
+}
+
+// dW[N_out, K_in] (fp32 dense) = G[M, N_out]^T X[M, K_in], fp32 operands; workspace >= wgrad_tcgen05_workspace_floats
+int wgrad_tf32x3_dispatch(const void* G, int64_t ldg, const void* X, int64_t ldx, float* dW, int64_t M_rows,
+                          int64_t N_out, int64_t K_in, int accumulate, float* workspace, cudaStream_t st) {
+  const char* fn = "egnn_gemm(tcgen05 3xTF32 wgrad)";
+  const int Nopad = (int)((N_out + 15) / 16 * 16);
+  const int MT = (int)((K_in + 127) / 128);
+  const int XB = MT * 4, GB = (Nopad + 31) / 32;
+  CUtensorMap tmX, tmG;
+  if (!make_map_f32(&tmX, X, M_rows, K_in, ldx, kSlab32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||
+      !make_map_f32(&tmG, G, M_rows, N_out, ldg, kSlab32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
+    return fail(fn, "cuTensorMapEncodeTiled failed");
+  const int stages = wgrad32_stages(XB, GB);
+  const size_t smem = (size_t)stages * 2 * (XB + GB) * kBlk32 + 256 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(gemm_wgrad_tf32x3_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(gemm_wgrad_tf32x3_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(gemm_wgrad_tf32x3_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(gemm_wgrad_tf32x3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_set = true;
+  }
+  const int n_slabs = (int)((M_rows + kSlab32 - 1) / kSlab32);
+  const int grid = n_slabs < kNumSMs ? n_slabs : kNumSMs;
+  const int P = wgrad32_phases(M_rows);
+  if (stages >= 6)
+    gemm_wgrad_tf32x3_kernel<6><<<grid, kThreadsWG32, smem, st>>>(tmX, tmG, (int)M_rows, (int)N_out, Nopad, (int)K_in, P, workspace);
+  else if (stages >= 4)
+    gemm_wgrad_tf32x3_kernel<4><<<grid, kThreadsWG32, (size_t)4 * 2 * (XB + GB) * kBlk32 + 256 + 1024, st>>>(
+        tmX, tmG, (int)M_rows, (int)N_out, Nopad, (int)K_in, P, workspace);
+  else if (stages == 3)
+    gemm_wgrad_tf32x3_kernel<3><<<grid, kThreadsWG32, smem, st>>>(tmX, tmG, (int)M_rows, (int)N_out, Nopad, (int)K_in, P, workspace);
+  else
+    gemm_wgrad_tf32x3_kernel<2><<<grid, kThreadsWG32, smem, st>>>(tmX, tmG, (int)M_rows, (int)N_out, Nopad, (int)K_in, P, workspace);
+  EGNN_LAUNCH_CHECK(fn);
+  const int64_t n_elem = N_out * K_in;
+  wgrad_reduce_kernel<<<(unsigned)ceil_div(n_elem, 64), 256, 0, st>>>(workspace, grid * P, n_elem, dW, accumulate);
+  EGNN_LAUNCH_CHECK(fn);
+  return 0;
+}
+
+size_t wgrad_tcgen05_workspace_floats(int64_t N_out, int64_t K_in) {
+  return (size_t)kNumSMs * kMaxPhases32 * N_out * K_in;   // (the fp32 kernel writes up to kMaxPhases32 partials per CTA)
+}
 
 bool wgrad_tcgen05_supported(const void* G, int64_t ldg, const void* X, int64_t ldx, int64_t M_rows, int64_t N_out,
                              int64_t K_in) {

@@ -270,6 +270,72 @@ int radix_sort_perm(const int* keys, const int* n_ptr, int64_t cap, int bits, Wo
   return 0;
 }
 
+
+// ---- re-entrant graph variants ------------------------------------------------------------------
+// Hub ablation (src/train_gnn.py:526-540, src/analysis/hub_ablation.py:56-71): deg = bincount(src) + bincount(dst);
+// hubs = the num_hubs nodes of largest degree; keep the edges touching no hub, in their original order.  The reference
+// round-trips the edge list through the CPU (`.cpu()`, torch.topk, boolean-mask indexing); here: degree histogram
+// (integer atomics) -> stable radix sort of (max_deg - deg) -> the first num_hubs nodes -> edge flags -> exclusive scan
+// -> stable compaction.  Ties at the k-th degree: LOWER node id first (torch.topk leaves ties unspecified -- its CPU
+// kernel switches between partial_sort and nth_element with n and k -- so the hub set equals the reference's whenever
+// the k-th and (k+1)-th largest degrees differ, and is the stable-sort choice otherwise).
+__global__ void __launch_bounds__(kThreads) abl_degree(const int64_t* __restrict__ ei, int64_t E, int64_t n_nodes,
+                                                       int* __restrict__ deg, int* __restrict__ n_bad) {
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= E) return;
+  const int64_t s = ei[i], d = ei[E + i];
+  if (s < 0 || s >= n_nodes || d < 0 || d >= n_nodes) {
+    atomicAdd(n_bad, 1);
+    return;
+  }
+  atomicAdd(deg + s, 1);
+  atomicAdd(deg + d, 1);
+}
+__global__ void __launch_bounds__(kThreads) abl_keys(const int* __restrict__ deg, int64_t n_nodes, int max_key,
+                                                     int* __restrict__ keys, int* __restrict__ n_dev) {
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i == 0) *n_dev = (int)n_nodes;
+  if (i < n_nodes) keys[i] = max_key - deg[i];   // ascending key = descending degree; the sort is stable in node id
+}
+__global__ void __launch_bounds__(kThreads) abl_mark(const int* __restrict__ perm, int64_t num_hubs,
+                                                     uint8_t* __restrict__ hub) {
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i < num_hubs) hub[perm[i]] = 1;
+}
+__global__ void __launch_bounds__(kThreads) abl_flags(const int64_t* __restrict__ ei, int64_t E, int64_t n_nodes,
+                                                      const uint8_t* __restrict__ hub, int* __restrict__ keep) {
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= E) return;
+  const int64_t s = ei[i], d = ei[E + i];
+  const bool ok = s >= 0 && s < n_nodes && d >= 0 && d < n_nodes;
+  keep[i] = (ok && !(hub[s] | hub[d])) ? 1 : 0;
+}
+__global__ void __launch_bounds__(kThreads) abl_compact(const int64_t* __restrict__ ei, int64_t E,
+                                                        const int* __restrict__ keep, const int* __restrict__ pos,
+                                                        int64_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= E || !keep[i]) return;
+  const int p = pos[i];
+  out[p] = ei[i];
+  out[E + p] = ei[E + i];
+}
+// Random edge drop (src/analysis/robustness.py:65-82): out[:, j] = ei[:, idx[j]] with idx = perm[drop_count:]
+__global__ void __launch_bounds__(kThreads) edge_gather(const int64_t* __restrict__ ei, int64_t E,
+                                                        const int64_t* __restrict__ idx, int64_t n_idx,
+                                                        int64_t* __restrict__ out, int* __restrict__ n_bad) {
+  const int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (j >= n_idx) return;
+  const int64_t i = idx[j];
+  if (i < 0 || i >= E) {
+    atomicAdd(n_bad, 1);
+    out[j] = 0;
+    out[n_idx + j] = 0;
+    return;
+  }
+  out[j] = ei[i];
+  out[n_idx + j] = ei[E + i];
+}
+
 // byte-wise comparison of two device buffers (train.HostFeed: rebuild the sorted views only when the edge list a
 // caller submits really differs from the one they were built from)
 __global__ void __launch_bounds__(kThreads) buffers_differ_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b,
@@ -308,6 +374,68 @@ extern "C" int egnn_buffers_differ(const void* a, const void* b, int64_t n_bytes
   buffers_differ_kernel<<<(unsigned)blocks, kThreads, 0, st>>>(
       reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b), n16,
       reinterpret_cast<const uint8_t*>(a) + 16 * n16, reinterpret_cast<const uint8_t*>(b) + 16 * n16, tail, flag);
+  EGNN_LAUNCH_CHECK(fn);
+  return 0;
+}
+
+extern "C" size_t egnn_hub_ablation_workspace_bytes(int64_t n_nodes, int64_t n_edges) {
+  Workspace w = carve(nullptr, n_nodes, n_edges, n_edges > 0 ? n_edges : 1);
+  return w.bytes + 256;
+}
+
+extern "C" int egnn_hub_ablation(const int64_t* ei, int64_t E, int64_t n_nodes, int64_t num_hubs, int64_t* ei_out,
+                                 int32_t* info, uint8_t* hub_mask, int32_t* deg_out, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  const char* fn = "egnn_hub_ablation";
+  EGNN_REQUIRE(n_nodes > 0 && E >= 0 && num_hubs >= 0 && num_hubs <= n_nodes, fn, "bad sizes");
+  EGNN_REQUIRE((E == 0 || (ei && ei_out)) && info && hub_mask && workspace, fn, "null pointer");
+  EGNN_REQUIRE(2 * E < (int64_t)2147483647 && n_nodes < (int64_t)2147483647, fn, "graph too large for int32 indices");
+  EGNN_REQUIRE(workspace_bytes >= egnn_hub_ablation_workspace_bytes(n_nodes, E), fn, "workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  char* base = reinterpret_cast<char*>(((uintptr_t)workspace + 255) & ~uintptr_t(255));
+  Workspace w = carve(base, n_nodes, E, E > 0 ? E : 1);
+  int* deg = deg_out ? deg_out : w.counts;
+  cudaMemsetAsync(deg, 0, sizeof(int) * (size_t)n_nodes, st);
+  cudaMemsetAsync(info, 0, sizeof(int) * 2, st);
+  cudaMemsetAsync(hub_mask, 0, (size_t)n_nodes, st);
+  const unsigned gE = (unsigned)ceil_div(E > 0 ? E : 1, kThreads), gN = (unsigned)ceil_div(n_nodes, kThreads);
+  if (E > 0) {
+    abl_degree<<<gE, kThreads, 0, st>>>(ei, E, n_nodes, deg, info + 1);
+    EGNN_LAUNCH_CHECK(fn);
+  }
+  if (num_hubs > 0) {
+    const int max_key = (int)(2 * E);
+    int bits = 1;
+    while (((int64_t)1 << bits) <= max_key) ++bits;
+    bits = (bits + 7) / 8 * 8;
+    abl_keys<<<gN, kThreads, 0, st>>>(deg, n_nodes, max_key, w.deg_keys, w.n_dev);
+    EGNN_LAUNCH_CHECK(fn);
+    int* perm = nullptr;
+    int rc = radix_sort_perm(w.deg_keys, w.n_dev, n_nodes, bits, w, &perm, st);
+    if (rc) return rc;
+    abl_mark<<<(unsigned)ceil_div(num_hubs, kThreads), kThreads, 0, st>>>(perm, num_hubs, hub_mask);
+    EGNN_LAUNCH_CHECK(fn);
+  }
+  if (E > 0) {
+    abl_flags<<<gE, kThreads, 0, st>>>(ei, E, n_nodes, hub_mask, w.keep);
+    EGNN_LAUNCH_CHECK(fn);
+    int rc = exclusive_scan(w.keep, w.inv, E, w.tile_sums, info, st);   // info[0] = edges kept
+    if (rc) return rc;
+    abl_compact<<<gE, kThreads, 0, st>>>(ei, E, w.keep, w.inv, ei_out);
+    EGNN_LAUNCH_CHECK(fn);
+  }
+  return 0;
+}
+
+extern "C" int egnn_edge_gather(const int64_t* ei, int64_t E, const int64_t* idx, int64_t n_idx, int64_t* out,
+                                int32_t* n_bad, void* stream) {
+  const char* fn = "egnn_edge_gather";
+  EGNN_REQUIRE(n_idx >= 0 && E >= 0 && n_bad, fn, "bad sizes");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(n_bad, 0, sizeof(int), st);
+  if (n_idx == 0) return 0;
+  EGNN_REQUIRE(ei && idx && out, fn, "null pointer");
+  edge_gather<<<(unsigned)ceil_div(n_idx, kThreads), kThreads, 0, st>>>(ei, E, idx, n_idx, out, n_bad);
   EGNN_LAUNCH_CHECK(fn);
   return 0;
 }

@@ -162,3 +162,59 @@ def cached_graph(edge_index: torch.Tensor, num_nodes: int, self_loops: bool = Fa
 
 def register_graph(edge_index: torch.Tensor, num_nodes: int, g: Graph, self_loops: bool = False) -> None:
     _GLOBAL_CACHE.put(edge_index, num_nodes, self_loops, g)
+
+
+def ablate_hubs(edge_index: torch.Tensor, num_nodes: int, frac: float):
+    """`build_edge_index_ablated` (`/root/reference/src/analysis/hub_ablation.py:56-71`, `src/train_gnn.py:526-540`) on
+    the device: remove every edge touching one of the `int(frac * num_nodes)` highest-degree nodes (degree = out + in
+    over the given edge list), keeping the original edge order.  The edge list never leaves the GPU (the reference
+    moves it to the CPU and back); the host reads back ONE int, the number of edges kept, to size the result.
+    Returns (edge_index_ablated [2, E_kept] int64, num_hubs, hub_mask bool [N]).  Ties at the k-th degree: lower node
+    id first (see `egnn_hub_ablation`)."""
+    if edge_index.dim() != 2 or edge_index.size(0) != 2 or edge_index.dtype != torch.int64:
+        raise TypeError("edge_index must be int64 [2, E]")
+    if not edge_index.is_cuda:
+        raise RuntimeError("egnn_b200 ablates hubs on the GPU only (no CPU fallback)")
+    ei = edge_index.contiguous()
+    dev = ei.device
+    E, N = int(ei.size(1)), int(num_nodes)
+    num_hubs = int(float(frac) * float(N))
+    L = lib()
+    out = torch.empty((2, max(E, 1)), dtype=torch.int64, device=dev)
+    info = torch.empty(2, dtype=torch.int32, device=dev)
+    hub = torch.empty(N, dtype=torch.uint8, device=dev)
+    ws_bytes = L.egnn_hub_ablation_workspace_bytes(N, E)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    check(L.egnn_hub_ablation(ptr(ei), E, N, num_hubs, ptr(out), ptr(info), ptr(hub), None, ptr(ws), ws_bytes, stream()))
+    kept, bad = (int(v) for v in info.tolist())
+    if bad:
+        raise IndexError(f"edge_index holds {bad} edges with node ids outside [0, {N})")
+    # rows of `out` are E apart: the kept columns as a [2, kept] tensor (contiguous copy of 16 * kept bytes)
+    return out[:, :kept].contiguous() if E > 0 else out[:, :0], num_hubs, hub.bool()
+
+
+def drop_edges(edge_index: torch.Tensor, drop_frac: float, perm: Optional[torch.Tensor] = None):
+    """`drop_edges` (`/root/reference/src/analysis/robustness.py:65-82`): `edge_index[:, perm[drop_count:]]` with
+    `perm = torch.randperm(E, device=...)` unless given (bit-exact for the same permutation).  Same argument checks and
+    return convention as the reference: (edge_index_kept, drop_count)."""
+    drop_frac = float(drop_frac)
+    if drop_frac < 0 or drop_frac > 1:
+        raise ValueError("drop_frac must be within [0, 1]")
+    if drop_frac <= 0:
+        return edge_index, 0
+    if not edge_index.is_cuda:
+        raise RuntimeError("egnn_b200 drops edges on the GPU only (no CPU fallback)")
+    E = int(edge_index.size(1))
+    drop_count = min(int(round(drop_frac * float(E))), E)
+    if drop_count == 0:
+        return edge_index, 0
+    if drop_count >= E:
+        raise RuntimeError("Dropping all edges would leave an empty graph.")
+    if perm is None:
+        perm = torch.randperm(E, device=edge_index.device)
+    keep_idx = perm[drop_count:].contiguous()
+    ei = edge_index.contiguous()
+    out = torch.empty((2, keep_idx.numel()), dtype=torch.int64, device=ei.device)
+    bad = torch.empty(1, dtype=torch.int32, device=ei.device)
+    check(lib().egnn_edge_gather(ptr(ei), E, ptr(keep_idx), keep_idx.numel(), ptr(out), ptr(bad), stream()))
+    return out, drop_count

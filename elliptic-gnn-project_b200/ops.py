@@ -138,7 +138,8 @@ GEMM_IMPL = 0  # 0 auto (tcgen05 for bf16 where supported), 1 force SIMT, 2 forc
 def _gemm(A, a_sm, a_sk, B, b_sk, b_sn, C, M, N, K, bias, accumulate, split_k=1, impl=None, row_div=None,
           need_ws=False, row_div_cols=0):
     L = lib()
-    nws = L.egnn_gemm_workspace_floats(M, N, K, split_k) if (need_ws or split_k > 1 or M <= 8) else 0
+    f32_tc = A.dtype == torch.float32 and B.dtype == torch.float32 and a_sk == 1 and b_sk == 1 and M >= 1024
+    nws = L.egnn_gemm_workspace_floats(M, N, K, split_k) if (need_ws or split_k > 1 or M <= 8 or f32_tc) else 0
     ws = torch.empty(nws, dtype=torch.float32, device=C.device) if nws else None
     check(L.egnn_gemm(ptr(A), dt(A), a_sm, a_sk, ptr(B), dt(B), b_sk, b_sn, ptr(C), dt(C), _ld(C), M, N, K,
                       ptr(bias), ptr(row_div), int(row_div_cols), int(accumulate), split_k, ptr(ws),

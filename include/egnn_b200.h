@@ -89,6 +89,21 @@ int egnn_graph_build(const int64_t* ei, int64_t n_edges_in, int64_t n_nodes, int
                      int64_t* ei2, float* dis, float* w_edge, float* w_csr, float* w_csc,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* Hub ablation on the device (src/train_gnn.py:526-540, src/analysis/hub_ablation.py:56-71):
+ *   deg = bincount(src) + bincount(dst); hubs = the num_hubs nodes of largest degree; kept = edges touching no hub,
+ *   ORIGINAL order preserved.  ei int64 [2, E] contiguous; ei_out int64 [2, E] (row stride E, first info[0] columns
+ *   valid); info int32 [2] = {edges kept, out-of-range node ids}; hub_mask uint8 [N]; deg_out int32 [N] or NULL.
+ *   Ties at the k-th largest degree are resolved towards the LOWER node id (a stable descending sort); torch.topk
+ *   leaves them unspecified, so the hub set equals the reference's whenever the k-th and (k+1)-th degrees differ.
+ * egnn_edge_gather: out[:, j] = ei[:, idx[j]]  (random edge drop `edge_index[:, perm[drop_count:]]`,
+ *   src/analysis/robustness.py:65-82; out int64 [2, n_idx]); n_bad counts indices outside [0, E). */
+size_t egnn_hub_ablation_workspace_bytes(int64_t n_nodes, int64_t n_edges);
+int egnn_hub_ablation(const int64_t* ei, int64_t n_edges, int64_t n_nodes, int64_t num_hubs, int64_t* ei_out,
+                      int32_t* info, uint8_t* hub_mask, int32_t* deg_out, void* workspace, size_t workspace_bytes,
+                      void* stream);
+int egnn_edge_gather(const int64_t* ei, int64_t n_edges, const int64_t* idx, int64_t n_idx, int64_t* out,
+                     int32_t* n_bad, void* stream);
+
 /* *flag = 1 when the two device buffers differ in any byte, else 0 (both 16-byte aligned).  train.HostFeed uses it
  * to rebuild the sorted views only when a submitted edge_index differs from the one they were built from (the
  * reference builds nothing per step: `data.to(device)` once, src/train_gnn.py:350). */

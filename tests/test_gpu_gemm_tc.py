@@ -83,3 +83,64 @@ def test_unsupported_layout_fails_loudly(egnn):
         ops.linear_fwd(a, w, impl=2)  # lda = 30 is not a multiple of 8 (TMA needs 16-byte strides)
     out = ops.linear_fwd(a, w)        # auto falls back to the SIMT *CUDA* kernel, never to CPU
     assert_close(out.float(), a.double() @ w.double().t(), 2 ** -7, "auto")
+
+
+# ---- fp32 operands on the tensor cores: 3xTF32 ---------------------------------------------------
+TOL_F32 = 5e-6   # rel ||ref||_inf vs fp64: a.w ~= a_lo.w_hi + a_hi.w_lo + a_hi.w_hi, fp32 accumulate (north_star bar: 1e-5)
+
+
+def _mk32(shape, seed, heavy=False):
+    g = torch.Generator().manual_seed(seed)
+    t = torch.randn(shape, generator=g)
+    if heavy:   # a few columns with outliers, like the standardised Elliptic features
+        t[:, ::17] *= torch.exp(0.75 * torch.randn((shape[0], t[:, ::17].shape[1]), generator=g))
+    return t.cuda()
+
+
+@pytest.mark.parametrize("M", [1024, 1025, 5000, 203769])
+@pytest.mark.parametrize("K,N", [(168, 64), (64, 64), (336, 128), (128, 128), (64, 168), (128, 256), (40, 32), (12, 8)])
+def test_fp32_tn_3xtf32_matches_fp64(egnn, M, K, N):
+    from egnn_b200 import ops
+    if M == 203769 and (K, N) not in ((168, 64), (336, 128)):
+        pytest.skip("full-size case kept to the bench shapes")
+    a, w = _mk32((M, K), 11, heavy=True), _mk32((N, K), 12) / K ** 0.5
+    ref = a.double() @ w.double().t()
+    out = ops.linear_fwd(a, w)                       # auto: 3xTF32 tcgen05 kernel for M >= 1024
+    assert_close(out, ref, TOL_F32, "3xTF32 fwd")
+    out_simt = ops.linear_fwd(a, w, impl=1)          # FFMA kernel
+    assert_close(out_simt, ref, TOL_F32, "SIMT fwd")
+    assert torch.equal(out, ops.linear_fwd(a, w))    # deterministic
+    bias = torch.randn(N, device="cuda")
+    outb = ops.linear_fwd(a, w, bias=bias)
+    assert_close(outb, ref + bias.double(), TOL_F32, "3xTF32 fwd + bias")
+    base = torch.randn(M, N, device="cuda")
+    acc = base.clone()
+    ops.linear_fwd(a, w, out=acc, accumulate=True)
+    assert_close(acc, base.double() + ref, TOL_F32, "3xTF32 accumulate")
+
+
+def test_fp32_dgrad_row_div_3xtf32(egnn):
+    from egnn_b200 import ops
+    M, K, N = 6000, 168, 64
+    cnt = torch.randint(0, 5, (M,))
+    ptr = torch.zeros(M + 1, dtype=torch.int32)
+    ptr[1:] = torch.cumsum(cnt, 0)
+    g, wt = _mk32((M, N), 13), _mk32((N, K), 14)
+    d = ops.linear_dgrad(g, wt, row_div=ptr.cuda())
+    refd = (g.double() @ wt.double()) / cnt.clamp(min=1).double().cuda().unsqueeze(1)
+    assert_close(d, refd, TOL_F32, "3xTF32 dgrad + row_div")
+
+
+@pytest.mark.parametrize("M", [1024, 1031, 6000, 203769])
+@pytest.mark.parametrize("N,K", [(64, 168), (64, 64), (128, 128), (8, 64), (32, 168), (64, 336), (128, 336), (64, 384),
+                                 (16, 40), (256, 128)])
+def test_fp32_wgrad_3xtf32_matches_fp64(egnn, M, N, K):
+    from egnn_b200 import ops
+    if M == 203769 and (N, K) not in ((64, 168), (64, 336), (128, 128)):
+        pytest.skip("full-size case kept to the bench shapes")
+    g, x = _mk32((M, N), 21), _mk32((M, K), 22, heavy=True)
+    ref = g.double().t() @ x.double()
+    out = ops.linear_wgrad(g, x)                     # auto: 3xTF32 tcgen05 wgrad for M >= 1024
+    assert_close(out, ref, TOL_F32, "3xTF32 wgrad")
+    assert torch.equal(out, ops.linear_wgrad(g, x))  # deterministic partial reduction
+    assert_close(ops.linear_wgrad(g, x, impl=1), ref, TOL_F32, "SIMT wgrad")
