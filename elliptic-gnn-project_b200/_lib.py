@@ -51,13 +51,15 @@ SIGNATURES = {
     "egnn_gemm": (_i32, [_vp, _i32, _i64, _i64, _vp, _i32, _i64, _i64, _vp, _i32, _i64, _i64, _i64, _i64,
                          _vp, _vp, _i64, _i32, _i32, _vp, _i32, _vp]),
     "egnn_linear_stats_parts": (_i64, [_i64]),
+    "egnn_linear_tc_workspace_floats": (_sz, [_i32, _i64, _i64]),
     "egnn_linear_tc": (_i32, [_vp, _i64, _vp, _i64, _vp, _i32, _i64, _i64, _i64, _i64, _vp, _vp, _i64, _i32, _vp, _i64,
-                              _i64, _vp, _i64, _vp]),
+                              _i64, _vp, _i64, _i32, _vp, _vp]),
     "egnn_wgrad_tc_workspace_floats": (_sz, [_i64, _i64]),
-    "egnn_wgrad_tc": (_i32, [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _vp]),
+    "egnn_wgrad_tc": (_i32, [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i32, _vp,
+                             _vp]),
     "egnn_colstats_reduce": (_i32, [_vp, _i64, _i64, _vp, _vp]),
     "egnn_bn_finalize_parts": (_i32, [_vp, _i64, _i64, _f64, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "egnn_pack_sage_weights": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "egnn_pack_sage_weights": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _i32, _vp]),
     "egnn_f64_to_f32": (_i32, [_vp, _vp, _i64, _vp]),
     "egnn_cast": (_i32, [_vp, _i32, _i64, _vp, _i32, _i64, _i64, _i64, _vp]),
     "egnn_inject_time": (_i32, [_vp, _i64, _vp, _vp, _i64, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _vp]),

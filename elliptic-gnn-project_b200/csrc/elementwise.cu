@@ -1377,10 +1377,11 @@ extern "C" int egnn_cast(const void* in, int in_dtype, int64_t ld_in, void* out,
 }
 
 // out[r, :] (bf16, [No + Nr, 2*Kp]) = r < No ? [w_l[r] | 0 | w_r[r] | 0] : [0 | w_res[r - No] | 0];  bias_out = [b_l | 0]
+template <typename TO>
 __global__ void __launch_bounds__(kThreads) pack_sage_weights_kernel(
     const float* __restrict__ w_l, const float* __restrict__ w_r, const float* __restrict__ w_res,
-    const float* __restrict__ b_l, int No, int Nr, int K, int Kp, __nv_bfloat16* __restrict__ out,
-    float* __restrict__ bias_out, __nv_bfloat16* __restrict__ out_t) {
+    const float* __restrict__ b_l, int No, int Nr, int K, int Kp, TO* __restrict__ out,
+    float* __restrict__ bias_out, TO* __restrict__ out_t) {
   const int i = blockIdx.x * kThreads + threadIdx.x;
   const int W = 2 * Kp;
   if (i < No + Nr && bias_out) bias_out[i] = (i < No && b_l) ? b_l[i] : 0.f;
@@ -1392,21 +1393,27 @@ __global__ void __launch_bounds__(kThreads) pack_sage_weights_kernel(
     if (r < No) v = half ? w_r[r * K + k] : w_l[r * K + k];
     else if (half) v = w_res[(r - No) * K + k];
   }
-  out[i] = __float2bfloat16_rn(v);
+  out[i] = from_f32<TO>(v);
   // [W_l | W_r]^T  ([2*Kp, No]): the contraction-contiguous B operand of the concatenated dgrad GEMM
-  if (out_t && r < No) out_t[(size_t)c * No + r] = __float2bfloat16_rn(v);
+  if (out_t && r < No) out_t[(size_t)c * No + r] = from_f32<TO>(v);
 }
 
 extern "C" int egnn_pack_sage_weights(const float* w_l, const float* w_r, const float* w_res, const float* b_l,
                                       int64_t n_out, int64_t n_res, int64_t K, int64_t K_padded, void* out_bf16,
-                                      float* bias_out, void* out_t_bf16, void* stream) {
+                                      float* bias_out, void* out_t_bf16, int out_dtype, void* stream) {
   const char* fn = "egnn_pack_sage_weights";
   EGNN_REQUIRE(w_l && w_r && out_bf16 && (n_res == 0 || w_res), fn, "null pointer");
+  EGNN_REQUIRE(out_dtype == EGNN_BF16 || out_dtype == EGNN_F32, fn, "bad output dtype");
   EGNN_REQUIRE(n_out > 0 && K > 0 && K_padded >= K && (n_out + n_res) * 2 * K_padded < (1 << 30), fn, "bad shape");
   const int64_t total = (n_out + n_res) * 2 * K_padded;
-  pack_sage_weights_kernel<<<(unsigned)ceil_div(total, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
-      w_l, w_r, w_res, b_l, (int)n_out, (int)n_res, (int)K, (int)K_padded, (__nv_bfloat16*)out_bf16, bias_out,
-      (__nv_bfloat16*)out_t_bf16);
+  if (out_dtype == EGNN_BF16)
+    pack_sage_weights_kernel<__nv_bfloat16><<<(unsigned)ceil_div(total, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        w_l, w_r, w_res, b_l, (int)n_out, (int)n_res, (int)K, (int)K_padded, (__nv_bfloat16*)out_bf16, bias_out,
+        (__nv_bfloat16*)out_t_bf16);
+  else
+    pack_sage_weights_kernel<float><<<(unsigned)ceil_div(total, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        w_l, w_r, w_res, b_l, (int)n_out, (int)n_res, (int)K, (int)K_padded, (float*)out_bf16, bias_out,
+        (float*)out_t_bf16);
   EGNN_LAUNCH_CHECK(fn);
   return 0;
 }

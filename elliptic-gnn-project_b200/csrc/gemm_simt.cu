@@ -399,7 +399,8 @@ int gemm_tf32x3_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw,
 bool wgrad_tf32x3_supported(const void* G, int64_t ldg, const void* X, int64_t ldx, int64_t M_rows, int64_t N_out,
                             int64_t K_in);
 int wgrad_tf32x3_dispatch(const void* G, int64_t ldg, const void* X, int64_t ldx, float* dW, int64_t M_rows,
-                          int64_t N_out, int64_t K_in, int accumulate, float* workspace, cudaStream_t st);
+                          int64_t N_out, int64_t K_in, int accumulate, float* workspace, cudaStream_t st,
+                          float* dst1 = nullptr, int64_t split = 0, int64_t valid = 0);
 bool gemm_tcgen05_epilogue_supported(bool bias, bool row_div, bool accumulate, bool addend, bool stats, int64_t stats_cols,
                                      int64_t add_col0);
 int64_t gemm_tcgen05_stats_parts(int64_t M);
@@ -419,12 +420,30 @@ using namespace egnn;
 // C[M,N] = A[M,K] . W[N,K]^T on the tcgen05 kernel with the fused layer epilogues (bf16 operands, both K-major).
 extern "C" int64_t egnn_linear_stats_parts(int64_t M) { return gemm_tcgen05_stats_parts(M); }
 
+extern "C" size_t egnn_linear_tc_workspace_floats(int ab_dtype, int64_t N, int64_t K) {
+  return ab_dtype == EGNN_F32 ? gemm_tf32x3_workspace_floats(N, K) : 0;
+}
+
 extern "C" int egnn_linear_tc(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int c_dtype, int64_t ld_c,
                               int64_t M, int64_t N, int64_t K, const float* bias, const int32_t* row_div_ptr,
                               int64_t row_div_cols, int accumulate, const void* addend, int64_t ld_addend,
-                              int64_t addend_col0, float* colstats, int64_t colstats_cols, void* stream) {
+                              int64_t addend_col0, float* colstats, int64_t colstats_cols, int ab_dtype,
+                              float* workspace, void* stream) {
   const char* fn = "egnn_linear_tc";
   EGNN_REQUIRE(A && W && C, fn, "null pointer");
+  EGNN_REQUIRE(ab_dtype == EGNN_BF16 || ab_dtype == EGNN_F32, fn, "bad operand dtype");
+  if (ab_dtype == EGNN_F32) {   // fp32 operands: 3xTF32, same epilogues
+    EGNN_REQUIRE(M >= 0 && N > 0 && K > 0 && ld_c >= N && workspace, fn, "bad shape / missing workspace");
+    EGNN_REQUIRE(!addend || (ld_addend >= N - addend_col0 && addend_col0 >= 0 && addend_col0 < N), fn, "bad addend range");
+    if (M == 0) return 0;
+    if (!gemm_tf32x3_supported(lda, ldw, M, N, K, A, W))
+      return fail(fn, "shape / alignment outside the 3xTF32 kernel (8 <= N <= 256, K % 4 == 0, 16-byte rows)");
+    if (!gemm_tcgen05_epilogue_supported(bias != nullptr, row_div_ptr != nullptr, accumulate != 0, addend != nullptr,
+                                         colstats != nullptr, colstats_cols, addend_col0))
+      return fail(fn, "epilogue combination not compiled in");
+    return gemm_tf32x3_dispatch(A, lda, W, ldw, C, c_dtype, ld_c, M, N, K, bias, accumulate, row_div_ptr, row_div_cols,
+                                workspace, (cudaStream_t)stream, addend, ld_addend, addend_col0, colstats, colstats_cols);
+  }
   EGNN_REQUIRE(M >= 0 && N > 0 && K > 0 && ld_c >= N, fn, "bad shape");
   EGNN_REQUIRE(c_dtype == EGNN_F32 || c_dtype == EGNN_BF16, fn, "bad output dtype");
   EGNN_REQUIRE(!addend || (ld_addend >= N - addend_col0 && addend_col0 >= 0 && addend_col0 < N), fn, "bad addend range");
@@ -446,10 +465,19 @@ extern "C" size_t egnn_wgrad_tc_workspace_floats(int64_t N_out, int64_t K_in) {
 }
 extern "C" int egnn_wgrad_tc(const void* G, int64_t ldg, const void* X, int64_t ldx, int64_t M, int64_t N_out,
                              int64_t K_in, float* dst0, float* dst1, int64_t split_col, int64_t valid_cols,
-                             const void* G2, int64_t ldg2, int64_t N2, float* dst2, float* workspace, void* stream) {
+                             const void* G2, int64_t ldg2, int64_t N2, float* dst2, int dtype, float* workspace,
+                             void* stream) {
   const char* fn = "egnn_wgrad_tc";
   EGNN_REQUIRE(G && X && dst0 && workspace, fn, "null pointer");
   EGNN_REQUIRE(M > 0 && split_col > 0 && split_col <= K_in && valid_cols > 0 && valid_cols <= split_col, fn, "bad split");
+  EGNN_REQUIRE(dtype == EGNN_BF16 || dtype == EGNN_F32, fn, "bad operand dtype");
+  if (dtype == EGNN_F32) {   // fp32 operands: 3xTF32 (one gradient operand per call)
+    EGNN_REQUIRE(!G2, fn, "the fp32 kernel takes one gradient operand");
+    if (!wgrad_tf32x3_supported(G, ldg, X, ldx, M, N_out, K_in))
+      return fail(fn, "shape / alignment outside the 3xTF32 wgrad kernel (N_out <= 256, K_in <= 384, 16-byte rows)");
+    return wgrad_tf32x3_dispatch(G, ldg, X, ldx, dst0, M, N_out, K_in, 0, workspace, (cudaStream_t)stream, dst1, split_col,
+                                 valid_cols);
+  }
   EGNN_REQUIRE(!G2 || (dst2 && N2 > 0 && N_out % 64 == 0 && ldg2 % 8 == 0 && (uintptr_t)G2 % 16 == 0 &&
                        2 * split_col == K_in),
                fn, "second gradient operand: N_out must be a multiple of 64, K_in = 2 * split_col, 16-byte rows");

@@ -1231,7 +1231,8 @@ bool wgrad_tf32x3_supported(const void* G, int64_t ldg, const void* X, int64_t l
 
 // dW[N_out, K_in] (fp32 dense) = G[M, N_out]^T X[M, K_in], fp32 operands; workspace >= wgrad_tcgen05_workspace_floats
 int wgrad_tf32x3_dispatch(const void* G, int64_t ldg, const void* X, int64_t ldx, float* dW, int64_t M_rows,
-                          int64_t N_out, int64_t K_in, int accumulate, float* workspace, cudaStream_t st) {
+                          int64_t N_out, int64_t K_in, int accumulate, float* workspace, cudaStream_t st, float* dst1,
+                          int64_t split, int64_t valid) {
   const char* fn = "egnn_gemm(tcgen05 3xTF32 wgrad)";
   const int Nopad = (int)((N_out + 15) / 16 * 16);
   const int MT = (int)((K_in + 127) / 128);
@@ -1264,7 +1265,12 @@ int wgrad_tf32x3_dispatch(const void* G, int64_t ldg, const void* X, int64_t ldx
     gemm_wgrad_tf32x3_kernel<2><<<grid, kThreadsWG32, smem, st>>>(tmX, tmG, (int)M_rows, (int)N_out, Nopad, (int)K_in, P, workspace);
   EGNN_LAUNCH_CHECK(fn);
   const int64_t n_elem = N_out * K_in;
-  wgrad_reduce_kernel<<<(unsigned)ceil_div(n_elem, 64), 256, 0, st>>>(workspace, grid * P, n_elem, dW, accumulate);
+  if (valid > 0)
+    wgrad_reduce_split_kernel<<<(unsigned)ceil_div(n_elem, 64), 256, 0, st>>>(workspace, grid * P, (int)N_out, (int)K_in,
+                                                                             dW, dst1, (int)split, (int)valid, 1 << 30,
+                                                                             nullptr);
+  else
+    wgrad_reduce_kernel<<<(unsigned)ceil_div(n_elem, 64), 256, 0, st>>>(workspace, grid * P, n_elem, dW, accumulate);
   EGNN_LAUNCH_CHECK(fn);
   return 0;
 }

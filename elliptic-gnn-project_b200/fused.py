@@ -1,4 +1,4 @@
-"""The SAGE-ResBN step as ONE explicit kernel sequence (forward and backward), bf16 autocast.
+"""The SAGE-ResBN step as ONE explicit kernel sequence (forward and backward), bf16 autocast or fp32.
 
 `/root/reference/src/models/gnn.py:182-194` composes, per hidden layer, PyG SAGEConv -> BatchNorm1d -> ReLU -> dropout
 -> `+ res_proj(h_in)`, and autograd replays it backwards op by op.  `ops.py` maps each of those ops to one
@@ -16,8 +16,9 @@ across them:
     hands in views of its flat gradient buffer), with no autograd bookkeeping kernels.
 
 `SageResBNFn` wraps the pair as a `torch.autograd.Function` for drop-in use (`loss.backward()`), `train.TrainStep`
-calls `forward` / `backward` directly.  Only shapes the tcgen05 kernels take are served (bf16 autocast, widths a
-multiple of 8, hidden <= 64 for the in-epilogue statistics); everything else keeps the per-op path of `ops.py`.
+calls `forward` / `backward` directly.  Only shapes the tcgen05 kernels take are served (widths a multiple of 8,
+hidden <= 128; bf16 operands under bf16 autocast, fp32 operands through the 3xTF32 kernels otherwise -- every
+`eval_split` forward is fp32, src/train_gnn.py:248-257); everything else keeps the per-op path of `ops.py`.
 """
 from __future__ import annotations
 
@@ -67,7 +68,7 @@ class StaticInputs:
 
     @staticmethod
     def _key(x, t, table, width):
-        k = (x.data_ptr(), tuple(x.shape), tuple(x.stride()), x._version, int(width))
+        k = (x.data_ptr(), tuple(x.shape), tuple(x.stride()), x._version, width)
         if t is not None:
             k += (t.data_ptr(), t._version, table.data_ptr(), table._version, tuple(table.shape))
         return k
@@ -96,7 +97,7 @@ STATIC_INPUTS = StaticInputs()
 
 def supported(net, x: torch.Tensor, bf16: bool) -> bool:
     """Shapes / modes the explicit path serves."""
-    if not bf16 or not x.is_cuda or x.dtype != torch.float32 or x.dim() != 2:
+    if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 2 or x.size(0) < 1024:
         return False
     H = net.convs[0].out_channels
     if H % 16 or H > 128 or net.in_dim > 248:        # 2H and 2K columns per GEMM: N <= 256, K <= 512
@@ -148,19 +149,24 @@ def _bn_stats_to_mean_rstd(parts, n_parts, F, n_total, bn, reducer, dev):
 def _linear_tc(A, W, out, bias=None, row_div=None, row_div_cols=0, addend=None, add_col0=0, stats=None, stats_cols=0):
     M, K = A.shape
     N = W.size(0)
-    check(lib().egnn_linear_tc(ptr(A), A.stride(0), ptr(W), W.stride(0), ptr(out), dt(out), out.stride(0), M, N, K,
-                               ptr(bias), ptr(row_div), int(row_div_cols), 0, ptr(addend),
-                               addend.stride(0) if addend is not None else 0, int(add_col0), ptr(stats),
-                               int(stats_cols), stream()))
+    L = lib()
+    nws = L.egnn_linear_tc_workspace_floats(dt(A), N, K)      # fp32 operands: room for the hi / lo split of W
+    ws = torch.empty(nws, dtype=torch.float32, device=A.device) if nws else None
+    check(L.egnn_linear_tc(ptr(A), A.stride(0), ptr(W), W.stride(0), ptr(out), dt(out), out.stride(0), M, N, K,
+                           ptr(bias), ptr(row_div), int(row_div_cols), 0, ptr(addend),
+                           addend.stride(0) if addend is not None else 0, int(add_col0), ptr(stats),
+                           int(stats_cols), dt(A), ptr(ws), stream()))
     return out
 
 
-def forward(net, x: torch.Tensor, g: Graph, t: Optional[torch.Tensor], training: bool, need_grad: bool):
-    """logits [N, C] fp32 and (when `need_grad`) the Saved state.  bf16 activations, fp32 statistics / logits."""
+def forward(net, x: torch.Tensor, g: Graph, t: Optional[torch.Tensor], training: bool, need_grad: bool,
+            bf16: bool = True):
+    """logits [N, C] fp32 and (when `need_grad`) the Saved state.  Activations in bf16 (`bf16`, autocast) or fp32;
+    fp32 statistics / logits either way."""
     L = lib()
     dev = x.device
     N = x.size(0)
-    cd = torch.bfloat16
+    cd = torch.bfloat16 if bf16 else torch.float32
     H = net.convs[0].out_channels
     n_hidden = len(net.convs) - 1
     reducer = net.stats_reducer
@@ -181,15 +187,20 @@ def forward(net, x: torch.Tensor, g: Graph, t: Optional[torch.Tensor], training:
     x = ops._rows(x)
 
     def build_h0():
-        h32 = torch.empty((N, K0p), dtype=torch.float32, device=dev)
         cat0 = torch.empty((N, 2 * K0p), dtype=cd, device=dev)
         tb = table.detach().contiguous().float() if table is not None else None
+        if bf16:     # fp32 copy for the aggregation (PyG aggregates the fp32 input in fp32) + bf16 for the GEMM
+            h32 = torch.empty((N, K0p), dtype=torch.float32, device=dev)
+            o32, ld32, o16 = h32, K0p, cat0[:, K0p:]
+        else:        # fp32: h0 lives in the right half of [agg | h0] only
+            h32 = cat0[:, K0p:]
+            o32, ld32, o16 = h32, 2 * K0p, None
         check(L.egnn_inject_time(ptr(x), ops._ld(x), ptr(t.contiguous()) if use_t else None, ptr(tb),
-                                 tb.size(0) if tb is not None else 0, tb.size(1) if tb is not None else 0, ptr(h32),
-                                 ptr(cat0[:, K0p:]), K0p, 2 * K0p, N, x.size(1), stream()))
+                                 tb.size(0) if tb is not None else 0, tb.size(1) if tb is not None else 0, ptr(o32),
+                                 ptr(o16), ld32, 2 * K0p if o16 is not None else 0, N, x.size(1), stream()))
         return h32, cat0
 
-    h32, cat = STATIC_INPUTS.get(x, t if use_t else None, table, K0p, build_h0)
+    h32, cat = STATIC_INPUTS.get(x, t if use_t else None, table, (K0p, bf16), build_h0)
     ops.spmm(g, "csr", _lib.SPMM_MEAN, h32, cd, out=cat[:, :K0p])
 
     # logits layer operand [W_l ; W_r] (fp32, [2C, H])
@@ -216,7 +227,7 @@ def forward(net, x: torch.Tensor, g: Graph, t: Optional[torch.Tensor], training:
         wt = torch.empty((2 * K, H), dtype=cd, device=dev) if want_wt else None
         check(L.egnn_pack_sage_weights(ptr(conv.lin_l.weight), ptr(conv.lin_r.weight),
                                        ptr(proj.weight) if has_proj else None, ptr(conv.lin_l.bias), H, Nr, Kraw, K,
-                                       ptr(wcat), ptr(bias), ptr(wt), stream()))
+                                       ptr(wcat), ptr(bias), ptr(wt), dt(wcat), stream()))
         zc = torch.empty((N, H + Nr), dtype=cd, device=dev)
         bn = net.bns[li] if net.use_bn else None
         stats_in_gemm = bn is not None and training and H <= 64
@@ -317,7 +328,7 @@ def backward(net, sv: Saved, dlogits: torch.Tensor, out: Optional[List[torch.Ten
     g = sv.g
     dev = dlogits.device
     N = dlogits.size(0)
-    cd = torch.bfloat16
+    cd = sv.layers[0].z.dtype
     H = sv.layers[0].No
     C = sv.C
     order = param_order(net)
@@ -341,7 +352,7 @@ def backward(net, sv: Saved, dlogits: torch.Tensor, out: Optional[List[torch.Ten
         N2 = G2.size(1) if G2 is not None else 0
         ws = torch.empty(L.egnn_wgrad_tc_workspace_floats(No + N2, Kin), **f32)
         check(L.egnn_wgrad_tc(ptr(G), G.stride(0), ptr(X), X.stride(0), N, No, Kin, ptr(d0), ptr(d1), K, Kraw,
-                              ptr(G2), G2.stride(0) if G2 is not None else 0, N2, ptr(d2), ptr(ws), stream()))
+                              ptr(G2), G2.stride(0) if G2 is not None else 0, N2, ptr(d2), dt(G), ptr(ws), stream()))
 
     overlap = (sv.reducer is not None) if OVERLAP_WGRAD == "auto" else bool(OVERLAP_WGRAD)
     main_st = torch.cuda.current_stream(dev)
@@ -430,7 +441,7 @@ def backward(net, sv: Saved, dlogits: torch.Tensor, out: Optional[List[torch.Ten
         Kraw = conv.in_channels
 
         def layer_wgrads():
-            if 2 * K <= 384 and ly.has_proj and H % 64 == 0 and 2 * H <= 128:
+            if 2 * K <= 384 and ly.has_proj and H % 64 == 0 and 2 * H <= 128 and cd == torch.bfloat16:
                 # one pass over [m | h]: [dz | dy]^T [m | h] -> d lin_l, d lin_r, and (dy x root half) d res_proj
                 wgrad(dz, cat, K, Kraw, dst(conv.lin_l.weight), dst(conv.lin_r.weight), G2=dy,
                       d2=dst(net.res_projs[li].weight))
@@ -476,12 +487,12 @@ def backward(net, sv: Saved, dlogits: torch.Tensor, out: Optional[List[torch.Ten
 
 
 class SageResBNFn(torch.autograd.Function):
-    """Drop-in autograd wrapper: logits = SageResBNFn.apply(net, x, g, t, *param_order(net))."""
+    """Drop-in autograd wrapper: logits = SageResBNFn.apply(net, x, g, t, bf16, *param_order(net))."""
 
     @staticmethod
-    def forward(ctx, net, x, g, t, *params):
-        need = any(ctx.needs_input_grad[4:])
-        logits, sv = forward(net, x, g, t, net.training, need)
+    def forward(ctx, net, x, g, t, bf16, *params):
+        need = any(ctx.needs_input_grad[5:])
+        logits, sv = forward(net, x, g, t, net.training, need, bf16)
         ctx.net, ctx.sv = net, sv
         return logits
 
@@ -489,4 +500,4 @@ class SageResBNFn(torch.autograd.Function):
     def backward(ctx, dlogits):
         grads = backward(ctx.net, ctx.sv, dlogits.float())
         ctx.sv = None
-        return (None, None, None, None) + tuple(grads)
+        return (None, None, None, None, None) + tuple(grads)

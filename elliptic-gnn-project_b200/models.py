@@ -177,10 +177,11 @@ class SAGEResBNNet(nn.Module, _DropoutMixin):
         return ops.inject_time(x, t_idx, table, self.in_dim)
 
     def forward(self, x, edge_index: Union[torch.Tensor, Graph], t_idx: Optional[torch.Tensor] = None):
-        if fused.supported(self, x, ops.amp_bf16()):
-            # bf16 autocast: the whole net as one explicit kernel sequence (fused.py), same arithmetic as below
+        bf16 = ops.amp_bf16()
+        if fused.supported(self, x, bf16) and (bf16 or ops.set_f32_tc()):
+            # the whole net as one explicit kernel sequence (fused.py): bf16 operands under autocast, 3xTF32 otherwise
             g = edge_index if isinstance(edge_index, Graph) else cached_graph(edge_index, x.size(0))
-            return fused.SageResBNFn.apply(self, x, g, t_idx, *fused.param_order(self))
+            return fused.SageResBNFn.apply(self, x, g, t_idx, bf16, *fused.param_order(self))
         x = self._inject_time(x, t_idx)
         h = x
         drop = None

@@ -52,6 +52,7 @@ def _graph_of(edge_index: Union[torch.Tensor, Graph], n: int, self_loops: bool) 
 
 
 def _check_input(x: torch.Tensor, in_channels: int):
+    ops.set_f32_tc()
     if not x.is_cuda:
         raise RuntimeError("egnn_b200 convs run on CUDA tensors only (no CPU fallback)")
     if x.dim() != 2 or x.size(1) != in_channels:

@@ -134,11 +134,32 @@ def spmm(g: Graph, view: str, mode: int, x: torch.Tensor, out_dtype: torch.dtype
 
 GEMM_IMPL = 0  # 0 auto (tcgen05 for bf16 where supported), 1 force SIMT, 2 force tcgen05
 
+# fp32 operands on the tensor cores (3xTF32, csrc/gemm_tcgen05.cu).  One product is ~2e-6 accurate, which keeps fp32
+# LOGITS inside the rel-1e-5 bar (every eval forward), but the tensor core adds into its fp32 accumulator with
+# truncation, a bias that does not average out: through three layers of forward + backward the parameter gradients land
+# at ~1e-4 of the oracle's.  So: inference (no autograd) uses the tensor cores, TRAINING in fp32 stays on the exact
+# FFMA kernels unless EGNN_F32_TC_TRAIN=1 (or ops.F32_TC_TRAIN = True) opts in to the faster, looser path.
+import os as _os
+
+F32_TC_TRAIN = _os.environ.get("EGNN_F32_TC_TRAIN", "0") == "1"
+_F32_TC = False
+
+
+def set_f32_tc():
+    """Called by the conv / net modules on entry (where autograd's mode is still visible): fp32 GEMMs of this forward
+    (and of its backward) may use the tensor cores iff no gradient will be taken or the caller opted in."""
+    global _F32_TC
+    _F32_TC = F32_TC_TRAIN or not torch.is_grad_enabled()
+    return _F32_TC
+
 
 def _gemm(A, a_sm, a_sk, B, b_sk, b_sn, C, M, N, K, bias, accumulate, split_k=1, impl=None, row_div=None,
           need_ws=False, row_div_cols=0):
     L = lib()
-    f32_tc = A.dtype == torch.float32 and B.dtype == torch.float32 and a_sk == 1 and b_sk == 1 and M >= 1024
+    both_f32 = A.dtype == torch.float32 and B.dtype == torch.float32
+    f32_tc = both_f32 and _F32_TC and a_sk == 1 and b_sk == 1 and M >= 1024
+    if both_f32 and not _F32_TC and impl is None and GEMM_IMPL == 0:
+        impl = 1                     # exact fp32: FFMA kernels
     nws = L.egnn_gemm_workspace_floats(M, N, K, split_k) if (need_ws or split_k > 1 or M <= 8 or f32_tc) else 0
     ws = torch.empty(nws, dtype=torch.float32, device=C.device) if nws else None
     check(L.egnn_gemm(ptr(A), dt(A), a_sm, a_sk, ptr(B), dt(B), b_sk, b_sn, ptr(C), dt(C), _ld(C), M, N, K,
@@ -261,7 +282,7 @@ class SageConvFn(torch.autograd.Function):
             check(lib().egnn_pack_sage_weights(ptr(w_l.contiguous()), ptr(w_r.contiguous()),
                                                ptr(w_res.contiguous()) if w_res is not None else None,
                                                ptr(b_l.contiguous()) if b_l is not None else None, No, Nr, K0, K,
-                                               ptr(wcat), ptr(bias), None, stream()))
+                                               ptr(wcat), ptr(bias), None, BF16, stream()))
             zc = linear_fwd(cat, wcat, bias=bias, out_dtype=cd)
             ctx.cat_path = True
             ctx.save_for_backward(cat, wcat)

@@ -127,6 +127,7 @@ class TrainStep:
         from .models import SAGEResBNNet
         m = self.model
         return (isinstance(m, SAGEResBNNet) and type(m).forward is SAGEResBNNet.forward
+                and (self.amp or ops.F32_TC_TRAIN)      # fp32 training: exact FFMA path unless opted in (ops.py)
                 and fused.supported(m, self.x, self.amp) and all(p.requires_grad for p in m.parameters())
                 and len(self.opt.params) == len(fused.param_order(m)))
 
@@ -139,7 +140,7 @@ class TrainStep:
         L = lib()
         g = self.edge_index if isinstance(self.edge_index, Graph) else cached_graph(self.edge_index, self.x.size(0))
         t = self.timestep if model_uses_time_embed(m) else None
-        logits, sv = fused.forward(m, self.x, g, t, True, True)
+        logits, sv = fused.forward(m, self.x, g, t, True, True, self.amp)
         n = logits.size(0)
         dlog = torch.empty_like(logits)
         ws = torch.empty(L.egnn_ce_workspace_floats(self.train_idx.numel()), dtype=torch.float32, device=logits.device)

@@ -179,10 +179,15 @@ int egnn_gemm(const void* A, int a_dtype, int64_t a_sm, int64_t a_sk, const void
  * Compiled epilogue combinations: everything egnn_gemm accepts; addend (+ row_div); colstats (+ bias).  Any other
  * shape or combination is an error (the callers then use egnn_gemm + egnn_colreduce). */
 int64_t egnn_linear_stats_parts(int64_t M);
+/* ab_dtype = EGNN_F32: fp32 operands through the 3xTF32 kernel (a = a_hi + a_lo in tf32; a.w ~= a_lo.w_hi + a_hi.w_lo +
+ * a_hi.w_hi with fp32 accumulate: ~2e-6 relative, inside the fp32 parity bar of 1e-5 that plain TF32 would break);
+ * needs workspace = egnn_linear_tc_workspace_floats(EGNN_F32, N, K) floats (the hi / lo split of W).  K % 4 == 0. */
+size_t egnn_linear_tc_workspace_floats(int ab_dtype, int64_t N, int64_t K);
 int egnn_linear_tc(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int c_dtype, int64_t ld_c,
                    int64_t M, int64_t N, int64_t K, const float* bias, const int32_t* row_div_ptr,
                    int64_t row_div_cols, int accumulate, const void* addend, int64_t ld_addend,
-                   int64_t addend_col0, float* colstats, int64_t colstats_cols, void* stream);
+                   int64_t addend_col0, float* colstats, int64_t colstats_cols, int ab_dtype, float* workspace,
+                   void* stream);
 /* Weight gradient of the concatenated SAGE GEMM on the tcgen05 wgrad kernel: dW[N_out, K_in] = G[M, N_out]^T . X[M, K_in]
  * (bf16 operands, rows 16-byte aligned, N_out <= 256, K_in <= 384; deterministic per-CTA partials + fixed-order sum),
  * written as TWO dense fp32 parameter gradients: columns [0, split_col) -> dst0, [split_col, K_in) -> dst1 (NULL: dropped),
@@ -195,7 +200,8 @@ int egnn_linear_tc(const void* A, int64_t lda, const void* W, int64_t ldw, void*
 size_t egnn_wgrad_tc_workspace_floats(int64_t N_out, int64_t K_in);
 int egnn_wgrad_tc(const void* G, int64_t ldg, const void* X, int64_t ldx, int64_t M, int64_t N_out, int64_t K_in,
                   float* dst0, float* dst1, int64_t split_col, int64_t valid_cols, const void* G2, int64_t ldg2,
-                  int64_t N2, float* dst2, float* workspace, void* stream);
+                  int64_t N2, float* dst2, int dtype /* EGNN_BF16 | EGNN_F32 (3xTF32, G2 must be NULL) */,
+                  float* workspace, void* stream);
 int egnn_colstats_reduce(const float* parts, int64_t n_parts, int64_t n_feat, double* sums, void* stream);
 int egnn_bn_finalize_parts(const float* parts, int64_t n_parts, int64_t n_feat, double count, float eps,
                            float momentum, float* mean, float* rstd, float* running_mean, float* running_var,
@@ -251,6 +257,7 @@ int egnn_skinny_dgrad(const float* dp, const float* W, int P, void* dh, int dtyp
 int egnn_pack_sage_weights(const float* w_l, const float* w_r, const float* w_res, const float* b_l,
                            int64_t n_out, int64_t n_res, int64_t K, int64_t K_padded, void* out_bf16,
                            float* bias_out, void* out_t_bf16 /* optional [2*K_padded, n_out] = [W_l | W_r]^T */,
+                           int out_dtype /* EGNN_BF16 | EGNN_F32: element type of the two packed matrices */,
                            void* stream);
 
 /* cast / copy with optional column padding: out[r, 0:F] = in[r, 0:F], out[r, F:ld_out] = 0 */

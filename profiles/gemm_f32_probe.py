@@ -10,6 +10,7 @@ import egnn_b200 as E
 from egnn_b200 import ops
 
 torch.cuda.set_device(0)
+ops._F32_TC = True
 N = 203769
 
 

@@ -89,6 +89,15 @@ def test_unsupported_layout_fails_loudly(egnn):
 TOL_F32 = 5e-6   # rel ||ref||_inf vs fp64: a.w ~= a_lo.w_hi + a_hi.w_lo + a_hi.w_hi, fp32 accumulate (north_star bar: 1e-5)
 
 
+@pytest.fixture(autouse=True)
+def _f32_tensor_cores():
+    """the fp32 sections below exercise the 3xTF32 kernels through the raw ops (the nets enable them for inference)"""
+    from egnn_b200 import ops
+    old, ops._F32_TC = ops._F32_TC, True
+    yield
+    ops._F32_TC = old
+
+
 def _mk32(shape, seed, heavy=False):
     g = torch.Generator().manual_seed(seed)
     t = torch.randn(shape, generator=g)
