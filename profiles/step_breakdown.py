@@ -19,6 +19,7 @@ ap.add_argument("--fp32", action="store_true")
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--seq", action="store_true", help="print the kernel sequence of the last step")
 ap.add_argument("--arch", default="rec_k8")
+ap.add_argument("--eval", action="store_true", help="profile the eval_split forward (fp32, no autocast) instead")
 args = ap.parse_args()
 torch.cuda.set_device(0)
 gr = bench.host_graph(1)
@@ -29,12 +30,18 @@ model = E.build_model(CFG["arch"], gr.x.size(1), CFG).cuda()
 model.set_dropout_seed(42, "cuda")
 step = TrainStep(model, gr.x.cuda(), ei, gr.timestep.cuda(), gr.y.cuda(), gr.train_mask.cuda(), lr=CFG["lr"],
                  weight_decay=CFG["weight_decay"], grad_clip=1.0, amp=not args.fp32)
+if args.eval:
+    from egnn_b200.train import eval_probs
+    xd, td = gr.x.cuda(), gr.timestep.cuda()
+    run = lambda: eval_probs(model, xd, ei, td)
+else:
+    run = step.run
 for _ in range(3):
-    step.run()
+    run()
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for _ in range(args.steps):
-        step.run()
+        run()
     torch.cuda.synchronize()
 evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
 agg = collections.defaultdict(lambda: [0, 0.0])
