@@ -36,6 +36,9 @@ SIGNATURES = {
     "egnn_hub_ablation_workspace_bytes": (_sz, [_i64, _i64]),
     "egnn_hub_ablation": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "egnn_edge_gather": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _vp]),
+    "egnn_txid_join_workspace_bytes": (_sz, [_i64, _i64]),
+    "egnn_txid_join": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "egnn_temporal_masks": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "egnn_buffers_differ": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "egnn_spmm": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _i64, _vp, _i32, _i64, _i64,
                          _i64, _vp, _i32, _i32, _vp, _i64, _vp]),
@@ -101,6 +104,9 @@ SIGNATURES = {
     "egnn_bn_bwd_sums_exchange": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _i64, _vp]),
     "egnn_bn_bwd_reduce_parts": (_i64, [_i64, _i64]),
     "egnn_masked_ce": (_i32, [_vp, _i32, _i64, _vp, _vp, _i64, _vp, _f64, _vp, _vp, _vp, _vp]),
+    "egnn_masked_loss": (_i32, [_vp, _i32, _i64, _vp, _vp, _i64, _vp, _f64, _f64, _vp, _f64, _f64, _i32, _vp, _vp, _vp,
+                                _vp]),
+    "egnn_l2_mean_penalty": (_i32, [_vp, _i64, _f64, _vp, _vp, _vp]),
     "egnn_adam_workspace_floats": (_sz, [_i64]),
     "egnn_clip_adam_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _vp, _vp,
                                    _vp, _vp]),

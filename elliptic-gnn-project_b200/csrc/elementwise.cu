@@ -1228,32 +1228,59 @@ __global__ void __launch_bounds__(kThreads) dropout_mask_kernel(uint8_t* __restr
     if (cb * 8 + k < F) mask[r * F + cb * 8 + k] = (keep >> k) & 1u;
 }
 
-// ---- masked weighted cross-entropy (2 classes) --------------------------------------------------
+// ---- masked loss over the train rows (2 classes): `_make_loss_fn` (src/train_gnn.py:136-183) ----------------------
+//   plain   : w[y] * CE                                  (F.cross_entropy(weight=cw, reduction='none'), :159-162)
+//   focal   : (1 - p_y)^gamma * CE, NO class weights     (:153-158)
+//   time    : * clamp(f((t - t_min) / max(t_max - t_min, 1)), 1e-3), f = identity | sqrt(clamp(., 0))   (:165-174)
+//   then .mean() over the train rows (inv_n = 1 / global train-row count).  d loss / d logits is produced in the same
+//   pass; for the focal term  d/dz_k = [gamma (1-p)^(gamma-1) p log p - (1-p)^gamma] (delta_ky - p_k).
 template <typename T>
 __global__ void __launch_bounds__(kThreads) masked_ce_kernel(const T* __restrict__ logits,
                                                              const int64_t* __restrict__ y,
                                                              const int64_t* __restrict__ idx,
                                                              int64_t n_idx, const float* __restrict__ cw,
-                                                             float inv_n, T* __restrict__ dlogits,
+                                                             float inv_n, float focal_gamma,
+                                                             const int64_t* __restrict__ timestep, float t_min,
+                                                             float t_denom, int time_scheme,
+                                                             T* __restrict__ dlogits,
                                                              float* __restrict__ partial) {
   __shared__ float sm[kThreads];
   int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   float li = 0.f;
   if (i < n_idx) {
-    int64_t r = idx[i];
+    int64_t r = idx ? idx[i] : i;
     float l0 = to_f32(logits[2 * r]), l1 = to_f32(logits[2 * r + 1]);
     int64_t yi = y[r];
     float m = fmaxf(l0, l1);
     float e0 = expf(l0 - m), e1 = expf(l1 - m);
     float s = e0 + e1;
     float lse = m + logf(s);
-    float w = cw[yi];
-    li = w * (lse - (yi == 0 ? l0 : l1));
+    float ce = lse - (yi == 0 ? l0 : l1);
     float p0 = e0 / s, p1 = e1 / s;
-    float g0 = w * (p0 - (yi == 0 ? 1.f : 0.f)) * inv_n;
-    float g1 = w * (p1 - (yi == 1 ? 1.f : 0.f)) * inv_n;
-    dlogits[2 * r] = from_f32<T>(g0);
-    dlogits[2 * r + 1] = from_f32<T>(g1);
+    float c;      // d li / d z_k = c * (p_k - delta_ky)
+    if (focal_gamma >= 0.f) {
+      float pt = yi == 0 ? p0 : p1;
+      float om = 1.f - pt;
+      float mod = powf(om, focal_gamma);
+      li = mod * ce;
+      // (1-p)^g - g (1-p)^(g-1) p log p, with log p = -ce; (1-p)^(g-1) p taken as 0 at p = 1
+      float dm = focal_gamma > 0.f ? focal_gamma * (om > 0.f ? powf(om, focal_gamma - 1.f) : (focal_gamma == 1.f ? 1.f : 0.f)) : 0.f;
+      c = mod + dm * pt * ce;
+    } else {
+      float w = cw[yi];
+      li = w * ce;
+      c = w;
+    }
+    if (time_scheme != 0) {
+      float wt = __fdiv_rn((float)timestep[r] - t_min, t_denom);
+      if (time_scheme == 2) wt = sqrtf(fmaxf(wt, 0.f));
+      wt = fmaxf(wt, 1e-3f);
+      li *= wt;
+      c *= wt;
+    }
+    c *= inv_n;
+    dlogits[2 * r] = from_f32<T>(c * (p0 - (yi == 0 ? 1.f : 0.f)));
+    dlogits[2 * r + 1] = from_f32<T>(c * (p1 - (yi == 1 ? 1.f : 0.f)));
   }
   sm[threadIdx.x] = li;
   __syncthreads();
@@ -1262,6 +1289,26 @@ __global__ void __launch_bounds__(kThreads) masked_ce_kernel(const T* __restrict
     __syncthreads();
   }
   if (threadIdx.x == 0) partial[blockIdx.x] = sm[0];
+}
+
+// loss += lambda * mean(w^2); grad += 2 lambda / n * w   (optional L2 on the learned time table, :178-180)
+__global__ void __launch_bounds__(kThreads) l2_mean_penalty_kernel(const float* __restrict__ w, int64_t n, float lambda,
+                                                                   float* __restrict__ loss, float* __restrict__ grad) {
+  __shared__ double sm[kThreads];
+  double s = 0;
+  const float gs = 2.f * lambda / (float)n;
+  for (int64_t i = threadIdx.x; i < n; i += kThreads) {
+    const float v = w[i];
+    s += (double)v * (double)v;
+    if (grad) grad[i] += gs * v;
+  }
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = kThreads / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *loss += lambda * (float)(sm[0] / (double)n);
 }
 
 __global__ void __launch_bounds__(kThreads) ce_final_kernel(const float* __restrict__ partial, int nblk,
@@ -1794,27 +1841,49 @@ extern "C" int egnn_counter_add(int64_t* counter, int64_t inc, void* stream) {
 
 extern "C" size_t egnn_ce_workspace_floats(int64_t n_idx) { return (size_t)ceil_div(n_idx, kThreads) + 8; }
 
-extern "C" int egnn_masked_ce(const void* logits, int dtype, int64_t n_rows, const int64_t* y,
-                              const int64_t* idx, int64_t n_idx, const float* cw, double n_total,
-                              float* loss, void* dlogits, float* workspace, void* stream) {
-  const char* fn = "egnn_masked_ce";
-  EGNN_REQUIRE(logits && y && cw && loss && dlogits && workspace, fn, "null pointer");
-  EGNN_REQUIRE(n_total > 0 && (n_idx == 0 || idx), fn, "bad arguments");
+extern "C" int egnn_masked_loss(const void* logits, int dtype, int64_t n_rows, const int64_t* y,
+                                const int64_t* idx, int64_t n_idx, const float* cw, double n_total,
+                                double focal_gamma, const int64_t* timestep, double t_min, double t_max,
+                                int time_scheme, float* loss, void* dlogits, float* workspace, void* stream) {
+  const char* fn = "egnn_masked_loss";
+  EGNN_REQUIRE(logits && y && loss && dlogits && workspace, fn, "null pointer");
+  EGNN_REQUIRE(focal_gamma >= 0 || cw, fn, "class weights missing");
+  EGNN_REQUIRE(n_total > 0 && n_idx >= 0 && (idx || n_idx <= n_rows), fn, "bad arguments");
+  EGNN_REQUIRE(time_scheme >= 0 && time_scheme <= 2 && (time_scheme == 0 || timestep), fn, "bad time weighting");
   cudaStream_t st = (cudaStream_t)stream;
   size_t es = dtype == EGNN_F32 ? 4 : 2;
   cudaMemsetAsync(dlogits, 0, (size_t)n_rows * 2 * es, st);
   int nblk = (int)ceil_div(n_idx, kThreads);
+  const float denom = (float)(t_max - t_min > 1.0 ? t_max - t_min : 1.0);   // _norm_train_time (:131-133)
   if (nblk > 0) {
     if (dtype == EGNN_F32)
-      masked_ce_kernel<float><<<nblk, kThreads, 0, st>>>((const float*)logits, y, idx, n_idx, cw,
-                                                         (float)(1.0 / n_total), (float*)dlogits, workspace);
+      masked_ce_kernel<float><<<nblk, kThreads, 0, st>>>((const float*)logits, y, idx, n_idx, cw, (float)(1.0 / n_total),
+                                                         (float)focal_gamma, timestep, (float)t_min, denom, time_scheme,
+                                                         (float*)dlogits, workspace);
     else
-      masked_ce_kernel<__nv_bfloat16><<<nblk, kThreads, 0, st>>>((const __nv_bfloat16*)logits, y, idx, n_idx,
-                                                                 cw, (float)(1.0 / n_total),
+      masked_ce_kernel<__nv_bfloat16><<<nblk, kThreads, 0, st>>>((const __nv_bfloat16*)logits, y, idx, n_idx, cw,
+                                                                 (float)(1.0 / n_total), (float)focal_gamma, timestep,
+                                                                 (float)t_min, denom, time_scheme,
                                                                  (__nv_bfloat16*)dlogits, workspace);
     EGNN_LAUNCH_CHECK(fn);
   }
   ce_final_kernel<<<1, kThreads, 0, st>>>(workspace, nblk, 1.0 / n_total, loss);
+  EGNN_LAUNCH_CHECK(fn);
+  return 0;
+}
+
+extern "C" int egnn_masked_ce(const void* logits, int dtype, int64_t n_rows, const int64_t* y,
+                              const int64_t* idx, int64_t n_idx, const float* cw, double n_total,
+                              float* loss, void* dlogits, float* workspace, void* stream) {
+  EGNN_REQUIRE(cw && (n_idx == 0 || idx), "egnn_masked_ce", "bad arguments");
+  return egnn_masked_loss(logits, dtype, n_rows, y, idx, n_idx, cw, n_total, -1.0, nullptr, 0.0, 1.0, 0, loss, dlogits,
+                          workspace, stream);
+}
+
+extern "C" int egnn_l2_mean_penalty(const float* w, int64_t n, double lambda, float* loss, float* grad, void* stream) {
+  const char* fn = "egnn_l2_mean_penalty";
+  EGNN_REQUIRE(w && loss && n > 0, fn, "bad arguments");
+  l2_mean_penalty_kernel<<<1, kThreads, 0, (cudaStream_t)stream>>>(w, n, (float)lambda, loss, grad);
   EGNN_LAUNCH_CHECK(fn);
   return 0;
 }

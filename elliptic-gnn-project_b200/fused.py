@@ -218,8 +218,9 @@ def forward(net, x: torch.Tensor, g: Graph, t: Optional[torch.Tensor], training:
         conv = net.convs[li]
         # the reference adds `res_projs[li](h_in)` whatever `residual` says (src/models/gnn.py:192; the flag is stored
         # but never read), and so does this path
-        proj = net.res_projs[li]
-        has_proj = not isinstance(proj, torch.nn.Identity)
+        no_res = getattr(net, "no_residual", False)      # plain SAGENet (gnn.py:35-53): dropout(relu(conv(h))), no skip
+        proj = None if no_res else net.res_projs[li]
+        has_proj = proj is not None and not isinstance(proj, torch.nn.Identity)
         Nr = H if has_proj else 0
         wcat = torch.empty((H + Nr, 2 * K), dtype=cd, device=dev)
         bias = torch.empty(H + Nr, dtype=torch.float32, device=dev)
@@ -237,7 +238,7 @@ def forward(net, x: torch.Tensor, g: Graph, t: Optional[torch.Tensor], training:
             parts = torch.empty((n_parts, 2, H), dtype=torch.float32, device=dev)
         _linear_tc(cat, wcat, zc, bias=bias, stats=parts, stats_cols=H if stats_in_gemm else 0)
         z = zc[:, :H]
-        res = zc[:, H:] if has_proj else h_in
+        res = zc[:, H:] if has_proj else (None if no_res else h_in)
         mean = rstd = None
         if bn is not None:
             if training:
@@ -275,7 +276,7 @@ def forward(net, x: torch.Tensor, g: Graph, t: Optional[torch.Tensor], training:
         if need_grad:
             ly = _Layer()
             ly.cat, ly.wcat, ly.wt, ly.z, ly.mean, ly.rstd, ly.kb = cat, wcat, wt, z, mean, rstd, kb
-            ly.has_proj, ly.res_is_input = has_proj, not has_proj
+            ly.has_proj, ly.res_is_input = has_proj, not has_proj and not no_res
             ly.K, ly.No, ly.Nr, ly.p_eff, ly.y = K, H, Nr, p_eff, y
             layers.append(ly)
         if not last:
@@ -311,7 +312,7 @@ def param_order(net) -> List[torch.nn.Parameter]:
         ps += [c.lin_l.weight, c.lin_l.bias, c.lin_r.weight]
         if net.use_bn:
             ps += [net.bns[li].weight, net.bns[li].bias]
-        if not isinstance(net.res_projs[li], torch.nn.Identity):
+        if not getattr(net, "no_residual", False) and not isinstance(net.res_projs[li], torch.nn.Identity):
             ps.append(net.res_projs[li].weight)
     c = net.convs[-1]
     ps += [c.lin_l.weight, c.lin_l.bias, c.lin_r.weight]

@@ -39,6 +39,11 @@ class _StackNet(nn.Module, _DropoutMixin):
     _act = ACT_RELU
 
     def forward(self, x, edge_index: Union[torch.Tensor, Graph], t_idx: Optional[torch.Tensor] = None):
+        if getattr(self, "no_residual", False) and type(self).forward is _StackNet.forward:
+            bf16 = ops.amp_bf16()
+            if fused.supported(self, x, bf16) and (bf16 or ops.set_f32_tc()):
+                g = edge_index if isinstance(edge_index, Graph) else cached_graph(edge_index, x.size(0))
+                return fused.SageResBNFn.apply(self, x, g, None, bf16, *fused.param_order(self))
         h = x
         drop = None
         if self.training and self.dropout > 0:
@@ -64,10 +69,18 @@ class GCNNet(_StackNet):
 
 
 class SAGENet(_StackNet):
+    """`SAGENet` (`/root/reference/src/models/gnn.py:35-53`): h = dropout(relu(SAGEConv(h))) per hidden layer.  Shapes the
+    explicit kernel sequence serves (fused.py: hidden % 16 == 0, <= 128) run through it -- the same sequence as
+    SAGE-ResBN with BatchNorm, residual and time features switched off; everything else takes the per-op path."""
+    # what fused.py reads from a net, fixed for this architecture
+    use_bn, no_residual, time_embed_dim, time_embed_type, time_emb, max_timestep = False, True, 0, "none", None, 0
+    bns, res_projs = (), ()
+
     def __init__(self, in_dim, hidden_dim=128, layers=3, dropout=0.2, num_classes=2):
         super().__init__()
         assert layers >= 2
         self.dropout = dropout
+        self.in_dim = in_dim
         self.convs = nn.ModuleList([SAGEConv(in_dim, hidden_dim)])
         for _ in range(layers - 2):
             self.convs.append(SAGEConv(hidden_dim, hidden_dim))

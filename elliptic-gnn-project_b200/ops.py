@@ -85,6 +85,13 @@ def pad_features(x: torch.Tensor, width: int, want_twin: bool):
     vectorised gathers and the TMA descriptors; e.g. the reference's 167 = 166 + scalar time,
     `src/train_gnn.py:314-317`), plus -- under bf16 autocast -- the bf16 copy inside an [agg | h]
     buffer, both written by one pass of the time-injection kernel with an empty time table."""
+    from . import fused                          # fused.static_inputs(False): inputs rewritten in place under a graph
+    memo = getattr(x, "_egnn_padded", None) if fused._STATIC else None   # rides on the tensor object, per data version
+    if want_twin:                                # the twin's [agg | h] buffer is saved for a backward: never shared
+        memo = None
+    if memo is not None and memo[0] == (x._version, x.data_ptr(), width):
+        return memo[1]
+    src = x
     x = _rows(x)
     N, F = x.shape
     out = torch.empty((N, width), dtype=torch.float32, device=x.device)
@@ -93,6 +100,8 @@ def pad_features(x: torch.Tensor, width: int, want_twin: bool):
                                  _ld(twin) if twin is not None else 0, N, F, stream()))
     if twin is not None:
         out._egnn_twin = twin
+    if twin is None and fused._STATIC and not src.requires_grad and not torch.cuda.is_current_stream_capturing():
+        src._egnn_padded = ((src._version, src.data_ptr(), width), out)
     return out
 
 
@@ -435,9 +444,9 @@ class GcnConvFn(torch.autograd.Function):
     def forward(ctx, x, w, b, g: Graph, bf16: bool, out_bf16: bool = False):
         cd = torch.bfloat16 if bf16 else torch.float32
         x = _rows(x)
-        pad = (-x.size(1)) % 8 if (bf16 and x.dtype == torch.float32) else 0
+        pad = (-x.size(1)) % 8 if x.dtype == torch.float32 else 0   # 16-byte rows: vectorised / TMA operand loads
         if pad:
-            x, w = pad_features(x, x.size(1) + pad, want_twin=True), _pad_cols(w, pad)
+            x, w = pad_features(x, x.size(1) + pad, want_twin=bf16), _pad_cols(w, pad)
         ctx.pad = pad
         xg = to_compute(x, cd)
         wc = w if w.dtype == cd else cast(w, cd)
@@ -526,9 +535,9 @@ class GatConvFn(torch.autograd.Function):
         cd = torch.bfloat16 if bf16 else torch.float32
         x = _rows(x)
         N = x.size(0)
-        pad = (-x.size(1)) % 8 if (bf16 and x.dtype == torch.float32) else 0
+        pad = (-x.size(1)) % 8 if x.dtype == torch.float32 else 0   # 16-byte rows: vectorised / TMA operand loads
         if pad:
-            x, w = pad_features(x, x.size(1) + pad, want_twin=True), _pad_cols(w, pad)
+            x, w = pad_features(x, x.size(1) + pad, want_twin=bf16), _pad_cols(w, pad)
         ctx.pad = pad
         xg = to_compute(x, cd)
         wc = w if w.dtype == cd else cast(w, cd)
@@ -776,32 +785,94 @@ def inject_time(x, t, table, width: int):
 
 
 # ------------------------------------------------------------------------------- loss ----
+TIME_SCHEMES = {"none": 0, "linear": 1, "sqrt": 2}
+
+
 class MaskedCEFn(torch.autograd.Function):
-    """`F.cross_entropy(logits[mask], y[mask], weight=cw, reduction='none').mean()`
-    (`src/train_gnn.py:159-176,201`) over precomputed train-row indices; forward also produces
-    d loss / d logits, so the backward is a scale."""
+    """`_make_loss_fn`'s per-row loss and mean (`src/train_gnn.py:136-176,201`) over precomputed train-row indices
+    (`idx=None`: all rows, for logits that were masked already): class-weighted CE, or the focal variant
+    (`focal_gamma >= 0`), times the optional time weight.  Forward also produces d loss / d logits, so the backward
+    is a scale."""
 
     @staticmethod
-    def forward(ctx, logits, y, idx, cw, n_total: float):
+    def forward(ctx, logits, y, idx, cw, n_total: float, focal_gamma: float = -1.0, timestep=None, t_min: float = 0.0,
+                t_max: float = 1.0, time_scheme: int = 0):
         logits = _rows(logits).contiguous()
         if logits.size(1) != 2:
             raise ValueError("masked_weighted_ce is specialised for the reference's 2 classes")
         L = lib()
         N = logits.size(0)
+        n_idx = N if idx is None else idx.numel()
         loss = torch.empty(1, dtype=torch.float32, device=logits.device)
         dlog = torch.empty_like(logits)
-        ws = torch.empty(L.egnn_ce_workspace_floats(idx.numel()), dtype=torch.float32, device=logits.device)
-        check(L.egnn_masked_ce(ptr(logits), dt(logits), N, ptr(y), ptr(idx), idx.numel(), ptr(cw),
-                               float(n_total), ptr(loss), ptr(dlog), ptr(ws), stream()))
+        ws = torch.empty(L.egnn_ce_workspace_floats(n_idx), dtype=torch.float32, device=logits.device)
+        check(L.egnn_masked_loss(ptr(logits), dt(logits), N, ptr(y), ptr(idx), n_idx, ptr(cw), float(n_total),
+                                 float(focal_gamma), ptr(timestep), float(t_min), float(t_max), int(time_scheme),
+                                 ptr(loss), ptr(dlog), ptr(ws), stream()))
         ctx.save_for_backward(dlog)
         return loss.squeeze(0)
 
     @staticmethod
     def backward(ctx, gout):
         (dlog,) = ctx.saved_tensors
-        return dlog * gout.to(dlog.dtype), None, None, None, None
+        return (dlog * gout.to(dlog.dtype),) + (None,) * 9
+
+
+class L2MeanPenaltyFn(torch.autograd.Function):
+    """loss + lambda * mean(w^2)  (`embed_l2 * model.time_emb.weight.pow(2).mean()`, `src/train_gnn.py:178-180`)."""
+
+    @staticmethod
+    def forward(ctx, loss, w, lam: float):
+        out = loss.detach().clone().reshape(1)
+        wc = w.detach().contiguous()
+        check(lib().egnn_l2_mean_penalty(ptr(wc), wc.numel(), float(lam), ptr(out), None, stream()))
+        ctx.save_for_backward(wc)
+        ctx.lam = float(lam)
+        return out.squeeze(0)
+
+    @staticmethod
+    def backward(ctx, gout):
+        (wc,) = ctx.saved_tensors
+        return gout, gout * (2.0 * ctx.lam / wc.numel()) * wc, None
 
 
 def masked_weighted_ce(logits, y, train_idx, cw, n_total: Optional[float] = None):
     n_total = float(train_idx.numel()) if n_total is None else float(n_total)
     return MaskedCEFn.apply(logits, y, train_idx, cw, n_total)
+
+
+def make_loss_fn(cfg: dict, cw: torch.Tensor, model, t_min, t_max):
+    """Drop-in for `_make_loss_fn(cfg, cw, model, t_min, t_max)` (`src/train_gnn.py:136-183`): returns
+    `loss_fn(logits, target, t_idx=None) -> scalar` over ALREADY-MASKED logits / targets, honouring `focal_loss`,
+    `focal_gamma`, `time_loss_weighting` in {none, linear, sqrt} and `time_embed_l2`; one kernel for the per-row loss,
+    its mean and d loss / d logits.  `loss_fn.on_rows(logits_all, y_all, idx, timestep_all, n_total)` is the same
+    loss addressed through train-row indices (no boolean-mask gathers; what `TrainStep` calls)."""
+    scheme = str(cfg.get("time_loss_weighting", "none"))
+    if scheme not in TIME_SCHEMES:
+        raise ValueError(f"unknown time_loss_weighting={scheme}")
+    embed_l2 = float(cfg.get("time_embed_l2", 0.0))
+    gamma = float(cfg.get("focal_gamma", 2.0)) if bool(cfg.get("focal_loss", False)) else -1.0
+
+    def _l2(loss):
+        te = getattr(model, "time_emb", None)
+        if embed_l2 > 0.0 and te is not None:
+            loss = L2MeanPenaltyFn.apply(loss, te.weight, embed_l2)
+        return loss
+
+    def loss_fn(logits, target, t_idx=None):
+        sc = TIME_SCHEMES[scheme] if t_idx is not None else 0
+        cwd = cw.to(logits.device)
+        return _l2(MaskedCEFn.apply(logits, target, None, cwd, float(logits.size(0)), gamma, t_idx, float(t_min),
+                                    float(t_max), sc))
+
+    def on_rows(logits, y, idx, timestep=None, n_total=None):
+        sc = TIME_SCHEMES[scheme] if timestep is not None else 0
+        n = float(idx.numel()) if n_total is None else float(n_total)
+        return _l2(MaskedCEFn.apply(logits, y, idx, cw.to(logits.device), n, gamma, timestep, float(t_min),
+                                    float(t_max), sc))
+
+    loss_fn.on_rows = on_rows
+    loss_fn.cw = cw
+    loss_fn.spec = dict(focal_gamma=gamma, time_scheme=TIME_SCHEMES[scheme], t_min=float(t_min), t_max=float(t_max),
+                        embed_l2=embed_l2)
+    return loss_fn

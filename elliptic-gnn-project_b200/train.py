@@ -99,7 +99,7 @@ class TrainStep:
     def __init__(self, model: nn.Module, x, edge_index, timestep, y, train_mask, *, lr: float,
                  weight_decay: float, grad_clip: float = 1.0, amp: bool = False,
                  cw: Optional[torch.Tensor] = None, n_train_total: Optional[int] = None,
-                 grad_reducer=None, health_check=None, static_inputs: bool = True):
+                 grad_reducer=None, health_check=None, static_inputs: bool = True, loss_fn=None):
         """`train_mask` and `y` are read ONCE here (train-row indices, class weights, loss normaliser are static per
         run in the reference too: `src/train_gnn.py:301-312,362-363`); a caller that changes them builds a new
         TrainStep.  `health_check`: callable run at host synchronisation points (`loss_value()`), e.g.
@@ -107,14 +107,21 @@ class TrainStep:
         `timestep` and `edge_index` are not rewritten in place between steps -- the reference moves the graph to the
         device once (`src/train_gnn.py:350`) -- so layouts derived from them (sorted graph views, the layer-0 input
         `[x | time features]`) are memoised per tensor version and a captured CUDA graph may bake them in.
-        `capture_dynamic()` / `run(dynamic=True)` is the variant that re-derives them every step (`HostFeed`)."""
+        `capture_dynamic()` / `run(dynamic=True)` is the variant that re-derives them every step (`HostFeed`).
+        `loss_fn`: an `ops.make_loss_fn(cfg, cw, model, t_min, t_max)` callable (focal / time-weighted / embed-L2
+        variants of `_make_loss_fn`, `src/train_gnn.py:136-183`); default = the plain class-weighted CE."""
         self.model, self.amp = model, amp
+        self.loss_fn = loss_fn
+        self.loss_spec = getattr(loss_fn, "spec", None) or dict(focal_gamma=-1.0, time_scheme=0, t_min=0.0, t_max=1.0,
+                                                                embed_l2=0.0)
         self.static_inputs = bool(static_inputs)
         self.graph_dynamic: Optional[torch.cuda.CUDAGraph] = None
         self._keepalive = []
         self.health_check = health_check
         self.x, self.edge_index, self.timestep, self.y = x, edge_index, timestep, y
         self.train_idx = torch.nonzero(train_mask, as_tuple=False).view(-1).contiguous()  # once per run
+        if cw is None and loss_fn is not None:
+            cw = getattr(loss_fn, "cw", None)
         self.cw = (cw if cw is not None else class_weight(y[train_mask])).to(x.device)
         self.n_train_total = float(n_train_total if n_train_total is not None else self.train_idx.numel())
         self.opt = FlatClipAdam(model.parameters(), lr=lr, weight_decay=weight_decay, max_norm=grad_clip)
@@ -124,9 +131,10 @@ class TrainStep:
         self._fused_views = None
 
     def _fused_ok(self) -> bool:
-        from .models import SAGEResBNNet
+        from .models import SAGENet, SAGEResBNNet, _StackNet
         m = self.model
-        return (isinstance(m, SAGEResBNNet) and type(m).forward is SAGEResBNNet.forward
+        return (((isinstance(m, SAGEResBNNet) and type(m).forward is SAGEResBNNet.forward)
+                 or (isinstance(m, SAGENet) and type(m).forward is _StackNet.forward))
                 and (self.amp or ops.F32_TC_TRAIN)      # fp32 training: exact FFMA path unless opted in (ops.py)
                 and fused.supported(m, self.x, self.amp) and all(p.requires_grad for p in m.parameters())
                 and len(self.opt.params) == len(fused.param_order(m)))
@@ -144,14 +152,20 @@ class TrainStep:
         n = logits.size(0)
         dlog = torch.empty_like(logits)
         ws = torch.empty(L.egnn_ce_workspace_floats(self.train_idx.numel()), dtype=torch.float32, device=logits.device)
-        check(L.egnn_masked_ce(ptr(logits), dt(logits), n, ptr(self.y), ptr(self.train_idx), self.train_idx.numel(),
-                               ptr(self.cw), float(self.n_train_total), ptr(self.loss), ptr(dlog), ptr(ws), stream()))
+        sp = self.loss_spec
+        check(L.egnn_masked_loss(ptr(logits), dt(logits), n, ptr(self.y), ptr(self.train_idx), self.train_idx.numel(),
+                                 ptr(self.cw), float(self.n_train_total), sp["focal_gamma"],
+                                 ptr(self.timestep) if sp["time_scheme"] else None, sp["t_min"], sp["t_max"],
+                                 sp["time_scheme"], ptr(self.loss), ptr(dlog), ptr(ws), stream()))
         if self._fused_views is None:
             by_id = {id(p): v for p, v in zip(self.opt.params, self.opt.views)}
             self._fused_views = [by_id[id(p)] for p in fused.param_order(m)]
             for p, v in zip(self.opt.params, self.opt.views):
                 p.grad = v
         fused.backward(m, sv, dlog, out=self._fused_views)
+        if sp["embed_l2"] > 0.0 and getattr(m, "time_emb", None) is not None:   # + lambda * mean(W_time^2) (:178-180)
+            w = m.time_emb.weight
+            check(L.egnn_l2_mean_penalty(ptr(w), w.numel(), sp["embed_l2"], ptr(self.loss), ptr(w.grad), stream()))
 
     def _body(self, dynamic: bool = False):
         m = self.model
@@ -164,7 +178,12 @@ class TrainStep:
                 t = self.timestep if model_uses_time_embed(m) else None
                 with torch.autocast(device_type="cuda", dtype=torch.bfloat16, enabled=self.amp):
                     logits = m(self.x, self.edge_index, t)
-                loss = ops.masked_weighted_ce(logits, self.y, self.train_idx, self.cw, self.n_train_total)
+                if self.loss_fn is not None:
+                    loss = self.loss_fn.on_rows(logits, self.y, self.train_idx,
+                                                self.timestep if self.loss_spec["time_scheme"] else None,
+                                                self.n_train_total)
+                else:
+                    loss = ops.masked_weighted_ce(logits, self.y, self.train_idx, self.cw, self.n_train_total)
                 loss.backward()
                 self.opt.gather_grads()
                 self.loss.copy_(loss.detach())

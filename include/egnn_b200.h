@@ -104,6 +104,24 @@ int egnn_hub_ablation(const int64_t* ei, int64_t n_edges, int64_t n_nodes, int64
 int egnn_edge_gather(const int64_t* ei, int64_t n_edges, const int64_t* idx, int64_t n_idx, int64_t* out,
                      int32_t* n_bad, void* stream);
 
+/* ---------------------------------------------------------------- ingestion --------- */
+/* The Elliptic tables -> the device edge list (src/data/dataset_elliptic.py:190-245; the reference walks a Python
+ * dict per edge endpoint on the host):
+ *   tx_ids int64 [N] in CSV row order (node i = row i); a txId occurring twice maps to its LAST row, like
+ *   `{int(tx): i for i, tx in enumerate(tx_ids)}` (:195-196); timestep int64 [N];
+ *   e_src_tx / e_dst_tx int64 [E_raw]: the raw txId pairs of elliptic_txs_edgelist.csv (:198-219).
+ *   An edge survives iff both endpoints are known txIds (:221-232) and lie in the same timestep (:235-241);
+ *   survivors keep their CSV order.  edge_index_out int64 [2, E_raw] (row stride E_raw, first info[0] columns valid),
+ *   node indices; info int32 [3] = {kept_in_graph, mapped (both endpoints known), extra rows of duplicated txIds}.
+ * egnn_temporal_masks: make_temporal_masks (:268-290); train_window_k < 0 = None; masks uint8 [N] (0/1). */
+size_t egnn_txid_join_workspace_bytes(int64_t n_nodes, int64_t n_edges_raw);
+int egnn_txid_join(const int64_t* tx_ids, const int64_t* timestep, int64_t n_nodes, const int64_t* e_src_tx,
+                   const int64_t* e_dst_tx, int64_t n_edges_raw, int64_t* edge_index_out, int32_t* info,
+                   void* workspace, size_t workspace_bytes, void* stream);
+int egnn_temporal_masks(const int64_t* y, const int64_t* timestep, int64_t n_nodes, int64_t t_train_end,
+                        int64_t t_val_end, int64_t train_window_k, uint8_t* train_mask, uint8_t* val_mask,
+                        uint8_t* test_mask, void* stream);
+
 /* *flag = 1 when the two device buffers differ in any byte, else 0 (both 16-byte aligned).  train.HostFeed uses it
  * to rebuild the sorted views only when a submitted edge_index differs from the one they were built from (the
  * reference builds nothing per step: `data.to(device)` once, src/train_gnn.py:350). */
@@ -435,6 +453,16 @@ size_t egnn_ce_workspace_floats(int64_t n_idx);
 int egnn_masked_ce(const void* logits, int dtype, int64_t n_rows, const int64_t* y,
                    const int64_t* idx, int64_t n_idx, const float* cw, double n_total,
                    float* loss, void* dlogits, float* workspace, void* stream);
+/* `_make_loss_fn` in full (src/train_gnn.py:136-183): focal_gamma >= 0 selects the focal branch ((1-p_y)^gamma * CE,
+ * no class weights, :153-158), < 0 the class-weighted CE; time_scheme 0 none / 1 linear / 2 sqrt multiplies each row's
+ * loss by clamp(f((t - t_min) / max(t_max - t_min, 1)), 1e-3) (:165-174); idx NULL = rows 0..n_idx-1 (the reference
+ * hands the loss already-masked logits).  Mean over n_total rows; dlogits as for egnn_masked_ce.
+ * egnn_l2_mean_penalty: *loss += lambda * mean(w^2), grad += 2 lambda / n * w (learned time table L2, :178-180). */
+int egnn_masked_loss(const void* logits, int dtype, int64_t n_rows, const int64_t* y, const int64_t* idx, int64_t n_idx,
+                     const float* cw, double n_total, double focal_gamma, const int64_t* timestep, double t_min,
+                     double t_max, int time_scheme, float* loss, void* dlogits, float* workspace, void* stream);
+int egnn_l2_mean_penalty(const float* w, int64_t n, double lambda, float* loss, float* grad, void* stream);
+
 
 /* Global-norm clip + Adam (coupled L2) over one flat fp32 parameter/grad buffer:
  * torch.nn.utils.clip_grad_norm_(params, max_norm) then torch.optim.Adam.step()

@@ -399,21 +399,57 @@ def masked_weighted_ce(logits, y, train_mask, cw):
     return lv.mean()
 
 
+def make_loss_fn(cfg, cw, model, t_min, t_max):
+    """`_make_loss_fn` (train_gnn.py:136-183): focal / class-weighted CE, optional linear|sqrt time weighting, optional
+    L2 on the learned time table.  Pinned against the reference's own function (tests/golden/make_loss_golden.py)."""
+    scheme = str(cfg.get("time_loss_weighting", "none"))
+    embed_l2 = float(cfg.get("time_embed_l2", 0.0))
+    use_focal = bool(cfg.get("focal_loss", False))
+    gamma = float(cfg.get("focal_gamma", 2.0))
+
+    def loss_fn(logits, target, t_idx=None):
+        if use_focal:
+            ce = F.cross_entropy(logits, target, reduction="none")
+            pt = torch.softmax(logits, dim=1)[torch.arange(len(target)), target]
+            lv = ((1 - pt) ** gamma) * ce
+        else:
+            lv = F.cross_entropy(logits, target, weight=cw, reduction="none")
+        if scheme != "none" and t_idx is not None:
+            wt = (t_idx.float() - float(t_min)) / max(float(t_max - t_min), 1.0)
+            if scheme == "sqrt":
+                wt = torch.sqrt(torch.clamp(wt, min=0.0))
+            elif scheme != "linear":
+                raise ValueError(f"unknown time_loss_weighting={scheme}")
+            lv = lv * torch.clamp(wt, min=1e-3)
+        loss = lv.mean()
+        if embed_l2 > 0.0 and getattr(model, "time_emb", None) is not None:
+            loss = loss + embed_l2 * model.time_emb.weight.pow(2).mean()
+        return loss
+
+    return loss_fn
+
+
 def train_step(model, x, edge_index, t_idx, y, train_mask, cw, optimizer, grad_clip=1.0,
-               amp_dtype=None, dropout_masks=None):
+               amp_dtype=None, dropout_masks=None, loss_fn=None, time_weighted=False):
     """One `train_epoch` body (train_gnn.py:187-209).  `amp_dtype=torch.bfloat16` runs the
     forward under CPU autocast(bf16) with no GradScaler."""
     model.train()
     optimizer.zero_grad(set_to_none=True)
     uses_t = getattr(model, "time_embed_dim", 0) > 0
     kw = {} if dropout_masks is None else {"dropout_masks": dropout_masks}
+
+    def _loss(lg):      # train_gnn.py:196-201: t_idx only when time weighting is configured
+        if loss_fn is None:
+            return masked_weighted_ce(lg, y, train_mask, cw)
+        return loss_fn(lg[train_mask], y[train_mask], t_idx[train_mask] if time_weighted else None)
+
     if amp_dtype is not None:
         with torch.autocast(device_type="cpu", dtype=amp_dtype):
             logits = model(x, edge_index, t_idx if uses_t else None, **kw)
-            loss = masked_weighted_ce(logits.float(), y, train_mask, cw)
+            loss = _loss(logits.float())
     else:
         logits = model(x, edge_index, t_idx if uses_t else None, **kw)
-        loss = masked_weighted_ce(logits, y, train_mask, cw)
+        loss = _loss(logits)
     loss.backward()
     if grad_clip and grad_clip > 0:
         torch.nn.utils.clip_grad_norm_(model.parameters(), grad_clip)
