@@ -80,16 +80,21 @@ def _lean4(F: int, *tensors) -> bool:
     return True
 
 
-def pad_features(x: torch.Tensor, width: int, want_twin: bool):
+def pad_features(x: torch.Tensor, width: int, want_twin: bool, twin_read_only: bool = False):
     """Raw fp32 node features zero-padded to `width` columns (a multiple of 8: 16-byte rows for the
     vectorised gathers and the TMA descriptors; e.g. the reference's 167 = 166 + scalar time,
     `src/train_gnn.py:314-317`), plus -- under bf16 autocast -- the bf16 copy inside an [agg | h]
-    buffer, both written by one pass of the time-injection kernel with an empty time table."""
+    buffer, both written by one pass of the time-injection kernel with an empty time table.
+
+    The result is memoised on the input tensor object per version of its data (static inputs: the reference moves the
+    graph to the device once) unless the caller will WRITE into the twin's buffer: a SAGEConv aggregates into the
+    [agg | h] slot and saves it for its backward, so it always gets a fresh one; GCN / GAT only read the twin
+    (`twin_read_only`)."""
     from . import fused                          # fused.static_inputs(False): inputs rewritten in place under a graph
-    memo = getattr(x, "_egnn_padded", None) if fused._STATIC else None   # rides on the tensor object, per data version
-    if want_twin:                                # the twin's [agg | h] buffer is saved for a backward: never shared
-        memo = None
-    if memo is not None and memo[0] == (x._version, x.data_ptr(), width):
+    share = fused._STATIC and (not want_twin or twin_read_only)
+    key = (x._version, x.data_ptr(), width, bool(want_twin))
+    memo = getattr(x, "_egnn_padded", None) if share else None
+    if memo is not None and memo[0] == key:
         return memo[1]
     src = x
     x = _rows(x)
@@ -100,8 +105,8 @@ def pad_features(x: torch.Tensor, width: int, want_twin: bool):
                                  _ld(twin) if twin is not None else 0, N, F, stream()))
     if twin is not None:
         out._egnn_twin = twin
-    if twin is None and fused._STATIC and not src.requires_grad and not torch.cuda.is_current_stream_capturing():
-        src._egnn_padded = ((src._version, src.data_ptr(), width), out)
+    if share and not src.requires_grad and not torch.cuda.is_current_stream_capturing():
+        src._egnn_padded = (key, out)
     return out
 
 
@@ -446,7 +451,7 @@ class GcnConvFn(torch.autograd.Function):
         x = _rows(x)
         pad = (-x.size(1)) % 8 if x.dtype == torch.float32 else 0   # 16-byte rows: vectorised / TMA operand loads
         if pad:
-            x, w = pad_features(x, x.size(1) + pad, want_twin=bf16), _pad_cols(w, pad)
+            x, w = pad_features(x, x.size(1) + pad, want_twin=bf16, twin_read_only=True), _pad_cols(w, pad)
         ctx.pad = pad
         xg = to_compute(x, cd)
         wc = w if w.dtype == cd else cast(w, cd)
@@ -537,16 +542,25 @@ class GatConvFn(torch.autograd.Function):
         N = x.size(0)
         pad = (-x.size(1)) % 8 if x.dtype == torch.float32 else 0   # 16-byte rows: vectorised / TMA operand loads
         if pad:
-            x, w = pad_features(x, x.size(1) + pad, want_twin=bf16), _pad_cols(w, pad)
+            x, w = pad_features(x, x.size(1) + pad, want_twin=bf16, twin_read_only=True), _pad_cols(w, pad)
         ctx.pad = pad
         xg = to_compute(x, cd)
         wc = w if w.dtype == cd else cast(w, cd)
-        xs = linear_fwd(xg, wc, out_dtype=torch.float32)  # [N, H*C]; attention path stays fp32
+        L = lib()
+        K = xg.size(1)
+        # the `hidden -> 2` logits layer (gnn.py:67): a [N, K] x [K, 2] product is a streaming pass over h, not a GEMM
+        # -- the narrow kernels of the SAGE / GCN logits layers (csrc/sage_out.cu), fp32 accumulation
+        ctx.skinny = H * C in (2, 4, 8) and K % 8 == 0 and K <= 1024 and _ld(xg) % 8 == 0
+        if ctx.skinny:
+            wc = (wc if wc.dtype == torch.float32 else cast(wc, torch.float32)).contiguous()  # bf16-rounded under autocast
+            xs = torch.empty((N, H * C), dtype=torch.float32, device=x.device)
+            check(L.egnn_skinny_project(ptr(xg), dt(xg), _ld(xg), N, K, ptr(wc), H * C, ptr(xs), stream()))
+        else:
+            xs = linear_fwd(xg, wc, out_dtype=torch.float32)  # [N, H*C]; attention path stays fp32
         dev = x.device
         a_s = torch.empty((N, H), dtype=torch.float32, device=dev)
         a_d = torch.empty((N, H), dtype=torch.float32, device=dev)
         asrc, adst = att_src.reshape(H * C).contiguous(), att_dst.reshape(H * C).contiguous()
-        L = lib()
         check(L.egnn_gat_scores(ptr(xs), N, H, C, ptr(asrc), ptr(adst), ptr(a_s), ptr(a_d), stream()))
         alpha = torch.empty((g.cap, H), dtype=torch.float32, device=dev)
         out = torch.empty((N, H * C if concat else C), dtype=torch.float32, device=dev)
@@ -584,14 +598,24 @@ class GatConvFn(torch.autograd.Function):
         datt = datt.float()
         # under bf16 autocast the Linear's backward runs in bf16 (PyG: grad of an autocast matmul): cast the fp32
         # attention-path gradient once so that wgrad / dgrad take the tensor-core kernels
-        dxs_c = dxs if dxs.dtype == xg.dtype else cast(dxs, xg.dtype)
-        dw = linear_wgrad(dxs_c, xg)
         dbias = colsum(dout).float()
         dx = None
-        if ctx.needs_input_grad[0]:
-            dx = linear_dgrad(dxs_c, wc, out_dtype=xg.dtype)
-            if dx.dtype != ctx.x_dtype:
-                dx = cast(dx, ctx.x_dtype)
+        if ctx.skinny:
+            P, K = H * C, xg.size(1)
+            dw = torch.empty((P, K), **f32)
+            dsum = torch.empty(P, **f32)
+            wsk = torch.empty(L.egnn_skinny_wgrad_workspace_floats(N, K, P), **f32)
+            check(L.egnn_skinny_wgrad(ptr(xg), dt(xg), _ld(xg), ptr(dxs), P, N, K, ptr(dw), ptr(dsum), ptr(wsk), stream()))
+            if ctx.needs_input_grad[0]:
+                dx = torch.empty((N, K), dtype=xg.dtype, device=dev)
+                check(L.egnn_skinny_dgrad(ptr(dxs), ptr(wc), P, ptr(dx), dt(dx), K, N, K, stream()))
+        else:
+            dxs_c = dxs if dxs.dtype == xg.dtype else cast(dxs, xg.dtype)
+            dw = linear_wgrad(dxs_c, xg)
+            if ctx.needs_input_grad[0]:
+                dx = linear_dgrad(dxs_c, wc, out_dtype=xg.dtype)
+        if dx is not None and dx.dtype != ctx.x_dtype:
+            dx = cast(dx, ctx.x_dtype)
         if ctx.pad:
             dw = dw[:, :dw.size(1) - ctx.pad]
             dx = dx[:, :dx.size(1) - ctx.pad] if dx is not None else None

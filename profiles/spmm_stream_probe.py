@@ -48,10 +48,19 @@ for W in ("2",):
 for W in ("2",):
     for cfg in ("8,1,8", "4,2,4", "4,2,6", "4,2,8"):
         sweeps.append((f"stream64 W={W} G,VPL,D={cfg}", dict(EGNN_SPMM_IMPL="stream", EGNN_STREAM_W=W, EGNN_STREAM_CFG=cfg, only=1)))
+if os.environ.get("PROBE_ONLY64"):      # wave / shape sweep of the narrow bf16 launches only (use with PROBE_REPLICAS=8)
+    sweeps = [(f"stream64 W={W} G,VPL,D={cfg}", dict(EGNN_SPMM_IMPL="stream", EGNN_STREAM_W=W, EGNN_STREAM_CFG=cfg, only=1))
+              for W in ("1", "2", "4") for cfg in ("8,1,8", "4,2,4", "4,2,6", "4,2,8")]
+if os.environ.get("PROBE_WAVES"):       # waves sweep with the default shapes, all widths
+    cases.insert(1, ("F128 bf16 csr", 128, torch.bfloat16, torch.bfloat16, 'csr', 4 if rep == 1 else 1))
+    sweeps = [(f"stream W={W}", dict(EGNN_SPMM_IMPL="stream", EGNN_STREAM_W=W)) for W in os.environ["PROBE_WAVES"].split(",")]
+if os.environ.get("PROBE_TASKS"):       # tasks-per-group sweep with the default shapes, all widths
+    cases.insert(1, ("F128 bf16 csr", 128, torch.bfloat16, torch.bfloat16, 'csr', 4 if rep == 1 else 1))
+    sweeps = [(f"stream T={T}", dict(EGNN_SPMM_IMPL="stream", EGNN_STREAM_T=T)) for T in os.environ["PROBE_TASKS"].split(",")]
 sweeps.append(("stream default", dict(EGNN_SPMM_IMPL="stream")))
 for name, env in sweeps:
     only = env.pop("only", None)
-    for k in ("EGNN_SPMM_IMPL", "EGNN_STREAM_W", "EGNN_STREAM_CFG"):
+    for k in ("EGNN_SPMM_IMPL", "EGNN_STREAM_W", "EGNN_STREAM_CFG", "EGNN_STREAM_T"):
         os.environ.pop(k, None)
     os.environ.update(env)
     for ci, (cname, F, di, do, view, nbuf) in enumerate(cases):
