@@ -41,7 +41,7 @@ def peaks():
 def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of the roofline kernel, per launch, from the committed
     `ncu --set full` capture (profiles/); None when no capture is recorded."""
-    p = os.path.join(ROOT, "profiles", "r01", "roofline_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r02", "roofline_traffic.json")
     try:
         d = json.load(open(p))
         return int(d["dram_bytes_read"]) + int(d["dram_bytes_write"])

@@ -119,6 +119,7 @@ class TrainStep:
         self._keepalive = []
         self.health_check = health_check
         self.x, self.edge_index, self.timestep, self.y = x, edge_index, timestep, y
+        self.train_mask = train_mask
         self.train_idx = torch.nonzero(train_mask, as_tuple=False).view(-1).contiguous()  # once per run
         if cw is None and loss_fn is not None:
             cw = getattr(loss_fn, "cw", None)
@@ -288,6 +289,15 @@ class HostFeed:
         self.ei_flag_host = torch.zeros(1, dtype=torch.int32).pin_memory()
         self.rebuilds = 0
         self.h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+        # `TrainStep` reads the train mask and the labels ONCE (train-row indices, class weights, loss normaliser;
+        # static per run in the reference too): a feed that changes them must not be served from the stale copies.
+        # Their staged bytes are compared with the device buffers on every submit; a difference raises in run().
+        frozen_ptrs = {t.data_ptr() for t in (step.y, getattr(step, "train_mask", None)) if t is not None}
+        self.frozen = [k for k in host if device_bufs[k].data_ptr() in frozen_ptrs
+                       and device_bufs[k].data_ptr() % 16 == 0]
+        dev = self.ei_flag.device
+        self.frozen_flag = torch.zeros(max(len(self.frozen), 1), dtype=torch.int32, device=dev)
+        self.frozen_flag_host = torch.zeros(max(len(self.frozen), 1), dtype=torch.int32).pin_memory()
 
     def submit(self) -> None:
         """Start copying the host tensors (their current contents) for the next `run()`."""
@@ -304,6 +314,12 @@ class HostFeed:
                     check(lib().egnn_buffers_differ(ptr(a), ptr(b), a.numel() * a.element_size(), ptr(self.ei_flag),
                                                     cs.cuda_stream))
                     self.ei_flag_host.copy_(self.ei_flag, non_blocking=True)
+            for j, k in enumerate(self.frozen):
+                a, b = self.stage[k], self.dst[k]
+                check(lib().egnn_buffers_differ(ptr(a), ptr(b), a.numel() * a.element_size(),
+                                                self.frozen_flag[j:].data_ptr(), cs.cuda_stream))
+            if self.frozen:
+                self.frozen_flag_host.copy_(self.frozen_flag, non_blocking=True)
             self.ev_ready.record(cs)
 
     def run(self):
@@ -311,9 +327,14 @@ class HostFeed:
         main = torch.cuda.current_stream()
         main.wait_event(self.ev_ready)
         ei_changed = False
-        if "ei" in self.dst:
+        if "ei" in self.dst or self.frozen:
             self.ev_ready.synchronize()        # the copy of THIS step's inputs has landed (it overlapped the last step)
-            ei_changed = bool(int(self.ei_flag_host[0]))
+            ei_changed = "ei" in self.dst and bool(int(self.ei_flag_host[0]))
+            changed = [k for j, k in enumerate(self.frozen) if int(self.frozen_flag_host[j])]
+            if changed:
+                raise RuntimeError(f"HostFeed: host tensor(s) {changed} changed, but TrainStep read the train mask / "
+                                   "labels once at construction (train-row indices, class weights, loss normaliser); "
+                                   "build a new TrainStep for new masks or labels")
         if ei_changed:
             self.rebuilds += 1
             self.dst["ei"].copy_(self.stage["ei"], non_blocking=True)

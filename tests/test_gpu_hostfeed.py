@@ -68,3 +68,23 @@ def test_feed_picks_up_new_host_contents(egnn):
     fresh = egnn.build_graph(dev["ei"], gr.num_nodes)
     assert torch.equal(g.csr_src[: g.n_edges], fresh.csr_src[: fresh.n_edges])
     assert torch.equal(g.csr_part, fresh.csr_part)
+
+
+def test_feed_rejects_changed_mask_or_labels(egnn):
+    """TrainStep reads the train mask / labels once; a feed that changes them fails loudly instead of
+    stepping on stale train-row indices and class weights."""
+    from egnn_b200.train import HostFeed
+    for key in ("m", "y"):
+        gr, host, dev, step = _setup(egnn, False)
+        g = egnn.cached_graph(dev["ei"], gr.num_nodes)
+        feed = HostFeed(step, host, dev, gr.num_nodes, g)
+        assert set(feed.frozen) == {"m", "y"}
+        feed.submit()
+        feed.run()
+        if key == "m":
+            host["m"][:10] = ~host["m"][:10]
+        else:
+            host["y"][:10] = 1 - host["y"][:10].clamp(min=0)
+        feed.submit()
+        with pytest.raises(RuntimeError, match="build a new TrainStep"):
+            feed.run()
