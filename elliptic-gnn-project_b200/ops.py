@@ -808,6 +808,25 @@ def inject_time(x, t, table, width: int):
     return out
 
 
+def append_scalar_time(x: torch.Tensor, timestep: torch.Tensor) -> torch.Tensor:
+    """`use_time_scalar` (`src/train_gnn.py:314-317`): `cat([x, (timestep.float() / float(timestep.max())).unsqueeze(1)], 1)`
+    on the device, bit-exact with the reference's CPU computation: the distinct quotients (one per timestep value) are
+    computed on the host with the same torch division and gathered by `egnn_inject_time` as a [T, 1] table.
+    One host read of (t_min, t_max), like the reference's `float(data.timestep.max())`."""
+    if not (x.is_cuda and timestep.is_cuda):
+        raise RuntimeError("egnn_b200 appends the time column on the GPU only (no CPU fallback)")
+    x = _rows(x)
+    N, F = x.shape
+    t_min, t_max = (int(v) for v in torch.stack([timestep.min(), timestep.max()]).tolist())
+    table = (torch.arange(t_min, t_max + 1, dtype=torch.int64).float() / float(t_max)).unsqueeze(1).to(x.device)
+    t_rel = timestep if t_min == 1 else timestep - (t_min - 1)        # the kernel reads table[clamp(t - 1)]
+    ld = (F + 1 + 7) // 8 * 8        # 16-byte rows (the kernel stores float4s); the view returned is [N, F + 1]
+    out = torch.empty((N, ld), dtype=torch.float32, device=x.device)
+    check(lib().egnn_inject_time(ptr(x), _ld(x), ptr(t_rel.contiguous()), ptr(table), table.size(0), 1, ptr(out), None,
+                                 ld, 0, N, F, stream()))
+    return out[:, :F + 1]
+
+
 # ------------------------------------------------------------------------------- loss ----
 TIME_SCHEMES = {"none": 0, "linear": 1, "sqrt": 2}
 

@@ -150,6 +150,12 @@ def test_inject_time_bitexact(egnn):
     tab = (torch.arange(1, T + 1).float() / float(tt.max())).unsqueeze(1)
     got = ops.InjectTimeFn.apply(x.cuda(), tt.cuda(), tab.cuda(), 168)[0].cpu()
     assert torch.equal(got[:, :167], torch.cat([x, tn], dim=1)) and (got[:, 167] == 0).all()
+    # the public helper (builds the [T, 1] table itself), also for timestep ranges that do not start at 1
+    for lo, hi in ((1, 50), (0, 37), (5, 12)):
+        tt = torch.randint(lo, hi, (n,))
+        ref = torch.cat([x, (tt.float() / float(tt.max())).unsqueeze(1)], dim=1)      # src/train_gnn.py:315-317 on the CPU
+        got = egnn.append_scalar_time(x.cuda(), tt.cuda())
+        assert got.shape == (n, f + 1) and torch.equal(got.cpu(), ref)
 
 
 def test_p2p_allreduce_single_rank_protocol(egnn):
