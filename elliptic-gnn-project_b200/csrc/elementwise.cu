@@ -317,12 +317,23 @@ __global__ void __launch_bounds__(kThreads) colreduce_partial(Prod prod, int64_t
   if (c < F) {
     float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     int cnt = 0;
-    for (int64_t r = r0 + rl; r < r1; r += RL) {
-      F4 v0, v1;
-      prod.eval(r, c, v0, v1);
-      a[0] += v0.x; a[1] += v0.y; a[2] += v0.z; a[3] += v0.w;
-      a[4] += v1.x; a[5] += v1.y; a[6] += v1.z; a[7] += v1.w;
-      if (++cnt == 32) {
+    // four rows in flight per thread (one row at a time left every thread with a single load group outstanding:
+    // 33 us for the 33 MB of the GAT attention gradient); rows past the end contribute exact zeros
+    for (int64_t r = r0 + rl; r < r1; r += 4 * (int64_t)RL) {
+      F4 v0[4], v1[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t rr = r + (int64_t)u * RL;
+        if (rr < r1) prod.eval(rr, c, v0[u], v1[u]);
+        else { v0[u] = F4{0.f, 0.f, 0.f, 0.f}; v1[u] = F4{0.f, 0.f, 0.f, 0.f}; }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        a[0] += v0[u].x; a[1] += v0[u].y; a[2] += v0[u].z; a[3] += v0[u].w;
+        a[4] += v1[u].x; a[5] += v1[u].y; a[6] += v1[u].z; a[7] += v1[u].w;
+      }
+      cnt += 4;
+      if (cnt >= 32) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) { d[k] += (double)a[k]; a[k] = 0.f; }
         cnt = 0;
@@ -378,7 +389,11 @@ int run_colreduce(const Prod& prod, int64_t n_rows, int F, double* out0, double*
   int CW4 = 1;
   while (CW4 < ncg && CW4 < kThreads) CW4 <<= 1;
   int RL = kThreads / CW4;
-  int64_t rpb = (int64_t)RL * 32;
+  // rows per thread: a multiple of 4 (the rows in flight), 32 for big inputs, fewer when that would leave the grid
+  // below ~4 blocks per SM
+  int64_t rpt = ceil_div(n_rows > 0 ? n_rows : 1, (int64_t)RL * kNumSMs * 4);
+  rpt = rpt < 4 ? 4 : rpt > 32 ? 32 : (rpt + 3) / 4 * 4;
+  int64_t rpb = (int64_t)RL * rpt;
   if (ceil_div(n_rows, rpb) > kMaxPartBlocks) rpb = ceil_div(ceil_div(n_rows, kMaxPartBlocks), RL) * RL;
   int nblk = (int)ceil_div(n_rows > 0 ? n_rows : 1, rpb);
   dim3 grid(nblk, (unsigned)ceil_div(ncg, CW4));
