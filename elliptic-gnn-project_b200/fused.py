@@ -35,7 +35,10 @@ _STATIC = True
 # weight-gradient GEMMs on a side stream: they depend on dz only, while the chain to the next layer (dgrad GEMM ->
 # transposed aggregation -> BatchNorm backward -> cross-rank exchange) is latency-bound on several GPUs -- the side
 # stream fills the exchange's waiting time.  "auto": when the step is sharded (a statistics reducer is attached).
-OVERLAP_WGRAD = "auto"
+# weight-gradient GEMMs (and the weight packing of the forward) on a side stream: they are off the dependency chain of
+# the step, so they fill the waiting time of a BatchNorm exchange when sharded and the tails / launch gaps of the
+# narrow kernels on one GPU (rec_k8, N=1: 485 -> 465-478 us per graphed step).  False: everything on one stream.
+OVERLAP_WGRAD = True
 _SIDE = {}
 
 
@@ -201,14 +204,42 @@ def forward(net, x: torch.Tensor, g: Graph, t: Optional[torch.Tensor], training:
         return h32, cat0
 
     h32, cat = STATIC_INPUTS.get(x, t if use_t else None, table, (K0p, bf16), build_h0)
-    ops.spmm(g, "csr", _lib.SPMM_MEAN, h32, cd, out=cat[:, :K0p])
 
-    # logits layer operand [W_l ; W_r] (fp32, [2C, H])
+    # Operand packing depends on the parameters only: every layer's [[W_l | W_r], [0 | W_res]] (+ its transpose for the
+    # dgrad) and the logits layer's [W_l ; W_r] are written on the side stream while the layer-0 aggregation runs.
     out_conv = net.convs[-1]
     C_out = out_conv.out_channels
     wout = torch.empty((2 * C_out, H), dtype=torch.float32, device=dev)
-    check(L.egnn_concat2_f32(ptr(out_conv.lin_l.weight), C_out * H, ptr(out_conv.lin_r.weight), C_out * H, ptr(wout),
-                             stream()))
+    no_res = getattr(net, "no_residual", False)      # plain SAGENet (gnn.py:35-53): dropout(relu(conv(h))), no skip
+    packed = []
+    Kp, Kr = K0p, K0
+    for li in range(n_hidden):
+        proj = None if no_res else net.res_projs[li]
+        has_proj = proj is not None and not isinstance(proj, torch.nn.Identity)
+        Nr = H if has_proj else 0
+        wcat = torch.empty((H + Nr, 2 * Kp), dtype=cd, device=dev)
+        bias = torch.empty(H + Nr, dtype=torch.float32, device=dev)
+        want_wt = need_grad and (li > 0 or net.time_emb is not None)
+        wt = torch.empty((2 * Kp, H), dtype=cd, device=dev) if want_wt else None
+        packed.append((proj, has_proj, Nr, wcat, bias, wt, Kp, Kr))
+        Kp, Kr = H, H
+    main_st = torch.cuda.current_stream(dev)
+    side_st = _side_stream(dev) if (OVERLAP_WGRAD and need_grad) else main_st   # inference: one stream (eager launches)
+    if side_st is not main_st:
+        ev_fork = torch.cuda.Event()
+        ev_fork.record(main_st)
+        side_st.wait_event(ev_fork)
+    with torch.cuda.stream(side_st):
+        for li, (proj, has_proj, Nr, wcat, bias, wt, Kp_, Kr_) in enumerate(packed):
+            conv = net.convs[li]
+            check(L.egnn_pack_sage_weights(ptr(conv.lin_l.weight), ptr(conv.lin_r.weight),
+                                           ptr(proj.weight) if has_proj else None, ptr(conv.lin_l.bias), H, Nr, Kr_, Kp_,
+                                           ptr(wcat), ptr(bias), ptr(wt), dt(wcat), stream()))
+        check(L.egnn_concat2_f32(ptr(out_conv.lin_l.weight), C_out * H, ptr(out_conv.lin_r.weight), C_out * H,
+                                 ptr(wout), stream()))
+    ops.spmm(g, "csr", _lib.SPMM_MEAN, h32, cd, out=cat[:, :K0p])
+    if side_st is not main_st:
+        main_st.wait_stream(side_st)
     p_out = None
 
     layers: List[_Layer] = []
@@ -218,17 +249,7 @@ def forward(net, x: torch.Tensor, g: Graph, t: Optional[torch.Tensor], training:
         conv = net.convs[li]
         # the reference adds `res_projs[li](h_in)` whatever `residual` says (src/models/gnn.py:192; the flag is stored
         # but never read), and so does this path
-        no_res = getattr(net, "no_residual", False)      # plain SAGENet (gnn.py:35-53): dropout(relu(conv(h))), no skip
-        proj = None if no_res else net.res_projs[li]
-        has_proj = proj is not None and not isinstance(proj, torch.nn.Identity)
-        Nr = H if has_proj else 0
-        wcat = torch.empty((H + Nr, 2 * K), dtype=cd, device=dev)
-        bias = torch.empty(H + Nr, dtype=torch.float32, device=dev)
-        want_wt = need_grad and (li > 0 or net.time_emb is not None)
-        wt = torch.empty((2 * K, H), dtype=cd, device=dev) if want_wt else None
-        check(L.egnn_pack_sage_weights(ptr(conv.lin_l.weight), ptr(conv.lin_r.weight),
-                                       ptr(proj.weight) if has_proj else None, ptr(conv.lin_l.bias), H, Nr, Kraw, K,
-                                       ptr(wcat), ptr(bias), ptr(wt), dt(wcat), stream()))
+        proj, has_proj, Nr, wcat, bias, wt, _, _ = packed[li]
         zc = torch.empty((N, H + Nr), dtype=cd, device=dev)
         bn = net.bns[li] if net.use_bn else None
         stats_in_gemm = bn is not None and training and H <= 64
@@ -355,7 +376,7 @@ def backward(net, sv: Saved, dlogits: torch.Tensor, out: Optional[List[torch.Ten
         check(L.egnn_wgrad_tc(ptr(G), G.stride(0), ptr(X), X.stride(0), N, No, Kin, ptr(d0), ptr(d1), K, Kraw,
                               ptr(G2), G2.stride(0) if G2 is not None else 0, N2, ptr(d2), dt(G), ptr(ws), stream()))
 
-    overlap = (sv.reducer is not None) if OVERLAP_WGRAD == "auto" else bool(OVERLAP_WGRAD)
+    overlap = bool(OVERLAP_WGRAD)
     main_st = torch.cuda.current_stream(dev)
     side_st = _side_stream(dev) if overlap else None
     keep = []          # operands of side-stream kernels stay referenced until the streams join
