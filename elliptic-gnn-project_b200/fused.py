@@ -372,6 +372,20 @@ def backward(net, sv: Saved, dlogits: torch.Tensor, out: Optional[List[torch.Ten
         """[d0 | d1] = G^T X split at column K, zero-padding columns >= Kraw dropped; d2 = (G2^T X)[:, K:]"""
         No, Kin = G.size(1), X.size(1)
         N2 = G2.size(1) if G2 is not None else 0
+        if cd == torch.float32 and not ops.F32_TC_WGRAD:
+            # fp32 weight gradient on the exact FFMA kernel: a tensor-core accumulator sees ~500 truncating additions
+            # over a CTA's share of the node axis, a bias that does not average out (ops.py); the forward / dgrad
+            # products (42 - 126 additions) stay within the fp32 bar
+            def put(src, dstt):
+                check(L.egnn_cast(ptr(src), dt(src), src.stride(0), ptr(dstt), dt(dstt), dstt.stride(0), src.size(0),
+                                  src.size(1), stream()))
+            dW = ops.linear_wgrad(G, X, impl=1)
+            put(dW[:, :Kraw], d0)
+            if d1 is not None:
+                put(dW[:, K:K + Kraw], d1)
+            if G2 is not None:
+                put(ops.linear_wgrad(G2, X[:, K:], impl=1)[:, :Kraw], d2)
+            return
         ws = torch.empty(L.egnn_wgrad_tc_workspace_floats(No + N2, Kin), **f32)
         check(L.egnn_wgrad_tc(ptr(G), G.stride(0), ptr(X), X.stride(0), N, No, Kin, ptr(d0), ptr(d1), K, Kraw,
                               ptr(G2), G2.stride(0) if G2 is not None else 0, N2, ptr(d2), dt(G), ptr(ws), stream()))

@@ -152,10 +152,14 @@ GEMM_IMPL = 0  # 0 auto (tcgen05 for bf16 where supported), 1 force SIMT, 2 forc
 # LOGITS inside the rel-1e-5 bar (every eval forward), but the tensor core adds into its fp32 accumulator with
 # truncation, a bias that does not average out: through three layers of forward + backward the parameter gradients land
 # at ~1e-4 of the oracle's.  So: inference (no autograd) uses the tensor cores, TRAINING in fp32 stays on the exact
-# FFMA kernels unless EGNN_F32_TC_TRAIN=1 (or ops.F32_TC_TRAIN = True) opts in to the faster, looser path.
+# FFMA kernels unless EGNN_F32_TC_TRAIN=1 (or ops.F32_TC_TRAIN = True) opts in to the faster, looser path (measured: sage.yaml
+# fp32 1.60 -> 1.13 ms, gcn.yaml 1.75 -> 1.33 ms per step; 4 of 249 fp32 parity tests then miss their bars at ~1e-4).
 import os as _os
 
 F32_TC_TRAIN = _os.environ.get("EGNN_F32_TC_TRAIN", "0") == "1"
+# the weight-gradient product (contraction over ALL nodes: ~500 truncating accumulator additions per CTA) is where the
+# bias comes from; it stays on FFMA even when the forward / dgrad products of fp32 training use the tensor cores
+F32_TC_WGRAD = _os.environ.get("EGNN_F32_TC_WGRAD", "0") == "1"
 _F32_TC = False
 
 
@@ -218,6 +222,8 @@ def linear_wgrad(g, x, impl=None):
     out = torch.empty((N, K), dtype=torch.float32, device=g.device)
     tiles = -(-N // 128) * -(-K // 64)
     split = max(1, min(-(-M // 512), -(-2 * 148 // tiles)))
+    if impl is None and g.dtype == torch.float32 and x.dtype == torch.float32 and not F32_TC_WGRAD:
+        impl = 1
     _gemm(g, 1, _ld(g), x, _ld(x), 1, out, N, K, M, None, False, split_k=split, impl=impl, need_ws=True)
     return out
 
