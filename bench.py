@@ -461,10 +461,12 @@ def run_ours(args):
 
     def e2e_run(n):
         feed.submit()
+        if n > 1:
+            feed.submit()       # one submission ahead: the copy of step i+2 is queued before run(i+1) wakes the host
         losses = []
         for i in range(n):
             prev = feed.run()
-            if i + 1 < n:
+            if i + 2 < n:
                 feed.submit()
             if prev is not None:
                 losses.append(prev)

@@ -265,7 +265,8 @@ class HostFeed:
     step reads (device-to-device, ~40 us for the 135 MB feature matrix), rebuilds the CSR/CSC views and the row
     partition from the new `edge_index` on a side stream, runs the step and starts the loss read-back.  The copy of
     step i+1 therefore overlaps the compute of step i, and the loss of step i is read while step i+1 runs:
-    steady-state time per step = max(PCIe copy, rebuild + step).  Call order: submit(); run(); submit(); run(); ...
+    steady-state time per step = max(PCIe copy, rebuild + step).  Call order: submit(); run(); submit(); run(); ... or,
+    to keep the link busy across the host-side gaps, one submission ahead: submit(); submit(); run(); submit(); run(); ...
     """
 
     def __init__(self, step: TrainStep, host: dict, device_bufs: dict, num_nodes: int, graph):
@@ -277,15 +278,20 @@ class HostFeed:
         for k, v in host.items():
             if not v.is_pinned():
                 raise ValueError(f"host tensor '{k}' must be pinned")
-        self.stage = {k: torch.empty_like(device_bufs[k]) for k in host}
+        # two staging sets: the copy of submission j+1 is queued behind the copy of submission j on the copy stream
+        # without waiting for run(j), so the PCIe link never idles between steps (one set left a ~0.18 ms gap per step:
+        # host wake-up after the copy + the Python time of run() and submit())
+        self.stage = [{k: torch.empty_like(device_bufs[k]) for k in host} for _ in range(2)]
         self.copy_stream, self.side = torch.cuda.Stream(), torch.cuda.Stream()
-        self.ev_ready, self.ev_free = torch.cuda.Event(), torch.cuda.Event()
-        self.ev_ei, self.ev_graph = torch.cuda.Event(), torch.cuda.Event()
+        self.ev_ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.ev_free = [torch.cuda.Event(), torch.cuda.Event()]
+        self.ev_ei, self.ev_graph, self.ev_cmp = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
         self.loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
         self.ev_loss = [torch.cuda.Event(), torch.cuda.Event()]
         self.i = 0
-        self._consumed_once = False
-        self.ei_flag = torch.zeros(1, dtype=torch.int32, device=next(iter(device_bufs.values())).device)
+        self.n_sub = self.n_run = 0
+        dev = next(iter(device_bufs.values())).device
+        self.ei_flag = torch.zeros(1, dtype=torch.int32, device=dev)
         self.ei_flag_host = torch.zeros(1, dtype=torch.int32).pin_memory()
         self.rebuilds = 0
         self.h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
@@ -295,49 +301,62 @@ class HostFeed:
         frozen_ptrs = {t.data_ptr() for t in (step.y, getattr(step, "train_mask", None)) if t is not None}
         self.frozen = [k for k in host if device_bufs[k].data_ptr() in frozen_ptrs
                        and device_bufs[k].data_ptr() % 16 == 0]
-        dev = self.ei_flag.device
-        self.frozen_flag = torch.zeros(max(len(self.frozen), 1), dtype=torch.int32, device=dev)
-        self.frozen_flag_host = torch.zeros(max(len(self.frozen), 1), dtype=torch.int32).pin_memory()
+        nf = max(len(self.frozen), 1)
+        self.frozen_flag = torch.zeros((2, nf), dtype=torch.int32, device=dev)
+        self.frozen_flag_host = torch.zeros((2, nf), dtype=torch.int32).pin_memory()
 
     def submit(self) -> None:
-        """Start copying the host tensors (their current contents) for the next `run()`."""
+        """Start copying the host tensors (their current contents) for a later `run()`; at most two submissions may be
+        ahead of the runs."""
+        if self.n_sub - self.n_run >= 2:
+            raise RuntimeError("HostFeed: two submissions are already waiting for their run()")
+        slot = self.n_sub & 1
         cs = self.copy_stream
-        if self._consumed_once:
-            cs.wait_event(self.ev_free)            # the previous step has taken its inputs out of the staging set
-        else:
+        if self.n_sub >= 2:
+            cs.wait_event(self.ev_free[slot])      # the run() of two submissions ago has emptied this staging set
+        elif self.n_sub == 0:
             cs.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(cs):
-            for k in sorted(self.host, key=lambda k: k != "ei"):   # edge_index first: its rebuild can start early
-                self.stage[k].copy_(self.host[k], non_blocking=True)
-                if k == "ei":   # did the edge list change?  (dst["ei"] is stable here: ev_free orders us after run())
-                    a, b = self.stage["ei"], self.dst["ei"]
-                    check(lib().egnn_buffers_differ(ptr(a), ptr(b), a.numel() * a.element_size(), ptr(self.ei_flag),
-                                                    cs.cuda_stream))
-                    self.ei_flag_host.copy_(self.ei_flag, non_blocking=True)
-            for j, k in enumerate(self.frozen):
-                a, b = self.stage[k], self.dst[k]
+            for k in sorted(self.host, key=lambda k: k != "ei"):   # edge_index first
+                self.stage[slot][k].copy_(self.host[k], non_blocking=True)
+            for j, k in enumerate(self.frozen):    # dst[k] never changes (a change raises), so this compare cannot race
+                a, b = self.stage[slot][k], self.dst[k]
                 check(lib().egnn_buffers_differ(ptr(a), ptr(b), a.numel() * a.element_size(),
-                                                self.frozen_flag[j:].data_ptr(), cs.cuda_stream))
+                                                self.frozen_flag[slot, j:].data_ptr(), cs.cuda_stream))
             if self.frozen:
-                self.frozen_flag_host.copy_(self.frozen_flag, non_blocking=True)
-            self.ev_ready.record(cs)
+                self.frozen_flag_host[slot].copy_(self.frozen_flag[slot], non_blocking=True)
+            self.ev_ready[slot].record(cs)
+        self.n_sub += 1
 
     def run(self):
-        """One step on the submitted inputs; returns the loss of the PREVIOUS step (None on the first call)."""
+        """One step on the oldest submitted inputs; returns the loss of the PREVIOUS step (None on the first call)."""
+        if self.n_run >= self.n_sub:
+            raise RuntimeError("HostFeed.run() without a submit()")
+        slot = self.n_run & 1
+        stage = self.stage[slot]
         main = torch.cuda.current_stream()
-        main.wait_event(self.ev_ready)
+        main.wait_event(self.ev_ready[slot])
         ei_changed = False
         if "ei" in self.dst or self.frozen:
-            self.ev_ready.synchronize()        # the copy of THIS step's inputs has landed (it overlapped the last step)
+            if "ei" in self.dst:
+                # did the edge list change?  Compared HERE, on the compute stream, against the edge list the views were
+                # built from as of this step (a compare at submit time could see dst["ei"] before the previous run()
+                # has updated it)
+                a, b = stage["ei"], self.dst["ei"]
+                check(lib().egnn_buffers_differ(ptr(a), ptr(b), a.numel() * a.element_size(), ptr(self.ei_flag),
+                                                main.cuda_stream))
+                self.ei_flag_host.copy_(self.ei_flag, non_blocking=True)
+            self.ev_cmp.record(main)
+            self.ev_cmp.synchronize()          # this step's inputs have landed (their copy overlapped the last step)
             ei_changed = "ei" in self.dst and bool(int(self.ei_flag_host[0]))
-            changed = [k for j, k in enumerate(self.frozen) if int(self.frozen_flag_host[j])]
+            changed = [k for j, k in enumerate(self.frozen) if int(self.frozen_flag_host[slot, j])]
             if changed:
                 raise RuntimeError(f"HostFeed: host tensor(s) {changed} changed, but TrainStep read the train mask / "
                                    "labels once at construction (train-row indices, class weights, loss normaliser); "
                                    "build a new TrainStep for new masks or labels")
         if ei_changed:
             self.rebuilds += 1
-            self.dst["ei"].copy_(self.stage["ei"], non_blocking=True)
+            self.dst["ei"].copy_(stage["ei"], non_blocking=True)
             self.ev_ei.record(main)
             with torch.cuda.stream(self.side):
                 self.side.wait_event(self.ev_ei)
@@ -346,19 +365,19 @@ class HostFeed:
             self._register(self.dst["ei"], self.n, self.graph)   # eager steps look the graph up by tensor version
         for k in self.host:
             if k != "ei":
-                self.dst[k].copy_(self.stage[k], non_blocking=True)
-        self.ev_free.record(main)
-        self._consumed_once = True
+                self.dst[k].copy_(stage[k], non_blocking=True)
+        self.ev_free[slot].record(main)
+        self.n_run += 1
         if ei_changed:
             main.wait_event(self.ev_graph)
         self.step.run(dynamic=True)
-        slot = self.i & 1
-        self.loss_host[slot].copy_(self.step.loss, non_blocking=True)
-        self.ev_loss[slot].record(main)
+        lslot = self.i & 1
+        self.loss_host[lslot].copy_(self.step.loss, non_blocking=True)
+        self.ev_loss[lslot].record(main)
         prev = None
         if self.i > 0:
-            self.ev_loss[slot ^ 1].synchronize()
-            prev = float(self.loss_host[slot ^ 1])
+            self.ev_loss[lslot ^ 1].synchronize()
+            prev = float(self.loss_host[lslot ^ 1])
         self.i += 1
         return prev
 

@@ -26,25 +26,32 @@ def _setup(egnn, capture):
     return gr, host, dev, step
 
 
+@pytest.mark.parametrize("ahead", [1, 2])
 @pytest.mark.parametrize("capture", [False, True])
-def test_feed_reproduces_resident_steps(egnn, capture):
+def test_feed_reproduces_resident_steps(egnn, capture, ahead):
+    """`ahead` = submissions in flight: 1 = submit(); run(); submit(); ...  2 = one submission ahead (two staging sets)."""
     from egnn_b200.train import HostFeed
     gr, host, dev, step = _setup(egnn, capture)
-    ref = [float(step.run()) for _ in range(4)]
+    ref = [float(step.run()) for _ in range(5)]
     gr2, host2, dev2, step2 = _setup(egnn, capture)           # identical second run, fed from the host
     g = egnn.cached_graph(dev2["ei"], gr2.num_nodes)
     feed = HostFeed(step2, host2, dev2, gr2.num_nodes, g)
     got = []
-    feed.submit()
-    for i in range(4):
+    for _ in range(ahead):
+        feed.submit()
+    for i in range(5):
         prev = feed.run()
-        if i < 3:
+        if i + ahead < 5:
             feed.submit()
         if prev is not None:
             got.append(prev)
     got.append(feed.drain())
     assert got == ref
     assert feed.rebuilds == 0          # unchanged edge list: the sorted views are never rebuilt
+    feed.submit()
+    feed.submit()
+    with pytest.raises(RuntimeError, match="already waiting"):
+        feed.submit()
 
 
 def test_feed_picks_up_new_host_contents(egnn):
