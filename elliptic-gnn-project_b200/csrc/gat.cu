@@ -799,6 +799,12 @@ extern "C" int egnn_gat_fwd(const int32_t* csr_ptr, const int32_t* csr_src, cons
 #define EGNN_GAT_FWD(HT_)                                                                                         \
   gat_fwd_kernel<kGatLanes, HT_><<<(unsigned)ceil_div(n_rows * kGatLanes, kThreads), kThreads, 0, (cudaStream_t)stream>>>( \
       csr_ptr, csr_src, xs, a_s, a_d, negative_slope, H, C, concat, bias, alpha, out, n_rows)
+  if (H == 1 && C <= 4) {   // the logits layer (1 head x 2): 4 lanes per row -- half the warps, half the waves
+    gat_fwd_kernel<4, 1><<<(unsigned)ceil_div(n_rows * 4, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        csr_ptr, csr_src, xs, a_s, a_d, negative_slope, H, C, concat, bias, alpha, out, n_rows);
+    EGNN_LAUNCH_CHECK(fn);
+    return 0;
+  }
   switch (H) {
     case 1: EGNN_GAT_FWD(1); break;
     case 2: EGNN_GAT_FWD(2); break;
@@ -836,6 +842,12 @@ extern "C" int egnn_gat_bwd_src(const int32_t* csc_ptr, const int32_t* csc_dst, 
 #define EGNN_GAT_BSRC(HT_)                                                                                        \
   gat_bwd_src_kernel<kGatLanes, HT_><<<(unsigned)ceil_div(n_rows * kGatLanes, kThreads), kThreads, 0, (cudaStream_t)stream>>>( \
       csc_ptr, csc_dst, csc_pos, alpha, dpre, dout, da_d, att_src, att_dst, H, C, concat, dxs, da_s, n_rows)
+  if (H == 1 && C <= 4) {
+    gat_bwd_src_kernel<4, 1><<<(unsigned)ceil_div(n_rows * 4, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        csc_ptr, csc_dst, csc_pos, alpha, dpre, dout, da_d, att_src, att_dst, H, C, concat, dxs, da_s, n_rows);
+    EGNN_LAUNCH_CHECK(fn);
+    return 0;
+  }
   switch (H) {
     case 1: EGNN_GAT_BSRC(1); break;
     case 2: EGNN_GAT_BSRC(2); break;
