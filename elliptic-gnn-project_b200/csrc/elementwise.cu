@@ -1194,7 +1194,18 @@ colstats_parts_kernel(const float* __restrict__ parts, int n_parts, int F, doubl
   if (c < F) {
     // group gq sums parts gq, gq + 16, ... in that order: every (group, column) chain is fixed, and so is the
     // order in which the 16 group totals are combined below
-    for (int p = gq; p < n_parts; p += kPartGroups) {
+    int p = gq;
+    for (; p + 3 * kPartGroups < n_parts; p += 4 * kPartGroups) {   // four parts in flight, same summation order
+      float a[4], b[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        a[u] = parts[(size_t)(p + u * kPartGroups) * 2 * F + c];
+        b[u] = parts[(size_t)(p + u * kPartGroups) * 2 * F + F + c];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { s += (double)a[u]; q += (double)b[u]; }
+    }
+    for (; p < n_parts; p += kPartGroups) {
       s += (double)parts[(size_t)p * 2 * F + c];
       q += (double)parts[(size_t)p * 2 * F + F + c];
     }
