@@ -495,7 +495,20 @@ def run_ours(args):
         eval_probs(model, devb["x"], devb["ei"], devb["t"])
     ev1.record()
     barrier()
-    ms_eval = ev0.elapsed_time(ev1) / 5
+    ms_eval_eager = ev0.elapsed_time(ev1) / 5
+    # the same forward replayed as one CUDA graph (train.EvalStep; what metrics.fit runs per epoch): device-bound
+    from egnn_b200.train import EvalStep
+    evs = EvalStep(model, devb["x"], devb["ei"], devb["t"]).capture()
+    for _ in range(3):
+        evs.run()
+    barrier()
+    ev0.record()
+    for _ in range(20):
+        evs.run()
+    ev1.record()
+    barrier()
+    ms_eval = ev0.elapsed_time(ev1) / 20
+    del evs
     # ---- epoch tail on the device: validation PR-AUC from the eval logits + early-stopping
     # bookkeeping with the best-parameter snapshot (the reference does these on the host, src/train_gnn.py:387-402)
     from egnn_b200 import metrics as dev_metrics
@@ -612,7 +625,7 @@ def run_ours(args):
             "metric": METRIC, "value": round(e_total / (ms_step * 1e-3) / 1e9, 4), "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4),
             "epoch_ms": round(ms_step, 4), "ms_per_step_inputs_rederived": round(ms_dyn, 4) if ms_dyn else None,
-            "eval_fwd_ms": round(ms_eval, 4),
+            "eval_fwd_ms": round(ms_eval, 4), "eval_fwd_eager_ms": round(ms_eval_eager, 4),
             "ref_epoch_ms": round(ms_step + ms_eval, 4), "epoch_tail_ms": round(ms_tail, 4),
             "val_pr_auc": {"value": round(val_ap[0], 6), "rows": int(val_ap[1]), "positives": int(val_ap[2]),
                            "where": "device (egnn_average_precision + egnn_early_stop_update)"},

@@ -229,7 +229,7 @@ def forward(net, x: torch.Tensor, g: Graph, t: Optional[torch.Tensor], training:
         ev_fork = torch.cuda.Event()
         ev_fork.record(main_st)
         side_st.wait_event(ev_fork)
-    with torch.cuda.stream(side_st):
+    with (torch.cuda.stream(side_st) if side_st is not main_st else contextlib.nullcontext()):   # no stream switch on the eager inference path
         for li, (proj, has_proj, Nr, wcat, bias, wt, Kp_, Kr_) in enumerate(packed):
             conv = net.convs[li]
             check(L.egnn_pack_sage_weights(ptr(conv.lin_l.weight), ptr(conv.lin_r.weight),

@@ -218,15 +218,21 @@ def fit(model, x, edge_index, timestep, y, train_mask, val_mask, *, lr: float, w
     from .train import TrainStep
     step = TrainStep(model, x, edge_index, timestep, y, train_mask, lr=lr, weight_decay=weight_decay,
                      grad_clip=grad_clip, amp=amp, health_check=health_check)
+    ev = None
     if capture:
+        from .train import EvalStep
         step.capture(warmup=2, preserve_state=True)
+        ev = EvalStep(model, x, edge_index, timestep).capture()     # the per-epoch eval forward as one graph too
     buffers = [b for b in model.buffers() if b.is_cuda and b.numel() > 0]
     stopper = EarlyStopper(patience=patience, flat_param=step.opt.flat_param, extra=buffers)
     ap = torch.empty(8, dtype=torch.float64, device=x.device)
     epochs = 0
     for epoch in range(1, max_epochs + 1):
         loss = step.run()
-        eval_pr_auc(model, x, edge_index, timestep, y, val_mask, out=ap)
+        if ev is not None:
+            average_precision(y, val_mask, logits=ev.run()[1].float().contiguous(), out=ap)
+        else:
+            eval_pr_auc(model, x, edge_index, timestep, y, val_mask, out=ap)
         stopper.update(ap)
         epochs = epoch
         if epoch % poll_every == 0 or epoch == max_epochs:

@@ -256,3 +256,27 @@ def test_final_metrics_matches_the_reference_run_tail(egnn):
         assert got["recall_at_precision"] == pytest.approx(M.recall_at_precision(yt, pt, 0.90), abs=2e-3)
         assert got["ece"] == pytest.approx(M.expected_calibration_error(yt, pt), abs=1e-5)
         assert got["n_test"] == int(tm.sum()) and got["pr_auc_illicit"] > 0.15
+
+
+def test_eval_step_graph_equals_eager(egnn, small_graph):
+    """train.EvalStep: the eval_split forward as one CUDA graph reproduces the eager forward bit for bit and follows
+    in-place changes of the parameters and the BatchNorm running statistics."""
+    from egnn_b200.train import EvalStep, eval_probs
+    gr = small_graph
+    cfg = dict(hidden_dim=64, layers=3, dropout=0.2, time_embed_dim=2, time_embed_type="sin", max_timestep=49)
+    torch.manual_seed(5)
+    model = egnn.build_model("sage_resbn", 166, cfg).cuda()
+    x, t = gr.x.cuda(), gr.timestep.cuda()
+    ei = torch.cat([gr.edge_index, gr.edge_index.flip(0)], 1).cuda()
+    ev = EvalStep(model, x, ei, t).capture()
+    for it in range(3):
+        p_e, l_e = eval_probs(model, x, ei, t)
+        p_g, l_g = ev.run()
+        assert torch.equal(l_g, l_e) and torch.equal(p_g, p_e), it
+        with torch.no_grad():                  # what a training step does between two evaluations
+            for p in model.parameters():
+                p.mul_(1.01)
+            for bn in model.bns:
+                bn.running_mean.add_(0.05)
+                bn.running_var.mul_(1.1)
+    assert not model.training
