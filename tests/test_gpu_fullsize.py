@@ -66,3 +66,44 @@ def test_full_size_train_step_fp32(egnn, full_graph, name):
         lr_ = ref(x, ei, gr.timestep if uses_t else None)
     assert_close(lo, lr_, REL_FP32, f"{name} eval logits")
     print(f"[full-size {name}] loss {float(loss_o.detach()):.6f} vs {float(loss_r.detach()):.6f}, worst grad rel {worst:.2e}")
+
+
+@pytest.mark.parametrize("name", ["rec_k8", "gat", "sage_l3"])
+def test_full_size_train_step_bf16(egnn, full_graph, name):
+    """The bf16-autocast step of the BASELINE configs that train under amp, at full size: the fused kernel sequence
+    (rec_k8, sage_l3) / the per-op path (gat) against the oracle's bf16-autocast step AND its fp32 step with the same
+    injected dropout masks -- loss within the stated bf16 tolerance, every gradient bounded relative to the bf16
+    oracle's own distance from fp32 (tests/util.py:assert_bf16_grads_bounded)."""
+    from egnn_b200 import ops
+    from egnn_b200.train import TrainStep
+    from util import REL_BF16, assert_bf16_grads_bounded
+    cfg = dict(CONFIGS[name])
+    gr = full_graph
+    x, ei = _inputs(gr, cfg)
+    ours, ref32 = _pair(lambda: egnn.build_model(cfg["arch"], cfg["in_dim"], cfg),
+                        lambda: O.build_model(cfg["arch"], cfg["in_dim"], cfg))
+    ref16 = O.build_model(cfg["arch"], cfg["in_dim"], cfg)
+    ref16.load_state_dict(ref32.state_dict())
+    ours.set_dropout_seed(77)
+    cw = O.class_weight(gr.y[gr.train_mask])
+    step = TrainStep(ours, x.cuda(), ei.cuda(), gr.timestep.cuda(), gr.y.cuda(), gr.train_mask.cuda(),
+                     lr=cfg["lr"], weight_decay=cfg["wd"], grad_clip=1.0, amp=True, cw=cw)
+    loss_o = float(step.run())
+    grads_o = [(n, p.grad.detach().clone().cpu()) for n, p in ours.named_parameters()]
+    masks = [ops.dropout_mask(gr.num_nodes, cfg["hidden_dim"], cfg["dropout"], 77, li, seed_off=ours._drop.offset).cpu()
+             for li in range(cfg["layers"] - 1)]
+
+    def oracle(net, bf16):
+        net.train()
+        uses_t = getattr(net, "time_embed_dim", 0) > 0
+        with torch.autocast(device_type="cpu", dtype=torch.bfloat16, enabled=bf16):
+            lg = net(x, ei, gr.timestep if uses_t else None, dropout_masks=masks)
+        loss = O.masked_weighted_ce(lg.float(), gr.y, gr.train_mask, cw)
+        loss.backward()
+        return float(loss), [(n, p.grad) for n, p in net.named_parameters()]
+
+    l32, g32 = oracle(ref32, False)
+    l16, g16 = oracle(ref16, True)
+    assert abs(loss_o - l32) <= max(REL_BF16 * abs(l32), 3 * abs(l16 - l32)), (name, loss_o, l32, l16)
+    worst = assert_bf16_grads_bounded(grads_o, g32, g16, what=f"full-size {name}")
+    print(f"[full-size bf16 {name}] loss {loss_o:.6f} vs fp32 {l32:.6f} / bf16 oracle {l16:.6f}, worst bound ratio {worst:.2f}")
