@@ -105,5 +105,13 @@ def test_full_size_train_step_bf16(egnn, full_graph, name):
     l32, g32 = oracle(ref32, False)
     l16, g16 = oracle(ref16, True)
     assert abs(loss_o - l32) <= max(REL_BF16 * abs(l32), 3 * abs(l16 - l32)), (name, loss_o, l32, l16)
-    worst = assert_bf16_grads_bounded(grads_o, g32, g16, what=f"full-size {name}")
+    # analytically-zero gradients (a conv bias feeding BatchNorm: what is left is the rounding noise of a cancelling
+    # sum, 1e-6 of the gradient scale in fp32 and 1e-5 in any bf16 path) are bounded against the global scale instead
+    gmax = max(g.abs().max().item() for _, g in g32)
+    zero = {n for n, g in g32 if g.abs().max().item() < 1e-4 * gmax}
+    for n, g in grads_o:
+        if n in zero:
+            assert g.abs().max().item() < 1e-3 * gmax, f"{name} grad {n}"
+    keep = lambda named: [(n, g) for n, g in named if n not in zero]
+    worst = assert_bf16_grads_bounded(keep(grads_o), keep(g32), keep(g16), what=f"full-size {name}")
     print(f"[full-size bf16 {name}] loss {loss_o:.6f} vs fp32 {l32:.6f} / bf16 oracle {l16:.6f}, worst bound ratio {worst:.2f}")
