@@ -205,7 +205,7 @@ def eval_pr_auc(model, x, edge_index, timestep, y, mask, out: Optional[torch.Ten
 
 def fit(model, x, edge_index, timestep, y, train_mask, val_mask, *, lr: float, weight_decay: float,
         grad_clip: float = 1.0, amp: bool = False, max_epochs: int = 200, patience: int = 20, poll_every: int = 10,
-        capture: bool = True, log=None, health_check=None) -> dict:
+        capture: bool = True, log=None, health_check=None, loss_fn=None) -> dict:
     """The reference's full-batch training loop (`/root/reference/src/train_gnn.py:375-417`) with the epoch tail on
     the device: per epoch one (captured) train step, one fp32 eval forward, the validation PR-AUC and the
     early-stopping update -- no host synchronisation.  The host looks at the device state every `poll_every`
@@ -214,10 +214,12 @@ def fit(model, x, edge_index, timestep, y, train_mask, val_mask, *, lr: float, w
     the reference's `best_state` even though the loop runs up to `poll_every - 1` steps past the stopping epoch.
     Epoch 1 is the first optimizer step from the initial weights: the CUDA-graph warm-up steps are rolled back
     (`TrainStep.capture(preserve_state=True)`).  `health_check` (e.g. `ShardedContext.check`) runs at every poll.
+    `loss_fn`: an `ops.make_loss_fn(cfg, cw, model, t_min, t_max)` callable for the focal / time-weighted / embed-L2
+    variants of `_make_loss_fn` (`src/train_gnn.py:136-183,372`); default = the class-weighted CE.
     Returns {best_val, best_epoch, epochs, stop_epoch, loss}."""
     from .train import TrainStep
     step = TrainStep(model, x, edge_index, timestep, y, train_mask, lr=lr, weight_decay=weight_decay,
-                     grad_clip=grad_clip, amp=amp, health_check=health_check)
+                     grad_clip=grad_clip, amp=amp, health_check=health_check, loss_fn=loss_fn)
     ev = None
     if capture:
         from .train import EvalStep
