@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(kThreads) gat_fwd_kernel(const int* __restrict
   // contiguous features of one head (F = 4 G, C % 4 == 0: the 4 x 8 hidden layer) -- one 16-byte gather and one
   // alpha per entry instead of four scalar walks over the row.  Products are rounded, adds sequential in stored
   // order (the oracle's scatter order) in every variant.
-  constexpr int kB = 8;
+  constexpr int kB = 4;   // entries in flight per batch: the usual row has 2-3 entries, 8 only cost registers
   if (concat && F == 4 * G && (C & 3) == 0) {
     const int f0 = 4 * lane, h = f0 / C;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -700,7 +700,7 @@ __global__ void __launch_bounds__(kThreads) gat_bwd_src_kernel(
   }
   __syncwarp();
   const float dscale = concat ? 1.f : 1.f / (float)Hc;
-  constexpr int kB = 8;  // entries in flight per batch (a hub row is walked by its lanes alone)
+  constexpr int kB = 4;  // entries in flight per batch (a hub row is walked by its lanes alone)
   if (concat && F == 4 * G && (C & 3) == 0) {  // four contiguous features of one head per lane: 16-byte gathers
     const int f0 = 4 * lane, h = f0 / C;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
