@@ -30,6 +30,7 @@ SIGNATURES = {
     "egnn_abi_version": (_i32, []),
     "egnn_last_error": (C.c_char_p, []),
     "egnn_launch_count": (_u64, []),
+    "egnn_set_f32_tc_exact": (_i32, [_i32]),
     "egnn_counter_add": (_i32, [_vp, _i64, _vp]),
     "egnn_graph_workspace_bytes": (_sz, [_i64, _i64, _i32]),
     "egnn_graph_build": (_i32, [_vp, _i64, _i64, _i32, _i32] + [_vp] * 16 + [_vp, _sz, _vp]),

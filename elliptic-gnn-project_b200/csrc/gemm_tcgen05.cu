@@ -107,6 +107,23 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// two 16-column slices, one wait: the second load's latency hides behind the first
+__device__ __forceinline__ void tmem_ld16x2(uint32_t taddr0, uint32_t taddr1, float* v0, float* v1) {
+  uint32_t r[16], u[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr0));
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+        "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+      : "r"(taddr1));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { v0[i] = __uint_as_float(r[i]); v1[i] = __uint_as_float(u[i]); }
+}
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
@@ -167,10 +184,18 @@ struct Epilogue {
 
 // Epilogue of gemm_tn_kernel for one warp: FLAGS bit 0 = +bias, bit 1 = /row count, bit 2 = += C, bit 3 = second
 // addend, bit 4 = column statistics.
-template <typename TC, int FLAGS>
+//
+// kExact (fp32 operands, Npad <= 128): the tensor core adds into its fp32 accumulator with TRUNCATION -- a bias of
+// half an ulp per MMA that does not average out over a 40-MMA chain and is coherent across outputs.  In this mode
+// every hi.hi product of one 8-wide k-step leaves the tensor core in a FRESH TMEM buffer (accumulate = 0) and is
+// added here, on the CUDA cores, with round-to-nearest into 64 accumulator registers per thread (the scheme of
+// Ootomo & Yokota for recovering fp32 accuracy).  TMEM is a ring of two "pairs" [2 k-steps][Npad columns]; t_full /
+// t_empty are that ring's barriers; K_exact = the contraction length (the pair sequence is derived from it exactly as
+// the MMA warp derives it).  The small hi.lo / lo.hi terms of a pair ride in its first buffer.
+template <typename TC, int FLAGS, bool kExact = false>
 __device__ __forceinline__ void epilogue_loop(const Epilogue& ep, const float* s_bias, uint64_t* t_full,
                                               uint64_t* t_empty, uint32_t tmem_base, int Npad, int M, int N,
-                                              int n_tiles, int q, int half, int lane) {
+                                              int n_tiles, int q, int half, int lane, int K_exact = 0) {
   constexpr bool kBias = FLAGS & 1, kDiv = (FLAGS & 2) != 0, kAcc = (FLAGS & 4) != 0;
   constexpr bool kAdd2 = (FLAGS & 8) != 0, kStats = (FLAGS & 16) != 0;
   float st_sum[kStats ? 2 : 1][16], st_sq[kStats ? 2 : 1][16];   // this warp's <= 2 chunks of the statistics columns
@@ -191,6 +216,7 @@ __device__ __forceinline__ void epilogue_loop(const Epilogue& ep, const float* s
   TC* __restrict__ Cbase = reinterpret_cast<TC*>(ep.C);
   const bool vec_ok = (ep.ld_c % 8 == 0) && ((uintptr_t)ep.C % 16 == 0);
   int it = 0;
+  uint32_t pc = 0;   // kExact: pairs consumed so far (ring position of the next one)
   for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
     const int buf = it & 1;
     const uint32_t use = (uint32_t)(it >> 1);
@@ -207,8 +233,44 @@ __device__ __forceinline__ void epilogue_loop(const Epilogue& ep, const float* s
         }
       }
     }
-    mbar_wait(&t_full[buf], use & 1);
-    tcgen05_fence_after();
+    float acc[kExact ? 4 : 1][16];
+    if constexpr (kExact) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[i][j] = 0.f;
+      const int n_steps = (K_exact + 7) >> 3;            // 8-wide k-steps of this tile
+      for (int k0 = 0; k0 < n_steps; k0 += 2, ++pc) {    // (a 32-wide chunk holds 4 steps: pairs never straddle chunks)
+        const uint32_t b = pc & 1;
+        mbar_wait(&t_full[b], (pc >> 1) & 1);
+        tcgen05_fence_after();
+        // a pair has its second k-step unless it is the last step of an odd-length tail
+        const bool two = k0 + 1 < n_steps;
+        const uint32_t p_addr = tmem_base + ((uint32_t)(q * 32) << 16) + b * 2u * (uint32_t)Npad;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c0 = half * 16 + 32 * i;
+          if (c0 < Npad) {
+            float v0[16], v1[16];
+            if (two) {
+              tmem_ld16x2(p_addr + c0, p_addr + Npad + c0, v0, v1);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) acc[kExact ? i : 0][j] = (acc[kExact ? i : 0][j] + v0[j]) + v1[j];
+            } else {
+              tmem_ld16(p_addr + c0, v0);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) acc[kExact ? i : 0][j] += v0[j];
+            }
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t_empty[b]);
+      }
+    } else {
+      mbar_wait(&t_full[buf], use & 1);
+      tcgen05_fence_after();
+    }
     float rdiv = 1.f, rinv = 1.f;
     if (kDiv && row_ok) {
       int d = ep.row_div_ptr[row + 1] - ep.row_div_ptr[row];
@@ -216,9 +278,19 @@ __device__ __forceinline__ void epilogue_loop(const Epilogue& ep, const float* s
       rinv = __frcp_rn(rdiv);
     }
     const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * Npad);
-    for (int c0 = half * 16; c0 < N; c0 += 32) {
+    constexpr int kSl = kExact ? 4 : 1;   // kExact: all (<= 4) slices of this warp, statically indexed registers
+    for (int cb = half * 16; cb < N; cb += 32 * kSl) {
+#pragma unroll
+    for (int sl = 0; sl < kSl; ++sl) {
+      const int c0 = cb + 32 * sl;
+      if (c0 >= N) break;
       float v[16];
-      tmem_ld16(t_addr + c0, v);
+      if constexpr (kExact) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = acc[kExact ? sl : 0][j];
+      } else {
+        tmem_ld16(t_addr + c0, v);
+      }
       if (!row_ok) continue;
       const int nv = min(16, N - c0);
       TC* c = Cbase + row * ep.ld_c + c0;
@@ -317,9 +389,12 @@ __device__ __forceinline__ void epilogue_loop(const Epilogue& ep, const float* s
         }
       }
     }
-    tcgen05_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&t_empty[buf]);
+    }
+    if constexpr (!kExact) {
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_empty[buf]);
+    }
   }
   if (kStats) {
     // fixed butterfly over the 32 rows of this warp, the four sub-partitions combined in order through shared
@@ -544,7 +619,9 @@ __global__ void split_tf32_kernel(const float* __restrict__ w, int64_t n, float*
 // barriers / TMEM slot / bias / statistics scratch as in gemm_tn_kernel
 // kConvWarps: 2 (warps 2-3; 384 threads, every epilogue compiled in) or 6 (warps 2-3 and 12-15; 512 threads, i.e. 128
 // registers per thread: the statistics epilogues, which need more, are left out of that variant)
-template <int kStages, int kConvWarps>
+// kExact: see epilogue_loop -- every hi.hi k-step product into a fresh TMEM buffer, summed with IEEE adds by the epilogue
+// warps (Npad <= 128: ring of 2 pairs x 2 buffers x Npad columns = the whole 512-column TMEM at Npad = 128).
+template <int kStages, int kConvWarps, bool kExact>
 __global__ void __launch_bounds__(kThreadsTN + (kConvWarps - 2) * 32, 1)
 gemm_tn_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWhi,
                       const __grid_constant__ CUtensorMap tmWlo, int M, int N, int Npad, int K, Epilogue ep, int dbg) {
@@ -565,7 +642,7 @@ gemm_tn_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
   for (int i = threadIdx.x; i < 256 + 16; i += blockDim.x) s_bias[i] = (ep.bias && i < N) ? ep.bias[i] : 0.f;
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < 2 * Npad) tmem_cols <<= 1;
+  while ((int)tmem_cols < (kExact ? 4 : 2) * Npad) tmem_cols <<= 1;
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&conv[s], kConvWarps); mbar_init(&empty[s], 1); }
@@ -619,11 +696,14 @@ gemm_tn_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     int s = 0;
     uint32_t ph = 0;
     int it = 0;
+    uint32_t pc = 0;   // kExact: pairs issued so far
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
       const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
-      mbar_wait(&t_empty[buf], (use & 1) ^ 1);
-      tcgen05_fence_after();
+      if constexpr (!kExact) {
+        mbar_wait(&t_empty[buf], (use & 1) ^ 1);
+        tcgen05_fence_after();
+      }
       const uint32_t d_tmem = tmem_base + (uint32_t)(buf * Npad);
       for (int kc = 0; kc < KC; ++kc) {
         mbar_wait(&conv[s], ph);
@@ -635,6 +715,31 @@ gemm_tn_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           const uint32_t a_lo = a_hi + kStageBytesA;
           const uint32_t w_hi = a_hi + 2 * kStageBytesA;
           const uint32_t w_lo = w_hi + w_chunk_bytes;
+          if constexpr (kExact) {
+            for (int k4 = 0; k4 < n_k; k4 += 2, ++pc) {
+              const uint32_t b = pc & 1;
+              mbar_wait(&t_empty[b], ((pc >> 1) & 1) ^ 1);
+              tcgen05_fence_after();
+              const uint32_t d0 = tmem_base + b * 2u * (uint32_t)Npad, d1 = d0 + (uint32_t)Npad;
+              const bool two = k4 + 1 < n_k;
+              const uint64_t ah0 = make_desc(a_hi + k4 * 32, 16, 1024), al0 = make_desc(a_lo + k4 * 32, 16, 1024);
+              const uint64_t wh0 = make_desc(w_hi + k4 * 32, 16, 1024), wl0 = make_desc(w_lo + k4 * 32, 16, 1024);
+              const uint64_t ah1 = make_desc(a_hi + k4 * 32 + 32, 16, 1024), al1 = make_desc(a_lo + k4 * 32 + 32, 16, 1024);
+              const uint64_t wh1 = make_desc(w_hi + k4 * 32 + 32, 16, 1024), wl1 = make_desc(w_lo + k4 * 32 + 32, 16, 1024);
+              // the small terms of both k-steps first (their truncation is 2^-11 of the main term's), then ONE hi.hi
+              // product on top of them and the other hi.hi product alone in the pair's second buffer
+              tcgen05_mma_tf32(d0, al0, wh0, idesc, 0u);
+              tcgen05_mma_tf32(d0, ah0, wl0, idesc, 1u);
+              if (two) {
+                tcgen05_mma_tf32(d0, al1, wh1, idesc, 1u);
+                tcgen05_mma_tf32(d0, ah1, wl1, idesc, 1u);
+              }
+              tcgen05_mma_tf32(d0, ah0, wh0, idesc, 1u);
+              if (two) tcgen05_mma_tf32(d1, ah1, wh1, idesc, 0u);
+              tcgen05_commit(&t_full[b]);
+            }
+            tcgen05_commit(&empty[s]);
+          } else {
           for (int k4 = 0; k4 < n_k; ++k4) {
             const uint64_t ah = make_desc(a_hi + k4 * 32, 16, 1024), al = make_desc(a_lo + k4 * 32, 16, 1024);
             const uint64_t wh = make_desc(w_hi + k4 * 32, 16, 1024), wl = make_desc(w_lo + k4 * 32, 16, 1024);
@@ -648,6 +753,7 @@ gemm_tn_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           }
           tcgen05_commit(&empty[s]);
           if (kc == KC - 1) tcgen05_commit(&t_full[buf]);
+          }
         }
         __syncwarp();
         if (++s == kStages) { s = 0; ph ^= 1; }
@@ -660,10 +766,11 @@ gemm_tn_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #define EGNN_EPI_CASE(F)                                                                                      \
   case F:                                                                                                     \
     if (ep.c_dtype == EGNN_F32)                                                                               \
-      epilogue_loop<float, F>(ep, s_bias, t_full, t_empty, tmem_base, Npad, M, N, n_tiles, q, half, lane);    \
+      epilogue_loop<float, F, kExact>(ep, s_bias, t_full, t_empty, tmem_base, Npad, M, N, n_tiles, q, half,   \
+                                      lane, K);                                                               \
     else                                                                                                      \
-      epilogue_loop<__nv_bfloat16, F>(ep, s_bias, t_full, t_empty, tmem_base, Npad, M, N, n_tiles, q, half,   \
-                                      lane);                                                                  \
+      epilogue_loop<__nv_bfloat16, F, kExact>(ep, s_bias, t_full, t_empty, tmem_base, Npad, M, N, n_tiles, q, \
+                                              half, lane, K);                                                 \
     break;
     switch (flags) {
       EGNN_EPI_CASE(0) EGNN_EPI_CASE(1) EGNN_EPI_CASE(2) EGNN_EPI_CASE(3)
@@ -1130,6 +1237,7 @@ int gemm_tcgen05_dispatch(const void* A, int64_t lda, const void* B, int64_t ldb
 }
 
 // ---- fp32 operands (3xTF32) ----------------------------------------------------------------------------------------
+std::atomic<int> g_f32_tc_exact{1};
 static int tf32_stages(int Npad, bool stats) {
   const size_t stage = 2 * (size_t)kStageBytesA + 2 * (size_t)Npad * 128;
   const size_t fixed = 256 + 1088 + 1024 + (stats ? kStatsSmem : 0) + 64;
@@ -1178,10 +1286,12 @@ int gemm_tf32x3_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw,
   const size_t smem = stages * stage + 256 + 1088 + 1024 + (stats ? kStatsSmem : 0) + 64;
   static bool attr_set = false;
   if (!attr_set) {
-#define EGNN_TF32_ATTR(S, C) \
-  cudaFuncSetAttribute(gemm_tn_tf32x3_kernel<S, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmemTN)
-    EGNN_TF32_ATTR(4, 2); EGNN_TF32_ATTR(3, 2); EGNN_TF32_ATTR(2, 2);
-    EGNN_TF32_ATTR(4, 6); EGNN_TF32_ATTR(3, 6); EGNN_TF32_ATTR(2, 6);
+#define EGNN_TF32_ATTR(S, C, X) \
+  cudaFuncSetAttribute(gemm_tn_tf32x3_kernel<S, C, X>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmemTN)
+    EGNN_TF32_ATTR(4, 2, false); EGNN_TF32_ATTR(3, 2, false); EGNN_TF32_ATTR(2, 2, false);
+    EGNN_TF32_ATTR(4, 6, false); EGNN_TF32_ATTR(3, 6, false); EGNN_TF32_ATTR(2, 6, false);
+    EGNN_TF32_ATTR(4, 2, true); EGNN_TF32_ATTR(3, 2, true); EGNN_TF32_ATTR(2, 2, true);
+    EGNN_TF32_ATTR(4, 6, true); EGNN_TF32_ATTR(3, 6, true); EGNN_TF32_ATTR(2, 6, true);
 #undef EGNN_TF32_ATTR
     attr_set = true;
   }
@@ -1191,13 +1301,22 @@ int gemm_tf32x3_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw,
               stats, (int)stats_cols};
   static int dbg = -1;
   if (dbg < 0) { const char* e = getenv("EGNN_TF32_DEBUG"); dbg = e ? atoi(e) : 0; }
-#define EGNN_TF32_LAUNCH(S, C)                                                                                  \
-  gemm_tn_tf32x3_kernel<S, C><<<grid, kThreadsTN + (C - 2) * 32, smem, st>>>(tmA, tmWhi, tmWlo, (int)M, (int)N, Npad, \
-                                                                             (int)K, ep, dbg)
-  if (stats) {   // statistics epilogue: the 384-thread variant
-    if (stages == 4) EGNN_TF32_LAUNCH(4, 2); else if (stages == 3) EGNN_TF32_LAUNCH(3, 2); else EGNN_TF32_LAUNCH(2, 2);
+#define EGNN_TF32_LAUNCH(S, C, X)                                                                                  \
+  gemm_tn_tf32x3_kernel<S, C, X><<<grid, kThreadsTN + (C - 2) * 32, smem, st>>>(tmA, tmWhi, tmWlo, (int)M, (int)N, Npad, \
+                                                                                (int)K, ep, dbg)
+  // exact accumulation (IEEE adds of the k-step products outside the tensor core) wherever the TMEM ring fits,
+  // unless the caller asked for the in-TMEM accumulate (egnn_set_f32_tc_exact(0): no-grad forwards)
+  const bool exact = Npad <= 128 && !(dbg & 4) && g_f32_tc_exact.load(std::memory_order_relaxed) != 0;
+  if (exact) {
+    if (stats) {   // statistics epilogue: the 384-thread variant
+      if (stages == 4) EGNN_TF32_LAUNCH(4, 2, true); else if (stages == 3) EGNN_TF32_LAUNCH(3, 2, true); else EGNN_TF32_LAUNCH(2, 2, true);
+    } else {
+      if (stages == 4) EGNN_TF32_LAUNCH(4, 6, true); else if (stages == 3) EGNN_TF32_LAUNCH(3, 6, true); else EGNN_TF32_LAUNCH(2, 6, true);
+    }
+  } else if (stats) {
+    if (stages == 4) EGNN_TF32_LAUNCH(4, 2, false); else if (stages == 3) EGNN_TF32_LAUNCH(3, 2, false); else EGNN_TF32_LAUNCH(2, 2, false);
   } else {
-    if (stages == 4) EGNN_TF32_LAUNCH(4, 6); else if (stages == 3) EGNN_TF32_LAUNCH(3, 6); else EGNN_TF32_LAUNCH(2, 6);
+    if (stages == 4) EGNN_TF32_LAUNCH(4, 6, false); else if (stages == 3) EGNN_TF32_LAUNCH(3, 6, false); else EGNN_TF32_LAUNCH(2, 6, false);
   }
 #undef EGNN_TF32_LAUNCH
   EGNN_LAUNCH_CHECK(fn);
@@ -1342,3 +1461,5 @@ int wgrad_tcgen05_dispatch(const void* G, int64_t ldg, const void* X, int64_t ld
 }
 
 }  // namespace egnn
+
+extern "C" int egnn_set_f32_tc_exact(int exact) { return egnn::g_f32_tc_exact.exchange(exact ? 1 : 0); }

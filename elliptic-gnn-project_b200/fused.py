@@ -373,9 +373,7 @@ def backward(net, sv: Saved, dlogits: torch.Tensor, out: Optional[List[torch.Ten
         No, Kin = G.size(1), X.size(1)
         N2 = G2.size(1) if G2 is not None else 0
         if cd == torch.float32 and not ops.F32_TC_WGRAD:
-            # fp32 weight gradient on the exact FFMA kernel: a tensor-core accumulator sees ~500 truncating additions
-            # over a CTA's share of the node axis, a bias that does not average out (ops.py); the forward / dgrad
-            # products (42 - 126 additions) stay within the fp32 bar
+            # EGNN_F32_TC_WGRAD=0: fp32 weight gradient on the exact FFMA kernel (ops.py)
             def put(src, dstt):
                 check(L.egnn_cast(ptr(src), dt(src), src.stride(0), ptr(dstt), dt(dstt), dstt.stride(0), src.size(0),
                                   src.size(1), stream()))

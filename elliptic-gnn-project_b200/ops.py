@@ -148,26 +148,34 @@ def spmm(g: Graph, view: str, mode: int, x: torch.Tensor, out_dtype: torch.dtype
 
 GEMM_IMPL = 0  # 0 auto (tcgen05 for bf16 where supported), 1 force SIMT, 2 force tcgen05
 
-# fp32 operands on the tensor cores (3xTF32, csrc/gemm_tcgen05.cu).  One product is ~2e-6 accurate, which keeps fp32
-# LOGITS inside the rel-1e-5 bar (every eval forward), but the tensor core adds into its fp32 accumulator with
-# truncation, a bias that does not average out: through three layers of forward + backward the parameter gradients land
-# at ~1e-4 of the oracle's.  So: inference (no autograd) uses the tensor cores, TRAINING in fp32 stays on the exact
-# FFMA kernels unless EGNN_F32_TC_TRAIN=1 (or ops.F32_TC_TRAIN = True) opts in to the faster, looser path (measured: sage.yaml
-# fp32 1.60 -> 1.13 ms, gcn.yaml 1.75 -> 1.33 ms per step; 4 of 249 fp32 parity tests then miss their bars at ~1e-4).
+# fp32 operands on the tensor cores (3xTF32 with EXACT accumulation, csrc/gemm_tcgen05.cu).  The tensor core adds into
+# its fp32 accumulator with truncation, a bias that does not average out (round 2, first version: parameter gradients at
+# ~1e-4 of the oracle's through three layers of forward + backward).  The kernels therefore take every 8-wide k-step
+# product out of the tensor core in a fresh TMEM buffer and add it with IEEE round-to-nearest on the CUDA cores (forward /
+# dgrad, `kExact`), and split the weight gradient's node axis into phases of <= 132 tensor-core additions combined with
+# IEEE adds.  Measured at full size against the CPU oracle (profiles/r02/f32_tc_probe.txt): gcn.yaml / sage.yaml
+# gradients within 2e-6 (FFMA: 4e-7), sage.yaml fp32 1.60 -> 0.66 ms, gcn.yaml 1.75 -> 1.13 ms, rec_k8 fp32 2.72 -> 1.29
+# ms per step.  EGNN_F32_TC_TRAIN=0 / EGNN_F32_TC_WGRAD=0 (or the module attributes) put fp32 TRAINING back on the exact
+# FFMA kernels (gemm_simt.cu); no-grad forwards always use the tensor cores.
 import os as _os
 
-F32_TC_TRAIN = _os.environ.get("EGNN_F32_TC_TRAIN", "0") == "1"
-# the weight-gradient product (contraction over ALL nodes: ~500 truncating accumulator additions per CTA) is where the
-# bias comes from; it stays on FFMA even when the forward / dgrad products of fp32 training use the tensor cores
-F32_TC_WGRAD = _os.environ.get("EGNN_F32_TC_WGRAD", "0") == "1"
+F32_TC_TRAIN = _os.environ.get("EGNN_F32_TC_TRAIN", "1") == "1"
+F32_TC_WGRAD = _os.environ.get("EGNN_F32_TC_WGRAD", "1") == "1"
 _F32_TC = False
+_F32_TC_EXACT = True      # the library's default
 
 
-def set_f32_tc():
-    """Called by the conv / net modules on entry (where autograd's mode is still visible): fp32 GEMMs of this forward
-    (and of its backward) may use the tensor cores iff no gradient will be taken or the caller opted in."""
-    global _F32_TC
-    _F32_TC = F32_TC_TRAIN or not torch.is_grad_enabled()
+def set_f32_tc(grad: Optional[bool] = None):
+    """Called by the conv / net modules on entry (where autograd's mode is still visible) and by the explicit train
+    step: fp32 GEMMs of this forward (and of its backward) use the tensor cores unless a gradient will be taken AND the
+    caller opted out; they accumulate exactly iff a gradient will be taken."""
+    global _F32_TC, _F32_TC_EXACT
+    if grad is None:
+        grad = torch.is_grad_enabled()
+    _F32_TC = F32_TC_TRAIN or not grad
+    if grad != _F32_TC_EXACT:        # exact accumulation for anything a gradient is taken of (include/egnn_b200.h)
+        lib().egnn_set_f32_tc_exact(int(grad))
+        _F32_TC_EXACT = grad
     return _F32_TC
 
 

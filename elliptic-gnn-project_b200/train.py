@@ -136,7 +136,7 @@ class TrainStep:
         m = self.model
         return (((isinstance(m, SAGEResBNNet) and type(m).forward is SAGEResBNNet.forward)
                  or (isinstance(m, SAGENet) and type(m).forward is _StackNet.forward))
-                and (self.amp or ops.F32_TC_TRAIN)      # fp32 training: exact FFMA path unless opted in (ops.py)
+                and (self.amp or ops.F32_TC_TRAIN)      # fp32: tensor cores with exact accumulation unless opted out (ops.py)
                 and fused.supported(m, self.x, self.amp) and all(p.requires_grad for p in m.parameters())
                 and len(self.opt.params) == len(fused.param_order(m)))
 
@@ -147,6 +147,8 @@ class TrainStep:
         m = self.model
         m.train()
         L = lib()
+        if not self.amp:
+            ops.set_f32_tc(True)      # fp32 operands: exact accumulation (a gradient is taken)
         g = self.edge_index if isinstance(self.edge_index, Graph) else cached_graph(self.edge_index, self.x.size(0))
         t = self.timestep if model_uses_time_embed(m) else None
         logits, sv = fused.forward(m, self.x, g, t, True, True, self.amp)

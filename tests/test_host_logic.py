@@ -134,3 +134,23 @@ def test_metrics_host_layer_rejects_cpu_tensors_and_bad_arguments():
         metrics.average_precision(y, None)
     with pytest.raises(ValueError):
         metrics.average_precision(y, None, scores=s, logits=torch.zeros(4, 2))
+
+
+def test_assert_close_gated_excuses_single_channels_only():
+    import pytest
+    import torch
+    from util import assert_close_gated
+    torch.manual_seed(0)
+    ref = torch.randn(64, 168)
+    got = ref + 1e-7 * torch.randn_like(ref)
+    assert assert_close_gated(got, ref, 2e-5)[1] == 0
+    flipped = got.clone()
+    flipped[61] += 2e-4 * ref.abs().max() * torch.randn(168).sign()      # one flipped gate: one output channel
+    e, n = assert_close_gated(flipped, ref, 2e-5)
+    assert n == 1 and e < 2e-5
+    with pytest.raises(AssertionError):                                   # a dense error is not excused
+        assert_close_gated(ref * (1 + 1e-4), ref, 2e-5)
+    with pytest.raises(AssertionError):                                   # nor a large one in a single channel
+        bad = got.clone()
+        bad[3] += 0.1
+        assert_close_gated(bad, ref, 2e-5)

@@ -20,6 +20,30 @@ def assert_close(got, ref, rel, what=""):
     return e
 
 
+def assert_close_gated(got, ref, rel, what="", max_units=2, loose=1e-3):
+    """`assert_close` for the gradient of a parameter that sits below a ReLU, at sizes where a gate is bound to sit on
+    its threshold: of the 13 M layer-0 pre-activations of rec_k8 on the full graph, ~10 lie within 1e-6 of zero in the
+    fp32 oracle (profiles/r02/f32_tc_probe.txt), i.e. within the distance between two CORRECT fp32 evaluations of the
+    layer (different summation orders; 3xTF32 products are ~1e-6 apart from FFMA ones).  Such a gate evaluated the
+    other way changes dz in ONE (row, channel) and therefore exactly ONE output channel of that layer's weight / bias
+    gradients (a rank-1 difference, shown by the probe) -- it is a discontinuity of the function, not an error of the
+    kernel.  So: every output channel (row of a 2-D gradient, element of a 1-D one) is held to `rel` of ||ref||_inf,
+    except that at most `max_units` of them may miss it, and those are held to `loose`.  Returns the worst error among
+    the channels held to `rel` and the number of excused channels."""
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    g, r = got.detach().double().cpu(), ref.detach().double().cpu()
+    denom = max(r.abs().max().item(), 1e-300)
+    err = (g - r).abs()
+    per_unit = (err.flatten(1).max(dim=1).values if err.dim() > 1 else err.flatten()) / denom
+    bad = per_unit > rel
+    n_bad = int(bad.sum())
+    assert n_bad <= max_units, f"{what}: {n_bad} output channels miss rel {rel:.1e} (worst {per_unit.max():.3e})"
+    if n_bad:
+        assert per_unit[bad].max().item() <= loose, f"{what}: excused channel at {per_unit[bad].max():.3e} > {loose:.1e}"
+    ok = per_unit[~bad]
+    return (ok.max().item() if ok.numel() else 0.0), n_bad
+
+
 def assert_bf16_grads_bounded(named_ours, named_ref32, named_ref16, what="", factor=3.0, floor=1.5 * REL_BF16):
     """bf16-autocast gradients, bounded RELATIVE TO THE bf16 ORACLE'S OWN DISTANCE FROM fp32: for every
     parameter, ||g_ours - g_fp32||_inf <= max(factor * ||g_oracle_bf16 - g_fp32||_inf, floor * ||g_fp32||_inf).
