@@ -11,4 +11,5 @@ from .graph import (Graph, GraphCache, ablate_hubs, build_graph, cached_graph, d
 from .nn import GATConv, GCNConv, SAGEConv  # noqa: F401
 from .models import GATNet, GCNNet, SAGENet, SAGEResBNNet, build_model  # noqa: F401
 from . import ingest, metrics, ops, synthetic  # noqa: F401
+from .loader import Batch, NeighborLoader  # noqa: F401
 from .ops import append_scalar_time, make_loss_fn  # noqa: F401

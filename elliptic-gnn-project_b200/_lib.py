@@ -37,6 +37,12 @@ SIGNATURES = {
     "egnn_hub_ablation_workspace_bytes": (_sz, [_i64, _i64]),
     "egnn_hub_ablation": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "egnn_edge_gather": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _vp]),
+    "egnn_neighbor_sample_caps": (_i32, [_i64, _i64, _i64, _vp, _i32, _vp, _vp]),
+    "egnn_neighbor_sample_workspace_bytes": (_sz, [_i64, _i64, _i64, _vp, _i32]),
+    "egnn_neighbor_sample_state_init": (_i32, [_vp, _i64, _vp]),
+    "egnn_neighbor_sample": (_i32, [_vp, _vp, _vp, _i64, _i64, _vp, _i64, _vp, _i32, _u64, _u64, _vp, _vp, _i64, _vp, _vp,
+                                    _i64, _vp, _vp, _vp, _sz, _vp]),
+    "egnn_gather_rows": (_i32, [_vp, _i64, _vp, _i64, _i64, _vp, _i64, _vp]),
     "egnn_txid_join_workspace_bytes": (_sz, [_i64, _i64]),
     "egnn_txid_join": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "egnn_temporal_masks": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),

@@ -450,3 +450,30 @@ def train_epoch(model, data, edge_index, optimizer, cw, cfg: dict, use_amp: bool
     optimizer.step()
     optimizer.zero_grad(set_to_none=True)
     return float(loss.item())
+
+
+def train_epoch_minibatch(model, loader, optimizer, loss_fn, cfg: dict, use_amp: bool = False) -> float:
+    """Mirror of the reference's `train_epoch_minibatch` (`src/train_gnn.py:212-245`) over an `egnn_b200.NeighborLoader`
+    (batches sampled and sliced on the device): per batch forward on the sampled subgraph, loss on the first
+    `batch.batch_size` rows (the seeds), backward, clip, optimizer step; returns the example-weighted mean loss.
+    `loss_fn(logits, target, t_idx)` as `make_loss_fn` returns it.  bf16 autocast instead of fp16 + GradScaler."""
+    model.train()
+    total_loss, total_examples = 0.0, 0
+    weighting = cfg.get("time_loss_weighting", "none") != "none"
+    for batch in loader:
+        batch = batch.to("cuda")
+        optimizer.zero_grad(set_to_none=True)
+        with torch.autocast(device_type="cuda", dtype=torch.bfloat16, enabled=use_amp):
+            logits = model(batch.x, batch.edge_index, batch.timestep if model_uses_time_embed(model) else None)
+        bs = batch.batch_size
+        t_idx = batch.timestep[:bs] if weighting else None
+        loss = loss_fn(logits[:bs], batch.y[:bs], t_idx)
+        loss.backward()
+        if cfg.get("grad_clip", 0) and cfg["grad_clip"] > 0:
+            torch.nn.utils.clip_grad_norm_(model.parameters(), cfg["grad_clip"])
+        optimizer.step()
+        optimizer.zero_grad(set_to_none=True)
+        total_loss += float(loss.item()) * int(bs)
+        total_examples += int(bs)
+    return float(total_loss / total_examples) if total_examples else 0.0
+

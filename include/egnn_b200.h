@@ -113,6 +113,35 @@ int egnn_hub_ablation(const int64_t* ei, int64_t n_edges, int64_t n_nodes, int64
 int egnn_edge_gather(const int64_t* ei, int64_t n_edges, const int64_t* idx, int64_t n_idx, int64_t* out,
                      int32_t* n_bad, void* stream);
 
+/* ---------------------------------------------------------------- mini-batch sampling -- */
+/* Replaces: torch_geometric.loader.NeighborLoader(data, num_neighbors=fanout, batch_size=..., input_nodes=...) as used by
+ * src/train_gnn.py:329-348 and consumed by train_epoch_minibatch (:212-245): one sampled subgraph per batch of seed nodes.
+ * Per hop h (fan-out fanouts[h], < 0 = all): every node added in the previous hop takes all its in-neighbours if it has
+ * at most fanouts[h] of them, else fanouts[h] distinct ones (Robert Floyd's algorithm over the positions of its row of
+ * the CSR-by-destination view, Philox4x32-10 keyed on (seed, batch_idx, hop, local id, draw)); sampled sources join the
+ * node list in order of first appearance; local id = position in the node list (seeds first, in the given order).
+ *   csr_ptr / csr_src / csr_eid  int32: the CSR-by-destination view of egnn_graph_build (stable: in-edges in original order)
+ *   seeds int64 [batch] DISTINCT node ids (device);  fanouts int32 [n_hops] on the HOST, n_hops <= 8
+ *   state int32 [2 * n_nodes]: set once by egnn_neighbor_sample_state_init, left clean by every call
+ *   n_id int64 [cap_nodes], edge_index int64 [2, cap_edges] (row stride cap_edges; row 0 = source, row 1 = destination,
+ *   LOCAL ids; edges ordered by hop, then frontier node, then draw), e_id int64 [cap_edges] (optional: original edge
+ *   column of every sampled edge), capacities from egnn_neighbor_sample_caps;
+ *   counts int32 [2 * n_hops + 2]: nodes after the seeds / every hop, then edges likewise; info int32 [2] = totals.
+ * Everything stays on the device (no synchronisation); the caller reads `info` to slice the outputs.
+ * egnn_gather_rows: out[i, :] = in[idx[i], :] for rows of row_bytes bytes (batch.x / y / timestep / masks). */
+int egnn_neighbor_sample_caps(int64_t n_nodes, int64_t n_edges, int64_t batch, const int32_t* fanouts, int n_hops,
+                              int64_t* cap_nodes, int64_t* cap_edges);
+size_t egnn_neighbor_sample_workspace_bytes(int64_t n_nodes, int64_t n_edges, int64_t batch, const int32_t* fanouts,
+                                            int n_hops);
+int egnn_neighbor_sample_state_init(int32_t* state, int64_t n_nodes, void* stream);
+int egnn_neighbor_sample(const int32_t* csr_ptr, const int32_t* csr_src, const int32_t* csr_eid, int64_t n_nodes,
+                         int64_t n_edges, const int64_t* seeds, int64_t batch, const int32_t* fanouts, int n_hops,
+                         uint64_t seed, uint64_t batch_idx, int32_t* state, int64_t* n_id, int64_t cap_nodes,
+                         int64_t* edge_index, int64_t* e_id, int64_t cap_edges, int32_t* counts, int32_t* info,
+                         void* workspace, size_t workspace_bytes, void* stream);
+int egnn_gather_rows(const void* in, int64_t ld_in_bytes, const int64_t* idx, int64_t n, int64_t row_bytes, void* out,
+                     int64_t ld_out_bytes, void* stream);
+
 /* ---------------------------------------------------------------- ingestion --------- */
 /* The Elliptic tables -> the device edge list (src/data/dataset_elliptic.py:190-245; the reference walks a Python
  * dict per edge endpoint on the host):
