@@ -221,6 +221,78 @@ def run_other_configs(dev, steps, peak):
     return out
 
 
+def run_minibatch(dev, with_cpu: bool):
+    """The mini-batch path (`mini_batch: true`, src/train_gnn.py:329-348,212-245) with the reference's defaults -- fanout
+    [10, 10], batch_size 8192 -- on the rec_k8 graph: per-batch time of the device-side NeighborLoader (sampling +
+    relabelling + row slices, one synchronisation per batch), batch 0 compared bit for bit with the sequential CPU
+    restatement of PyG's sampler (timed beside it), and the wall time of one mini-batch training epoch."""
+    import time as _time
+    import egnn_b200 as E
+    from egnn_b200 import _lib, synthetic
+    from egnn_b200.train import class_weight, train_epoch_minibatch
+    gr = synthetic.make_elliptic_like(train_window_k=CFG["train_window_k"])
+
+    class _D:
+        pass
+    d = _D()
+    d.x, d.y, d.timestep = gr.x.to(dev), gr.y.to(dev), gr.timestep.to(dev)
+    d.train_mask = gr.train_mask.to(dev)
+    ei_h = torch.cat([gr.edge_index, gr.edge_index.flip(0)], 1)
+    d.edge_index = ei_h.to(dev)
+    idx = torch.nonzero(d.train_mask).view(-1)
+    fan, bs = [10, 10], 8192
+    mk = lambda: E.NeighborLoader(d, num_neighbors=fan, batch_size=bs, input_nodes=idx, shuffle=False, seed=42)
+    loader = mk()
+    first = next(iter(loader))
+    for _ in loader:      # warm-up epoch
+        pass
+    torch.cuda.synchronize()
+    n0 = _lib.launch_count()
+    t0 = _time.perf_counter()
+    nb = nn = ne = 0
+    for _ in range(5):
+        for b in loader:
+            nb, nn, ne = nb + 1, nn + b.num_nodes, ne + int(b.edge_index.size(1))
+    torch.cuda.synchronize()
+    ms_batch = (_time.perf_counter() - t0) / nb * 1e3
+    out = {"workload": f"NeighborLoader(num_neighbors={fan}, batch_size={bs}, input_nodes=train_idx) on the rec_k8 graph "
+                       f"({idx.numel()} seed nodes, {len(loader)} batches per epoch)",
+           "ms_per_batch": round(ms_batch, 4), "nodes_per_batch": nn // nb, "edges_per_batch": ne // nb,
+           "gpu_launches_per_batch": int((_lib.launch_count() - n0) // nb),
+           "includes": "multi-hop sampling, relabelling, x / y / timestep / mask row slices, one 8-byte read-back"}
+    if with_cpu:
+        from oracle.neighbor_sample_np import csc_by_destination, neighbor_sample
+        ip, src, eid = csc_by_destination(ei_h.numpy(), gr.num_nodes)
+        t0 = _time.perf_counter()
+        n_id, le, e_id, _, _ = neighbor_sample(ip, src, eid, idx[:bs].cpu().numpy(), fan, seed=42, batch_idx=0)
+        cpu_ms = (_time.perf_counter() - t0) * 1e3
+        import numpy as _np
+        out["parity"] = {"what": "batch 0 vs the sequential CPU restatement of PyG's sampler (same Philox stream): "
+                                 "node list, local edge list, edge ids",
+                         "bit_exact": bool(_np.array_equal(first.n_id.cpu().numpy(), n_id)
+                                           and _np.array_equal(first.edge_index.cpu().numpy(), le)
+                                           and _np.array_equal(first.e_id.cpu().numpy(), e_id))}
+        out["cpu_ms_per_batch"] = round(cpu_ms, 1)
+        out["cpu_kind"] = "port (pure-Python sequential restatement, 1 core; sampling only, no row slices)"
+    torch.manual_seed(0)
+    model = E.build_model("sage_resbn", 166, {k: CFG[k] for k in ("hidden_dim", "layers", "dropout", "time_embed_dim",
+                                                                   "time_embed_type", "max_timestep") if k in CFG}).to(dev)
+    loss_fn = E.make_loss_fn({}, class_weight(d.y[d.train_mask]), model, 1, 49)
+    opt = torch.optim.Adam(model.parameters(), lr=5e-4, weight_decay=5e-5)
+    loader = E.NeighborLoader(d, num_neighbors=fan, batch_size=bs, input_nodes=idx, shuffle=True, seed=42)
+    train_epoch_minibatch(model, loader, opt, loss_fn, {"grad_clip": 1.0}, use_amp=True)
+    torch.cuda.synchronize()
+    t0 = _time.perf_counter()
+    for _ in range(3):
+        loss = train_epoch_minibatch(model, loader, opt, loss_fn, {"grad_clip": 1.0}, use_amp=True)
+    torch.cuda.synchronize()
+    out["epoch_ms"] = round((_time.perf_counter() - t0) / 3 * 1e3, 3)
+    out["epoch_loss"] = round(float(loss), 6)
+    out["epoch_what"] = "train_epoch_minibatch, rec_k8 net, bf16 autocast, eager (per batch: sample, graph build, fwd, bwd, clip, Adam)"
+    E.graph._GLOBAL_CACHE.clear()
+    return out
+
+
 def run_sage_l3_x64(dev, rank, world, steps, barrier, replicas=64):
     """BASELINE config 5 / north_star 'replicated scale-up': 3-layer SAGE (configs/sage_l3_k18.yaml) on 64 block-diagonal
     replicas of the Elliptic-shaped graph (N = 13 041 216, E' = 29 997 440), STRONG scaling: the 64 x 49 (replica, timestep)
@@ -608,6 +680,13 @@ def run_ours(args):
     other = None
     if world == 1 and rank == 0 and not args.skip_configs:
         other = run_other_configs(dev, max(10, min(args.steps, 30)), peak)
+    minib = None
+    if world == 1 and rank == 0 and not args.skip_configs:
+        try:
+            minib = run_minibatch(dev, with_cpu=not args.no_cpu_baseline)
+        except Exception as ex:   # never lose the headline line to a secondary workload
+            minib = {"failed": f"{type(ex).__name__}: {ex}"}
+        torch.cuda.empty_cache()
     x64 = None
     if not args.skip_x64:
         try:
@@ -655,7 +734,8 @@ def run_ours(args):
             "gpu_launches": int(launches_per_step * args.steps),
             "gpu_launches_per_step": int(launches_per_step),
             "roofline": roof, "kernels": kernels, "cpu_baseline": cpu,
-            "loss": round(final_loss, 6), "parity": parity, "configs": other, "sage_l3_x64": x64,
+            "loss": round(final_loss, 6), "parity": parity, "configs": other, "minibatch": minib,
+            "sage_l3_x64": x64,
         }
         if stdout_fd is not None:
             sys.stdout.flush()
