@@ -1135,6 +1135,15 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 EncodeTiledFn encode_fn() {
+  // cuTensorMapEncodeTiled is a DRIVER call: it needs a current context on the calling thread and returns
+  // CUDA_ERROR_INVALID_CONTEXT (201) otherwise.  A thread whose first piece of CUDA work is a tensor-core GEMM -- the
+  // autograd engine's worker when a backward starts with a weight gradient -- has none yet (the runtime binds the
+  // primary context lazily, on its own first call): bind it once per thread.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    cudaFree(nullptr);
+    ctx_bound = true;
+  }
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     void* p = nullptr;
@@ -1160,6 +1169,7 @@ bool make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int6
   return r == CUDA_SUCCESS;
 }
 
+thread_local char g_map_err[256] = "cuTensorMapEncodeTiled failed";
 // fp32 [rows, cols] row-major, box = 32 cols (128 bytes) x box_rows
 bool make_map_f32(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
                   CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
@@ -1172,6 +1182,9 @@ bool make_map_f32(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, 
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    snprintf(g_map_err, sizeof(g_map_err), "cuTensorMapEncodeTiled(f32) -> %d: base %p rows %lld cols %lld ld %lld box_rows %d swizzle %d",
+             (int)r, base, (long long)rows, (long long)cols, (long long)ld, box_rows, (int)swz);
   return r == CUDA_SUCCESS;
 }
 
@@ -1264,6 +1277,33 @@ int gemm_tf32x3_dispatch(const void* A, int64_t lda, const void* W, int64_t ldw,
                          const void* addend, int64_t ld_add, int64_t add_col0, float* stats, int64_t stats_cols) {
   const char* fn = "egnn_gemm(tcgen05 3xTF32)";
   const int Npad = (int)((N + 15) / 16 * 16);
+  if (Npad > 128 && g_f32_tc_exact.load(std::memory_order_relaxed) != 0) {
+    // exact accumulation holds one 128-column tile in TMEM: a wider product (the [dm | dx_root] dgrad of a 128-wide
+    // fp32 SAGE layer) runs as column blocks of 128 -- A is read once per block, every block exact
+    const size_t c_es = c_dtype == EGNN_F32 ? 4 : 2;
+    for (int64_t c0 = 0; c0 < N; c0 += 128) {
+      const int64_t n = N - c0 < 128 ? N - c0 : 128;
+      const int32_t* rd = row_div_ptr;
+      int64_t rdc = row_div_cols;
+      if (rd && row_div_cols > 0) {
+        rdc = row_div_cols - c0;
+        if (rdc <= 0) rd = nullptr;
+        else if (rdc > n) rdc = n;
+      }
+      const void* ad = nullptr;
+      int64_t ac0 = 0;
+      if (addend && add_col0 < c0 + n) {
+        ac0 = add_col0 > c0 ? add_col0 - c0 : 0;
+        ad = reinterpret_cast<const char*>(addend) + (size_t)(c0 > add_col0 ? c0 - add_col0 : 0) * c_es;
+      }
+      int rc = gemm_tf32x3_dispatch(A, lda, reinterpret_cast<const float*>(W) + c0 * ldw, ldw,
+                                    reinterpret_cast<char*>(C) + (size_t)c0 * c_es, c_dtype, ld_c, M, n, K,
+                                    bias ? bias + c0 : nullptr, accumulate, rd, rdc, workspace, st, ad, ld_add, ac0,
+                                    c0 == 0 ? stats : nullptr, c0 == 0 ? stats_cols : 0);
+      if (rc) return rc;
+    }
+    return 0;
+  }
   // dense [N, K] hi / lo copies of the weight (16-byte aligned halves of the workspace)
   float* whi = reinterpret_cast<float*>(((uintptr_t)workspace + 15) & ~uintptr_t(15));
   float* wlo = whi + ((N * K + 3) / 4) * 4;
@@ -1359,7 +1399,7 @@ int wgrad_tf32x3_dispatch(const void* G, int64_t ldg, const void* X, int64_t ldx
   CUtensorMap tmX, tmG;
   if (!make_map_f32(&tmX, X, M_rows, K_in, ldx, kSlab32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||
       !make_map_f32(&tmG, G, M_rows, N_out, ldg, kSlab32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
-    return fail(fn, "cuTensorMapEncodeTiled failed");
+    return fail(fn, g_map_err);
   const int stages = wgrad32_stages(XB, GB);
   const size_t smem = (size_t)stages * 2 * (XB + GB) * kBlk32 + 256 + 1024;
   static bool attr_set = false;

@@ -56,9 +56,9 @@ const char* egnn_last_error(void);
 uint64_t egnn_launch_count(void);
 /* How the fp32-operand tensor-core GEMMs (3xTF32: egnn_gemm / egnn_linear_tc with EGNN_F32 operands) accumulate.
  *   1 (default): exact -- every 8-wide k-step product leaves the tensor core in a fresh TMEM buffer and is added with IEEE
- *     round-to-nearest on the CUDA cores (the tensor core's own accumulator TRUNCATES, a bias that does not average out
- *     through a training step); fp32 logits AND gradients within 2e-6 of the fp32 oracle (N <= 128 output columns;
- *     wider products fall back to 0).  What fp32 training uses (src/train_gnn.py:187-209 with amp off).
+ *    round-to-nearest on the CUDA cores (the tensor core's own accumulator TRUNCATES, a bias that does not average out
+ *     through a training step); fp32 logits AND gradients within 2e-6 of the fp32 oracle (products wider than 128
+ *     output columns run as 128-column blocks).  What fp32 training uses (src/train_gnn.py:187-209 with amp off).
  *   0: accumulate in TMEM (~2e-6 per product, inside the 1e-5 logits bar): no-grad forwards (`eval_split`,
  *     src/train_gnn.py:248-257), ~15 % faster.
  * Process-wide host state read when a GEMM is enqueued (also under CUDA-graph capture); returns the previous value. */

@@ -4,7 +4,7 @@ the SIMT path; plus epilogue options (bias, accumulate, row-count division, fp32
 import pytest
 import torch
 
-from util import assert_close
+from util import assert_close, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -153,3 +153,79 @@ def test_fp32_wgrad_3xtf32_matches_fp64(egnn, M, N, K):
     assert_close(out, ref, TOL_F32, "3xTF32 wgrad")
     assert torch.equal(out, ops.linear_wgrad(g, x))  # deterministic partial reduction
     assert_close(ops.linear_wgrad(g, x, impl=1), ref, TOL_F32, "SIMT wgrad")
+
+
+@pytest.mark.parametrize("K,N", [(336, 128), (168, 64), (128, 256), (64, 128), (40, 24)])
+def test_fp32_exact_accumulation_modes(egnn, K, N):
+    """`egnn_set_f32_tc_exact`: 1 = every 8-wide k-step product summed with IEEE adds outside the tensor core (what
+    anything with a gradient runs; products wider than 128 columns as 128-column blocks), 0 = accumulate in TMEM (no-grad
+    forwards).  Both inside the fp32 bar; the exact mode as close to fp64 as the FFMA kernel, and its error free of the
+    truncation BIAS (mean signed error of positive sums ~0, where the in-TMEM mode leans towards zero)."""
+    from egnn_b200 import _lib, ops
+    L = _lib.lib()
+    M = 20000
+    a, w = _mk32((M, K), 31, heavy=True).abs(), _mk32((N, K), 32).abs() / K ** 0.5     # all-positive: sums never cancel
+    ref = a.double() @ w.double().t()
+    prev = L.egnn_set_f32_tc_exact(1)
+    try:
+        exact = ops.linear_fwd(a, w)
+        assert L.egnn_set_f32_tc_exact(0) == 1
+        fast = ops.linear_fwd(a, w)
+        assert L.egnn_set_f32_tc_exact(1) == 0
+        simt = ops.linear_fwd(a, w, impl=1)
+        e_exact, e_fast, e_simt = (rel_err(t, ref) for t in (exact, fast, simt))
+        assert e_exact <= TOL_F32 and e_fast <= TOL_F32
+        assert e_exact <= max(3 * e_simt, 1.5e-6), (e_exact, e_simt)
+        bias_exact = float(((exact.double() - ref) / ref).mean())
+        bias_fast = float(((fast.double() - ref) / ref).mean())
+        assert abs(bias_exact) < 2e-7, bias_exact
+        if K >= 128:
+            assert bias_fast < -3 * abs(bias_exact) - 1e-7, (bias_fast, bias_exact)   # truncation leans towards zero
+        # epilogues through the exact path, incl. a 256-wide product split into column blocks
+        cnt = torch.randint(0, 5, (M,))
+        ptr = torch.zeros(M + 1, dtype=torch.int32)
+        ptr[1:] = torch.cumsum(cnt, 0)
+        half = N // 2 if N % 32 == 0 else 0
+        d = torch.empty((M, N), device="cuda")
+        ops._gemm(a, a.stride(0), 1, w, 1, w.stride(0), d, M, N, K, None, False, row_div=ptr.cuda(), row_div_cols=half)
+        want = ref.clone()
+        cols = slice(0, half) if half else slice(0, N)
+        want[:, cols] = want[:, cols] / cnt.clamp(min=1).double().cuda().unsqueeze(1)
+        assert_close(d, want, TOL_F32, "exact + row_div on the left columns")
+        bias = torch.randn(N, device="cuda")
+        base = torch.randn(M, N, device="cuda")
+        acc = base.clone()
+        ops.linear_fwd(a, w, bias=bias, out=acc, accumulate=True)
+        assert_close(acc, base.double() + ref + bias.double(), TOL_F32, "exact + bias + accumulate")
+    finally:
+        L.egnn_set_f32_tc_exact(prev)
+
+
+def test_tensor_core_gemm_from_a_fresh_thread(egnn):
+    """The TMA descriptor encode is a driver call and needs a current context: a thread whose FIRST CUDA work is one of
+    these GEMMs (the autograd worker when a backward starts with a weight gradient) must not fail with
+    CUDA_ERROR_INVALID_CONTEXT."""
+    import threading
+    from egnn_b200 import ops
+    g, x = _mk32((6000, 64), 41), _mk32((6000, 168), 42)
+    a16, w16 = _mk((4096, 64), 43), _mk((64, 64), 44)
+    torch.cuda.synchronize()
+    res = {}
+
+    def work(tag, fn):
+        try:
+            res[tag] = fn()
+        except Exception as ex:          # noqa: BLE001 -- reported by the assert below
+            res[tag] = ex
+    old, ops._F32_TC = ops._F32_TC, True
+    try:
+        for tag, fn in (("f32 wgrad", lambda: ops.linear_wgrad(g, x)), ("f32 fwd", lambda: ops.linear_fwd(x, _mk32((64, 168), 45))),
+                        ("bf16 fwd", lambda: ops.linear_fwd(a16, w16))):
+            t = threading.Thread(target=work, args=(tag, fn))
+            t.start()
+            t.join()
+            assert isinstance(res[tag], torch.Tensor), (tag, res[tag])
+    finally:
+        ops._F32_TC = old
+    torch.cuda.synchronize()
+    assert_close(res["f32 wgrad"], g.double().t() @ x.double(), TOL_F32, "wgrad from a fresh thread")
