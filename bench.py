@@ -49,6 +49,14 @@ def ncu_traffic():
         return None
 
 
+def ncu_l2_hit():
+    """L2 hit rate (%) of the roofline kernel from the same committed capture; None when not recorded."""
+    try:
+        return float(json.load(open(os.path.join(ROOT, "profiles", "r02", "roofline_traffic.json")))["l2_hit_rate_pct"])
+    except Exception:
+        return None
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons through NVML while the timed region runs."""
 
@@ -643,7 +651,12 @@ def run_ours(args):
         roof = {"kernel": "egnn_spmm mean fp32->bf16 F=168 (layer-0 aggregation, spmm_stream)", "bound": "hbm",
                 "achieved": round(b168 / t168 / 1e6, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(b168 / t168 / 1e6 / peak, 4), "traffic": ncu_traffic(), "peak_source": peak_src,
-                "algorithmic_bytes": b168, "us": round(t168 * 1e3, 2)}
+                "algorithmic_bytes": b168, "us": round(t168 * 1e3, 2),
+                # the gather-counted figure (every edge's source row counted, not each row once) and the
+                # measured L2 hit rate beside the compulsory-traffic fraction -- the base graph is L2-scale
+                "gather_counted_bytes": int(e_local * 168 * 4 + N * 168 * 2 + 4 * e_local + 4 * (N + 1)),
+                "gather_counted_GBps": round((e_local * 168 * 4 + N * 168 * 2 + 4 * e_local + 4 * (N + 1)) / t168 / 1e6, 1),
+                "l2_hit_rate_pct": ncu_l2_hit()}
         kernels = [
             {"kernel": "spmm mean fwd F=64 bf16", "us": round(t64 * 1e3, 2), "GBps": round(b64 / t64 / 1e6, 1)},
             {"kernel": "spmm transposed sum + addend (CSC) F=64 bf16", "us": round(t64b * 1e3, 2),
@@ -731,6 +744,8 @@ def run_ours(args):
                                 "overlapping the previous step), byte-wise device comparison of the submitted edge_index "
                                 "with the one the CSR/CSC views were built from (rebuild only when it differs), step, "
                                 "loss -> host"},
+            # edges visited by the aggregation kernels of one step = E' x (3 forward + 2 backward SpMM)
+            "edge_traversals_per_step": int(e_total * 5),
             "gpu_launches": int(launches_per_step * args.steps),
             "gpu_launches_per_step": int(launches_per_step),
             "roofline": roof, "kernels": kernels, "cpu_baseline": cpu,
@@ -849,7 +864,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--eager", action="store_true", help="do not capture a CUDA graph (profiling runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU baseline leg (profiling runs)")

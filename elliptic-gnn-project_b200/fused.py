@@ -349,6 +349,7 @@ def backward(net, sv: Saved, dlogits: torch.Tensor, out: Optional[List[torch.Ten
     L = lib()
     g = sv.g
     dev = dlogits.device
+    ops._ensure_exact()       # fp32 operands: the backward's GEMMs accumulate exactly (ops.set_f32_tc)
     N = dlogits.size(0)
     cd = sv.layers[0].z.dtype
     H = sv.layers[0].No

@@ -179,6 +179,15 @@ def set_f32_tc(grad: Optional[bool] = None):
     return _F32_TC
 
 
+def _ensure_exact():
+    """Input / weight gradients are only ever computed for a gradient: exact accumulation, whatever a no-grad forward
+    that ran between this graph's forward and its backward left the library in."""
+    global _F32_TC_EXACT
+    if not _F32_TC_EXACT:
+        lib().egnn_set_f32_tc_exact(1)
+        _F32_TC_EXACT = True
+
+
 def _gemm(A, a_sm, a_sk, B, b_sk, b_sn, C, M, N, K, bias, accumulate, split_k=1, impl=None, row_div=None,
           need_ws=False, row_div_cols=0):
     L = lib()
@@ -210,6 +219,8 @@ def linear_dgrad(g, W, out=None, accumulate=False, out_dtype=None, row_div=None,
     g, W = _rows(g), _rows(W)
     M, N = g.shape
     K = W.size(1)
+    if g.dtype == torch.float32:
+        _ensure_exact()
     if out is None:
         out = torch.empty((M, K), dtype=out_dtype or g.dtype, device=g.device)
     if g.dtype == W.dtype and g.dtype in (torch.bfloat16, torch.float32):
@@ -227,6 +238,8 @@ def linear_wgrad(g, x, impl=None):
     g, x = _rows(g), _rows(x)
     M, N = g.shape
     K = x.size(1)
+    if g.dtype == torch.float32:
+        _ensure_exact()
     out = torch.empty((N, K), dtype=torch.float32, device=g.device)
     tiles = -(-N // 128) * -(-K // 64)
     split = max(1, min(-(-M // 512), -(-2 * 148 // tiles)))

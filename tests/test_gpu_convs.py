@@ -395,3 +395,27 @@ def test_convs_drop_into_a_reference_style_module(egnn, small_graph, kind, amp):
         if b.abs().max() < 1e-5 * max(q.grad.abs().max() for q in ref.parameters()):
             continue
         assert_close(p1.grad, p2.grad, 5 * REL_FP32, f"{kind} grad {n1}")
+
+
+def test_backward_after_a_no_grad_forward_accumulates_exactly(egnn, small_graph):
+    """fp32 tensor-core GEMMs accumulate in TMEM for no-grad forwards and exactly for everything a gradient is taken of
+    (`egnn_set_f32_tc_exact`): an `eval_split`-style forward between a graph's forward and its backward must not leave
+    the backward's dgrad / wgrad products in the truncating mode."""
+    from egnn_b200 import _lib
+    L = _lib.lib()
+    gr = small_graph
+    ei = torch.cat([gr.edge_index, gr.edge_index.flip(0)], 1)
+    ours, ref = _pair(lambda: egnn.SAGEConv(168, 64), lambda: O.SAGEConv(168, 64))
+    torch.manual_seed(4)
+    x = torch.randn(gr.num_nodes, 168)
+    xr, xc = x.clone().requires_grad_(True), x.cuda().requires_grad_(True)
+    yo = ours(xc, ei.cuda())
+    with torch.no_grad():
+        ours(xc, ei.cuda())
+    assert L.egnn_set_f32_tc_exact(0) == 0          # the no-grad forward switched to the in-TMEM accumulate
+    g = torch.randn(gr.num_nodes, 64)
+    yo.backward(g.cuda())
+    assert L.egnn_set_f32_tc_exact(1) == 1          # ... and the backward switched back before its first GEMM
+    ref(xr, ei).backward(g)
+    assert_close(xc.grad, xr.grad, REL_FP32, "sage dx")
+    _grads_close(ours, ref, REL_FP32, "sage")
