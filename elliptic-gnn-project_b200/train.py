@@ -477,3 +477,24 @@ def train_epoch_minibatch(model, loader, optimizer, loss_fn, cfg: dict, use_amp:
         total_examples += int(bs)
     return float(total_loss / total_examples) if total_examples else 0.0
 
+
+@torch.no_grad()
+def eval_val_minibatch(model, loader, device=None, as_numpy: bool = True):
+    """Mirror of the reference's `eval_val_minibatch` (`src/train_gnn.py:258-277`): eval-mode forward on every sampled
+    subgraph of `loader`, softmax probability of the illicit class for the seeds.  Returns `(y, probs)` -- numpy arrays
+    like the reference (`as_numpy=True`: one device-to-host copy at the end, not one per batch), or device tensors for
+    `metrics.average_precision`.  Empty loader -> two empty arrays."""
+    model.eval()
+    ys, ps = [], []
+    for batch in loader:
+        batch = batch.to("cuda")
+        logits = model(batch.x, batch.edge_index, batch.timestep if model_uses_time_embed(model) else None)
+        bs = batch.batch_size
+        ps.append(torch.softmax(logits[:bs].float(), dim=1)[:, 1])
+        ys.append(batch.y[:bs])
+    if not ys:
+        import numpy as np
+        return (np.array([]), np.array([])) if as_numpy else (torch.empty(0), torch.empty(0))
+    y, p = torch.cat(ys), torch.cat(ps)
+    return (y.cpu().numpy(), p.cpu().numpy()) if as_numpy else (y, p)
+

@@ -165,3 +165,24 @@ def test_full_fanout_minibatch_equals_full_batch(egnn, small_graph):
     assert abs(loss_o - tot / cnt) <= 1e-4 * abs(tot / cnt), (loss_o, tot / cnt)
     for (n, p), (_, q) in zip(ours.named_parameters(), ref.named_parameters()):
         assert_close(p.detach().cpu(), q.detach(), 1e-3, f"parameters after one mini-batch epoch: {n}")
+
+
+def test_eval_val_minibatch_matches_full_graph_eval(egnn, small_graph):
+    """`eval_val_minibatch` (`src/train_gnn.py:258-277`) with full fan-outs = the `eval_split` probabilities of the same
+    nodes (SAGE-ResBN in eval mode: BatchNorm on its running statistics, so a sampled subgraph changes nothing)."""
+    from egnn_b200.train import eval_probs, eval_val_minibatch
+    gr = small_graph
+    sym = torch.cat([gr.edge_index, gr.edge_index.flip(0)], 1)
+    data = _Data(gr, sym)
+    cfg = dict(hidden_dim=64, layers=3, dropout=0.2, time_embed_dim=2, time_embed_type="sin", max_timestep=12)
+    torch.manual_seed(0)
+    model = egnn.build_model("sage_resbn", 166, cfg).cuda()
+    idx = torch.nonzero(gr.val_mask).view(-1)
+    loader = egnn.NeighborLoader(data, num_neighbors=[-1, -1, -1], batch_size=128, input_nodes=idx, shuffle=False)
+    y, p = eval_val_minibatch(model, loader)
+    probs_full, _ = eval_probs(model, gr.x.cuda(), sym.cuda(), gr.timestep.cuda())
+    assert y.shape == p.shape == (idx.numel(),) and (y == gr.y[idx].numpy()).all()
+    assert_close(torch.from_numpy(p), probs_full[idx.cuda()].cpu(), REL_FP32, "mini-batch eval probabilities")
+    yd, pd = eval_val_minibatch(model, loader, as_numpy=False)
+    assert yd.is_cuda and torch.equal(pd.cpu(), torch.from_numpy(p))
+
