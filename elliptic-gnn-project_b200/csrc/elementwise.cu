@@ -636,10 +636,13 @@ __global__ void __launch_bounds__(kThreads, (BN || PROJ || sizeof(T) == 4) ? 2 :
   const uint64_t seed = C.seed + (C.seed_off ? (uint64_t)*C.seed_off : 0ull);
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(n_rows, r0 + rows_per_block);
   // uniform trip count over the block (rows_per_block is a multiple of RL * kRows8): every lane reaches the shuffles
-  for (int64_t rb = r0 + rl; rb < r0 + rows_per_block; rb += (int64_t)RL * kRows8) {
-    Raw8<T> zr[kRows8], rr[kRows8];
+  // fp32 rows with the projection folded in: 2 rows in flight (32-byte raw rows of z and res x 4 rows + the 32
+  // projection weights + the 32 BatchNorm constants do not fit 128 registers: 0.9 KB of spill traffic per thread-row)
+  constexpr int kR = (sizeof(T) == 4 && PROJ && BN) ? 2 : kRows8;
+  for (int64_t rb = r0 + rl; rb < r0 + rows_per_block; rb += (int64_t)RL * kR) {
+    Raw8<T> zr[kR], rr[kR];
 #pragma unroll
-    for (int u = 0; u < kRows8; ++u) {
+    for (int u = 0; u < kR; ++u) {
       const int64_t r = rb + (int64_t)u * RL;
       if (r < r1) {
         zr[u].load(z + r * ld + c);
@@ -647,7 +650,7 @@ __global__ void __launch_bounds__(kThreads, (BN || PROJ || sizeof(T) == 4) ? 2 :
       }
     }
 #pragma unroll
-    for (int u = 0; u < kRows8; ++u) {
+    for (int u = 0; u < kR; ++u) {
       const int64_t r = rb + (int64_t)u * RL;
       const bool valid = r < r1;
       float y[8];
