@@ -458,7 +458,7 @@ def train_epoch_minibatch(model, loader, optimizer, loss_fn, cfg: dict, use_amp:
     `batch.batch_size` rows (the seeds), backward, clip, optimizer step; returns the example-weighted mean loss.
     `loss_fn(logits, target, t_idx)` as `make_loss_fn` returns it.  bf16 autocast instead of fp16 + GradScaler."""
     model.train()
-    total_loss, total_examples = 0.0, 0
+    total_loss, total_examples = None, 0      # the running sum stays on the device: one read-back per epoch, not per batch
     weighting = cfg.get("time_loss_weighting", "none") != "none"
     for batch in loader:
         batch = batch.to("cuda")
@@ -473,9 +473,10 @@ def train_epoch_minibatch(model, loader, optimizer, loss_fn, cfg: dict, use_amp:
             torch.nn.utils.clip_grad_norm_(model.parameters(), cfg["grad_clip"])
         optimizer.step()
         optimizer.zero_grad(set_to_none=True)
-        total_loss += float(loss.item()) * int(bs)
+        part = loss.detach().float() * float(bs)
+        total_loss = part if total_loss is None else total_loss + part
         total_examples += int(bs)
-    return float(total_loss / total_examples) if total_examples else 0.0
+    return float(total_loss.item() / total_examples) if total_examples else 0.0
 
 
 @torch.no_grad()
