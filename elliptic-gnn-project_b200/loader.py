@@ -68,7 +68,7 @@ class NeighborLoader:
         if not 1 <= len(self.fanouts) <= 8:
             raise ValueError("num_neighbors: 1 to 8 hops")
         self.batch_size, self.shuffle, self.drop_last, self.seed = int(batch_size), bool(shuffle), bool(drop_last), int(seed)
-        self.rows = {k: getattr(data, k).to(dev) for k in _ROW_KEYS if getattr(data, k, None) is not None}
+        self.rows = {k: getattr(data, k).to(dev).contiguous() for k in _ROW_KEYS if getattr(data, k, None) is not None}
         ei = data.edge_index.to(dev)
         self.N = int(self.rows["x"].size(0))
         self.E = int(ei.size(1))
