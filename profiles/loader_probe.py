@@ -43,7 +43,6 @@ for fan, bs in (([10, 10], 8192), ([25, 10], 8192), ([-1, -1], 8192), ([10, 10],
 cfg = dict(hidden_dim=64, layers=3, dropout=0.2, time_embed_dim=2, time_embed_type="sin", max_timestep=49)
 torch.manual_seed(0)
 model = E.build_model("sage_resbn", 166, cfg).cuda()
-cw = E.train.class_weight(data.y[data.train_mask]) if hasattr(E, "train") else None
 from egnn_b200.train import class_weight
 cw = class_weight(data.y[data.train_mask])
 loss_fn = E.make_loss_fn({}, cw, model, 1, 49)
