@@ -498,7 +498,9 @@ class GcnConvFn(torch.autograd.Function):
         dout = _rows(dout)
         dh = spmm(g, "csc", _lib.SPMM_WEIGHTED, dout, xg.dtype)
         dw = linear_wgrad(dh, xg)
-        db = colsum(dout).float()
+        db = _take_colsum(dout)
+        if db is None:
+            db = colsum(dout).float()
         dx = None
         if ctx.needs_input_grad[0]:
             dx = linear_dgrad(dh, wc)
@@ -768,9 +770,13 @@ class BnActDropResFn(torch.autograd.Function):
             _publish_colsum(dz, dzsum)
             dbeta, dgamma = sgf[0], sgf[1]
         else:
+            # the column sums of dz (the bias gradient of the conv that produced z) ride along, as in the BN branch
+            dzsum = torch.empty(F, dtype=torch.float32, device=z.device)
+            ws2 = torch.empty(L.egnn_colreduce_workspace_bytes(F) + 64 * F, dtype=torch.uint8, device=z.device)
             check(L.egnn_bn_act_dropout_bwd_apply(ptr(dy), ptr(z), ptr(dz), dt(z), F, N, F, None, None, None,
                                                   None, act, p_eff, seed, ptr(soff), layer, row0, None, None,
-                                                  1.0, None, None, _ld(z), ptr(ctx.kb), stream()))
+                                                  1.0, ptr(dzsum), ptr(ws2), _ld(z), ptr(ctx.kb), stream()))
+            _publish_colsum(dz, dzsum)
         dres = dy if has_res else None
         return (dz, dres, dgamma, dbeta) + (None,) * 11
 
