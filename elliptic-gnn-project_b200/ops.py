@@ -154,7 +154,7 @@ GEMM_IMPL = 0  # 0 auto (tcgen05 for bf16 where supported), 1 force SIMT, 2 forc
 # product out of the tensor core in a fresh TMEM buffer and add it with IEEE round-to-nearest on the CUDA cores (forward /
 # dgrad, `kExact`), and split the weight gradient's node axis into phases of <= 132 tensor-core additions combined with
 # IEEE adds.  Measured at full size against the CPU oracle (profiles/r02/f32_tc_probe.txt): gcn.yaml / sage.yaml
-# gradients within 2e-6 (FFMA: 4e-7), sage.yaml fp32 1.60 -> 0.66 ms, gcn.yaml 1.75 -> 1.13 ms, rec_k8 fp32 2.72 -> 1.29
+# gradients within 2e-6 (FFMA: 4e-7), sage.yaml fp32 1.60 -> 0.66 ms, gcn.yaml 1.75 -> 1.07 ms, rec_k8 fp32 2.72 -> 1.29
 # ms per step.  EGNN_F32_TC_TRAIN=0 / EGNN_F32_TC_WGRAD=0 (or the module attributes) put fp32 TRAINING back on the exact
 # FFMA kernels (gemm_simt.cu); no-grad forwards always use the tensor cores.
 import os as _os
