@@ -186,3 +186,30 @@ def test_eval_val_minibatch_matches_full_graph_eval(egnn, small_graph):
     yd, pd = eval_val_minibatch(model, loader, as_numpy=False)
     assert yd.is_cuda and torch.equal(pd.cpu(), torch.from_numpy(p))
 
+
+
+def test_sampler_matches_the_committed_golden_vectors(egnn):
+    """tests/golden/neighbor_sample_golden.json (made by make_neighbor_sample_golden.py from the oracle): pins the Philox
+    keying, the Floyd draw and the relabelling order of the kernel against a committed file, not only against the oracle
+    of the day."""
+    import json
+    import os
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "neighbor_sample_golden.json")))
+    for name, g in gold.items():
+        n = g["num_nodes"]
+
+        class D:
+            pass
+        d = D()
+        d.x = torch.zeros(n, 4)
+        d.y = torch.arange(n)
+        d.timestep = torch.ones(n, dtype=torch.int64)
+        d.edge_index = torch.tensor(g["edge_index"], dtype=torch.int64)
+        seeds = torch.tensor(g["seeds"], dtype=torch.int64, device="cuda")
+        for c in g["cases"]:
+            loader = egnn.NeighborLoader(d, num_neighbors=c["fanouts"], batch_size=len(g["seeds"]), seed=c["seed"])
+            b = loader.sample(seeds, c["batch_idx"])
+            assert b.n_id.cpu().tolist() == c["n_id"], (name, c["fanouts"])
+            assert b.edge_index.cpu().tolist() == c["edge_index"] and b.e_id.cpu().tolist() == c["e_id"]
+            assert b.counts.cpu().tolist() == c["nodes_after"] + c["edges_after"]
+            assert torch.equal(b.y.cpu(), torch.tensor(c["n_id"]))

@@ -65,3 +65,18 @@ def test_floyd_draw_is_uniform():
         hits[n_id[le[0]]] += 1
     p = hits[1:] / trials
     assert np.all(np.abs(p - 1 / 3) < 0.035), p          # 4 sigma of a Binomial(3000, 1/3) proportion
+
+
+def test_oracle_reproduces_the_committed_golden_vectors():
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "neighbor_sample_golden.json")
+    gold = json.load(open(path))
+    for name, g in gold.items():
+        ei = np.asarray(g["edge_index"])
+        ip, src, eid = csc_by_destination(ei, g["num_nodes"])
+        for c in g["cases"]:
+            n_id, le, e_id, nodes, edges = neighbor_sample(ip, src, eid, g["seeds"], c["fanouts"], seed=c["seed"],
+                                                           batch_idx=c["batch_idx"])
+            assert n_id.tolist() == c["n_id"] and le.tolist() == c["edge_index"] and e_id.tolist() == c["e_id"], name
+            assert nodes == c["nodes_after"] and edges == c["edges_after"]
