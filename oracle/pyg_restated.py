@@ -12,6 +12,8 @@ same ATen ops PyG dispatches (`index_select`, `scatter_add_`, `scatter_reduce_`,
 
 What pins it instead:
   * hand-derived known-answer vectors (SURVEY.md A.5) in `tests/test_oracle_known_answers.py`;
+  * an independent float64 dense-adjacency evaluation of the three layer equations (values and
+    gradients, 1e-12) in `tests/test_oracle_dense_algebra.py`;
   * `tests/golden/make_golden.py` imports the reference's *own* `src/models/gnn.py` and
     `src/train_gnn.py` (unmodified, from /root/reference) with these restated convs
     injected under the name `torch_geometric.nn`, and records what the reference's
