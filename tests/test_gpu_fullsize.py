@@ -104,7 +104,7 @@ def test_full_size_train_step_bf16(egnn, full_graph, name):
             lg = net(x, ei, gr.timestep if uses_t else None, dropout_masks=masks)
         loss = O.masked_weighted_ce(lg.float(), gr.y, gr.train_mask, cw)
         loss.backward()
-        return float(loss), [(n, p.grad) for n, p in net.named_parameters()]
+        return float(loss.detach()), [(n, p.grad) for n, p in net.named_parameters()]
 
     l32, g32 = oracle(ref32, False)
     l16, g16 = oracle(ref16, True)

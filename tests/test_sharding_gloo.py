@@ -103,7 +103,7 @@ def test_two_rank_shards_reproduce_the_single_process_step(tmp_path):
     loss = O.masked_weighted_ce(model(gr.x, ei, None), gr.y, tm, O.class_weight(gr.y[tm]))
     loss.backward()
     flat = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
-    assert abs(float(r["loss"]) - float(loss)) <= 1e-6 * abs(float(loss))
+    assert abs(float(r["loss"]) - float(loss.detach())) <= 1e-6 * abs(float(loss.detach()))
     assert (r["grad"] - flat).abs().max() <= 1e-5 * flat.abs().max()
     # the gathered (padded, masked) rows carry exactly the whole graph's validation set: same PR-AUC as one process
     from oracle import metrics_np as M
