@@ -399,7 +399,7 @@ def step1_parity(init_state, masks, host_gr, ei_host, loss_bf16_gpu, gnorm_bf16_
             loss = O.masked_weighted_ce(logits, host_gr.y, host_gr.train_mask, cw)
         loss.backward()
         gn = float(torch.nn.utils.clip_grad_norm_(ref.parameters(), CFG["grad_clip"]))
-        res[f"cpu_{tag}"] = {"loss": float(loss), "grad_norm": gn}
+        res[f"cpu_{tag}"] = {"loss": float(loss.detach()), "grad_norm": gn}
     rel = lambda a, b: abs(a - b) / abs(b)
     c32, c16 = res["cpu_fp32"], res["cpu_bf16"]
     return {"what": "step 1 from the initial weights, same graph / weights / dropout masks: GPU vs CPU oracle",
