@@ -159,7 +159,7 @@ def dt(t: torch.Tensor) -> int:
     if t.dtype == torch.bfloat16:
         return BF16
     raise TypeError(f"egnn_b200 kernels take float32 or bfloat16 tensors, got {t.dtype} "
-                    "(fp16 autocast is not supported: use autocast(dtype=torch.bfloat16))")
+                    "(there are no fp16 kernels: the convs / nets widen fp16 inputs to fp32, ops.widen_fp16)")
 
 
 def ptr(t):

@@ -39,6 +39,7 @@ class _StackNet(nn.Module, _DropoutMixin):
     _act = ACT_RELU
 
     def forward(self, x, edge_index: Union[torch.Tensor, Graph], t_idx: Optional[torch.Tensor] = None):
+        x = ops.widen_fp16(x)
         if getattr(self, "no_residual", False) and type(self).forward is _StackNet.forward:
             bf16 = ops.amp_bf16()
             if fused.supported(self, x, bf16) and (bf16 or ops.set_f32_tc()):
@@ -105,7 +106,7 @@ class _ResProj(nn.Linear):
 
     def forward(self, x):
         bf16 = ops.amp_bf16()
-        return _LinearFn.apply(x, self.weight, bf16)
+        return _LinearFn.apply(ops.widen_fp16(x), self.weight, bf16)
 
 
 class _LinearFn(torch.autograd.Function):
@@ -190,6 +191,7 @@ class SAGEResBNNet(nn.Module, _DropoutMixin):
         return ops.inject_time(x, t_idx, table, self.in_dim)
 
     def forward(self, x, edge_index: Union[torch.Tensor, Graph], t_idx: Optional[torch.Tensor] = None):
+        x = ops.widen_fp16(x)
         bf16 = ops.amp_bf16()
         if fused.supported(self, x, bf16) and (bf16 or ops.set_f32_tc()):
             # the whole net as one explicit kernel sequence (fused.py): bf16 operands under autocast, 3xTF32 otherwise

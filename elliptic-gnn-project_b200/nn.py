@@ -51,12 +51,13 @@ def _graph_of(edge_index: Union[torch.Tensor, Graph], n: int, self_loops: bool) 
     return cached_graph(edge_index, n, self_loops=self_loops)
 
 
-def _check_input(x: torch.Tensor, in_channels: int):
+def _check_input(x: torch.Tensor, in_channels: int) -> torch.Tensor:
     ops.set_f32_tc()
     if not x.is_cuda:
         raise RuntimeError("egnn_b200 convs run on CUDA tensors only (no CPU fallback)")
     if x.dim() != 2 or x.size(1) != in_channels:
         raise ValueError(f"expected x of shape [N, {in_channels}], got {tuple(x.shape)}")
+    return ops.widen_fp16(x)          # fp16 from a caller's fp16-autocast modules: computed in fp32 (ops.amp_bf16)
 
 
 class SAGEConv(nn.Module):
@@ -73,7 +74,7 @@ class SAGEConv(nn.Module):
         self.lin_r.reset_parameters()
 
     def forward(self, x: torch.Tensor, edge_index: Union[torch.Tensor, Graph]) -> torch.Tensor:
-        _check_input(x, self.in_channels)
+        x = _check_input(x, self.in_channels)
         g = _graph_of(edge_index, x.size(0), self_loops=False)
         if ops.sage_out_supported(x, self.out_channels):
             # narrow output (the logits layer): project first, aggregate at width out_channels
@@ -84,7 +85,7 @@ class SAGEConv(nn.Module):
     def forward_with_res(self, x: torch.Tensor, edge_index: Union[torch.Tensor, Graph], res_weight: torch.Tensor):
         """(conv(x, edge_index), x @ res_weight.T): SAGEResBNNet's residual projection
         (`src/models/gnn.py:141-144,192`) folded into the conv's GEMM."""
-        _check_input(x, self.in_channels)
+        x = _check_input(x, self.in_channels)
         g = _graph_of(edge_index, x.size(0), self_loops=False)
         return ops.SageConvFn.apply(x, self.lin_l.weight, self.lin_l.bias, self.lin_r.weight, res_weight, g,
                                     ops.amp_bf16())
@@ -108,7 +109,7 @@ class GCNConv(nn.Module):
             self.bias.zero_()
 
     def forward(self, x: torch.Tensor, edge_index: Union[torch.Tensor, Graph]) -> torch.Tensor:
-        _check_input(x, self.in_channels)
+        x = _check_input(x, self.in_channels)
         g = _graph_of(edge_index, x.size(0), self_loops=True)
         if self.out_channels in (2, 4) and ops.sage_out_supported(x, self.out_channels):
             # narrow output (the logits layer): project first, aggregate at width out_channels
@@ -137,7 +138,7 @@ class GATConv(nn.Module):
         _glorot_(self.att_dst)
 
     def forward(self, x: torch.Tensor, edge_index: Union[torch.Tensor, Graph]) -> torch.Tensor:
-        _check_input(x, self.in_channels)
+        x = _check_input(x, self.in_channels)
         g = _graph_of(edge_index, x.size(0), self_loops=True)
         return ops.GatConvFn.apply(x, self.lin.weight, self.att_src, self.att_dst, self.bias, g, self.heads,
                                    self.out_channels, self.concat, self.negative_slope, ops.amp_bf16())

@@ -8,6 +8,8 @@ autograd bookkeeping and a few O(F)-sized conversions.
 """
 from __future__ import annotations
 
+import os
+import warnings
 from typing import Optional
 
 import torch
@@ -19,16 +21,53 @@ from .graph import Graph
 _TD = {F32: torch.float32, BF16: torch.bfloat16}
 
 
+_FP16_WARNED = False
+
+
+def _fp16_policy() -> str:
+    """`EGNN_FP16_AUTOCAST`: "fp32" (default) computes an fp16-autocast region in fp32; "raise" rejects it."""
+    p = os.environ.get("EGNN_FP16_AUTOCAST", "fp32").strip().lower()
+    if p not in ("fp32", "raise"):
+        raise ValueError(f"EGNN_FP16_AUTOCAST must be 'fp32' or 'raise', got {p!r}")
+    return p
+
+
 def amp_bf16() -> bool:
-    """True when the caller runs us under torch.autocast(device_type='cuda', dtype=bfloat16)."""
+    """True when the caller runs us under torch.autocast(device_type='cuda', dtype=bfloat16).
+
+    The reference's `amp: true` is fp16 autocast + GradScaler (`src/train_gnn.py:36-47,202-207`).  There are no fp16
+    kernels here: under fp16 autocast the convs and nets compute in fp32 (tensor cores, 3xTF32 with exact
+    accumulation) -- every value the reference rounds to fp16 is the fp32 value computed here, so the results lie
+    inside the reference's own rounding error -- and emit fp32, which `GradScaler.scale / unscale_ / step` handle
+    like any fp32 gradient.  It costs the bf16 path's speed (use autocast(dtype=torch.bfloat16) for that), hence the
+    one-time warning; `EGNN_FP16_AUTOCAST=raise` turns the widening into an error."""
+    global _FP16_WARNED
     if not torch.is_autocast_enabled("cuda"):
         return False
     d = torch.get_autocast_dtype("cuda")
-    if d != torch.bfloat16:
-        raise RuntimeError(
-            "egnn_b200 implements bf16 autocast only; the reference's `amp: true` defaults to fp16 + "
-            "GradScaler (src/train_gnn.py:36-47).  Use torch.autocast('cuda', dtype=torch.bfloat16).")
-    return True
+    if d == torch.bfloat16:
+        return True
+    if d == torch.float16 and _fp16_policy() == "fp32":
+        if not _FP16_WARNED:
+            _FP16_WARNED = True
+            warnings.warn("egnn_b200: fp16 autocast region computed in fp32 (no fp16 kernels; results are at least as "
+                          "accurate as fp16).  Use torch.autocast('cuda', dtype=torch.bfloat16) for the fast path.",
+                          RuntimeWarning, stacklevel=3)
+        return False
+    raise RuntimeError(
+        "egnn_b200 implements bf16 autocast only; the reference's `amp: true` defaults to fp16 + "
+        "GradScaler (src/train_gnn.py:36-47).  Use torch.autocast('cuda', dtype=torch.bfloat16).")
+
+
+def widen_fp16(x: torch.Tensor) -> torch.Tensor:
+    """fp16 activations (what a caller's own `nn.Linear` emits under fp16 autocast) enter the kernels as fp32: the
+    conversion is exact and differentiable (the upstream module receives an fp16 gradient, as autocast would give it)."""
+    if x.dtype != torch.float16:
+        return x
+    if _fp16_policy() == "raise":
+        raise TypeError("egnn_b200 kernels take float32 or bfloat16 tensors, got torch.float16 "
+                        "(EGNN_FP16_AUTOCAST=raise)")
+    return x.float()
 
 
 def _rows(t: torch.Tensor) -> torch.Tensor:

@@ -161,7 +161,7 @@ def test_full_fanout_minibatch_equals_full_batch(egnn, small_graph):
         loss.backward()
         torch.nn.utils.clip_grad_norm_(ref.parameters(), 1.0)
         opt_r.step()
-        tot, cnt = tot + float(loss) * bs, cnt + bs
+        tot, cnt = tot + float(loss.detach()) * bs, cnt + bs
     assert abs(loss_o - tot / cnt) <= 1e-4 * abs(tot / cnt), (loss_o, tot / cnt)
     for (n, p), (_, q) in zip(ours.named_parameters(), ref.named_parameters()):
         assert_close(p.detach().cpu(), q.detach(), 1e-3, f"parameters after one mini-batch epoch: {n}")
