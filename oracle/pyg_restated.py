@@ -466,3 +466,41 @@ def eval_probs(model, x, edge_index, t_idx):
     uses_t = getattr(model, "time_embed_dim", 0) > 0
     logits = model(x, edge_index, t_idx if uses_t else None)
     return torch.softmax(logits, dim=1)[:, 1], logits
+
+
+def train_epoch_minibatch(model, batches, optimizer, loss_fn, cfg: dict) -> float:
+    """`train_epoch_minibatch` (train_gnn.py:212-245) without AMP: per batch forward on the sampled subgraph, loss on
+    the first `batch_size` rows (the seeds), backward, clip, step; returns the seed-weighted mean of the batch losses.
+    `batches`: iterable of objects with `x`, `edge_index`, `y`, `timestep`, `batch_size` (CPU tensors)."""
+    model.train()
+    uses_t = getattr(model, "time_embed_dim", 0) > 0
+    total_loss, total_examples = 0.0, 0
+    for batch in batches:
+        optimizer.zero_grad(set_to_none=True)
+        bs = int(batch.batch_size)
+        logits = model(batch.x, batch.edge_index, batch.timestep if uses_t else None)
+        t_idx = batch.timestep[:bs] if cfg.get("time_loss_weighting", "none") != "none" else None    # :229-233
+        loss = loss_fn(logits[:bs], batch.y[:bs], t_idx)
+        loss.backward()
+        if cfg.get("grad_clip", 0) and cfg["grad_clip"] > 0:
+            torch.nn.utils.clip_grad_norm_(model.parameters(), cfg["grad_clip"])
+        optimizer.step()
+        total_loss += loss.item() * bs                                                                # :242-243
+        total_examples += bs
+    return float(total_loss / total_examples) if total_examples else 0.0
+
+
+@torch.no_grad()
+def eval_val_minibatch(model, batches):
+    """`eval_val_minibatch` (train_gnn.py:261-280): (labels, P(illicit)) of the seeds of every batch, concatenated."""
+    model.eval()
+    uses_t = getattr(model, "time_embed_dim", 0) > 0
+    ys, ps = [], []
+    for batch in batches:
+        bs = int(batch.batch_size)
+        logits = model(batch.x, batch.edge_index, batch.timestep if uses_t else None)[:bs]
+        ps.append(torch.softmax(logits, dim=1)[:, 1])
+        ys.append(batch.y[:bs])
+    if not ys:
+        return torch.empty(0, dtype=torch.long), torch.empty(0)
+    return torch.cat(ys), torch.cat(ps)
